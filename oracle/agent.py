@@ -1,0 +1,37 @@
+"""Actor-side policy evaluation (reference: surreal/agent/ppo_agent.py:106-154, ddpg_agent.py:155-184)."""
+import numpy as np
+import torch
+
+from . import nets
+from . import pd as PD
+
+
+def ppo_act(obs_row, actor_layers, log_var, zfilter, log_noise, eps=None, deterministic=False):
+    """One env step of one PPO actor.  ``eps`` are the N(0,1) draws np.random.randn would return
+    (float64).  Returns (action float64 [A], pd float32 [2A]); pd stds are scaled by exp(noise)
+    BEFORE sampling and before being recorded (ppo_agent.py:139,149)."""
+    A = log_var.numel()
+    with torch.no_grad():
+        x = torch.tensor(obs_row, dtype=torch.float32).unsqueeze(0)
+        if zfilter is not None:
+            x = zfilter.forward(x)
+        pdv = nets.ppo_actor(x, actor_layers, log_var).numpy()
+    pdv[:, A:] *= np.exp(log_noise)
+    if deterministic:
+        act = PD.maxprob(pdv, A).copy()
+    else:
+        act = PD.sample(pdv, A, np.asarray(eps).reshape(1, A))
+    act = np.clip(act, -1, 1)
+    return act.reshape(-1), pdv.reshape(-1)
+
+
+def ddpg_act(obs_row, actor_layers, sigma, unit_noise=None, deterministic=False):
+    """ddpg_agent.py:155-184 with NormalActionNoise(0, sigma) (action_noise.py:9-16):
+    clip -> + noise -> clip.  ``unit_noise`` ~ N(0,1) so that noise = sigma * unit_noise."""
+    with torch.no_grad():
+        x = torch.tensor(obs_row, dtype=torch.float32).unsqueeze(0)
+        a = nets.ddpg_actor(x, actor_layers).numpy()[0]
+    a = a.clip(-1, 1)
+    if not deterministic:
+        a += sigma * np.asarray(unit_noise)        # in-place on the float32 array (ddpg_agent.py:181)
+    return a.clip(-1, 1)
