@@ -1,0 +1,86 @@
+"""ctypes binding of libsurreal_b200.so (the C-ABI declared in include/surreal_b200.h).
+
+The library is built in-tree by ``surreal_b200/build.py`` (nvcc, sm_100a).  There is NO fallback:
+if the shared object is missing or a kernel call fails, an exception is raised.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libsurreal_b200.so')
+MAX_LAYERS = 4
+ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
+
+c_f32p = C.POINTER(C.c_float)
+
+
+class SB200Error(RuntimeError):
+    pass
+
+
+class Mlp(C.Structure):
+    _fields_ = [('n_layers', C.c_int),
+                ('dims', C.c_int * (MAX_LAYERS + 1)),
+                ('act', C.c_int * MAX_LAYERS),
+                ('W', C.c_void_p * MAX_LAYERS),
+                ('b', C.c_void_p * MAX_LAYERS),
+                ('ldw', C.c_int * MAX_LAYERS),
+                ('aux_layer', C.c_int),
+                ('aux_dim', C.c_int)]
+
+
+class ZFilter(C.Structure):
+    _fields_ = [('stats', C.c_void_p), ('eps', C.c_float)]
+
+
+class Rows(C.Structure):
+    _fields_ = [('x', C.c_void_p), ('x_next', C.c_void_p), ('ldx', C.c_int64), ('rows', C.c_int64),
+                ('win_n', C.c_int), ('aux', C.c_void_p), ('aux_ld', C.c_int64)]
+
+
+_lib = None
+
+
+def _declare(lib):
+    P, I, L, D, F, S = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_float, C.c_size_t
+    sig = {
+        'sb200_version': (I, []),
+        'sb200_status_string': (C.c_char_p, [I]),
+        'sb200_device_info': (I, [C.POINTER(I), C.POINTER(I), C.POINTER(I)]),
+        'sb200_mlp_forward_f32': (I, [C.POINTER(Mlp), C.POINTER(ZFilter), C.POINTER(Rows),
+                                      C.POINTER(P), C.POINTER(L), P]),
+        'sb200_gae_workspace_bytes': (S, [I, I, I]),
+        'sb200_gae_window_f32': (I, [P, P, P, I, I, I, D, D, I, P, P, P, P]),
+    }
+    sig.update(_EXTRA_SIGS)
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return sig
+
+
+_EXTRA_SIGS = {}
+
+
+def exported_symbols():
+    """Names the header declares (used by the CPU-side 'library loads and exports' test)."""
+    return list(_declare(lib()).keys())
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SB200Error(
+                'libsurreal_b200.so is not built (%s). Run `python -m surreal_b200.build` '
+                '(needs nvcc); there is no CPU fallback.' % LIB_PATH)
+        _lib = C.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+def check(status, what=''):
+    if status != 0:
+        msg = lib().sb200_status_string(status).decode()
+        raise SB200Error('%s failed: %s (status %d)' % (what or 'libsurreal_b200 call', msg, status))

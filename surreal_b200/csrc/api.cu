@@ -1,0 +1,25 @@
+// Library-level entry points of libsurreal_b200.
+#include "common.cuh"
+
+extern "C" int sb200_version(void) { return 100; }
+
+extern "C" const char* sb200_status_string(int status) {
+    switch (status) {
+        case SB200_OK: return "ok";
+        case SB200_ERR_ARG: return "invalid argument";
+        case SB200_ERR_CUDA: return "CUDA error";
+        case SB200_ERR_UNSUPPORTED: return "unsupported configuration";
+        default: return "unknown status";
+    }
+}
+
+extern "C" int sb200_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    int dev = 0;
+    SB200_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    SB200_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return SB200_OK;
+}

@@ -1,0 +1,165 @@
+// Windowed GAE + n-step return (surreal/learner/ppo.py:372-374, 387-418).
+//
+// One warp per window: lanes stride over the n steps with coalesced loads of the window's
+// rewards / values / dones rows, products are formed exactly as the reference does
+// ((td * gamma^k) * lam^k with fp32 tables), the window sums are accumulated in fp64 and reduced with
+// warp shuffles.  The horizon-truncated (RNN-mode) variant stages td / r through shared memory.
+// Batch normalisation of the advantages (unbiased std, floor 1e-4) is fused through a last-block
+// ticket: the last CTA to finish reduces all B*E advantages in a fixed order (deterministic).
+//
+// Algorithmic HBM bytes per window: (3n+1)*4 read + 2*E*4 written (1548 B at n=128).
+#include "common.cuh"
+
+namespace {
+
+constexpr int GAE_WARPS = 8;
+
+struct GaeWs {
+    unsigned int counter;
+    unsigned int pad[3];
+};
+
+__device__ __forceinline__ float pow_table(float base_f32, int k) {
+    // torch.pow(python_float, fp32 tensor): base rounded to fp32, result within 1 ulp (ppo.py:373-374)
+    return (float)pow((double)base_f32, (double)k);
+}
+
+__device__ void normalize_all(float* adv, long long total, double* sh) {
+    // mean and UNBIASED std over all advantages (torch .mean() / .std(), ppo.py:413-416), two-pass fp64
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < total; i += blockDim.x) s += (double)adv[i];
+    const double mean = block_sum(s, sh) / (double)total;
+    double q = 0.0;
+    for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+        const double d = (double)adv[i] - mean;
+        q += d * d;
+    }
+    const double var = block_sum(q, sh) / (double)(total - 1);
+    const float mean_f = (float)mean;
+    const float std_f = (float)sqrt(var);
+    const float denom = (std_f > 1e-4f) ? std_f : 1e-4f;   // Python max(std, 1e-4)
+    for (long long i = threadIdx.x; i < total; i += blockDim.x) adv[i] = (adv[i] - mean_f) / denom;
+}
+
+// MLP branch: horizon == n, one (adv, ret) per window.
+__global__ void __launch_bounds__(GAE_WARPS * 32) gae_full_kernel(const float* __restrict__ rewards,
+                                                                   const float* __restrict__ values,
+                                                                   const float* __restrict__ dones, int B, int n,
+                                                                   float gamma_f, float lam_f, float gamma_pow_n,
+                                                                   int norm_adv, float* __restrict__ adv,
+                                                                   float* __restrict__ ret, GaeWs* ws) {
+    __shared__ double sh[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * GAE_WARPS + warp;
+    if (b < B) {
+        const float* r = rewards + (long long)b * n;
+        const float* v = values + (long long)b * (n + 1);
+        const float* d = dones + (long long)b * n;
+        double a_sum = 0.0, r_sum = 0.0;
+        for (int k = lane; k < n; k += 32) {
+            const float g = pow_table(gamma_f, k), l = pow_table(lam_f, k);
+            const float rk = r[k];
+            const float v0 = (k > 0) ? __fmul_rn(v[k], __fsub_rn(1.0f, d[k - 1])) : v[0];
+            const float v1 = __fmul_rn(v[k + 1], __fsub_rn(1.0f, d[k]));
+            // td = r + gamma*V[k+1] - V[k]; each op rounded separately like the eager reference
+            const float td = __fsub_rn(__fadd_rn(rk, __fmul_rn(gamma_f, v1)), v0);
+            a_sum += (double)__fmul_rn(__fmul_rn(td, g), l);
+            r_sum += (double)__fmul_rn(g, rk);
+        }
+        a_sum = warp_sum(a_sum);
+        r_sum = warp_sum(r_sum);
+        if (lane == 0) {
+            const float vn = __fmul_rn(v[n], __fsub_rn(1.0f, d[n - 1]));
+            adv[b] = (float)a_sum;
+            ret[b] = __fadd_rn((float)r_sum, __fmul_rn(vn, gamma_pow_n));
+        }
+    }
+    if (norm_adv) {
+        if (last_block_ticket(&ws->counter, gridDim.x)) normalize_all(adv, (long long)B, sh);
+    }
+}
+
+// RNN branch: E = n - H + 1 outputs per window, each an H-term sum (ppo.py:389-406).
+__global__ void __launch_bounds__(GAE_WARPS * 32) gae_horizon_kernel(const float* __restrict__ rewards,
+                                                                      const float* __restrict__ values,
+                                                                      const float* __restrict__ dones, int B, int n,
+                                                                      int H, float gamma_f, float lam_f,
+                                                                      float gamma_pow_h, int norm_adv,
+                                                                      float* __restrict__ adv,
+                                                                      float* __restrict__ ret, GaeWs* ws) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ double sh[32];
+    const int E = n - H + 1;
+    float* gl = sm;                       // [H] gamma^k * ... tables: g[k], then l[k]
+    float* ll = sm + H;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* w_r = sm + 2 * H + warp * (3 * n + 1);    // per-warp: r[n], td[n], vm[n+1]
+    float* w_td = w_r + n;
+    float* w_v = w_td + n;
+    for (int k = threadIdx.x; k < H; k += blockDim.x) {
+        gl[k] = pow_table(gamma_f, k);
+        ll[k] = pow_table(lam_f, k);
+    }
+    const int b = blockIdx.x * GAE_WARPS + warp;
+    if (b < B) {
+        const float* r = rewards + (long long)b * n;
+        const float* v = values + (long long)b * (n + 1);
+        const float* d = dones + (long long)b * n;
+        for (int k = lane; k <= n; k += 32) w_v[k] = (k > 0) ? __fmul_rn(v[k], __fsub_rn(1.0f, d[k - 1])) : v[0];
+        for (int k = lane; k < n; k += 32) w_r[k] = r[k];
+    }
+    __syncthreads();
+    if (b < B) {
+        for (int k = lane; k < n; k += 32)
+            w_td[k] = __fsub_rn(__fadd_rn(w_r[k], __fmul_rn(gamma_f, w_v[k + 1])), w_v[k]);
+    }
+    __syncthreads();
+    if (b < B) {
+        for (int s = lane; s < E; s += 32) {
+            double a_sum = 0.0, r_sum = 0.0;
+            for (int k = 0; k < H; ++k) {
+                a_sum += (double)__fmul_rn(__fmul_rn(w_td[s + k], gl[k]), ll[k]);
+                r_sum += (double)__fmul_rn(gl[k], w_r[s + k]);
+            }
+            adv[(long long)b * E + s] = (float)a_sum;
+            ret[(long long)b * E + s] = __fadd_rn((float)r_sum, __fmul_rn(w_v[s + H], gamma_pow_h));
+        }
+    }
+    if (norm_adv) {
+        if (last_block_ticket(&ws->counter, gridDim.x)) normalize_all(adv, (long long)B * E, sh);
+    }
+}
+
+}  // namespace
+
+extern "C" size_t sb200_gae_workspace_bytes(int B, int n, int horizon) {
+    (void)B; (void)n; (void)horizon;
+    return sizeof(GaeWs);
+}
+
+extern "C" int sb200_gae_window_f32(const float* rewards, const float* values, const float* dones, int B, int n,
+                                    int horizon, double gamma, double lam, int norm_adv, float* adv, float* ret,
+                                    void* workspace, void* stream) {
+    SB200_REQUIRE(rewards && values && dones && adv && ret && workspace);
+    SB200_REQUIRE(B >= 1 && n >= 1 && horizon >= 1 && horizon <= n);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float gamma_f = (float)gamma, lam_f = (float)lam;
+    const int grid = (B + GAE_WARPS - 1) / GAE_WARPS;
+    if (horizon == n) {
+        const float gpn = (float)pow(gamma, (double)n);          // Python `gamma ** n_step` (double) -> fp32 scalar
+        gae_full_kernel<<<grid, GAE_WARPS * 32, 0, st>>>(rewards, values, dones, B, n, gamma_f, lam_f, gpn, norm_adv,
+                                                         adv, ret, (GaeWs*)workspace);
+    } else {
+        const float gph = (float)pow(gamma, (double)horizon);
+        const size_t smem = (size_t)(2 * horizon + GAE_WARPS * (3 * n + 1)) * sizeof(float);
+        SB200_REQUIRE(smem <= 200 * 1024);
+        static size_t configured = 0;
+        if (smem > 48 * 1024 && smem > configured) {
+            SB200_CUDA(cudaFuncSetAttribute(gae_horizon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        gae_horizon_kernel<<<grid, GAE_WARPS * 32, smem, st>>>(rewards, values, dones, B, n, horizon, gamma_f, lam_f,
+                                                             gph, norm_adv, adv, ret, (GaeWs*)workspace);
+    }
+    return sb200_launch_status();
+}

@@ -1,0 +1,349 @@
+// Fused MLP forward (z-filter -> [Linear + activation] x L) on row tiles, fp32 SIMT FFMA.
+//
+// One CTA owns BM = 8*TM rows and walks the layers; activations never leave shared memory (two
+// ping-pong buffers), weights stream through a double-buffered cp.async stage of BK x 256 floats.
+// Thread (ty = warp, tx = lane) accumulates a TM x 8 register tile: rows ty*TM.., columns
+// n0 + tx*4 + {0..3} and n0 + 128 + tx*4 + {0..3}; A fragments are warp-broadcast LDS.128 along k,
+// B fragments are conflict-free LDS.128.  Layers with <= 32 outputs (policy mean, value head) take a
+// warp-per-row dot-product path instead of a 256-wide pass.
+//
+// Replaces the stock-torch calls of surreal/model/ppo_net.py:253-315, builders.py:114-132,160-175,
+// 35-84 and the z-filter of z_filter.py:59-79.  Algorithmic HBM bytes per row: 4*D read + saved
+// activations written (critic pass: 4 bytes); weights are L2-resident.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BK = 16;
+constexpr int PASS_N = 256;
+
+struct FwdParams {
+    const float* x;
+    const float* x_next;
+    long long ldx;
+    long long rows;
+    int win_n;
+    const float* aux;
+    long long aux_ld;
+    int aux_layer;
+    int aux_dim;
+    const float* zf;
+    float zf_eps;
+    int n_layers;
+    int dims[SB200_MAX_LAYERS + 1];
+    int act[SB200_MAX_LAYERS];
+    const float* W[SB200_MAX_LAYERS];
+    const float* b[SB200_MAX_LAYERS];
+    int ldw[SB200_MAX_LAYERS];
+    float* save[SB200_MAX_LAYERS];
+    long long ld_save[SB200_MAX_LAYERS];
+    int ldh;
+};
+
+__host__ __device__ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == SB200_ACT_RELU) return fmaxf(v, 0.0f);
+    if (act == SB200_ACT_TANH) return tanhf(v);
+    return v;
+}
+
+template <int TM>
+__global__ void __launch_bounds__(SB200_THREADS, 1) mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
+    constexpr int BM = 8 * TM;
+    extern __shared__ __align__(16) float smem[];
+    const int ldh = p.ldh;
+    float* Hin = smem;
+    float* Hout = smem + BM * ldh;
+    float* Ws = smem + 2 * BM * ldh;   // [2][BK][PASS_N]
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const long long row0 = (long long)blockIdx.x * BM;
+
+    // ---- stage 0: input tile (+ optional z-filter, + optional aux columns for layer 0)
+    const int K0 = p.dims[0];
+    if (p.zf != nullptr) {             // per-column mean / std once per CTA (scratch: the W stage)
+        const float cnt = p.zf[2 * K0];
+        for (int k = tid; k < K0; k += SB200_THREADS) {
+            const float mean = p.zf[k] / cnt;
+            const float var = p.zf[K0 + k] / cnt - mean * mean;
+            Ws[k] = mean;
+            Ws[K0 + k] = fmaxf(sqrtf(var), p.zf_eps);
+        }
+        __syncthreads();
+    }
+    {
+        const int in_w = K0 + (p.aux_layer == 0 ? p.aux_dim : 0);
+        const int in_wp = round_up(in_w, BK);
+        for (int idx = tid; idx < BM * in_wp; idx += SB200_THREADS) {
+            const int m = idx / in_wp, k = idx - m * in_wp;
+            const long long r = row0 + m;
+            float v = 0.0f;
+            if (r < p.rows) {
+                if (k < K0) {
+                    const float* src;
+                    if (p.win_n > 0) {
+                        const long long b = r / (p.win_n + 1);
+                        const int kk = (int)(r - b * (p.win_n + 1));
+                        src = (kk < p.win_n) ? p.x + (b * p.win_n + kk) * p.ldx : p.x_next + b * p.ldx;
+                    } else {
+                        src = p.x + r * p.ldx;
+                    }
+                    v = src[k];
+                    if (p.zf != nullptr) v = fminf(fmaxf((v - Ws[k]) / Ws[K0 + k], -5.0f), 5.0f);
+                } else if (k < in_w) {
+                    v = p.aux[r * p.aux_ld + (k - K0)];
+                }
+            }
+            Hin[m * ldh + k] = v;
+        }
+    }
+    __syncthreads();
+
+    for (int l = 0; l < p.n_layers; ++l) {
+        const int K = p.dims[l] + (p.aux_layer == l ? p.aux_dim : 0);
+        const int N = p.dims[l + 1];
+        const float* __restrict__ W = p.W[l];
+        const float* __restrict__ bias = p.b[l];
+        const int ldw = p.ldw[l];
+        const int act = p.act[l];
+        const bool last = (l == p.n_layers - 1);
+        float* sv = p.save[l];
+        const long long lds = p.ld_save[l];
+
+        if (N > 32) {
+            // ------------------------------ wide path: 256-column passes ------------------------------
+            const int nchunks = (K + BK - 1) / BK;
+            const bool vec_ok = sv != nullptr && (lds % 4 == 0) && ((((uintptr_t)sv) & 15) == 0);
+            for (int n0 = 0; n0 < N; n0 += PASS_N) {
+                float acc[TM][8];
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+                const bool hi = (n0 + 128 < N);
+
+                auto load_chunk = [&](int stage, int k0) {
+                    float* dst = Ws + stage * (BK * PASS_N);
+#pragma unroll
+                    for (int i = 0; i < (BK * PASS_N / 4) / SB200_THREADS; ++i) {
+                        const int f = tid + i * SB200_THREADS;
+                        const int kr = f >> 6, c4 = f & 63;
+                        const int k = k0 + kr, n = n0 + c4 * 4;
+                        const bool ok = (k < K) && (n < ldw);
+                        const float* src = ok ? (W + (long long)k * ldw + n) : W;
+                        cp_async16(dst + kr * PASS_N + c4 * 4, src, ok ? 16 : 0);
+                    }
+                };
+
+                load_chunk(0, 0);
+                cp_async_commit();
+                for (int c = 0; c < nchunks; ++c) {
+                    if (c + 1 < nchunks) load_chunk((c + 1) & 1, (c + 1) * BK);
+                    cp_async_commit();
+                    cp_async_wait<1>();
+                    __syncthreads();
+                    const float* Wst = Ws + (c & 1) * (BK * PASS_N);
+                    const float* A = Hin + (ty * TM) * ldh + c * BK;
+#pragma unroll
+                    for (int kk = 0; kk < BK; kk += 4) {
+                        float4 a[TM];
+#pragma unroll
+                        for (int i = 0; i < TM; ++i) a[i] = *reinterpret_cast<const float4*>(A + i * ldh + kk);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 b0 = *reinterpret_cast<const float4*>(Wst + (kk + j) * PASS_N + tx * 4);
+#pragma unroll
+                            for (int i = 0; i < TM; ++i) {
+                                const float av = (j == 0) ? a[i].x : (j == 1) ? a[i].y : (j == 2) ? a[i].z : a[i].w;
+                                acc[i][0] = fmaf(av, b0.x, acc[i][0]);
+                                acc[i][1] = fmaf(av, b0.y, acc[i][1]);
+                                acc[i][2] = fmaf(av, b0.z, acc[i][2]);
+                                acc[i][3] = fmaf(av, b0.w, acc[i][3]);
+                            }
+                            if (hi) {
+                                const float4 b1 =
+                                    *reinterpret_cast<const float4*>(Wst + (kk + j) * PASS_N + 128 + tx * 4);
+#pragma unroll
+                                for (int i = 0; i < TM; ++i) {
+                                    const float av =
+                                        (j == 0) ? a[i].x : (j == 1) ? a[i].y : (j == 2) ? a[i].z : a[i].w;
+                                    acc[i][4] = fmaf(av, b1.x, acc[i][4]);
+                                    acc[i][5] = fmaf(av, b1.y, acc[i][5]);
+                                    acc[i][6] = fmaf(av, b1.z, acc[i][6]);
+                                    acc[i][7] = fmaf(av, b1.w, acc[i][7]);
+                                }
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+                cp_async_wait<0>();
+
+                // epilogue: bias + activation -> next activation buffer (+ optional global save)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int n = n0 + h * 128 + tx * 4;
+                    if (n >= round_up(N, 4)) continue;
+                    float bv[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) bv[c] = (n + c < N) ? bias[n + c] : 0.0f;
+#pragma unroll
+                    for (int i = 0; i < TM; ++i) {
+                        const int m = ty * TM + i;
+                        float4 o;
+                        o.x = (n + 0 < N) ? apply_act(acc[i][h * 4 + 0] + bv[0], act) : 0.0f;
+                        o.y = (n + 1 < N) ? apply_act(acc[i][h * 4 + 1] + bv[1], act) : 0.0f;
+                        o.z = (n + 2 < N) ? apply_act(acc[i][h * 4 + 2] + bv[2], act) : 0.0f;
+                        o.w = (n + 3 < N) ? apply_act(acc[i][h * 4 + 3] + bv[3], act) : 0.0f;
+                        if (!last) *reinterpret_cast<float4*>(Hout + m * ldh + n) = o;
+                        const long long r = row0 + m;
+                        if (sv != nullptr && r < p.rows) {
+                            float* dst = sv + r * lds + n;
+                            if (vec_ok && n + 3 < N) {
+                                *reinterpret_cast<float4*>(dst) = o;
+                            } else {
+                                if (n + 0 < N) dst[0] = o.x;
+                                if (n + 1 < N) dst[1] = o.y;
+                                if (n + 2 < N) dst[2] = o.z;
+                                if (n + 3 < N) dst[3] = o.w;
+                            }
+                        }
+                    }
+                }
+            }
+        } else {
+            // ------------------------------ narrow path: N <= 32 ------------------------------------
+            // warp ty owns rows ty*TM..; lanes split k; 8 outputs at a time, shuffle-reduced.
+            for (int i = 0; i < TM; ++i) {
+                const int m = ty * TM + i;
+                const long long r = row0 + m;
+                const float* hrow = Hin + m * ldh;
+                for (int n8 = 0; n8 < N; n8 += 8) {
+                    float s[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) s[j] = 0.0f;
+                    const bool second = (n8 + 4 < ldw);
+                    for (int k = tx; k < K; k += 32) {
+                        const float hv = hrow[k];
+                        const float* wr = W + (long long)k * ldw + n8;
+                        const float4 w0 = *reinterpret_cast<const float4*>(wr);
+                        s[0] = fmaf(hv, w0.x, s[0]);
+                        s[1] = fmaf(hv, w0.y, s[1]);
+                        s[2] = fmaf(hv, w0.z, s[2]);
+                        s[3] = fmaf(hv, w0.w, s[3]);
+                        if (second) {
+                            const float4 w1 = *reinterpret_cast<const float4*>(wr + 4);
+                            s[4] = fmaf(hv, w1.x, s[4]);
+                            s[5] = fmaf(hv, w1.y, s[5]);
+                            s[6] = fmaf(hv, w1.z, s[6]);
+                            s[7] = fmaf(hv, w1.w, s[7]);
+                        }
+                    }
+                    float mine = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float t = warp_sum(s[j]);
+                        if (tx == j) mine = t;
+                    }
+                    const int n = n8 + tx;
+                    if (tx < 8 && n < N) {
+                        const float o = apply_act(mine + bias[n], act);
+                        if (!last) Hout[m * ldh + n] = o;
+                        if (sv != nullptr && r < p.rows) sv[r * lds + n] = o;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (!last) {
+            // columns [N, N+aux) <- aux input of the next layer; [.., pad16) <- 0
+            const int auxd = (p.aux_layer == l + 1) ? p.aux_dim : 0;
+            const int wp = round_up(N + auxd, BK);
+            const int span = wp - N;
+            if (span > 0) {
+                for (int idx = tid; idx < BM * span; idx += SB200_THREADS) {
+                    const int m = idx / span, c = N + (idx - m * span);
+                    const long long r = row0 + m;
+                    float v = 0.0f;
+                    if (c < N + auxd && r < p.rows) v = p.aux[r * p.aux_ld + (c - N)];
+                    Hout[m * ldh + c] = v;
+                }
+            }
+            __syncthreads();
+            float* t = Hin;
+            Hin = Hout;
+            Hout = t;
+        }
+    }
+}
+
+template <int TM>
+int launch_fwd(const FwdParams& p, cudaStream_t st) {
+    constexpr int BM = 8 * TM;
+    const size_t smem = (size_t)(2 * BM * p.ldh + 2 * BK * PASS_N) * sizeof(float);
+    static size_t configured = 0;
+    if (smem > configured) {
+        SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const long long grid = (p.rows + BM - 1) / BM;
+    mlp_fwd_kernel<TM><<<(unsigned)grid, SB200_THREADS, smem, st>>>(p);
+    return sb200_launch_status();
+}
+
+}  // namespace
+
+extern "C" int sb200_mlp_forward_f32(const sb200_mlp* net, const sb200_zfilter* zf, const sb200_rows* in,
+                                     float* const* save, const int64_t* ld_save, void* stream) {
+    SB200_REQUIRE(net != nullptr && in != nullptr);
+    SB200_REQUIRE(net->n_layers >= 1 && net->n_layers <= SB200_MAX_LAYERS);
+    SB200_REQUIRE(in->rows >= 0 && in->x != nullptr);
+    if (in->rows == 0) return SB200_OK;
+    FwdParams p;
+    p.x = in->x;
+    p.x_next = in->x_next;
+    p.ldx = in->ldx;
+    p.rows = in->rows;
+    p.win_n = in->win_n;
+    SB200_REQUIRE(p.win_n == 0 || (p.x_next != nullptr && p.rows % (p.win_n + 1) == 0));
+    p.aux = in->aux;
+    p.aux_ld = in->aux_ld;
+    p.aux_layer = net->aux_layer;
+    p.aux_dim = (net->aux_layer >= 0) ? net->aux_dim : 0;
+    SB200_REQUIRE(net->aux_layer < net->n_layers);
+    SB200_REQUIRE(p.aux_layer < 0 || (p.aux != nullptr && p.aux_dim > 0));
+    p.zf = (zf != nullptr) ? zf->stats : nullptr;
+    p.zf_eps = (zf != nullptr) ? zf->eps : 0.0f;
+    p.n_layers = net->n_layers;
+    SB200_REQUIRE(net->dims[0] >= 1 && net->dims[0] <= 4096 && p.ldx >= net->dims[0]);
+    int maxw = 0;
+    for (int l = 0; l <= net->n_layers; ++l) p.dims[l] = net->dims[l];
+    for (int l = 0; l < SB200_MAX_LAYERS; ++l) {
+        const bool on = l < net->n_layers;
+        p.act[l] = on ? net->act[l] : 0;
+        p.W[l] = on ? net->W[l] : nullptr;
+        p.b[l] = on ? net->b[l] : nullptr;
+        p.ldw[l] = on ? net->ldw[l] : 0;
+        p.save[l] = (on && save != nullptr) ? save[l] : nullptr;
+        p.ld_save[l] = (on && save != nullptr && ld_save != nullptr) ? ld_save[l] : 0;
+        if (on) {
+            SB200_REQUIRE(p.W[l] != nullptr && p.b[l] != nullptr);
+            SB200_REQUIRE(p.dims[l + 1] >= 1 && p.ldw[l] >= p.dims[l + 1] && p.ldw[l] % 4 == 0);
+            SB200_REQUIRE((((uintptr_t)p.W[l]) & 15) == 0);
+            SB200_REQUIRE(p.save[l] == nullptr || p.ld_save[l] >= p.dims[l + 1]);
+            const int w = p.dims[l] + (p.aux_layer == l ? p.aux_dim : 0);
+            if (w > maxw) maxw = w;
+        }
+    }
+    p.ldh = round_up(maxw, BK) + 4;
+    const size_t budget = 200 * 1024;
+    auto fits = [&](int bm) { return (size_t)(2 * bm * p.ldh + 2 * BK * PASS_N) * 4 <= budget; };
+    SB200_REQUIRE(fits(8));
+    cudaStream_t st = (cudaStream_t)stream;
+    // largest row tile that still yields >= ~1 CTA per SM; small batches fall back to 16-row tiles
+    const long long want = 120;
+    if (fits(64) && (p.rows + 63) / 64 >= want) return launch_fwd<8>(p, st);
+    if (fits(32) && (p.rows + 31) / 32 >= want) return launch_fwd<4>(p, st);
+    if (fits(16)) return launch_fwd<2>(p, st);
+    return launch_fwd<1>(p, st);
+}

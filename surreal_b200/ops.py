@@ -1,0 +1,182 @@
+"""Torch-tensor front end of the C-ABI: device buffers come from torch, kernels from libsurreal_b200.
+
+Nothing here computes on the CPU or through torch ops on the hot path; torch only owns memory and
+streams (``tensor.data_ptr()`` / ``torch.cuda.current_stream()``).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import Mlp, ZFilter, Rows, ACT_NONE, ACT_RELU, ACT_TANH, MAX_LAYERS, check  # noqa: F401
+
+
+def _ru(v, m):
+    return (v + m - 1) // m * m
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _f32c(t):
+    assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), \
+        'expected a contiguous float32 CUDA tensor, got %s %s' % (t.dtype, t.device)
+    return t
+
+
+class FlatNet:
+    """An MLP whose parameters live in ONE flat fp32 device buffer in the kernel layout
+    (W[l] = [in_l][ldw_l], the transpose of torch.nn.Linear.weight; ldw = out rounded up to 4;
+    padding stays zero).  Gradients / Adam moments use buffers of the same layout, so optimiser and
+    NCCL all-reduce are single flat kernels / one collective.  ``extra`` trailing floats hold
+    non-layer parameters (PPO's log_var, builders.py:112)."""
+
+    def __init__(self, dims, acts, device, aux_layer=-1, aux_dim=0, extra=0):
+        assert 1 <= len(dims) - 1 <= MAX_LAYERS and len(acts) == len(dims) - 1
+        self.dims = list(dims)
+        self.acts = list(acts)
+        self.aux_layer, self.aux_dim = aux_layer, (aux_dim if aux_layer >= 0 else 0)
+        self.n_layers = len(dims) - 1
+        self.layout = []
+        off = 0
+        for l in range(self.n_layers):
+            K = dims[l] + (self.aux_dim if aux_layer == l else 0)
+            N = dims[l + 1]
+            ldw = _ru(N, 4)
+            self.layout.append(dict(w=off, b=off + K * ldw, K=K, N=N, ldw=ldw))
+            off += K * ldw + ldw
+        self.extra = extra
+        self.extra_off = off
+        off += _ru(extra, 4)
+        self.size = off
+        self.device = torch.device(device)
+        self.params = torch.zeros(off, dtype=torch.float32, device=self.device)
+
+    # -- views -----------------------------------------------------------------------------------
+    def W(self, l, buf=None):
+        lay = self.layout[l]
+        buf = self.params if buf is None else buf
+        return buf[lay['w']:lay['w'] + lay['K'] * lay['ldw']].view(lay['K'], lay['ldw'])
+
+    def b(self, l, buf=None):
+        lay = self.layout[l]
+        buf = self.params if buf is None else buf
+        return buf[lay['b']:lay['b'] + lay['ldw']]
+
+    def extra_view(self, buf=None):
+        buf = self.params if buf is None else buf
+        return buf[self.extra_off:self.extra_off + self.extra]
+
+    def set_layer(self, l, weight, bias):
+        """weight: [out, in] (torch.nn.Linear convention), bias: [out]."""
+        N = self.layout[l]['N']
+        self.W(l)[:, :N] = torch.as_tensor(weight, dtype=torch.float32).t().to(self.device)
+        self.b(l)[:N] = torch.as_tensor(bias, dtype=torch.float32).to(self.device)
+
+    def get_layer(self, l, buf=None):
+        N = self.layout[l]['N']
+        return self.W(l, buf)[:, :N].t().contiguous(), self.b(l, buf)[:N].clone()
+
+    def load_layers(self, layers, extra=None):
+        for l, (w, b) in enumerate(layers):
+            self.set_layer(l, w, b)
+        if extra is not None:
+            self.extra_view()[:] = torch.as_tensor(extra, dtype=torch.float32).reshape(-1).to(self.device)
+        return self
+
+    def clone_like(self):
+        n = FlatNet(self.dims, self.acts, self.device, self.aux_layer, self.aux_dim, self.extra)
+        n.params.copy_(self.params)
+        return n
+
+    def desc(self, buf=None):
+        """ctypes descriptor over ``buf`` (defaults to the live parameters)."""
+        buf = self.params if buf is None else buf
+        m = Mlp()
+        m.n_layers = self.n_layers
+        for i, d in enumerate(self.dims):
+            m.dims[i] = d
+        base = buf.data_ptr()
+        for l, lay in enumerate(self.layout):
+            m.act[l] = self.acts[l]
+            m.W[l] = base + 4 * lay['w']
+            m.b[l] = base + 4 * lay['b']
+            m.ldw[l] = lay['ldw']
+        m.aux_layer = self.aux_layer
+        m.aux_dim = self.aux_dim
+        return m
+
+
+def zfilter_desc(stats, eps=1e-5):
+    z = ZFilter()
+    z.stats = stats.data_ptr() if stats is not None else None
+    z.eps = eps
+    return z
+
+
+def mlp_forward(net, x, zf_stats=None, zf_eps=1e-5, x_next=None, win_n=0, aux=None, save_all=False,
+                params=None, out=None):
+    """Run the fused forward.  ``x``: [rows, D] (or [B, n, D] with ``x_next`` [B, 1, D] and win_n=n for the
+    virtual cat of ppo.py:376-383).  Returns the network output [rows, out_dim]; with ``save_all`` a
+    list of every layer's post-activation output (for the backward pass)."""
+    L = _lib.lib()
+    _f32c(x)
+    D = net.dims[0]
+    r = Rows()
+    if win_n > 0:
+        B = x.shape[0]
+        assert x.shape[1] == win_n and x.shape[2] == D and x_next is not None
+        _f32c(x_next)
+        rows = B * (win_n + 1)
+        r.x, r.x_next, r.ldx, r.rows, r.win_n = x.data_ptr(), x_next.data_ptr(), D, rows, win_n
+    else:
+        x2 = x.reshape(-1, x.shape[-1])
+        rows = x2.shape[0]
+        r.x, r.x_next, r.ldx, r.rows, r.win_n = x2.data_ptr(), None, x2.stride(0), rows, 0
+    if net.aux_layer >= 0:
+        _f32c(aux)
+        r.aux, r.aux_ld = aux.data_ptr(), aux.stride(0)
+    else:
+        r.aux, r.aux_ld = None, 0
+    saves = [None] * MAX_LAYERS
+    outs = []
+    for l in range(net.n_layers):
+        last = l == net.n_layers - 1
+        if save_all or last:
+            t = out if (last and out is not None) else torch.empty(rows, net.dims[l + 1], dtype=torch.float32,
+                                                                   device=x.device)
+            saves[l] = t
+            outs.append(t)
+    sv = (C.c_void_p * MAX_LAYERS)(*[(t.data_ptr() if t is not None else None) for t in saves])
+    ld = (C.c_int64 * MAX_LAYERS)(*[(t.stride(0) if t is not None else 0) for t in saves])
+    zf = zfilter_desc(zf_stats, zf_eps)
+    d = net.desc(params)
+    check(L.sb200_mlp_forward_f32(C.byref(d), C.byref(zf), C.byref(r), sv, ld, _stream()), 'sb200_mlp_forward_f32')
+    return outs if save_all else outs[-1]
+
+
+_gae_ws = {}
+
+
+def gae_window(rewards, values, dones, gamma, lam, horizon=None, norm_adv=True):
+    """rewards [B,n], values [B,n+1] raw critic output, dones [B,n] -> (adv [B,E], ret [B,E])."""
+    L = _lib.lib()
+    _f32c(rewards), _f32c(values), _f32c(dones)
+    B, n = rewards.shape
+    H = n if horizon is None else int(horizon)
+    E = n - H + 1
+    adv = torch.empty(B, E, dtype=torch.float32, device=rewards.device)
+    ret = torch.empty(B, E, dtype=torch.float32, device=rewards.device)
+    key = rewards.device
+    if key not in _gae_ws:
+        _gae_ws[key] = torch.zeros(max(16, L.sb200_gae_workspace_bytes(B, n, H)), dtype=torch.uint8,
+                                   device=rewards.device)
+    check(L.sb200_gae_window_f32(_ptr(rewards), _ptr(values), _ptr(dones), B, n, H, float(gamma), float(lam),
+                                 int(bool(norm_adv)), _ptr(adv), _ptr(ret), _ptr(_gae_ws[key]), _stream()),
+          'sb200_gae_window_f32')
+    return adv, ret

@@ -1,0 +1,133 @@
+"""GPU parity tests: CUDA kernels (through the C-ABI) vs the CPU oracle and the golden fixtures."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nets as onets
+from oracle.filters import ZFilter as OZFilter
+from oracle.gae import gae_from_values
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device('cuda:0')
+
+
+def rms(x):
+    return float(x.double().pow(2).mean().sqrt())
+
+
+def assert_close_scale(got, exp, tol=1e-5, what=''):
+    """max|a-b| <= tol * max(1, rms(b))   (BASELINE.md §5)."""
+    got, exp = got.detach().cpu().double(), exp.detach().cpu().double()
+    err = float((got - exp).abs().max())
+    lim = tol * max(1.0, rms(exp))
+    assert err <= lim, '%s: max err %.3e > %.3e' % (what, err, lim)
+
+
+def _rand_layers(dims, gen, aux_layer=-1, aux_dim=0):
+    layers = []
+    for l in range(len(dims) - 1):
+        k = dims[l] + (aux_dim if aux_layer == l else 0)
+        bound = 1.0 / np.sqrt(k)
+        w = (torch.rand(dims[l + 1], k, generator=gen) * 2 - 1) * bound
+        b = (torch.rand(dims[l + 1], generator=gen) * 2 - 1) * bound
+        layers.append((w, b))
+    return layers
+
+
+@pytest.mark.parametrize('dims,rows,zf', [
+    ([11, 32, 24, 3], 37, True),          # all-narrow layers, ragged rows
+    ([64, 256, 256, 8], 1024, True),      # cfg2 actor
+    ([64, 256, 256, 1], 3000, False),     # cfg2 critic, rows not a tile multiple
+    ([17, 300, 200, 6], 333, True),       # reference default hidden sizes (K, N not multiples of 16/256)
+    ([9, 40, 1], 5, False),               # 2-layer net
+    ([64, 256, 256, 1], 20000, True),     # large-M tile path (BM=64)
+])
+def test_mlp_forward_matches_oracle(dims, rows, zf):
+    from surreal_b200 import ops
+    gen = torch.Generator().manual_seed(sum(dims) + rows)
+    layers = _rand_layers(dims, gen)
+    acts = [ops.ACT_RELU] * (len(dims) - 2) + [ops.ACT_TANH if dims[-1] > 1 else ops.ACT_NONE]
+    x = torch.randn(rows, dims[0], generator=gen) * 2 + 0.5
+    ozf = None
+    stats = None
+    if zf:
+        ozf = OZFilter(dims[0])
+        ozf.update(torch.randn(200, dims[0], generator=gen) * 1.7 + 0.4)
+        stats = torch.cat([ozf.running_sum, ozf.running_sumsq, ozf.count]).to(_dev())
+    net = ops.FlatNet(dims, acts, _dev()).load_layers(layers)
+    outs = ops.mlp_forward(net, x.to(_dev()), zf_stats=stats, save_all=True)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        h = ozf.forward(x) if zf else x
+        exp = []
+        for l, (w, b) in enumerate(layers):
+            h = torch.nn.functional.linear(h, w, b)
+            h = torch.relu(h) if acts[l] == ops.ACT_RELU else (torch.tanh(h) if acts[l] == ops.ACT_TANH else h)
+            exp.append(h)
+    assert len(outs) == len(exp)
+    for l, (o, e) in enumerate(zip(outs, exp)):
+        assert o.shape == e.shape
+        assert_close_scale(o, e, 1e-5, 'layer %d' % l)
+
+
+def test_mlp_forward_window_rows_and_aux():
+    """virtual cat([obs, obs_next]) row mapping (ppo.py:376-383) and the DDPG critic's cat(h, action)."""
+    from surreal_b200 import ops
+    gen = torch.Generator().manual_seed(3)
+    B, n, D, A = 13, 7, 10, 4
+    layers = _rand_layers([D, 48, 36, 1], gen)
+    obs = torch.randn(B, n, D, generator=gen)
+    obs_next = torch.randn(B, 1, D, generator=gen)
+    net = ops.FlatNet([D, 48, 36, 1], [ops.ACT_RELU, ops.ACT_RELU, ops.ACT_NONE], _dev()).load_layers(layers)
+    out = ops.mlp_forward(net, obs.to(_dev()), x_next=obs_next.to(_dev()), win_n=n)
+    with torch.no_grad():
+        exp = onets.ppo_critic(torch.cat([obs, obs_next], 1).view(-1, D), layers)
+    assert_close_scale(out, exp, 1e-5, 'window rows')
+
+    layers = _rand_layers([D, 400, 300, 1], gen, aux_layer=1, aux_dim=A)
+    x = torch.randn(77, D, generator=gen)
+    act = torch.rand(77, A, generator=gen) * 2 - 1
+    net = ops.FlatNet([D, 400, 300, 1], [ops.ACT_RELU, ops.ACT_RELU, ops.ACT_NONE], _dev(), aux_layer=1,
+                      aux_dim=A).load_layers(layers)
+    out = ops.mlp_forward(net, x.to(_dev()), aux=act.to(_dev()))
+    with torch.no_grad():
+        exp = onets.ddpg_critic(x, act, layers)
+    assert_close_scale(out, exp, 1e-5, 'ddpg critic concat')
+
+
+@pytest.mark.parametrize('tag', ['mlp', 'mlp_nonorm', 'rnn'])
+def test_gae_matches_golden(golden, tag):
+    from surreal_b200 import ops
+    g = golden('gae_' + tag)
+    r = torch.tensor(g['rewards'], dtype=torch.float32).to(_dev())
+    v = torch.tensor(g['values_raw']).to(_dev())
+    d = torch.tensor(g['dones']).to(_dev())
+    H = int(g['horizon']) if 'horizon' in g else None
+    adv, ret = ops.gae_window(r, v, d, float(g['gamma']), float(g['lam']), horizon=H, norm_adv=bool(g['norm_adv']))
+    exp_adv, exp_ret = torch.tensor(g['adv']), torch.tensor(g['ret'])
+    assert_close_scale(adv.view(-1), exp_adv.view(-1), 1e-5, 'adv')
+    assert_close_scale(ret.view(-1), exp_ret.view(-1), 1e-5, 'ret')
+
+
+@pytest.mark.parametrize('B,n,H,norm', [(1024, 128, None, True), (4096, 256, None, True), (64, 25, 5, True),
+                                        (3, 1, None, False), (257, 33, 33, True), (40, 50, 7, False)])
+def test_gae_matches_oracle(B, n, H, norm):
+    from surreal_b200 import ops
+    gen = torch.Generator().manual_seed(B + n)
+    r = torch.randn(B, n, generator=gen) * 0.5
+    v = torch.randn(B, n + 1, generator=gen)
+    d = (torch.rand(B, n, generator=gen) < 0.05).float()
+    adv, ret = ops.gae_window(r.to(_dev()), v.to(_dev()), d.to(_dev()), 0.995, 0.97, horizon=H, norm_adv=norm)
+    e_adv, e_ret = gae_from_values(r, v, d, 0.995, 0.97, horizon=H, norm_adv=norm)
+    tol = 1e-5
+    if norm:   # normalised advantages: absolute 1e-5
+        assert float((adv.cpu().view(-1) - e_adv.view(-1)).abs().max()) <= tol
+    else:
+        assert_close_scale(adv.view(-1), e_adv.view(-1), tol, 'adv')
+    assert_close_scale(ret.view(-1), e_ret.view(-1), tol, 'ret')
+    # a second call must reuse the (self-resetting) workspace correctly
+    adv2, _ = ops.gae_window(r.to(_dev()), v.to(_dev()), d.to(_dev()), 0.995, 0.97, horizon=H, norm_adv=norm)
+    assert torch.equal(adv, adv2)
