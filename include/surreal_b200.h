@@ -72,6 +72,8 @@ typedef struct {
     int win_n;
     const float* aux;                   /* [rows][aux_ld] or NULL */
     int64_t aux_ld;
+    float* save_x;                      /* optional: receives the z-filtered input rows [rows][ld_save_x] */
+    int64_t ld_save_x;
 } sb200_rows;
 
 /* Fused forward of a whole MLP on row tiles (z-filter -> Linear/act x n_layers): activations stay in
@@ -81,6 +83,19 @@ typedef struct {
  * ddpg_net.py:63-91. */
 int sb200_mlp_forward_f32(const sb200_mlp* net, const sb200_zfilter* zf, const sb200_rows* in,
                           float* const* save, const int64_t* ld_save, void* stream);
+
+/* Backward of one Linear layer (kernel layout), replacing torch autograd in ppo.py:242,347 and
+ * ddpg.py:306,330.
+ *   dx: dX[M,K] = (dY[M,N] . W^T), multiplied by relu'(x_act) when x_act != NULL (x_act = the layer's
+ *       saved post-ReLU input, so dX is directly the previous layer's pre-activation gradient).
+ *   dw: `splits` partial slabs, slab z covering rows [z*rps, (z+1)*rps): dW_slabs + z*slab_stride is a
+ *       [K][ldw] matrix, db_slabs + z*slab_stride a [ldw] vector (db_slabs may be NULL).  The slabs are
+ *       summed in fixed order by sb200_grad_reduce_norm_f32 (deterministic, no atomics). */
+int sb200_linear_bwd_dx_f32(const float* dY, int64_t ldy, const float* W, int ldw, const float* x_act,
+                            int64_t ld_xact, float* dX, int64_t lddx, int M, int N, int K, void* stream);
+int sb200_linear_bwd_dw_f32(const float* X, int64_t ldx, const float* dY, int64_t ldy, float* dW_slabs,
+                            float* db_slabs, int64_t slab_stride, int splits, int ldw, int M, int K, int N,
+                            void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Windowed GAE + n-step return (surreal/learner/ppo.py:372-374,387-418).
@@ -93,6 +108,66 @@ size_t sb200_gae_workspace_bytes(int B, int n, int horizon);
 int sb200_gae_window_f32(const float* rewards, const float* values, const float* dones, int B, int n,
                          int horizon, double gamma, double lam, int norm_adv, float* adv, float* ret,
                          void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * PPO losses: forward + gradient in one pass (replaces surreal/learner/ppo.py:194-225, 250-285,
+ * 311-332, 553-557, 568-575 and DiagGauss of surreal/model/ppo_net.py:29-72 with torch autograd).
+ * stats[] is a device float array of SB200_STAT_COUNT slots. */
+#define SB200_STAT_SURR 0            /* _surr_loss */
+#define SB200_STAT_LOSS 1            /* _clip_surr_loss (clip) / _kl_loss_adapt (adapt) */
+#define SB200_STAT_ENTROPY 2         /* _entropy */
+#define SB200_STAT_KL_PRE 3          /* adapt: _pol_kl inside the loss (before the step) */
+#define SB200_STAT_KL_POST 4         /* _pol_kl after the step (early-stop test, ppo.py:553-556) */
+#define SB200_STAT_GRAD_NORM_ACTOR 5
+#define SB200_STAT_VAL_LOSS 6
+#define SB200_STAT_EXPLAINED_VAR 7
+#define SB200_STAT_GRAD_NORM_CRITIC 8
+#define SB200_STAT_RETURN_MEAN 9     /* _avg_return_targ */
+#define SB200_STAT_LOG_SIG 10        /* _avg_log_sig */
+#define SB200_STAT_BEHAVE_LIK 11     /* _avg_behave_likelihood */
+#define SB200_STAT_IS_WEIGHT 12      /* _avg_is_weight */
+#define SB200_STAT_REF_BEHAVE_KL 13  /* _ref_behave_diff */
+#define SB200_STAT_EPOCHS 14         /* number of policy epochs executed this learn() */
+#define SB200_STAT_COUNT 32
+
+size_t sb200_ppo_loss_workspace_bytes(int B, int A);   /* zero-initialise once */
+/* mode 0 = clip (hyper[0] = clip_epsilon), mode 1 = adapt (hyper[1] = beta; needs sb200_ppo_kl_f32(ref, learn)
+ * to have run on the same workspace first).  mean: actor output after tanh [B,ldm]; dpre: gradient w.r.t.
+ * the pre-tanh output [B,ldd] (padding columns zeroed); dlog_var [A].  hyper is a DEVICE array of doubles so
+ * that publish-time adaptation (ppo.py:648-661) does not invalidate captured graphs.
+ * stop_flag (may be NULL): when *stop_flag != 0 the kernel is a no-op (device-side KL early stop). */
+int sb200_ppo_policy_loss_f32(int mode, const float* mean, int64_t ldm, const float* log_var,
+                              const float* actions, int64_t lda, const float* adv, const float* behave_pd,
+                              int64_t ldb, const float* ref_pd, int64_t ldr, int B, int A,
+                              const double* hyper, double eta, double kl_target, float* dpre, int64_t ldd,
+                              float* dlog_var, float* stats, void* workspace, const int* stop_flag, void* stream);
+/* mean KL(p0 || (mean, exp(log_var))) -> stats[stat_slot] (slot < 0: none) and the workspace; raises *stop_flag
+ * when the mean exceeds stop_threshold (> 0). */
+int sb200_ppo_kl_f32(const float* p0, int64_t ld0, const float* mean, int64_t ldm, const float* log_var,
+                     int B, int A, float* stats, int stat_slot, double stop_threshold, int* stop_flag,
+                     void* workspace, void* stream);
+int sb200_value_loss_f32(const float* values, int64_t ldv, const float* returns, int B, float* dpre,
+                         int64_t ldd, float* stats, void* workspace, void* stream);
+int sb200_ppo_final_stats_f32(const float* mean, int64_t ldm, const float* log_var, const float* actions,
+                              int64_t lda, const float* behave_pd, int64_t ldb, const float* ref_pd,
+                              int64_t ldr, int B, int A, float* stats, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Optimiser over one flat parameter buffer (replaces clip_grad_norm_/clip_grad_value_ + torch.optim.Adam:
+ * ppo.py:159-168,244-247,349-352; ddpg.py:145-165,309-310,332-333).
+ *   grad_reduce_norm: grad[i] = sum_z slabs[z*slab_stride + i] (fixed order), global L2 norm and step += 1
+ *                     into the workspace.
+ *   clip_adam: clip_mode 0 none / 1 global norm (clip_value = max_norm) / 2 by value; lr is a DEVICE double.
+ *   workspace: sb200_optim_workspace_bytes(), zero-initialised once (it holds the Adam step count). */
+size_t sb200_optim_workspace_bytes(void);
+int sb200_grad_reduce_norm_f32(const float* slabs, int64_t slab_stride, int splits, float* grad, int64_t n,
+                               void* workspace, const int* stop_flag, void* stream);
+int sb200_clip_adam_f32(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                        const double* lr, double beta1, double beta2, double eps, double weight_decay,
+                        int clip_mode, double clip_value, void* workspace, float* norm_out,
+                        const int* stop_flag, void* stream);
+/* target = target*(1-tau) + tau*src (soft target update, ddpg.py:410-418). */
+int sb200_soft_update_f32(float* target, const float* src, int64_t n, double tau, void* stream);
 
 #ifdef __cplusplus
 }

@@ -35,7 +35,8 @@ class ZFilter(C.Structure):
 
 class Rows(C.Structure):
     _fields_ = [('x', C.c_void_p), ('x_next', C.c_void_p), ('ldx', C.c_int64), ('rows', C.c_int64),
-                ('win_n', C.c_int), ('aux', C.c_void_p), ('aux_ld', C.c_int64)]
+                ('win_n', C.c_int), ('aux', C.c_void_p), ('aux_ld', C.c_int64),
+                ('save_x', C.c_void_p), ('ld_save_x', C.c_int64)]
 
 
 _lib = None
@@ -49,7 +50,18 @@ def _declare(lib):
         'sb200_device_info': (I, [C.POINTER(I), C.POINTER(I), C.POINTER(I)]),
         'sb200_mlp_forward_f32': (I, [C.POINTER(Mlp), C.POINTER(ZFilter), C.POINTER(Rows),
                                       C.POINTER(P), C.POINTER(L), P]),
+        'sb200_linear_bwd_dx_f32': (I, [P, L, P, I, P, L, P, L, I, I, I, P]),
+        'sb200_linear_bwd_dw_f32': (I, [P, L, P, L, P, P, L, I, I, I, I, I, P]),
         'sb200_gae_workspace_bytes': (S, [I, I, I]),
+        'sb200_ppo_loss_workspace_bytes': (S, [I, I]),
+        'sb200_ppo_policy_loss_f32': (I, [I, P, L, P, P, L, P, P, L, P, L, I, I, P, D, D, P, L, P, P, P, P, P]),
+        'sb200_ppo_kl_f32': (I, [P, L, P, L, P, I, I, P, I, D, P, P, P]),
+        'sb200_value_loss_f32': (I, [P, L, P, I, P, L, P, P, P]),
+        'sb200_ppo_final_stats_f32': (I, [P, L, P, P, L, P, L, P, L, I, I, P, P, P]),
+        'sb200_optim_workspace_bytes': (S, []),
+        'sb200_grad_reduce_norm_f32': (I, [P, L, I, P, L, P, P, P]),
+        'sb200_clip_adam_f32': (I, [P, P, P, P, L, P, D, D, D, D, I, D, P, P, P, P]),
+        'sb200_soft_update_f32': (I, [P, P, L, D, P]),
         'sb200_gae_window_f32': (I, [P, P, P, I, I, I, D, D, I, P, P, P, P]),
     }
     sig.update(_EXTRA_SIGS)

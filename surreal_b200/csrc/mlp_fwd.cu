@@ -29,6 +29,8 @@ struct FwdParams {
     int aux_dim;
     const float* zf;
     float zf_eps;
+    float* save_x;
+    long long ld_save_x;
     int n_layers;
     int dims[SB200_MAX_LAYERS + 1];
     int act[SB200_MAX_LAYERS];
@@ -95,6 +97,7 @@ __global__ void __launch_bounds__(SB200_THREADS, 1) mlp_fwd_kernel(const __grid_
                 }
             }
             Hin[m * ldh + k] = v;
+            if (p.save_x != nullptr && r < p.rows && k < K0) p.save_x[r * p.ld_save_x + k] = v;
         }
     }
     __syncthreads();
@@ -314,6 +317,9 @@ extern "C" int sb200_mlp_forward_f32(const sb200_mlp* net, const sb200_zfilter* 
     SB200_REQUIRE(p.aux_layer < 0 || (p.aux != nullptr && p.aux_dim > 0));
     p.zf = (zf != nullptr) ? zf->stats : nullptr;
     p.zf_eps = (zf != nullptr) ? zf->eps : 0.0f;
+    p.save_x = in->save_x;
+    p.ld_save_x = in->ld_save_x;
+    SB200_REQUIRE(p.save_x == nullptr || p.ld_save_x >= net->dims[0]);
     p.n_layers = net->n_layers;
     SB200_REQUIRE(net->dims[0] >= 1 && net->dims[0] <= 4096 && p.ldx >= net->dims[0]);
     int maxw = 0;
