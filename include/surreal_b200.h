@@ -102,12 +102,25 @@ int sb200_linear_bwd_dw_f32(const float* X, int64_t ldx, const float* dY, int64_
  *   rewards [B,n], values [B,n+1] (raw critic output; the (1-done) mask of ppo.py:387 is applied
  *   inside), dones [B,n].  horizon == n -> MLP branch (one output per window), horizon < n ->
  *   RNN branch (E = n-horizon+1 outputs per window).  adv/ret are [B,E].  norm_adv applies
- *   (adv-mean)/max(unbiased_std, 1e-4) over all B*E advantages.
+ *   (adv-mean)/max(unbiased_std, 1e-4) over all B*E advantages.  rewards are multiplied by reward_scale
+ *   (ppo.py:452) on load.
  *   workspace: sb200_gae_workspace_bytes() bytes, zero-initialised once by the caller. */
 size_t sb200_gae_workspace_bytes(int B, int n, int horizon);
 int sb200_gae_window_f32(const float* rewards, const float* values, const float* dones, int B, int n,
-                         int horizon, double gamma, double lam, int norm_adv, float* adv, float* ret,
-                         void* workspace, void* stream);
+                         int horizon, double gamma, double lam, double reward_scale, int norm_adv, float* adv,
+                         float* ret, void* workspace, void* stream);
+
+/* pd[b] = [mean(A) | exp(log_var)(A) * exp(log_noise[b])]  (builders.py:127-129; per-actor noise of
+ * ppo_agent.py:139 when log_noise != NULL). */
+int sb200_make_pd_f32(const float* mean, int64_t ldm, const float* log_var, const float* log_noise, int B,
+                      int A, float* pd, int64_t ldp, void* stream);
+/* ZFilter.z_update (z_filter.py:44-57): stats = running_sum[D] | running_sumsq[D] | count[1], updated in place. */
+int sb200_zfilter_update_f32(const float* x, int64_t ldx, int64_t rows, int D, float* stats, void* stream);
+
+/* RewardFilter as called from ppo.py:452-456: out = forward(rewards*reward_scale) with the current statistics,
+ * then update (running_sumsq is OVERWRITTEN, reward_filter.py:42).  stats = count | running_sum | running_sumsq. */
+int sb200_reward_filter_f32(const float* rewards, int64_t n, double reward_scale, double eps, float* stats,
+                            float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * PPO losses: forward + gradient in one pass (replaces surreal/learner/ppo.py:194-225, 250-285,

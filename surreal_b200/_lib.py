@@ -52,6 +52,9 @@ def _declare(lib):
                                       C.POINTER(P), C.POINTER(L), P]),
         'sb200_linear_bwd_dx_f32': (I, [P, L, P, I, P, L, P, L, I, I, I, P]),
         'sb200_linear_bwd_dw_f32': (I, [P, L, P, L, P, P, L, I, I, I, I, I, P]),
+        'sb200_make_pd_f32': (I, [P, L, P, P, I, I, P, L, P]),
+        'sb200_zfilter_update_f32': (I, [P, L, L, I, P, P]),
+        'sb200_reward_filter_f32': (I, [P, L, D, D, P, P, P]),
         'sb200_gae_workspace_bytes': (S, [I, I, I]),
         'sb200_ppo_loss_workspace_bytes': (S, [I, I]),
         'sb200_ppo_policy_loss_f32': (I, [I, P, L, P, P, L, P, P, L, P, L, I, I, P, D, D, P, L, P, P, P, P, P]),
@@ -62,7 +65,7 @@ def _declare(lib):
         'sb200_grad_reduce_norm_f32': (I, [P, L, I, P, L, P, P, P]),
         'sb200_clip_adam_f32': (I, [P, P, P, P, L, P, D, D, D, D, I, D, P, P, P, P]),
         'sb200_soft_update_f32': (I, [P, P, L, D, P]),
-        'sb200_gae_window_f32': (I, [P, P, P, I, I, I, D, D, I, P, P, P, P]),
+        'sb200_gae_window_f32': (I, [P, P, P, I, I, I, D, D, D, I, P, P, P, P]),
     }
     sig.update(_EXTRA_SIGS)
     for name, (res, args) in sig.items():

@@ -45,7 +45,7 @@ __device__ void normalize_all(float* adv, long long total, double* sh) {
 __global__ void __launch_bounds__(GAE_WARPS * 32) gae_full_kernel(const float* __restrict__ rewards,
                                                                    const float* __restrict__ values,
                                                                    const float* __restrict__ dones, int B, int n,
-                                                                   float gamma_f, float lam_f, float gamma_pow_n,
+                                                                   float gamma_f, float lam_f, float gamma_pow_n, float rscale,
                                                                    int norm_adv, float* __restrict__ adv,
                                                                    float* __restrict__ ret, GaeWs* ws) {
     __shared__ double sh[32];
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(GAE_WARPS * 32) gae_full_kernel(const float* _
         double a_sum = 0.0, r_sum = 0.0;
         for (int k = lane; k < n; k += 32) {
             const float g = pow_table(gamma_f, k), l = pow_table(lam_f, k);
-            const float rk = r[k];
+            const float rk = __fmul_rn(r[k], rscale);   // ppo.py:452 (x reward_scale, rounded to fp32)
             const float v0 = (k > 0) ? __fmul_rn(v[k], __fsub_rn(1.0f, d[k - 1])) : v[0];
             const float v1 = __fmul_rn(v[k + 1], __fsub_rn(1.0f, d[k]));
             // td = r + gamma*V[k+1] - V[k]; each op rounded separately like the eager reference
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(GAE_WARPS * 32) gae_horizon_kernel(const float
                                                                       const float* __restrict__ values,
                                                                       const float* __restrict__ dones, int B, int n,
                                                                       int H, float gamma_f, float lam_f,
-                                                                      float gamma_pow_h, int norm_adv,
+                                                                      float gamma_pow_h, float rscale, int norm_adv,
                                                                       float* __restrict__ adv,
                                                                       float* __restrict__ ret, GaeWs* ws) {
     extern __shared__ __align__(16) float sm[];
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(GAE_WARPS * 32) gae_horizon_kernel(const float
         const float* v = values + (long long)b * (n + 1);
         const float* d = dones + (long long)b * n;
         for (int k = lane; k <= n; k += 32) w_v[k] = (k > 0) ? __fmul_rn(v[k], __fsub_rn(1.0f, d[k - 1])) : v[0];
-        for (int k = lane; k < n; k += 32) w_r[k] = r[k];
+        for (int k = lane; k < n; k += 32) w_r[k] = __fmul_rn(r[k], rscale);
     }
     __syncthreads();
     if (b < B) {
@@ -138,8 +138,8 @@ extern "C" size_t sb200_gae_workspace_bytes(int B, int n, int horizon) {
 }
 
 extern "C" int sb200_gae_window_f32(const float* rewards, const float* values, const float* dones, int B, int n,
-                                    int horizon, double gamma, double lam, int norm_adv, float* adv, float* ret,
-                                    void* workspace, void* stream) {
+                                    int horizon, double gamma, double lam, double reward_scale, int norm_adv, float* adv,
+                                    float* ret, void* workspace, void* stream) {
     SB200_REQUIRE(rewards && values && dones && adv && ret && workspace);
     SB200_REQUIRE(B >= 1 && n >= 1 && horizon >= 1 && horizon <= n);
     cudaStream_t st = (cudaStream_t)stream;
@@ -147,7 +147,7 @@ extern "C" int sb200_gae_window_f32(const float* rewards, const float* values, c
     const int grid = (B + GAE_WARPS - 1) / GAE_WARPS;
     if (horizon == n) {
         const float gpn = (float)pow(gamma, (double)n);          // Python `gamma ** n_step` (double) -> fp32 scalar
-        gae_full_kernel<<<grid, GAE_WARPS * 32, 0, st>>>(rewards, values, dones, B, n, gamma_f, lam_f, gpn, norm_adv,
+        gae_full_kernel<<<grid, GAE_WARPS * 32, 0, st>>>(rewards, values, dones, B, n, gamma_f, lam_f, gpn, (float)reward_scale, norm_adv,
                                                          adv, ret, (GaeWs*)workspace);
     } else {
         const float gph = (float)pow(gamma, (double)horizon);
@@ -159,7 +159,7 @@ extern "C" int sb200_gae_window_f32(const float* rewards, const float* values, c
             configured = smem;
         }
         gae_horizon_kernel<<<grid, GAE_WARPS * 32, smem, st>>>(rewards, values, dones, B, n, horizon, gamma_f, lam_f,
-                                                             gph, norm_adv, adv, ret, (GaeWs*)workspace);
+                                                             gph, (float)reward_scale, norm_adv, adv, ret, (GaeWs*)workspace);
     }
     return sb200_launch_status();
 }

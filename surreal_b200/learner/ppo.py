@@ -1,0 +1,353 @@
+"""PPOLearner: drop-in for surreal/learner/ppo.py:12-682 whose learn() runs entirely as hand-written
+sm_100a kernels (critic pass -> windowed GAE -> fused loss+grad -> backward GEMMs -> clip+Adam).
+
+Same constructor, config keys, method names, statistics names and control flow as the reference
+(clip / adapt modes, KL early stop ppo.py:556, publish-time adaptation ppo.py:637-666).  The batch a
+``learn(batch)`` call receives has the aggregator's layout (aggregator.py:176-183); its arrays may be
+numpy (copied through pinned memory) or CUDA tensors (zero copy).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib, ops
+from .._lib import check
+from ..model.ppo_net import PPOModel, DiagGauss
+from ..session import ConfigError
+from .aggregator import MultistepAggregatorWithInfo
+from .base import Learner
+from .scheduler import make_lr_scheduler
+
+S = dict(SURR=0, LOSS=1, ENTROPY=2, KL_PRE=3, KL_POST=4, GN_ACTOR=5, VAL_LOSS=6, EXPL_VAR=7, GN_CRITIC=8,
+         RET_MEAN=9, LOG_SIG=10, BEHAVE_LIK=11, IS_WEIGHT=12, REF_BEHAVE=13, EPOCHS=14, COUNT=32)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class PPOLearner(Learner):
+    def __init__(self, learner_config, env_config, session_config):
+        super().__init__(learner_config, env_config, session_config)
+        if not torch.cuda.is_available():
+            raise RuntimeError('surreal_b200.PPOLearner needs a CUDA device (there is no CPU fallback)')
+        self.device = torch.device('cuda', torch.cuda.current_device())
+        self.gpu_option = 'cuda:all'
+        self.use_cuda = True
+        self.current_iteration = 0
+        self.global_step = 0
+        lc = self.learner_config
+
+        # RL general parameters (ppo.py:75-85)
+        self.gamma = lc.algo.gamma
+        self.lam = lc.algo.advantage.lam
+        self.n_step = lc.algo.n_step
+        self.use_z_filter = lc.algo.use_z_filter
+        self.use_r_filter = lc.algo.use_r_filter
+        self.norm_adv = lc.algo.advantage.norm_adv
+        self.batch_size = lc.replay.batch_size
+        self.action_dim = self.env_config.action_spec.dim[0]
+        self.obs_spec = self.env_config.obs_spec
+        self.init_log_sig = lc.algo.consts.init_log_sig
+
+        # PPO parameters (ppo.py:88-118)
+        self.ppo_mode = lc.algo.ppo_mode
+        if self.ppo_mode not in ('adapt', 'clip'):
+            raise ConfigError('ppo_mode must be "adapt" or "clip"')
+        self.if_rnn_policy = lc.algo.rnn.if_rnn_policy
+        self.horizon = lc.algo.rnn.horizon
+        self.lr_actor = lc.algo.network.lr_actor
+        self.lr_critic = lc.algo.network.lr_critic
+        self.epoch_policy = lc.algo.consts.epoch_policy
+        self.epoch_baseline = lc.algo.consts.epoch_baseline
+        self.kl_target = lc.algo.consts.kl_target
+        self.adjust_threshold = lc.algo.consts.adjust_threshold
+        self.reward_scale = lc.algo.advantage.reward_scale
+        self.kl_cutoff_coeff = lc.algo.adapt_consts.kl_cutoff_coeff
+        self.beta_init = lc.algo.adapt_consts.beta_init
+        self.beta_range = lc.algo.adapt_consts.beta_range
+        self.clip_range = lc.algo.clip_consts.clip_range
+        self.clip_epsilon_init = lc.algo.clip_consts.clip_epsilon_init
+        if self.ppo_mode == 'adapt':
+            self.beta = self.beta_init
+            self.eta = self.kl_cutoff_coeff
+            self.beta_upper, self.beta_lower = self.beta_range[1], self.beta_range[0]
+            self.beta_adjust_threshold = self.adjust_threshold
+        else:
+            self.clip_epsilon = self.clip_epsilon_init
+            self.clip_adjust_threshold = self.adjust_threshold
+            self.clip_upper, self.clip_lower = self.clip_range[1], self.clip_range[0]
+            self.eta = self.kl_cutoff_coeff
+
+        self.exp_counter = 0
+        self.kl_record = []
+
+        pixel = bool(self.env_config.pixel_input) if 'pixel_input' in self.env_config else False
+        mk = dict(obs_spec=self.obs_spec, action_dim=self.action_dim, model_config=lc.model, use_cuda=True,
+                  init_log_sig=self.init_log_sig, use_z_filter=self.use_z_filter, if_pixel_input=pixel,
+                  rnn_config=lc.algo.rnn, device=self.device)
+        self.model = PPOModel(**mk)
+        self.ref_target_model = PPOModel(**mk)
+        self.ref_target_model.update_target_params(self.model)
+
+        net = lc.algo.network
+        self.clip_actor_gradient = net.clip_actor_gradient
+        self.actor_gradient_clip_value = net.actor_gradient_norm_clip
+        self.clip_critic_gradient = net.clip_critic_gradient
+        self.critic_gradient_clip_value = net.critic_gradient_norm_clip
+
+        B, n, A = self.batch_size, self.n_step, self.action_dim
+        D = self.model.low_dim
+        self.low_dim = D
+        dev = self.device
+        self.actor_optim = ops.MlpTrainer(self.model.actor, B, self.lr_actor,
+                                          clip_mode=1 if self.clip_actor_gradient else 0,
+                                          clip_value=self.actor_gradient_clip_value,
+                                          weight_decay=net.actor_regularization)
+        self.critic_optim = ops.MlpTrainer(self.model.critic, B, self.lr_critic,
+                                           clip_mode=1 if self.clip_critic_gradient else 0,
+                                           clip_value=self.critic_gradient_clip_value,
+                                           weight_decay=net.critic_regularization)
+
+        # learning-rate schedule (ppo.py:121-125,171-178)
+        an = net.anneal
+        num_updates = int(an.frames_to_anneal / lc.parameter_publish.exp_interval)
+        self.actor_lr_scheduler = make_lr_scheduler(an.lr_scheduler, self.actor_optim, self.lr_actor, num_updates,
+                                                    update_freq=an.lr_update_frequency, min_lr=an.min_lr)
+        self.critic_lr_scheduler = make_lr_scheduler(an.lr_scheduler, self.critic_optim, self.lr_critic, num_updates,
+                                                     update_freq=an.lr_update_frequency, min_lr=an.min_lr)
+
+        self.aggregator = MultistepAggregatorWithInfo(self.env_config.obs_spec, self.env_config.action_spec)
+        self.pd = DiagGauss(self.action_dim)
+        self.cells = None
+
+        # ---- device state of one learn(): allocated once, reused (graph-friendly, no allocator traffic)
+        f = lambda *sh: torch.zeros(*sh, dtype=torch.float32, device=dev)  # noqa: E731
+        self._obs, self._obs_next = f(B, n, D), f(B, 1, D)
+        self._actions, self._pds = f(B, n, A), f(B, n, 2 * A)
+        self._rewards, self._dones = f(B, n), f(B, n)
+        self._rewards_f = f(B, n) if self.use_r_filter else None
+        self._values = f(B * (n + 1), 1)
+        self._adv, self._ret = f(B, 1), f(B, 1)
+        self._ref_mean, self._ref_pd = f(B, A), f(B, 2 * A)
+        self._cur_mean = f(B, A)
+        self._stats = f(S['COUNT'])
+        self._hyper = torch.zeros(2, dtype=torch.float64, device=dev)
+        self._stop = torch.zeros(1, dtype=torch.int32, device=dev)
+        L = _lib.lib()
+        self._loss_ws = torch.zeros(L.sb200_ppo_loss_workspace_bytes(B, A), dtype=torch.uint8, device=dev)
+        self._rfilter_stats = torch.tensor([1e-5, 0.0, 0.0], dtype=torch.float32, device=dev) \
+            if self.use_r_filter else None
+        self._pin = {}
+        self._sync_hyper()
+        self.last_n_policy_epochs = 0
+
+    # ------------------------------------------------------------------------------------------------
+    def _sync_hyper(self):
+        self._hyper.copy_(torch.tensor([getattr(self, 'clip_epsilon', 0.0), getattr(self, 'beta', 0.0)],
+                                       dtype=torch.float64))
+
+    def _h2d(self, name, arr, dst):
+        """numpy -> pinned staging -> device buffer (non-blocking); CUDA tensors are copied device-side."""
+        if isinstance(arr, torch.Tensor):
+            dst.copy_(arr.reshape(dst.shape), non_blocking=True)
+            return 0
+        a = np.asarray(arr)
+        if name not in self._pin:
+            self._pin[name] = torch.empty(dst.shape, dtype=torch.float32, pin_memory=True)
+        self._pin[name].numpy()[...] = a.reshape(tuple(dst.shape))      # float64 -> float32 like torch.tensor(..)
+        dst.copy_(self._pin[name], non_blocking=True)
+        return dst.numel() * 4
+
+    @staticmethod
+    def _low_dim(obs):
+        if isinstance(obs, dict):
+            xs = [obs['low_dim'][k] for k in obs['low_dim']]
+            if len(xs) == 1:
+                return xs[0]
+            return torch.cat(xs, -1) if isinstance(xs[0], torch.Tensor) else np.concatenate(xs, -1)
+        return obs
+
+    def _preprocess_batch_ppo(self, batch):
+        """ppo.py:420-484: everything becomes fp32 on the device; reward scaling happens inside the GAE kernel
+        (or the reward-filter kernel)."""
+        get = (lambda k: batch[k]) if isinstance(batch, dict) else (lambda k: getattr(batch, k))
+        nbytes = 0
+        nbytes += self._h2d('obs', self._low_dim(get('obs')), self._obs)
+        nbytes += self._h2d('obs_next', self._low_dim(get('obs_next')), self._obs_next)
+        nbytes += self._h2d('actions', get('actions'), self._actions)
+        nbytes += self._h2d('rewards', get('rewards'), self._rewards)
+        nbytes += self._h2d('dones', get('dones'), self._dones)
+        pinfo = get('persistent_infos')
+        if pinfo is None:
+            raise ValueError('PPO needs the behaviour policy in persistent_infos (ppo_agent.py:149)')
+        nbytes += self._h2d('pds', pinfo[-1], self._pds)
+        self.last_h2d_bytes = nbytes
+        return batch
+
+    # ------------------------------------------------------------------------------------------------
+    def _gae_and_return(self):
+        """ppo.py:355-418 (MLP branch): critic over all B*(n+1) rows without materialising the cat, then GAE."""
+        B, n = self.batch_size, self.n_step
+        m = self.model
+        ops.mlp_forward(m.critic, self._obs, x_next=self._obs_next, win_n=n, zf_stats=m.z_stats, zf_eps=m.z_eps,
+                        out=self._values)
+        rewards, scale = self._rewards, self.reward_scale
+        if self.use_r_filter:
+            check(_lib.lib().sb200_reward_filter_f32(_ptr(self._rewards), B * n, float(self.reward_scale), 1e-5,
+                                                     _ptr(self._rfilter_stats), _ptr(self._rewards_f), ops._stream()),
+                  'sb200_reward_filter_f32')
+            rewards, scale = self._rewards_f, 1.0
+        ops.gae_window(rewards, self._values.view(B, n + 1), self._dones, self.gamma, self.lam, norm_adv=self.norm_adv,
+                       reward_scale=scale, adv=self._adv, ret=self._ret)
+        return self._adv, self._ret
+
+    def _policy_epoch(self):
+        L = _lib.lib()
+        B, n, A, D = self.batch_size, self.n_step, self.action_dim, self.low_dim
+        m, tr, st = self.model, self.actor_optim, ops._stream()
+        mean = tr.forward(self._obs, zf_stats=m.z_stats, zf_eps=m.z_eps, rows=B, ldx=n * D)
+        mode = 0 if self.ppo_mode == 'clip' else 1
+        if mode == 1:
+            check(L.sb200_ppo_kl_f32(_ptr(self._ref_pd), 2 * A, _ptr(mean), mean.stride(0), _ptr(m.log_var), B, A,
+                                     _ptr(self._stats), S['KL_PRE'], 0.0, None, _ptr(self._loss_ws), st),
+                  'sb200_ppo_kl_f32')
+        dlog_var = tr.slabs[0, m.actor.extra_off:m.actor.extra_off + A]
+        check(L.sb200_ppo_policy_loss_f32(mode, _ptr(mean), mean.stride(0), _ptr(m.log_var), _ptr(self._actions), n * A,
+                                          _ptr(self._adv), _ptr(self._pds), n * 2 * A, _ptr(self._ref_pd), 2 * A, B, A,
+                                          _ptr(self._hyper), float(self.eta), float(self.kl_target), _ptr(tr.d[-1]),
+                                          tr.d[-1].stride(0), _ptr(dlog_var), _ptr(self._stats), _ptr(self._loss_ws),
+                                          None, st), 'sb200_ppo_policy_loss_f32')
+        tr.backward()
+        tr.step(norm_out=self._stats[S['GN_ACTOR']:S['GN_ACTOR'] + 1])
+        # post-step KL(ref || current) (ppo.py:553-556)
+        ops.mlp_forward(m.actor, self._obs, zf_stats=m.z_stats, zf_eps=m.z_eps, rows=B, ldx=n * D, out=self._cur_mean)
+        check(L.sb200_ppo_kl_f32(_ptr(self._ref_pd), 2 * A, _ptr(self._cur_mean), A, _ptr(m.log_var), B, A,
+                                 _ptr(self._stats), S['KL_POST'], 4.0 * self.kl_target, _ptr(self._stop),
+                                 _ptr(self._loss_ws), st), 'sb200_ppo_kl_f32')
+
+    def _value_epoch(self):
+        L = _lib.lib()
+        B, n, D = self.batch_size, self.n_step, self.low_dim
+        m, tr, st = self.model, self.critic_optim, ops._stream()
+        v = tr.forward(self._obs, zf_stats=m.z_stats, zf_eps=m.z_eps, rows=B, ldx=n * D)
+        check(L.sb200_value_loss_f32(_ptr(v), v.stride(0), _ptr(self._ret), B, _ptr(tr.d[-1]), tr.d[-1].stride(0),
+                                     _ptr(self._stats), _ptr(self._loss_ws), st), 'sb200_value_loss_f32')
+        tr.backward()
+        tr.step(norm_out=self._stats[S['GN_CRITIC']:S['GN_CRITIC'] + 1])
+
+    def _optimize(self):
+        """ppo.py:487-586."""
+        L = _lib.lib()
+        B, n, A, D = self.batch_size, self.n_step, self.action_dim, self.low_dim
+        m, ref, st = self.model, self.ref_target_model, ops._stream()
+        self._gae_and_return()
+        ops.mlp_forward(ref.actor, self._obs, zf_stats=ref.z_stats, zf_eps=ref.z_eps, rows=B, ldx=n * D,
+                        out=self._ref_mean)
+        ops.make_pd(self._ref_mean, ref.log_var, B, A, self._ref_pd)
+        self._stats.zero_()
+        self._stop.zero_()
+        n_ep = 0
+        kl = 0.0
+        for _ in range(self.epoch_policy):
+            self._policy_epoch()
+            n_ep += 1
+            kl = float(self._stats[S['KL_POST']].item())          # one host sync per epoch (ppo.py:555-556)
+            if kl > self.kl_target * 4:
+                break
+        self.last_n_policy_epochs = n_ep
+        self.kl_record.append(kl)
+        for _ in range(self.epoch_baseline):
+            self._value_epoch()
+        check(L.sb200_ppo_final_stats_f32(_ptr(self._cur_mean), A, _ptr(m.log_var), _ptr(self._actions), n * A,
+                                          _ptr(self._pds), n * 2 * A, _ptr(self._ref_pd), 2 * A, B, A,
+                                          _ptr(self._stats), _ptr(self._loss_ws), st), 'sb200_ppo_final_stats_f32')
+        if self.use_z_filter:
+            ops.zfilter_update(self._obs, B, D, n * D, m.z_stats)  # step-0 rows only, AFTER the updates (ppo.py:578)
+        s = self._stats.cpu().numpy()                             # single D2H of all statistics
+        self.last_d2h_bytes = s.nbytes
+        stats = {'_surr_loss': float(s[S['SURR']]), '_entropy': float(s[S['ENTROPY']])}
+        if self.ppo_mode == 'clip':
+            stats['_clip_surr_loss'] = float(s[S['LOSS']])
+            stats['_clip_epsilon'] = self.clip_epsilon
+        else:
+            stats['_kl_loss_adapt'] = float(s[S['LOSS']])
+            stats['_beta'] = self.beta
+        if self.clip_actor_gradient:
+            stats['grad_norm_actor'] = float(s[S['GN_ACTOR']])
+        stats['_pol_kl'] = float(s[S['KL_POST']])
+        stats['_val_loss'] = float(s[S['VAL_LOSS']])
+        stats['_val_explained_var'] = float(s[S['EXPL_VAR']])
+        if self.clip_critic_gradient:
+            stats['grad_norm_critic'] = float(s[S['GN_CRITIC']])
+        stats['_avg_return_targ'] = float(s[S['RET_MEAN']])
+        stats['_avg_log_sig'] = float(s[S['LOG_SIG']])
+        stats['_avg_behave_likelihood'] = float(s[S['BEHAVE_LIK']])
+        stats['_avg_is_weight'] = float(s[S['IS_WEIGHT']])
+        stats['_ref_behave_diff'] = float(s[S['REF_BEHAVE']])
+        stats['_lr'] = self.actor_lr_scheduler.get_lr()[0]
+        if self.use_z_filter:
+            z = m.z_stats.cpu().double().numpy()
+            zs, zq, zc = z[:D], z[D:2 * D], z[2 * D]
+            stats['obs_running_mean'] = float(np.mean((zs / zc).astype(np.float32)))
+            stats['obs_running_square'] = float(np.mean((zq / zc).astype(np.float32)))
+            stats['obs_running_std'] = float(np.mean(np.sqrt((zq / zc) - (zs / zc) ** 2).astype(np.float32)))
+        if self.use_r_filter:
+            rf = self._rfilter_stats.cpu().numpy()
+            stats['reward_mean'] = float(rf[1] / rf[0])
+        return stats
+
+    # ------------------------------------------------------------------------------------------------
+    def learn(self, batch):
+        """ppo.py:588-613."""
+        self.current_iteration += 1
+        self._preprocess_batch_ppo(batch)
+        stats = self._optimize()
+        self.periodic_checkpoint(global_steps=self.current_iteration, score=None)
+        self.tensorplex.add_scalars(stats, self.global_step)
+        self.exp_counter += self.batch_size
+        self.global_step += 1
+        return stats
+
+    def module_dict(self):
+        return {'ppo': self.model}
+
+    def publish_parameter(self, iteration, message=''):
+        """ppo.py:623-635: publish only once exp_interval experiences were consumed."""
+        if self.exp_counter >= self.learner_config.parameter_publish.exp_interval:
+            self._ps_publisher.publish(iteration, message=message)
+            self._post_publish()
+
+    def _post_publish(self):
+        """ppo.py:637-666."""
+        final_kl = np.mean(self.kl_record)
+        lc = self.learner_config
+        if self.ppo_mode == 'clip':
+            if final_kl > self.kl_target * self.clip_adjust_threshold[1]:
+                if self.clip_lower < self.clip_epsilon:
+                    self.clip_epsilon = self.clip_epsilon / lc.algo.clip_consts.scale_constant
+            elif final_kl < self.kl_target * self.clip_adjust_threshold[0]:
+                if self.clip_upper > self.clip_epsilon:
+                    self.clip_epsilon = self.clip_epsilon * lc.algo.clip_consts.scale_constant
+        else:
+            if final_kl > self.kl_target * self.beta_adjust_threshold[1]:
+                if self.beta_upper > self.beta:
+                    self.beta = self.beta * lc.algo.adapt_consts.scale_constant
+            elif final_kl < self.kl_target * self.beta_adjust_threshold[0]:
+                if self.beta_lower < self.beta:
+                    self.beta = self.beta / lc.algo.adapt_consts.scale_constant
+        self._sync_hyper()
+        self.ref_target_model.update_target_params(self.model)
+        self.kl_record = []
+        self.exp_counter = 0
+        self.actor_lr_scheduler.step()
+        self.critic_lr_scheduler.step()
+
+    def checkpoint_attributes(self):
+        return ['model', 'ref_target_model', 'actor_lr_scheduler', 'critic_lr_scheduler', 'current_iteration']
+
+    def _prefetcher_preprocess(self, batch):
+        if isinstance(batch, dict):          # the HBM replay already returns an aggregated device batch
+            return batch
+        return self.aggregator.aggregate(batch)

@@ -1,0 +1,71 @@
+"""DDPG default config trees (behavioural mirror of surreal/main/ddpg_configs.py:16-174); pinned against the
+reference's trees by tests/test_default_configs.py."""
+import argparse
+
+from ..session import Config, LOCAL_SESSION_CONFIG, BASE_LEARNER_CONFIG, BASE_ENV_CONFIG
+
+DDPG_DEFAULT_LEARNER_CONFIG = Config({
+    'model': {
+        'convs': [], 'actor_fc_hidden_sizes': [300, 200], 'critic_fc_hidden_sizes': [400, 300],
+        'use_layernorm': False,
+        'conv_spec': {'out_channels': [16, 32], 'kernel_sizes': [8, 4], 'strides': [4, 2],
+                      'hidden_output_dim': 200},
+    },
+    'algo': {
+        'gamma': .99, 'n_step': 3, 'stride': 1,
+        'network': {
+            'lr_actor': 1e-4, 'lr_critic': 1e-3,
+            'clip_actor_gradient': True, 'actor_gradient_value_clip': 1.,
+            'clip_critic_gradient': False, 'critic_gradient_value_clip': 5.,
+            'actor_regularization': 0.0, 'critic_regularization': 0.0,
+            'use_action_regularization': False, 'use_double_critic': False,
+            'target_update': {'type': 'hard', 'interval': 500},
+        },
+        'exploration': {
+            'param_noise_type': None, 'param_noise_sigma': 0.05, 'param_noise_alpha': 1.15,
+            'param_noise_target_stddev': 0.005, 'noise_type': 'normal', 'max_sigma': 1.0, 'theta': 0.15,
+            'dt': 1e-3,
+        },
+    },
+    'replay': {'batch_size': 512, 'memory_size': int(1000000 / 3), 'sampling_start_size': 3000, 'replay_shards': 3},
+    'parameter_publish': {'min_publish_interval': 3},
+})
+DDPG_DEFAULT_LEARNER_CONFIG.extend(BASE_LEARNER_CONFIG)
+
+DDPG_DEFAULT_ENV_CONFIG = Config({
+    'env_name': '_str_', 'num_agents': '_int_', 'demonstration': None, 'use_depth': False, 'render': False,
+    'use_demonstration': False, 'pixel_input': False, 'use_grayscale': False, 'frame_stacks': 3,
+    'action_repeat': 1, 'frame_stack_concatenate_on_env': False, 'sleep_time': 0.0, 'limit_episode_length': 0,
+    'video': {'record_video': True, 'save_folder': None, 'max_videos': 500, 'record_every': 20},
+    'observation': {
+        'pixel': ['camera0', 'depth'],
+        'low_dim': ['position', 'velocity', 'proprio', 'robot-state', 'cube_pos', 'cube_quat', 'gripper_to_cube',
+                    'low-dim'],
+    },
+})
+DDPG_DEFAULT_ENV_CONFIG.extend(BASE_ENV_CONFIG)
+
+DDPG_DEFAULT_SESSION_CONFIG = Config({
+    'folder': '_str_',
+    'tensorplex': {'update_schedule': {'training_env': 20, 'eval_env': 5, 'eval_env_sleep': 30, 'agent': 50,
+                                       'learner': 20}},
+    'agent': {'fetch_parameter_mode': 'step', 'fetch_parameter_interval': 200, 'num_gpus': 0},
+    'sender': {'flush_iteration': 100},
+    'learner': {'prefetch_processes': 3, 'num_gpus': 0},
+})
+DDPG_DEFAULT_SESSION_CONFIG.extend(LOCAL_SESSION_CONFIG)
+
+
+def ddpg_argparser():
+    """ddpg_configs.py:249-271."""
+    p = argparse.ArgumentParser()
+    p.add_argument('--env', type=str, required=True)
+    p.add_argument('--num-agents', type=int, required=True)
+    p.add_argument('--num-gpus', type=int, default=0)
+    p.add_argument('--agent-num-gpus', type=int, default=0)
+    p.add_argument('--restore-folder', type=str, default=None)
+    p.add_argument('--experiment-folder', required=True)
+    p.add_argument('--agent-batch', type=int, default=1)
+    p.add_argument('--eval-batch', type=int, default=1)
+    p.add_argument('--unit-test', action='store_true')
+    return p

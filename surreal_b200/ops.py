@@ -120,63 +120,170 @@ def zfilter_desc(stats, eps=1e-5):
 
 
 def mlp_forward(net, x, zf_stats=None, zf_eps=1e-5, x_next=None, win_n=0, aux=None, save_all=False,
-                params=None, out=None):
-    """Run the fused forward.  ``x``: [rows, D] (or [B, n, D] with ``x_next`` [B, 1, D] and win_n=n for the
-    virtual cat of ppo.py:376-383).  Returns the network output [rows, out_dim]; with ``save_all`` a
-    list of every layer's post-activation output (for the backward pass)."""
+                params=None, out=None, rows=None, ldx=None, saves=None, save_x=None):
+    """Run the fused forward.
+
+    ``x``: [rows, D] (any row stride via ``ldx``), or [B, n, D] with ``x_next`` [B, 1, D] and win_n=n for
+    the virtual cat of ppo.py:376-383.  Returns the network output [rows, out_dim]; with ``save_all`` a
+    list of every layer's post-activation output.  ``saves``: optional explicit list of per-layer output
+    buffers ([rows, ld] each, or None) -- used by MlpTrainer; ``save_x`` receives the z-filtered input."""
     L = _lib.lib()
-    _f32c(x)
+    assert x.is_cuda and x.dtype == torch.float32
     D = net.dims[0]
     r = Rows()
     if win_n > 0:
+        _f32c(x), _f32c(x_next)
         B = x.shape[0]
-        assert x.shape[1] == win_n and x.shape[2] == D and x_next is not None
-        _f32c(x_next)
-        rows = B * (win_n + 1)
-        r.x, r.x_next, r.ldx, r.rows, r.win_n = x.data_ptr(), x_next.data_ptr(), D, rows, win_n
+        assert x.shape[1] == win_n and x.shape[2] == D
+        nrows = B * (win_n + 1)
+        r.x, r.x_next, r.ldx, r.rows, r.win_n = x.data_ptr(), x_next.data_ptr(), D, nrows, win_n
     else:
-        x2 = x.reshape(-1, x.shape[-1])
-        rows = x2.shape[0]
-        r.x, r.x_next, r.ldx, r.rows, r.win_n = x2.data_ptr(), None, x2.stride(0), rows, 0
+        if rows is None:
+            x2 = x.reshape(-1, x.shape[-1]) if x.is_contiguous() else x
+            assert x2.dim() == 2 and x2.stride(1) == 1
+            nrows, stride = x2.shape[0], x2.stride(0)
+        else:
+            nrows, stride = rows, ldx
+            x2 = x
+        r.x, r.x_next, r.ldx, r.rows, r.win_n = x2.data_ptr(), None, stride, nrows, 0
     if net.aux_layer >= 0:
-        _f32c(aux)
+        assert aux is not None and aux.is_cuda and aux.stride(-1) == 1
         r.aux, r.aux_ld = aux.data_ptr(), aux.stride(0)
     else:
         r.aux, r.aux_ld = None, 0
-    saves = [None] * MAX_LAYERS
+    if save_x is not None:
+        r.save_x, r.ld_save_x = save_x.data_ptr(), save_x.stride(0)
+    else:
+        r.save_x, r.ld_save_x = None, 0
     outs = []
-    for l in range(net.n_layers):
-        last = l == net.n_layers - 1
-        if save_all or last:
-            t = out if (last and out is not None) else torch.empty(rows, net.dims[l + 1], dtype=torch.float32,
-                                                                   device=x.device)
-            saves[l] = t
-            outs.append(t)
+    if saves is None:
+        saves = [None] * net.n_layers
+        for l in range(net.n_layers):
+            last = l == net.n_layers - 1
+            if save_all or last:
+                t = out if (last and out is not None) else torch.empty(nrows, net.dims[l + 1], dtype=torch.float32,
+                                                                       device=x.device)
+                saves[l] = t
+                outs.append(t)
+    saves = list(saves) + [None] * (MAX_LAYERS - len(saves))
     sv = (C.c_void_p * MAX_LAYERS)(*[(t.data_ptr() if t is not None else None) for t in saves])
     ld = (C.c_int64 * MAX_LAYERS)(*[(t.stride(0) if t is not None else 0) for t in saves])
     zf = zfilter_desc(zf_stats, zf_eps)
     d = net.desc(params)
     check(L.sb200_mlp_forward_f32(C.byref(d), C.byref(zf), C.byref(r), sv, ld, _stream()), 'sb200_mlp_forward_f32')
+    if not outs:
+        return None
     return outs if save_all else outs[-1]
+
+
+class MlpTrainer:
+    """Forward-with-saved-activations, hand-written backward and Adam for one FlatNet on a fixed
+    batch size M.  All buffers are allocated once; every method only launches kernels (graph-safe)."""
+
+    def __init__(self, net, M, lr, clip_mode=0, clip_value=0.0, weight_decay=0.0, splits=None):
+        L = _lib.lib()
+        self.net, self.M = net, M
+        dev = net.device
+        self.splits = splits if splits is not None else max(1, min(16, M // 128))
+        z = lambda *sh: torch.zeros(*sh, dtype=torch.float32, device=dev)  # noqa: E731
+        self.slabs = z(self.splits, net.size)
+        self.grad, self.exp_avg, self.exp_avg_sq = z(net.size), z(net.size), z(net.size)
+        self.ws = torch.zeros(L.sb200_optim_workspace_bytes(), dtype=torch.uint8, device=dev)
+        self.lr = torch.tensor([lr], dtype=torch.float64, device=dev)
+        self.clip_mode, self.clip_value, self.weight_decay = clip_mode, float(clip_value), float(weight_decay)
+        self.x_in = z(M, _ru(net.dims[0], 4))
+        self.h = [z(M, _ru(n, 4)) for n in net.dims[1:]]          # post-activation outputs
+        self.d = [z(M, _ru(n, 4)) for n in net.dims[1:]]          # gradients w.r.t. pre-activations
+        self.aux = None
+
+    @property
+    def out(self):
+        return self.h[-1][:, :self.net.dims[-1]]
+
+    def forward(self, x, zf_stats=None, zf_eps=1e-5, aux=None, rows=None, ldx=None):
+        self.aux = aux
+        mlp_forward(self.net, x, zf_stats=zf_stats, zf_eps=zf_eps, aux=aux, rows=rows, ldx=ldx,
+                    saves=self.h, save_x=self.x_in)
+        return self.out
+
+    def backward(self, need_dx0=False):
+        """self.d[-1] must hold dL/d(pre-activation of the last layer)."""
+        L, net, M = _lib.lib(), self.net, self.M
+        st = _stream()
+        base = self.slabs.data_ptr()
+        for l in reversed(range(net.n_layers)):
+            lay = net.layout[l]
+            K0, N, ldw = net.dims[l], lay['N'], lay['ldw']
+            X = self.x_in if l == 0 else self.h[l - 1]
+            dY = self.d[l]
+            check(L.sb200_linear_bwd_dw_f32(_ptr(X), X.stride(0), _ptr(dY), dY.stride(0),
+                                            C.c_void_p(base + 4 * lay['w']), C.c_void_p(base + 4 * lay['b']),
+                                            net.size, self.splits, ldw, M, K0, N, st), 'sb200_linear_bwd_dw_f32')
+            if net.aux_layer == l:
+                a = self.aux
+                check(L.sb200_linear_bwd_dw_f32(_ptr(a), a.stride(0), _ptr(dY), dY.stride(0),
+                                                C.c_void_p(base + 4 * (lay['w'] + K0 * ldw)), None, net.size,
+                                                self.splits, ldw, M, net.aux_dim, N, st), 'sb200_linear_bwd_dw_f32(aux)')
+            if l > 0:
+                Xa = self.h[l - 1]
+                dX = self.d[l - 1]
+                check(L.sb200_linear_bwd_dx_f32(_ptr(dY), dY.stride(0), C.c_void_p(net.params.data_ptr() + 4 * lay['w']),
+                                                ldw, _ptr(Xa), Xa.stride(0), _ptr(dX), dX.stride(0), M, N, K0, st),
+                      'sb200_linear_bwd_dx_f32')
+
+    def grad_wrt_aux(self, l, out):
+        """d loss / d aux input of layer l (the DDPG actor gradient dQ/da, ddpg.py:324-330)."""
+        L, net = _lib.lib(), self.net
+        lay = net.layout[l]
+        dY = self.d[l]
+        w_aux = net.params.data_ptr() + 4 * (lay['w'] + net.dims[l] * lay['ldw'])
+        check(L.sb200_linear_bwd_dx_f32(_ptr(dY), dY.stride(0), C.c_void_p(w_aux), lay['ldw'], None, 0, _ptr(out),
+                                        out.stride(0), self.M, lay['N'], net.aux_dim, _stream()),
+              'sb200_linear_bwd_dx_f32(aux)')
+
+    def step(self, norm_out=None, stop_flag=None):
+        L, net = _lib.lib(), self.net
+        st = _stream()
+        check(L.sb200_grad_reduce_norm_f32(_ptr(self.slabs), net.size, self.splits, _ptr(self.grad), net.size,
+                                           _ptr(self.ws), _ptr(stop_flag), st), 'sb200_grad_reduce_norm_f32')
+        check(L.sb200_clip_adam_f32(_ptr(net.params), _ptr(self.grad), _ptr(self.exp_avg), _ptr(self.exp_avg_sq),
+                                    net.size, _ptr(self.lr), 0.9, 0.999, 1e-8, self.weight_decay, self.clip_mode,
+                                    self.clip_value, _ptr(self.ws), _ptr(norm_out), _ptr(stop_flag), st),
+              'sb200_clip_adam_f32')
+
+    def set_lr(self, lr):
+        self.lr.fill_(float(lr))
 
 
 _gae_ws = {}
 
 
-def gae_window(rewards, values, dones, gamma, lam, horizon=None, norm_adv=True):
+def gae_window(rewards, values, dones, gamma, lam, horizon=None, norm_adv=True, reward_scale=1.0, adv=None, ret=None):
     """rewards [B,n], values [B,n+1] raw critic output, dones [B,n] -> (adv [B,E], ret [B,E])."""
     L = _lib.lib()
     _f32c(rewards), _f32c(values), _f32c(dones)
     B, n = rewards.shape
     H = n if horizon is None else int(horizon)
     E = n - H + 1
-    adv = torch.empty(B, E, dtype=torch.float32, device=rewards.device)
-    ret = torch.empty(B, E, dtype=torch.float32, device=rewards.device)
+    if adv is None:
+        adv = torch.empty(B, E, dtype=torch.float32, device=rewards.device)
+    if ret is None:
+        ret = torch.empty(B, E, dtype=torch.float32, device=rewards.device)
     key = rewards.device
     if key not in _gae_ws:
         _gae_ws[key] = torch.zeros(max(16, L.sb200_gae_workspace_bytes(B, n, H)), dtype=torch.uint8,
                                    device=rewards.device)
     check(L.sb200_gae_window_f32(_ptr(rewards), _ptr(values), _ptr(dones), B, n, H, float(gamma), float(lam),
-                                 int(bool(norm_adv)), _ptr(adv), _ptr(ret), _ptr(_gae_ws[key]), _stream()),
-          'sb200_gae_window_f32')
+                                 float(reward_scale), int(bool(norm_adv)), _ptr(adv), _ptr(ret), _ptr(_gae_ws[key]),
+                                 _stream()), 'sb200_gae_window_f32')
     return adv, ret
+
+
+def make_pd(mean, log_var, B, A, pd, log_noise=None):
+    check(_lib.lib().sb200_make_pd_f32(_ptr(mean), mean.stride(0), _ptr(log_var), _ptr(log_noise), B, A, _ptr(pd),
+                                       pd.stride(0), _stream()), 'sb200_make_pd_f32')
+    return pd
+
+
+def zfilter_update(x, rows, D, ldx, stats):
+    check(_lib.lib().sb200_zfilter_update_f32(_ptr(x), ldx, rows, D, _ptr(stats), _stream()), 'sb200_zfilter_update_f32')

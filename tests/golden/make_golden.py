@@ -21,6 +21,7 @@ every number stored here is produced by the reference's own functions:
   aggregate.npz         surreal/learner/aggregator.py:33-103,106-262
   ppo_act.npz           surreal/agent/ppo_agent.py:106-154
   ddpg_act.npz          surreal/agent/ddpg_agent.py:155-184 + action_noise.py:9-39
+  configs.npz           the default config trees of main/{ppo,ddpg}_configs.py + session/default_configs.py
 
 All inputs are seeded here and stored next to the outputs, so the fixtures are self-contained.
 """
@@ -588,7 +589,22 @@ def gen_act():
     save('ddpg_act', obs=obs, unit_noise=eps, sigma=Ag.sigma, actions=acts, **sd_np(Ag.model, 'model/'))
 
 
+def gen_configs():
+    """Default config trees exactly as the reference builds them (main/ppo_configs.py:15-175,
+    main/ddpg_configs.py:16-174, session/default_configs.py:4-259)."""
+    from surreal.session import BASE_LEARNER_CONFIG, BASE_ENV_CONFIG, BASE_SESSION_CONFIG, LOCAL_SESSION_CONFIG
+
+    def js(c):
+        return json.loads(json.dumps(c.to_dict() if hasattr(c, 'to_dict') else c, default=str))
+    save('configs', ppo_learner=js(PPO_DEFAULT_LEARNER_CONFIG), ppo_env=js(PPO_DEFAULT_ENV_CONFIG),
+         ppo_session=js(PPO_DEFAULT_SESSION_CONFIG), ddpg_learner=js(DDPG_DEFAULT_LEARNER_CONFIG),
+         ddpg_env=js(DDPG_DEFAULT_ENV_CONFIG), ddpg_session=js(DDPG_DEFAULT_SESSION_CONFIG),
+         base_learner=js(BASE_LEARNER_CONFIG), base_env=js(BASE_ENV_CONFIG), base_session=js(BASE_SESSION_CONFIG),
+         local_session=js(dict(LOCAL_SESSION_CONFIG)))
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['pd', 'filters', 'gae', 'ppo_learn', 'ddpg', 'replay', 'window', 'aggregate', 'act']
+    which = sys.argv[1:] or ['pd', 'filters', 'gae', 'ppo_learn', 'ddpg', 'replay', 'window', 'aggregate', 'act',
+                             'configs']
     for w in which:
         globals()['gen_' + w]()
