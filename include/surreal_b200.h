@@ -182,6 +182,67 @@ int sb200_clip_adam_f32(float* params, const float* grad, float* exp_avg, float*
 /* target = target*(1-tau) + tau*src (soft target update, ddpg.py:410-418). */
 int sb200_soft_update_f32(float* target, const float* src, int64_t n, double tau, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Batched actors (one call serves all N co-located actors of a step).
+ *   ppo_sample: PPOAgent.act after the network (surreal/agent/ppo_agent.py:138-149): pd = [mean | exp(log_var)*
+ *     exp(log_noise_i)], action = clip(eps*std+mean, -1, 1).  eps [N,A] injected N(0,1) draws or NULL for
+ *     Philox4x32-10 keyed by (seed, *step_counter, actor).  When stage_act != NULL the step's action / pd rows
+ *     are also written to the window staging area at stage_pos[i] (see ppo_window_step).
+ *   ddpg_noise: DDPGAgent.act after the network (ddpg_agent.py:176-183): clip -> + sigma_i*N(0,1) -> clip. */
+int sb200_ppo_sample_f32(const float* mean, int64_t ldm, const float* log_var, const float* log_noise,
+                         const float* eps, int N, int A, int deterministic, uint64_t seed,
+                         const uint64_t* step_counter, float* action, float* pd, const int* stage_pos,
+                         float* stage_act, float* stage_pd, int n_step, void* stream);
+int sb200_ddpg_noise_f32(const float* mean, int64_t ldm, const float* sigma, const float* unit_noise, int N,
+                         int A, int deterministic, uint64_t seed, const uint64_t* step_counter,
+                         float* action, void* stream);
+/* Synthetic device-resident environment of the benchmark configs: s' = tanh(Ws s + Wa a) + 0.01 xi,
+ * r = -|s|^2/D + 0.1 xi', done at max_steps (MaxStepWrapper, env/wrapper.py:142-163) with auto-reset.
+ * state [N,D] is updated in place to what the agent observes next; obs_next is the true successor. */
+int sb200_synth_env_step_f32(float* state, const float* action, const float* Ws, const float* Wa, int N,
+                             int D, int A, int max_steps, int* ep_step, uint64_t seed,
+                             const uint64_t* step_counter, float* obs_next, float* reward, float* done,
+                             void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Experience staging + HBM replay.
+ *   ppo_window_step: ExpSenderWrapperMultiStepMovingWindowWithInfo._step (exp_sender_wrapper.py:209-228) for N
+ *     actors + FIFOReplay.insert (fifo_replay.py:27,34-35): per-actor deque in HBM (stage_*: obs [N][n+1][D],
+ *     act [N][n][A], pd [N][n][2A], rew/done [N][n], pos [N]); completed windows are copied into FIFO slots in
+ *     (step, actor) order, drop-oldest at capacity; `stride` items are popped; done clears the deque.
+ *     Replay storage r_*: obs [C][n+1][D] (row n = obs_next), act [C][n][A], pd [C][n][2A], rew/done [C][n].
+ *   fifo_state: sb200_fifo_state_bytes() bytes {int head,count,capacity,dropped; int64 total_in,total_out}.
+ *   fifo_pop: FIFOReplay.sample (fifo_replay.py:37-39): slot ids of the `batch` oldest windows; *status = 1
+ *     if fewer are queued.   fifo_push: host-side Replay.insert() of k windows -> their slot ids.
+ *   replay_gather: out[b] = src[idx[b]] for records of record_floats floats (idx32 or idx64 non-NULL). */
+size_t sb200_fifo_state_bytes(void);
+int sb200_ppo_window_step_f32(const float* obs_next, const float* obs_reset, const float* reward,
+                              const float* done, int N, int n_step, int stride, int D, int A,
+                              int* stage_pos, float* stage_obs, float* stage_act, float* stage_pd,
+                              float* stage_rew, float* stage_done, int* dest_scratch, void* fifo_state,
+                              float* r_obs, float* r_act, float* r_pd, float* r_rew, float* r_done,
+                              uint64_t* step_counter, void* stream);
+int sb200_fifo_pop(void* fifo_state, int batch, int* idx, int* status, void* stream);
+int sb200_fifo_push(void* fifo_state, int k, int* slots, void* stream);
+int sb200_replay_gather_f32(const float* src, int64_t record_floats, const int* idx32, const int64_t* idx64,
+                            int batch, float* out, void* stream);
+/*   ssar_step: ExpSenderWrapperSSARNStepBootstrap._step (exp_sender_wrapper.py:96-112) for N actors +
+ *     UniformReplay.insert (uniform_replay.py:36-41): k-th insert -> slot k % capacity, actor order.
+ *     uniform_state: sb200_uniform_state_bytes() bytes {int64 next_idx,size,capacity,total_in}. */
+size_t sb200_uniform_state_bytes(void);
+int sb200_ssar_step_f32(const float* obs, const float* action, const float* obs_next, const float* reward,
+                        const float* done, int N, int n_step, double gamma, int D, int A, int* dq_len,
+                        float* dq_obs, float* dq_act, double* dq_rew, int* dest_scratch, float* emit_scratch,
+                        void* uniform_state, float* r_obs, float* r_obs_next, float* r_act, float* r_rew,
+                        float* r_done, uint64_t* step_counter, void* stream);
+/* CPython random.Random-compatible MT19937 on the HOST (uniform_replay.py:43-45 draws
+ * random.randint(0, len-1) per sample).  state_h: sb200_mt19937_state_bytes() bytes. */
+size_t sb200_mt19937_state_bytes(void);
+int sb200_mt19937_seed_h(void* state_h, const uint32_t* key_h, int key_len);     /* random.seed(int): 32-bit limbs */
+int sb200_mt19937_set_state_h(void* state_h, const uint32_t* words624_h, int index);   /* random.getstate()[1] */
+int sb200_mt19937_get_state_h(const void* state_h, uint32_t* words624_h, int* index);
+int sb200_mt19937_randint_fill_h(void* state_h, int64_t population, int64_t count, int64_t* out_h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,21 @@ def _declare(lib):
         'sb200_ppo_kl_f32': (I, [P, L, P, L, P, I, I, P, I, D, P, P, P]),
         'sb200_value_loss_f32': (I, [P, L, P, I, P, L, P, P, P]),
         'sb200_ppo_final_stats_f32': (I, [P, L, P, P, L, P, L, P, L, I, I, P, P, P]),
+        'sb200_ppo_sample_f32': (I, [P, L, P, P, P, I, I, I, C.c_uint64, P, P, P, P, P, P, I, P]),
+        'sb200_ddpg_noise_f32': (I, [P, L, P, P, I, I, I, C.c_uint64, P, P, P]),
+        'sb200_synth_env_step_f32': (I, [P, P, P, P, I, I, I, I, P, C.c_uint64, P, P, P, P, P]),
+        'sb200_fifo_state_bytes': (S, []),
+        'sb200_ppo_window_step_f32': (I, [P, P, P, P, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P]),
+        'sb200_fifo_pop': (I, [P, I, P, P, P]),
+        'sb200_fifo_push': (I, [P, I, P, P]),
+        'sb200_replay_gather_f32': (I, [P, L, P, P, I, P, P]),
+        'sb200_uniform_state_bytes': (S, []),
+        'sb200_ssar_step_f32': (I, [P, P, P, P, P, I, I, D, I, I, P, P, P, P, P, P, P, P, P, P, P, P, P, P]),
+        'sb200_mt19937_state_bytes': (S, []),
+        'sb200_mt19937_seed_h': (I, [P, P, I]),
+        'sb200_mt19937_set_state_h': (I, [P, P, I]),
+        'sb200_mt19937_get_state_h': (I, [P, P, C.POINTER(I)]),
+        'sb200_mt19937_randint_fill_h': (I, [P, L, L, P]),
         'sb200_optim_workspace_bytes': (S, []),
         'sb200_grad_reduce_norm_f32': (I, [P, L, I, P, L, P, P, P]),
         'sb200_clip_adam_f32': (I, [P, P, P, P, L, P, D, D, D, D, I, D, P, P, P, P]),

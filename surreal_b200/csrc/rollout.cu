@@ -1,0 +1,388 @@
+// Actor-side kernels of the batched rollout: policy sampling, exploration noise, the synthetic
+// device-resident environment, and the per-actor experience staging that replaces the Python deques of
+// surreal/env/exp_sender_wrapper.py (windows for PPO, n-step SSAR records for DDPG).
+//
+// All per-actor control state (deque length, episode step, RNG counter) lives in HBM so that a whole
+// T-step rollout is a fixed launch sequence (CUDA-graph capturable) with no host round trip.
+#include "common.cuh"
+
+namespace {
+
+constexpr int RT = 256;
+
+// ------------------------------------------------------------------------------------------------
+// PPOAgent.act after the network (ppo_agent.py:138-149): pd = [mean | exp(log_var)*exp(noise_i)],
+// action = clip(eps*std + mean, -1, 1) (or the mean when deterministic).  eps: injected N(0,1) draws
+// [N,A] or NULL -> Philox4x32-10 keyed by (seed, step counter, actor).  Also writes the step's action
+// and pd rows into the window staging area at the actor's current deque position.
+__global__ void __launch_bounds__(RT) ppo_sample_kernel(const float* __restrict__ mean, long long ldm,
+                                                        const float* __restrict__ log_var,
+                                                        const float* __restrict__ log_noise,
+                                                        const float* __restrict__ eps, int N, int A,
+                                                        int deterministic, unsigned long long seed,
+                                                        const unsigned long long* __restrict__ step_ctr,
+                                                        float* __restrict__ action, float* __restrict__ pd,
+                                                        const int* __restrict__ stage_pos,
+                                                        float* __restrict__ stage_act,
+                                                        float* __restrict__ stage_pd, int n_step) {
+    const int i = blockIdx.x * RT + threadIdx.x;
+    if (i >= N) return;
+    const float sc = (log_noise != nullptr) ? expf(log_noise[i]) : 1.0f;
+    const unsigned long long ctr = (step_ctr != nullptr) ? *step_ctr : 0ull;
+    const int p = (stage_pos != nullptr) ? stage_pos[i] : 0;
+    for (int j0 = 0; j0 < A; j0 += 4) {
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
+        if (!deterministic && eps == nullptr) {
+            const Philox4 r = philox4x32_10(seed, ctr, ((unsigned long long)i << 16) | (unsigned long long)(j0 >> 2));
+            const float2 a = box_muller(r.x, r.y), b = box_muller(r.z, r.w);
+            z[0] = a.x; z[1] = a.y; z[2] = b.x; z[3] = b.y;
+        }
+        for (int c = 0; c < 4 && j0 + c < A; ++c) {
+            const int j = j0 + c;
+            const float mu = mean[(long long)i * ldm + j];
+            const float sd = __fmul_rn(expf(log_var[j]), sc);
+            float a = mu;
+            if (!deterministic) {
+                const float e = (eps != nullptr) ? eps[(long long)i * A + j] : z[c];
+                a = __fadd_rn(__fmul_rn(e, sd), mu);
+            }
+            a = fminf(fmaxf(a, -1.0f), 1.0f);
+            action[(long long)i * A + j] = a;
+            pd[(long long)i * 2 * A + j] = mu;
+            pd[(long long)i * 2 * A + A + j] = sd;
+            if (stage_act != nullptr) {
+                stage_act[((long long)i * n_step + p) * A + j] = a;
+                stage_pd[((long long)i * n_step + p) * 2 * A + j] = mu;
+                stage_pd[((long long)i * n_step + p) * 2 * A + A + j] = sd;
+            }
+        }
+    }
+}
+
+// DDPGAgent.act after the network (ddpg_agent.py:176-183): clip -> + N(0, sigma_i) -> clip.
+__global__ void __launch_bounds__(RT) ddpg_noise_kernel(const float* __restrict__ mean, long long ldm,
+                                                        const float* __restrict__ sigma,
+                                                        const float* __restrict__ unit_noise, int N, int A,
+                                                        int deterministic, unsigned long long seed,
+                                                        const unsigned long long* __restrict__ step_ctr,
+                                                        float* __restrict__ action) {
+    const int i = blockIdx.x * RT + threadIdx.x;
+    if (i >= N) return;
+    const unsigned long long ctr = (step_ctr != nullptr) ? *step_ctr : 0ull;
+    const float sg = sigma[i];
+    for (int j0 = 0; j0 < A; j0 += 4) {
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
+        if (!deterministic && unit_noise == nullptr) {
+            const Philox4 r = philox4x32_10(seed, ctr, ((unsigned long long)i << 16) | (unsigned long long)(j0 >> 2));
+            const float2 a = box_muller(r.x, r.y), b = box_muller(r.z, r.w);
+            z[0] = a.x; z[1] = a.y; z[2] = b.x; z[3] = b.y;
+        }
+        for (int c = 0; c < 4 && j0 + c < A; ++c) {
+            const int j = j0 + c;
+            float a = fminf(fmaxf(mean[(long long)i * ldm + j], -1.0f), 1.0f);
+            if (!deterministic) {
+                const float e = (unit_noise != nullptr) ? unit_noise[(long long)i * A + j] : z[c];
+                a = (float)((double)a + (double)sg * (double)e);      // float32 array += float64 noise
+            }
+            action[(long long)i * A + j] = fminf(fmaxf(a, -1.0f), 1.0f);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Synthetic environment of SURVEY §8(d) cfg 2/3/5, batched and device-resident:
+//   s' = tanh(Ws s + Wa a) + 0.01*xi,   r = -|s|^2 / D + 0.1*xi',   done when the episode reaches
+//   `max_steps` (MaxStepWrapper, env/wrapper.py:142-163); on done the state is re-drawn ~ N(0,1).
+// One block per 4 actors; Ws/Wa are read through L1/L2 (18 KB).  obs_next = the true successor (terminal
+// when done), state = what the agent observes next (reset when done).
+__global__ void __launch_bounds__(RT) synth_env_step_kernel(float* __restrict__ state, const float* __restrict__ action,
+                                                            const float* __restrict__ Ws, const float* __restrict__ Wa,
+                                                            int N, int D, int A, int max_steps,
+                                                            int* __restrict__ ep_step, unsigned long long seed,
+                                                            const unsigned long long* __restrict__ step_ctr,
+                                                            float* __restrict__ obs_next, float* __restrict__ reward,
+                                                            float* __restrict__ done) {
+    extern __shared__ float sm[];                  // [4][D] states, [4][A] actions, [4] reward partials
+    const int per = 4;
+    const int a0 = blockIdx.x * per;
+    float* s_s = sm;
+    float* s_a = sm + per * D;
+    __shared__ float s_r[4][8];
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < per * D; idx += RT) {
+        const int q = idx / D, d = idx - q * D;
+        s_s[idx] = (a0 + q < N) ? state[(long long)(a0 + q) * D + d] : 0.0f;
+    }
+    for (int idx = tid; idx < per * A; idx += RT) {
+        const int q = idx / A, j = idx - q * A;
+        s_a[idx] = (a0 + q < N) ? action[(long long)(a0 + q) * A + j] : 0.0f;
+    }
+    __syncthreads();
+    const unsigned long long ctr = (step_ctr != nullptr) ? *step_ctr : 0ull;
+    // reward: -|s|^2/D (+ noise), one warp per actor (warps 0..3)
+    const int warp = tid >> 5, lane = tid & 31;
+    if (warp < per) {
+        float q = 0.0f;
+        for (int d = lane; d < D; d += 32) q += s_s[warp * D + d] * s_s[warp * D + d];
+        q = warp_sum(q);
+        if (lane == 0) s_r[warp][0] = q;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < per * D; idx += RT) {
+        const int q = idx / D, d = idx - q * D;
+        const int i = a0 + q;
+        if (i >= N) continue;
+        float acc = 0.0f;
+        const float* ws = Ws + (long long)d * D;
+        for (int k = 0; k < D; ++k) acc = fmaf(ws[k], s_s[q * D + k], acc);
+        const float* wa = Wa + (long long)d * A;
+        for (int k = 0; k < A; ++k) acc = fmaf(wa[k], s_a[q * A + k], acc);
+        const Philox4 r = philox4x32_10(seed ^ 0x5851F42D4C957F2Dull, ctr, ((unsigned long long)i << 20) | (unsigned long long)d);
+        const float2 g = box_muller(r.x, r.y);
+        const float nxt = tanhf(acc) + 0.01f * g.x;
+        const int t = ep_step[i] + 1;
+        const bool dn = (max_steps > 0) && (t >= max_steps);
+        obs_next[(long long)i * D + d] = nxt;
+        state[(long long)i * D + d] = dn ? box_muller(r.z, r.w).x : nxt;
+        if (d == 0) {
+            reward[i] = -s_r[q][0] / (float)D + 0.1f * g.y;
+            done[i] = dn ? 1.0f : 0.0f;
+        }
+    }
+    __syncthreads();
+    for (int q = tid; q < per; q += RT) {
+        const int i = a0 + q;
+        if (i < N) {
+            const int t = ep_step[i] + 1;
+            ep_step[i] = ((max_steps > 0) && (t >= max_steps)) ? 0 : t;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ExpSenderWrapperMultiStepMovingWindowWithInfo._step (exp_sender_wrapper.py:209-228), batched.
+// Phase 1 (single block, ordered): append (reward, done) at the actor's deque position, detect windows
+// that reached n_step, assign FIFO slots in (step, actor) order with drop-oldest at `capacity`
+// (fifo_replay.py:27), advance the RNG/step counter.
+struct FifoState {
+    int head;        // physical index of the oldest window
+    int count;       // windows currently queued
+    int capacity;    // memory_size + 3
+    int dropped;     // windows silently dropped so far (diagnostic)
+    long long total_in;
+    long long total_out;
+};
+
+__global__ void __launch_bounds__(1024) ppo_window_flags_kernel(const float* __restrict__ reward,
+                                                                const float* __restrict__ done, int N, int n_step,
+                                                                int* __restrict__ stage_pos,
+                                                                float* __restrict__ stage_rew,
+                                                                float* __restrict__ stage_done,
+                                                                int* __restrict__ dest, FifoState* fifo,
+                                                                unsigned long long* step_ctr) {
+    __shared__ int warp_tot[32];
+    __shared__ int warp_excl[32];
+    __shared__ int chunk_total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int base = 0;                                  // windows completed by actors before this chunk
+    for (int i0 = 0; i0 < N; i0 += 1024) {
+        const int i = i0 + tid;
+        int flag = 0;
+        if (i < N) {
+            const int p = stage_pos[i];
+            stage_rew[(long long)i * n_step + p] = reward[i];
+            stage_done[(long long)i * n_step + p] = done[i];
+            flag = (p + 1 == n_step) ? 1 : 0;
+        }
+        int incl = flag;                           // inclusive scan inside the warp (actor order)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = warp_tot[lane];
+            int wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            warp_excl[lane] = wi - w;
+            if (lane == 31) chunk_total = wi;
+        }
+        __syncthreads();
+        if (i < N) dest[i] = flag ? (base + warp_excl[warp] + incl - flag) : -1;
+        base += chunk_total;
+        __syncthreads();
+    }
+    // translate ranks into physical slots; advance the queue
+    const int K = base;
+    const int cap = fifo->capacity;
+    const int head = fifo->head, count = fifo->count;
+    for (int i = tid; i < N; i += 1024) {
+        const int r = dest[i];
+        if (r >= 0) {
+            // more arrivals than the deque holds: the earliest of THIS step fall out immediately
+            dest[i] = (K > cap && r < K - cap) ? -1 : (int)(((long long)head + count + r) % cap);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int nc = count + K, nh = head, dr = 0;
+        if (nc > cap) {                       // deque(maxlen): the oldest entries fall out
+            dr = nc - cap;
+            nh = (int)(((long long)head + dr) % cap);
+            nc = cap;
+        }
+        fifo->head = nh;
+        fifo->count = nc;
+        fifo->dropped += dr;
+        fifo->total_in += K;
+        if (step_ctr != nullptr) *step_ctr += 1ull;
+    }
+}
+
+// Phase 2: one block per actor.  Writes obs_next at deque position p+1; if the window completed, copies it
+// into the replay slot (coalesced float4 where aligned) and pops `stride` items; if the episode ended,
+// clears the deque (exp_sender_wrapper.py:204-207) and seeds position 0 with the reset observation.
+__global__ void __launch_bounds__(128) ppo_window_commit_kernel(const float* __restrict__ obs_next,
+                                                                const float* __restrict__ obs_reset,
+                                                                const float* __restrict__ done, int N, int n_step,
+                                                                int stride, int D, int A,
+                                                                int* __restrict__ stage_pos,
+                                                                float* __restrict__ stage_obs,
+                                                                float* __restrict__ stage_act,
+                                                                float* __restrict__ stage_pd,
+                                                                float* __restrict__ stage_rew,
+                                                                float* __restrict__ stage_done,
+                                                                const int* __restrict__ dest,
+                                                                float* __restrict__ r_obs, float* __restrict__ r_act,
+                                                                float* __restrict__ r_pd, float* __restrict__ r_rew,
+                                                                float* __restrict__ r_done) {
+    const int i = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int p = stage_pos[i];
+    float* so = stage_obs + (long long)i * (n_step + 1) * D;
+    float* sa = stage_act + (long long)i * n_step * A;
+    float* sp = stage_pd + (long long)i * n_step * 2 * A;
+    float* sr = stage_rew + (long long)i * n_step;
+    float* sd = stage_done + (long long)i * n_step;
+    for (int d = tid; d < D; d += blockDim.x) so[(long long)(p + 1) * D + d] = obs_next[(long long)i * D + d];
+    __syncthreads();
+    int len = p + 1;
+    const int slot = dest[i];
+    if (slot >= 0) {                                         // len == n_step: ship the window
+        float* o = r_obs + (long long)slot * (n_step + 1) * D;
+        for (int k = tid; k < (n_step + 1) * D; k += blockDim.x) o[k] = so[k];
+        float* a = r_act + (long long)slot * n_step * A;
+        for (int k = tid; k < n_step * A; k += blockDim.x) a[k] = sa[k];
+        float* q = r_pd + (long long)slot * n_step * 2 * A;
+        for (int k = tid; k < n_step * 2 * A; k += blockDim.x) q[k] = sp[k];
+        float* r = r_rew + (long long)slot * n_step;
+        float* dn = r_done + (long long)slot * n_step;
+        for (int k = tid; k < n_step; k += blockDim.x) {
+            r[k] = sr[k];
+            dn[k] = sd[k];
+        }
+        __syncthreads();
+        const int pop = min(stride, len);
+        const int keep = len - pop;
+        if (keep > 0) {                                      // overlapping windows: slide the deque down
+            for (int k0 = 0; k0 < (keep + 1) * D; k0 += blockDim.x) {
+                const int k = k0 + tid;
+                float v = 0.f;
+                if (k < (keep + 1) * D) v = so[(long long)pop * D + k];
+                __syncthreads();
+                if (k < (keep + 1) * D) so[k] = v;
+                __syncthreads();
+            }
+            for (int k0 = 0; k0 < keep * 2 * A; k0 += blockDim.x) {
+                const int k = k0 + tid;
+                float va = 0.f, vp = 0.f;
+                if (k < keep * A) va = sa[(long long)pop * A + k];
+                if (k < keep * 2 * A) vp = sp[(long long)pop * 2 * A + k];
+                __syncthreads();
+                if (k < keep * A) sa[k] = va;
+                if (k < keep * 2 * A) sp[k] = vp;
+                __syncthreads();
+            }
+            for (int k0 = 0; k0 < keep; k0 += blockDim.x) {
+                const int k = k0 + tid;
+                float vr = 0.f, vd = 0.f;
+                if (k < keep) { vr = sr[pop + k]; vd = sd[pop + k]; }
+                __syncthreads();
+                if (k < keep) { sr[k] = vr; sd[k] = vd; }
+                __syncthreads();
+            }
+        } else {
+            for (int d = tid; d < D; d += blockDim.x) so[d] = so[(long long)len * D + d];   // obs_next -> next obs
+        }
+        len = keep;
+    }
+    __syncthreads();
+    if (done[i] > 0.5f) {                                    // episode over: deque cleared, new episode's first obs
+        for (int d = tid; d < D; d += blockDim.x) so[d] = obs_reset[(long long)i * D + d];
+        len = 0;
+    }
+    if (tid == 0) stage_pos[i] = len;
+}
+
+}  // namespace
+
+extern "C" int sb200_ppo_sample_f32(const float* mean, int64_t ldm, const float* log_var, const float* log_noise,
+                                    const float* eps, int N, int A, int deterministic, uint64_t seed,
+                                    const uint64_t* step_counter, float* action, float* pd, const int* stage_pos,
+                                    float* stage_act, float* stage_pd, int n_step, void* stream) {
+    SB200_REQUIRE(mean && log_var && action && pd && N >= 1 && A >= 1 && ldm >= A);
+    SB200_REQUIRE(stage_act == nullptr || (stage_pos != nullptr && stage_pd != nullptr && n_step >= 1));
+    ppo_sample_kernel<<<(N + RT - 1) / RT, RT, 0, (cudaStream_t)stream>>>(
+        mean, ldm, log_var, log_noise, eps, N, A, deterministic, (unsigned long long)seed,
+        (const unsigned long long*)step_counter, action, pd, stage_pos, stage_act, stage_pd, n_step);
+    return sb200_launch_status();
+}
+
+extern "C" int sb200_ddpg_noise_f32(const float* mean, int64_t ldm, const float* sigma, const float* unit_noise, int N,
+                                    int A, int deterministic, uint64_t seed, const uint64_t* step_counter,
+                                    float* action, void* stream) {
+    SB200_REQUIRE(mean && sigma && action && N >= 1 && A >= 1 && ldm >= A);
+    ddpg_noise_kernel<<<(N + RT - 1) / RT, RT, 0, (cudaStream_t)stream>>>(
+        mean, ldm, sigma, unit_noise, N, A, deterministic, (unsigned long long)seed,
+        (const unsigned long long*)step_counter, action);
+    return sb200_launch_status();
+}
+
+extern "C" int sb200_synth_env_step_f32(float* state, const float* action, const float* Ws, const float* Wa, int N,
+                                        int D, int A, int max_steps, int* ep_step, uint64_t seed,
+                                        const uint64_t* step_counter, float* obs_next, float* reward, float* done,
+                                        void* stream) {
+    SB200_REQUIRE(state && action && Ws && Wa && ep_step && obs_next && reward && done);
+    SB200_REQUIRE(N >= 1 && D >= 1 && A >= 1 && (size_t)(4 * (D + A)) * 4 <= 40 * 1024);
+    const size_t smem = (size_t)(4 * (D + A)) * sizeof(float);
+    synth_env_step_kernel<<<(N + 3) / 4, RT, smem, (cudaStream_t)stream>>>(
+        state, action, Ws, Wa, N, D, A, max_steps, ep_step, (unsigned long long)seed,
+        (const unsigned long long*)step_counter, obs_next, reward, done);
+    return sb200_launch_status();
+}
+
+extern "C" size_t sb200_fifo_state_bytes(void) { return sizeof(FifoState); }
+
+extern "C" int sb200_ppo_window_step_f32(const float* obs_next, const float* obs_reset, const float* reward,
+                                         const float* done, int N, int n_step, int stride, int D, int A,
+                                         int* stage_pos, float* stage_obs, float* stage_act, float* stage_pd,
+                                         float* stage_rew, float* stage_done, int* dest_scratch, void* fifo_state,
+                                         float* r_obs, float* r_act, float* r_pd, float* r_rew, float* r_done,
+                                         uint64_t* step_counter, void* stream) {
+    SB200_REQUIRE(obs_next && obs_reset && reward && done && stage_pos && stage_obs && stage_act && stage_pd);
+    SB200_REQUIRE(stage_rew && stage_done && dest_scratch && fifo_state && r_obs && r_act && r_pd && r_rew && r_done);
+    SB200_REQUIRE(N >= 1 && n_step >= 1 && stride >= 1 && D >= 1 && A >= 1);
+    cudaStream_t st = (cudaStream_t)stream;
+    ppo_window_flags_kernel<<<1, 1024, 0, st>>>(reward, done, N, n_step, stage_pos, stage_rew, stage_done, dest_scratch,
+                                                (FifoState*)fifo_state, (unsigned long long*)step_counter);
+    ppo_window_commit_kernel<<<N, 128, 0, st>>>(obs_next, obs_reset, done, N, n_step, stride, D, A, stage_pos, stage_obs,
+                                                stage_act, stage_pd, stage_rew, stage_done, dest_scratch, r_obs, r_act,
+                                                r_pd, r_rew, r_done);
+    return sb200_launch_status();
+}

@@ -47,8 +47,11 @@ def test_ppo_learn_matches_reference(golden, tag):
         got = L.model.state_dict()
         worst = 0.0
         for k, e in after.items():
-            d = float((got[k].cpu().reshape(e.shape) - e).abs().max())
-            worst = max(worst, d)
+            gk = got[k].cpu().reshape(e.shape)
+            if k.startswith('z_filter'):      # running sums (~1e2): fp32 accumulation order -> a few ulp, relative bar
+                assert float(((gk - e).abs() / e.abs().clamp_min(1.0)).max()) <= 1e-6, k
+                continue
+            worst = max(worst, float((gk - e).abs().max()))
         # 20 Adam steps of size <= lr each: agree to a small fraction of ONE step
         assert worst <= max(2e-6, 0.02 * lr), 'params drifted by %.3e' % worst
         if cfg['mode'] == 'clip':
