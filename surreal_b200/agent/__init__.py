@@ -1,0 +1,2 @@
+from .base import Agent, AGENT_MODES  # noqa: F401
+from .ppo_agent import PPOAgent  # noqa: F401

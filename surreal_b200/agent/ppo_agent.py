@@ -1,0 +1,123 @@
+"""PPOAgent: drop-in for surreal/agent/ppo_agent.py:15-190 serving a whole batch of actors per call.
+
+``act(obs)`` runs the fused actor MLP for all N actors in one launch, then one sampling kernel that
+applies each actor's constant exploration scale exp(noise_i) (drawn once, ppo_agent.py:57-61), samples
+N(mean, std), clips to [-1, 1] and records the behaviour policy AFTER scaling (ppo_agent.py:139,149).
+numpy observations (a single actor's [D] vector or an [N, D] batch) are accepted for external CPU envs."""
+import ctypes as C
+import time
+
+import numpy as np
+import torch
+
+from .. import _lib, ops
+from .._lib import check
+from ..model.ppo_net import PPOModel, DiagGauss
+from ..env import ExpSenderWrapperMultiStepMovingWindowWithInfo
+from .base import Agent
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class PPOAgent(Agent):
+    def __init__(self, learner_config, env_config, session_config, agent_id, agent_mode, render=False):
+        super().__init__(learner_config=learner_config, env_config=env_config, session_config=session_config,
+                         agent_id=agent_id, agent_mode=agent_mode, render=render)
+        if not torch.cuda.is_available():
+            raise RuntimeError('surreal_b200.PPOAgent needs a CUDA device (there is no CPU fallback)')
+        self.device = torch.device('cuda', torch.cuda.current_device())
+        self.action_dim = self.env_config.action_spec.dim[0]
+        self.obs_spec = self.env_config.obs_spec
+        self.use_z_filter = self.learner_config.algo.use_z_filter
+        self.init_log_sig = self.learner_config.algo.consts.init_log_sig
+        self.log_sig_range = self.learner_config.algo.consts.log_sig_range
+        if self.agent_mode != 'training':
+            if self.agent_mode not in ['eval_deterministic_local', 'eval_stochastic_local']:
+                self.agent_mode = 'eval_stochastic' if self.env_config.stochastic_eval else 'eval_deterministic'
+        N = self.num_envs
+        if self.agent_mode != 'training':
+            self.noise = np.zeros(N)
+        else:                                  # one constant per actor (ppo_agent.py:60-61)
+            self.noise = np.random.uniform(low=-self.log_sig_range, high=self.log_sig_range, size=N)
+        self.rnn_config = self.learner_config.algo.rnn
+        self.gpu_ids = 'cuda:all'
+        self.pd = DiagGauss(self.action_dim)
+        self.cells = None
+        pixel = bool(self.env_config.pixel_input) if 'pixel_input' in self.env_config else False
+        self.model = PPOModel(obs_spec=self.obs_spec, action_dim=self.action_dim, model_config=self.learner_config.model,
+                              use_cuda=True, init_log_sig=self.init_log_sig, use_z_filter=self.use_z_filter,
+                              if_pixel_input=pixel, rnn_config=self.rnn_config, device=self.device)
+        A, D = self.action_dim, self.model.low_dim
+        self._log_noise = torch.tensor(self.noise, dtype=torch.float32, device=self.device)
+        self._mean = torch.zeros(N, A, device=self.device)
+        self._action = torch.zeros(N, A, device=self.device)
+        self._pd = torch.zeros(N, 2 * A, device=self.device)
+        self._obs_dev = torch.zeros(N, D, device=self.device)
+        self._obs_pin = None
+        self._counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.seed = 2 + 1000003 * int(agent_id)
+
+    def set_noise(self, noise):
+        self.noise = np.asarray(noise, dtype=np.float64).reshape(self.num_envs)
+        self._log_noise.copy_(torch.tensor(self.noise, dtype=torch.float32))
+
+    def act(self, obs, eps=None):
+        """-> action (eval) or (action, [onetime_infos, [pd]]) in training, like ppo_agent.py:151-154.
+        Device observations give device results; numpy in, numpy out."""
+        N, A, D = self.num_envs, self.action_dim, self.model.low_dim
+        x = obs
+        if isinstance(obs, dict):
+            xs = [obs['low_dim'][k] for k in obs['low_dim']]
+            x = xs[0] if len(xs) == 1 else (torch.cat(xs, -1) if isinstance(xs[0], torch.Tensor)
+                                            else np.concatenate(xs, -1))
+        host = not isinstance(x, torch.Tensor)
+        if host:
+            if self._obs_pin is None:
+                self._obs_pin = torch.empty(N, D, dtype=torch.float32, pin_memory=True)
+            self._obs_pin.numpy()[...] = np.asarray(x, dtype=np.float32).reshape(N, D)
+            self._obs_dev.copy_(self._obs_pin, non_blocking=True)
+            x = self._obs_dev
+        x = x.reshape(N, D)
+        m = self.model
+        ops.mlp_forward(m.actor, x, zf_stats=m.z_stats, zf_eps=m.z_eps, out=self._mean)
+        det = self.agent_mode in ['eval_deterministic', 'eval_deterministic_local']
+        env = self.env
+        staged = self.agent_mode == 'training' and isinstance(env, ExpSenderWrapperMultiStepMovingWindowWithInfo)
+        counter = env.step_counter if (env is not None and hasattr(env, 'step_counter')) else self._counter
+        eps_dev = None
+        if eps is not None:
+            eps_dev = torch.as_tensor(np.asarray(eps, dtype=np.float32).reshape(N, A)).to(self.device)
+        check(_lib.lib().sb200_ppo_sample_f32(
+            _p(self._mean), A, _p(m.log_var), _p(self._log_noise), _p(eps_dev), N, A, int(det), self.seed, _p(counter),
+            _p(self._action), _p(self._pd), _p(env.stage_pos) if staged else None,
+            _p(env.stage_act) if staged else None, _p(env.stage_pd) if staged else None,
+            env.n_step if staged else 1, ops._stream()), 'sb200_ppo_sample_f32')
+        if not staged and counter is self._counter:
+            self._counter += 1
+        if host:
+            action = self._action.cpu().numpy().astype(np.float64)
+            pd = self._pd.cpu().numpy()
+            if N == 1 and np.asarray(obs['low_dim'][next(iter(obs['low_dim']))] if isinstance(obs, dict) else obs).ndim == 1:
+                action, pd = action.reshape(-1), pd.reshape(-1)
+        else:
+            action, pd = self._action, self._pd
+        if self.agent_mode != 'training':
+            return action
+        if self.env_config.sleep_time:
+            time.sleep(self.env_config.sleep_time)
+        return action, [[], [pd]]
+
+    def module_dict(self):
+        return {'ppo': self.model}
+
+    def default_config(self):
+        return {'model': {'convs': '_list_', 'fc_hidden_sizes': '_list_'}}
+
+    def reset(self):
+        pass                                   # LSTM cells only (RNN stem is a "next" row)
+
+    def prepare_env_agent(self, env):
+        env = super().prepare_env_agent(env)
+        return ExpSenderWrapperMultiStepMovingWindowWithInfo(env, self.learner_config, self.session_config)

@@ -27,7 +27,10 @@ class ModuleDict:
 
     def load(self, state):
         for k, m in self._module_dict.items():
-            m.load_state_dict(state[k])
+            if '__flat__' in state[k]:
+                m.load_flat_state(state[k]['__flat__'])
+            else:
+                m.load_state_dict(state[k])
 
 
 class ParameterPublisher:
@@ -45,7 +48,10 @@ class ParameterPublisher:
     def publish(self, iteration, message=''):
         snap = {}
         for name, m in self._module_dict.items():
-            snap[name] = {k: v.detach().clone() for k, v in m.state_dict().items()}
+            if hasattr(m, 'flat_state'):       # flat device buffers: a publish is a handful of D2D copies
+                snap[name] = {'__flat__': {k: v.detach().clone() for k, v in m.flat_state().items()}}
+            else:
+                snap[name] = {k: v.detach().clone() for k, v in m.state_dict().items()}
         self._snapshot = snap
         self.version += 1
         self.info = {'time': time.time(), 'iteration': iteration, 'message': message, 'hash': self.version}
@@ -78,3 +84,25 @@ class ParameterClient:
 
     def fetch_info(self):
         return self._publisher.info if self._publisher is not None else None
+
+
+class LocalHub:
+    """In-process rendezvous that replaces the SYMPH_* host/port environment variables
+    (launch/setup_network.py:21-45): components of one experiment (same session folder) find each other
+    here -- replay shards, the learner's parameter publisher -- instead of dialling ZeroMQ sockets."""
+    _hubs = {}
+
+    def __init__(self):
+        self.replays = {}
+        self.publisher = None
+
+    @classmethod
+    def get(cls, session_config):
+        key = session_config.folder if 'folder' in session_config else '__default__'
+        if key not in cls._hubs:
+            cls._hubs[key] = LocalHub()
+        return cls._hubs[key]
+
+    @classmethod
+    def reset(cls):
+        cls._hubs = {}

@@ -1,0 +1,3 @@
+from .synthetic import SyntheticEnv  # noqa: F401
+from .exp_sender_wrapper import (ExpSenderWrapperMultiStepMovingWindowWithInfo,  # noqa: F401
+                                 ExpSenderWrapperSSARNStepBootstrap)

@@ -1,0 +1,116 @@
+"""Experience-sender wrappers for BATCHED device-resident envs (mirror of
+surreal/env/exp_sender_wrapper.py:72-112,153-264).
+
+The reference keeps one Python deque per actor process and ships finished windows / n-step transitions
+through pyarrow + ZeroMQ to the replay server.  Here the N deques are HBM arrays, the "send" is a kernel
+that copies the record into the HBM replay's ring in (step, actor) order, and the md5 de-duplication of
+overlapping windows (exp_sender.py:10-59) has nothing left to do."""
+import ctypes as C
+
+import torch
+
+from .. import _lib
+from .._lib import check
+from ..distributed import LocalHub
+from ..session import ConfigError
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _st():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _WrapperBase:
+    def __init__(self, env, learner_config, session_config, replay=None):
+        self.env = env
+        self.learner_config = learner_config
+        self.session_config = session_config
+        self.replay = replay if replay is not None else LocalHub.get(session_config).replays.get(0)
+        if self.replay is None:
+            raise RuntimeError('no replay registered for this session: construct the Replay before the agent '
+                               'wraps its env (the ZeroMQ collector address of the reference is gone)')
+        self.N, self.D, self.A = env.N, env.D, env.A
+        self.device = env.device
+
+    @property
+    def unwrapped(self):
+        return getattr(self.env, 'unwrapped', self.env)
+
+    def __getattr__(self, k):
+        return getattr(self.env, k)
+
+
+class ExpSenderWrapperMultiStepMovingWindowWithInfo(_WrapperBase):
+    """n_step windows with stride (exp_sender_wrapper.py:153-264) -> FIFOReplay ring."""
+
+    def __init__(self, env, learner_config, session_config, replay=None):
+        super().__init__(env, learner_config, session_config, replay)
+        self.n_step = self.learner_config.algo.n_step
+        self.stride = self.learner_config.algo.stride
+        if self.stride < 1:
+            raise ConfigError('stride {} for experience generation cannot be less than 1'.format(self.stride))
+        N, n, D, A = self.N, self.n_step, self.D, self.A
+        f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.device)  # noqa: E731
+        self.stage_pos = torch.zeros(N, dtype=torch.int32, device=self.device)
+        self.stage_obs, self.stage_act, self.stage_pd = f(N, n + 1, D), f(N, n, A), f(N, n, 2 * A)
+        self.stage_rew, self.stage_done = f(N, n), f(N, n)
+        self._dest = torch.zeros(N, dtype=torch.int32, device=self.device)
+        r = self.replay
+        assert (r.n_step, r.D, r.A) == (n, D, A), 'replay record shape does not match the env / n_step'
+
+    def reset(self):
+        obs, info = self.env.reset()
+        self.stage_pos.zero_()                                     # deque.clear() (exp_sender_wrapper.py:204-207)
+        self.stage_obs[:, 0].copy_(obs['low_dim']['flat_inputs'])
+        return obs, info
+
+    def step(self, action):
+        """``action`` = (action_choice, action_info) as PPOAgent.act returns in training mode; the agent has
+        already staged action / pd rows for this step (sb200_ppo_sample_f32)."""
+        obs, reward, done, info = self.env.step(action[0] if isinstance(action, tuple) else action)
+        r = self.replay
+        check(_lib.lib().sb200_ppo_window_step_f32(
+            _p(info['obs_next']), _p(obs['low_dim']['flat_inputs']), _p(reward), _p(done), self.N, self.n_step,
+            self.stride, self.D, self.A, _p(self.stage_pos), _p(self.stage_obs), _p(self.stage_act),
+            _p(self.stage_pd), _p(self.stage_rew), _p(self.stage_done), _p(self._dest), _p(r.state), _p(r.r_obs),
+            _p(r.r_act), _p(r.r_pd), _p(r.r_rew), _p(r.r_done), _p(self.env.step_counter), _st()),
+            'sb200_ppo_window_step_f32')
+        return obs, reward, done, info
+
+
+class ExpSenderWrapperSSARNStepBootstrap(_WrapperBase):
+    """n-step bootstrapped SSAR transitions (exp_sender_wrapper.py:72-112) -> UniformReplay ring."""
+
+    def __init__(self, env, learner_config, session_config, replay=None):
+        super().__init__(env, learner_config, session_config, replay)
+        self.n_step = self.learner_config.algo.n_step
+        self.gamma = self.learner_config.algo.gamma
+        N, n, D, A = self.N, self.n_step, self.D, self.A
+        self.dq_len = torch.zeros(N, dtype=torch.int32, device=self.device)
+        self.dq_obs = torch.zeros(N, n, D, device=self.device)
+        self.dq_act = torch.zeros(N, n, A, device=self.device)
+        self.dq_rew = torch.zeros(N, n, dtype=torch.float64, device=self.device)
+        self._dest = torch.zeros(N, dtype=torch.int32, device=self.device)
+        self._emit = torch.zeros(N, device=self.device)
+        self._obs = torch.zeros(N, D, device=self.device)
+
+    def reset(self):
+        obs, info = self.env.reset()
+        self.dq_len.zero_()
+        self._obs.copy_(obs['low_dim']['flat_inputs'])
+        return obs, info
+
+    def step(self, action):
+        obs, reward, done, info = self.env.step(action)
+        r = self.replay
+        check(_lib.lib().sb200_ssar_step_f32(
+            _p(self._obs), _p(action), _p(info['obs_next']), _p(reward), _p(done), self.N, self.n_step,
+            float(self.gamma), self.D, self.A, _p(self.dq_len), _p(self.dq_obs), _p(self.dq_act), _p(self.dq_rew),
+            _p(self._dest), _p(self._emit), _p(r.state), _p(r.r_obs), _p(r.r_obs_next), _p(r.r_act), _p(r.r_rew),
+            _p(r.r_done), _p(self.env.step_counter), _st()), 'sb200_ssar_step_f32')
+        r.mark_device_inserts()
+        self._obs.copy_(obs['low_dim']['flat_inputs'])             # s_t of the next transition (reset obs where done)
+        return obs, reward, done, info

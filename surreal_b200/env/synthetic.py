@@ -1,0 +1,67 @@
+"""Batched, device-resident synthetic environment of the benchmark configs (cfg 2/3/5):
+
+    s' = tanh(Ws s + Wa a) + 0.01 xi,   r = -|s|^2 / D + 0.1 xi',   Ws, Wa ~ N(0, 1/sqrt(D)),  s0 ~ N(0,1)
+
+with the episode cap of MaxStepWrapper (surreal/env/wrapper.py:142-163) folded in: ``done`` when an
+actor's episode reaches ``limit_episode_length``; done actors auto-reset.  All N actors advance with ONE
+kernel launch and every tensor stays in HBM.  The gym / MuJoCo / robosuite adapters of surreal/env are out
+of scope; an external CPU env can still drive ``agent.act`` with numpy observations."""
+import ctypes as C
+
+import torch
+
+from .. import _lib
+from .._lib import check
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class SyntheticEnv:
+    metadata = {}
+
+    def __init__(self, num_envs, obs_dim=64, action_dim=8, limit_episode_length=200, seed=0, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError('SyntheticEnv is device-resident: a CUDA device is required')
+        self.device = torch.device(device if device is not None else ('cuda:%d' % torch.cuda.current_device()))
+        self.N, self.D, self.A = num_envs, obs_dim, action_dim
+        self.max_steps = int(limit_episode_length)
+        self.seed = int(seed)
+        g = torch.Generator().manual_seed(self.seed)
+        scale = 1.0 / (obs_dim ** 0.5)
+        self.Ws = (torch.randn(obs_dim, obs_dim, generator=g) * scale).to(self.device)
+        self.Wa = (torch.randn(obs_dim, action_dim, generator=g) * scale).to(self.device)
+        self._g = torch.Generator().manual_seed(self.seed + 1)
+        self.state = torch.zeros(num_envs, obs_dim, device=self.device)
+        self.ep_step = torch.zeros(num_envs, dtype=torch.int32, device=self.device)
+        self.obs_next = torch.zeros(num_envs, obs_dim, device=self.device)
+        self.reward = torch.zeros(num_envs, device=self.device)
+        self.done = torch.zeros(num_envs, device=self.device)
+        self.step_counter = torch.zeros(1, dtype=torch.int64, device=self.device)   # shared Philox counter
+        self._own_counter = True
+
+    def observation_spec(self):
+        return {'low_dim': {'flat_inputs': (self.D,)}}
+
+    def action_spec(self):
+        return {'dim': (self.A,), 'type': 'continuous'}
+
+    def reset(self):
+        self.state.copy_(torch.randn(self.N, self.D, generator=self._g).to(self.device))
+        self.ep_step.zero_()
+        return {'low_dim': {'flat_inputs': self.state}}, {}
+
+    def step(self, action):
+        """action: [N, A] CUDA tensor.  Returns (obs, reward, done, info): obs is what every actor observes NEXT
+        (already reset where done); ``info['obs_next']`` is the true successor (terminal where done)."""
+        if isinstance(action, tuple):
+            action = action[0]
+        check(_lib.lib().sb200_synth_env_step_f32(
+            _p(self.state), _p(action), _p(self.Ws), _p(self.Wa), self.N, self.D, self.A, self.max_steps,
+            _p(self.ep_step), self.seed + 7, _p(self.step_counter), _p(self.obs_next), _p(self.reward), _p(self.done),
+            C.c_void_p(torch.cuda.current_stream().cuda_stream)), 'sb200_synth_env_step_f32')
+        return {'low_dim': {'flat_inputs': self.state}}, self.reward, self.done, {'obs_next': self.obs_next}
+
+    def close(self):
+        pass

@@ -11,7 +11,7 @@ import time
 from pathlib import Path
 
 from .. import utils as U
-from ..distributed import ParameterPublisher
+from ..distributed import ParameterPublisher, LocalHub
 from ..session import Config
 
 
@@ -47,6 +47,7 @@ class Learner(metaclass=U.AutoInitializeMeta):
             self.restore_checkpoint()
         self._ps_publish_tracker = U.TimedTracker(self.learner_config.parameter_publish.min_publish_interval)
         self._ps_publisher = ParameterPublisher(module_dict=self.module_dict())
+        LocalHub.get(self.session_config).publisher = self._ps_publisher
 
     def attach_replay(self, replay):
         self._replay = replay

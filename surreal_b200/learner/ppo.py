@@ -124,9 +124,11 @@ class PPOLearner(Learner):
 
         # ---- device state of one learn(): allocated once, reused (graph-friendly, no allocator traffic)
         f = lambda *sh: torch.zeros(*sh, dtype=torch.float32, device=dev)  # noqa: E731
-        self._obs, self._obs_next = f(B, n, D), f(B, 1, D)
-        self._actions, self._pds = f(B, n, A), f(B, n, 2 * A)
-        self._rewards, self._dones = f(B, n), f(B, n)
+        # own batch buffers (host-batch path); a device batch from the HBM replay is used in place instead
+        self._own = dict(obs_full=f(B, n + 1, D), actions=f(B, n, A), pds=f(B, n, 2 * A), rewards=f(B, n),
+                         dones=f(B, n))
+        self._obs_full, self._actions, self._pds = self._own['obs_full'], self._own['actions'], self._own['pds']
+        self._rewards, self._dones = self._own['rewards'], self._own['dones']
         self._rewards_f = f(B, n) if self.use_r_filter else None
         self._values = f(B * (n + 1), 1)
         self._adv, self._ret = f(B, 1), f(B, 1)
@@ -169,20 +171,50 @@ class PPOLearner(Learner):
             return torch.cat(xs, -1) if isinstance(xs[0], torch.Tensor) else np.concatenate(xs, -1)
         return obs
 
+    @staticmethod
+    def _dev_ok(t, shape):
+        return isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() \
+            and tuple(t.shape) == tuple(shape)
+
     def _preprocess_batch_ppo(self, batch):
-        """ppo.py:420-484: everything becomes fp32 on the device; reward scaling happens inside the GAE kernel
-        (or the reward-filter kernel)."""
+        """ppo.py:420-484: everything becomes fp32 on the device.  The learner's working layout is
+        obs_full [B, n+1, D] (row n = obs_next), i.e. the reference's cat([obs, obs_next], 1) (ppo.py:380)
+        done once at ingest.  A device batch from the HBM replay (which already stores windows that way) is
+        used in place -- zero copies; a host batch goes through pinned staging.  Reward scaling happens inside
+        the GAE / reward-filter kernel."""
         get = (lambda k: batch[k]) if isinstance(batch, dict) else (lambda k: getattr(batch, k))
-        nbytes = 0
-        nbytes += self._h2d('obs', self._low_dim(get('obs')), self._obs)
-        nbytes += self._h2d('obs_next', self._low_dim(get('obs_next')), self._obs_next)
-        nbytes += self._h2d('actions', get('actions'), self._actions)
-        nbytes += self._h2d('rewards', get('rewards'), self._rewards)
-        nbytes += self._h2d('dones', get('dones'), self._dones)
+        B, n, A, D = self.batch_size, self.n_step, self.action_dim, self.low_dim
         pinfo = get('persistent_infos')
         if pinfo is None:
             raise ValueError('PPO needs the behaviour policy in persistent_infos (ppo_agent.py:149)')
-        nbytes += self._h2d('pds', pinfo[-1], self._pds)
+        full = batch.get('obs_full') if isinstance(batch, dict) else None
+        if self._dev_ok(full, (B, n + 1, D)) and self._dev_ok(get('actions'), (B, n, A)) and \
+                self._dev_ok(pinfo[-1], (B, n, 2 * A)) and self._dev_ok(get('rewards'), (B, n)) and \
+                self._dev_ok(get('dones'), (B, n)):
+            self._obs_full, self._actions, self._pds = full, get('actions'), pinfo[-1]
+            self._rewards, self._dones = get('rewards'), get('dones')
+            self.last_h2d_bytes = 0
+            return batch
+        own = self._own
+        self._obs_full, self._actions, self._pds = own['obs_full'], own['actions'], own['pds']
+        self._rewards, self._dones = own['rewards'], own['dones']
+        obs, obs_next = self._low_dim(get('obs')), self._low_dim(get('obs_next'))
+        nbytes = 0
+        if isinstance(obs, torch.Tensor):
+            own['obs_full'][:, :n].copy_(obs.reshape(B, n, D), non_blocking=True)
+            own['obs_full'][:, n:].copy_(obs_next.reshape(B, 1, D), non_blocking=True)
+        else:
+            if 'obs_full' not in self._pin:
+                self._pin['obs_full'] = torch.empty(B, n + 1, D, dtype=torch.float32, pin_memory=True)
+            pf = self._pin['obs_full'].numpy()
+            pf[:, :n] = np.asarray(obs).reshape(B, n, D)
+            pf[:, n:] = np.asarray(obs_next).reshape(B, 1, D)
+            own['obs_full'].copy_(self._pin['obs_full'], non_blocking=True)
+            nbytes += own['obs_full'].numel() * 4
+        nbytes += self._h2d('actions', get('actions'), own['actions'])
+        nbytes += self._h2d('rewards', get('rewards'), own['rewards'])
+        nbytes += self._h2d('dones', get('dones'), own['dones'])
+        nbytes += self._h2d('pds', pinfo[-1], own['pds'])
         self.last_h2d_bytes = nbytes
         return batch
 
@@ -191,7 +223,7 @@ class PPOLearner(Learner):
         """ppo.py:355-418 (MLP branch): critic over all B*(n+1) rows without materialising the cat, then GAE."""
         B, n = self.batch_size, self.n_step
         m = self.model
-        ops.mlp_forward(m.critic, self._obs, x_next=self._obs_next, win_n=n, zf_stats=m.z_stats, zf_eps=m.z_eps,
+        ops.mlp_forward(m.critic, self._obs_full.view(B * (n + 1), -1), zf_stats=m.z_stats, zf_eps=m.z_eps,
                         out=self._values)
         rewards, scale = self._rewards, self.reward_scale
         if self.use_r_filter:
@@ -207,7 +239,7 @@ class PPOLearner(Learner):
         L = _lib.lib()
         B, n, A, D = self.batch_size, self.n_step, self.action_dim, self.low_dim
         m, tr, st = self.model, self.actor_optim, ops._stream()
-        mean = tr.forward(self._obs, zf_stats=m.z_stats, zf_eps=m.z_eps, rows=B, ldx=n * D)
+        mean = tr.forward(self._obs_full, zf_stats=m.z_stats, zf_eps=m.z_eps, rows=B, ldx=(n + 1) * D)
         mode = 0 if self.ppo_mode == 'clip' else 1
         if mode == 1:
             check(L.sb200_ppo_kl_f32(_ptr(self._ref_pd), 2 * A, _ptr(mean), mean.stride(0), _ptr(m.log_var), B, A,
@@ -222,7 +254,7 @@ class PPOLearner(Learner):
         tr.backward()
         tr.step(norm_out=self._stats[S['GN_ACTOR']:S['GN_ACTOR'] + 1])
         # post-step KL(ref || current) (ppo.py:553-556)
-        ops.mlp_forward(m.actor, self._obs, zf_stats=m.z_stats, zf_eps=m.z_eps, rows=B, ldx=n * D, out=self._cur_mean)
+        ops.mlp_forward(m.actor, self._obs_full, zf_stats=m.z_stats, zf_eps=m.z_eps, rows=B, ldx=(n + 1) * D, out=self._cur_mean)
         check(L.sb200_ppo_kl_f32(_ptr(self._ref_pd), 2 * A, _ptr(self._cur_mean), A, _ptr(m.log_var), B, A,
                                  _ptr(self._stats), S['KL_POST'], 4.0 * self.kl_target, _ptr(self._stop),
                                  _ptr(self._loss_ws), st), 'sb200_ppo_kl_f32')
@@ -231,7 +263,7 @@ class PPOLearner(Learner):
         L = _lib.lib()
         B, n, D = self.batch_size, self.n_step, self.low_dim
         m, tr, st = self.model, self.critic_optim, ops._stream()
-        v = tr.forward(self._obs, zf_stats=m.z_stats, zf_eps=m.z_eps, rows=B, ldx=n * D)
+        v = tr.forward(self._obs_full, zf_stats=m.z_stats, zf_eps=m.z_eps, rows=B, ldx=(n + 1) * D)
         check(L.sb200_value_loss_f32(_ptr(v), v.stride(0), _ptr(self._ret), B, _ptr(tr.d[-1]), tr.d[-1].stride(0),
                                      _ptr(self._stats), _ptr(self._loss_ws), st), 'sb200_value_loss_f32')
         tr.backward()
@@ -243,7 +275,7 @@ class PPOLearner(Learner):
         B, n, A, D = self.batch_size, self.n_step, self.action_dim, self.low_dim
         m, ref, st = self.model, self.ref_target_model, ops._stream()
         self._gae_and_return()
-        ops.mlp_forward(ref.actor, self._obs, zf_stats=ref.z_stats, zf_eps=ref.z_eps, rows=B, ldx=n * D,
+        ops.mlp_forward(ref.actor, self._obs_full, zf_stats=ref.z_stats, zf_eps=ref.z_eps, rows=B, ldx=(n + 1) * D,
                         out=self._ref_mean)
         ops.make_pd(self._ref_mean, ref.log_var, B, A, self._ref_pd)
         self._stats.zero_()
@@ -264,7 +296,7 @@ class PPOLearner(Learner):
                                           _ptr(self._pds), n * 2 * A, _ptr(self._ref_pd), 2 * A, B, A,
                                           _ptr(self._stats), _ptr(self._loss_ws), st), 'sb200_ppo_final_stats_f32')
         if self.use_z_filter:
-            ops.zfilter_update(self._obs, B, D, n * D, m.z_stats)  # step-0 rows only, AFTER the updates (ppo.py:578)
+            ops.zfilter_update(self._obs_full, B, D, (n + 1) * D, m.z_stats)  # step-0 rows only, AFTER the updates (ppo.py:578)
         s = self._stats.cpu().numpy()                             # single D2H of all statistics
         self.last_d2h_bytes = s.nbytes
         stats = {'_surr_loss': float(s[S['SURR']]), '_entropy': float(s[S['ENTROPY']])}

@@ -72,3 +72,53 @@ def ppo_argparser():
     p.add_argument('--agent-batch', type=int, default=1)
     p.add_argument('--unit-test', action='store_true')
     return p
+
+
+def make_synthetic_env_config(env_config, num_envs, obs_dim=64, action_dim=8, seed=0):
+    """What surreal.env.make_env_config does for a real env (ppo_configs.py:213-214): fill obs_spec /
+    action_spec.  Here for the device-resident synthetic env of the benchmark configs."""
+    env_config.env_name = 'synthetic'
+    env_config.num_envs = int(num_envs)
+    env_config.seed = int(seed)
+    env_config.obs_spec = {'low_dim': {'flat_inputs': (obs_dim,)}}
+    env_config.action_spec = {'dim': (action_dim,), 'type': 'continuous'}
+    return env_config
+
+
+class PPOLauncher:
+    """PPOLauncher of ppo_configs.py:178-228 (constructed lazily so importing configs needs no GPU)."""
+
+    def __new__(cls, *a, **k):
+        from ..launch import SurrealDefaultLauncher
+        from ..agent import PPOAgent
+        from ..learner import PPOLearner
+        from ..replay import FIFOReplay
+
+        class _PPOLauncher(SurrealDefaultLauncher):
+            def __init__(self):
+                super().__init__(PPOAgent, PPOLearner, FIFOReplay, PPO_DEFAULT_SESSION_CONFIG.copy(),
+                                 PPO_DEFAULT_ENV_CONFIG.copy(), PPO_DEFAULT_LEARNER_CONFIG.copy())
+
+            def setup(self, argv):
+                args = ppo_argparser().parse_args(args=argv)
+                name = args.env
+                dims = name.split(':')[1:] if ':' in name else []
+                D = int(dims[0]) if len(dims) > 0 else 64
+                A = int(dims[1]) if len(dims) > 1 else 8
+                make_synthetic_env_config(self.env_config, args.num_agents, D, A)
+                self.session_config.folder = args.experiment_folder
+                self.session_config.agent.num_gpus = args.agent_num_gpus
+                self.session_config.learner.num_gpus = args.num_gpus
+                if args.restore_folder is not None:
+                    self.session_config.checkpoint.restore = True
+                    self.session_config.checkpoint.restore_folder = args.restore_folder
+                self.agent_batch_size = args.agent_batch
+                self.eval_batch_size = args.agent_batch
+                if args.unit_test:
+                    self.learner_config.replay.batch_size = 2
+                    self.learner_config.replay.sampling_start_size = 2
+        return _PPOLauncher()
+
+
+def main():
+    PPOLauncher().main()

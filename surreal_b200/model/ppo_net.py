@@ -75,6 +75,19 @@ class PPOModel:
         if self.use_z_filter:
             self.z_stats.copy_(net.z_stats)
 
+    def flat_state(self):
+        """The raw device buffers (kernel layout) -- what the collapsed parameter wire ships."""
+        st = {'actor': self.actor.params, 'critic': self.critic.params}
+        if self.use_z_filter:
+            st['z_stats'] = self.z_stats
+        return st
+
+    def load_flat_state(self, st):
+        self.actor.params.copy_(st['actor'])
+        self.critic.params.copy_(st['critic'])
+        if self.use_z_filter and 'z_stats' in st:
+            self.z_stats.copy_(st['z_stats'])
+
     def state_dict(self):
         """Keys follow the reference module tree (actor.log_var, actor.model.*, critic.model.*, z_filter.*);
         Linear weights are exported in torch's [out, in] convention."""

@@ -1,0 +1,259 @@
+"""HBM replay, device-side experience windowing and batched actors vs the reference-generated goldens
+and the CPU oracle.  Bit-exact for indices / ordering / slot assignment."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import ppo_configs, ddpg_configs, ref_state_dict
+from oracle.windowing import multistep_windows, ssar_nstep
+from oracle.replay import FIFO as OFIFO
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _window(i, n, D, A):
+    """a host window whose every field encodes the id i"""
+    ob = lambda v: {'low_dim': {'flat_inputs': np.full((D,), v, dtype=np.float32)}}  # noqa: E731
+    return dict(obs=[ob(i + 0.001 * k) for k in range(n)], obs_next=ob(i + 0.5),
+                actions=[np.full((A,), i, dtype=np.float64) for _ in range(n)], rewards=[float(i)] * n,
+                dones=[False] * (n - 1) + [True], persistent_infos=[[np.full((2 * A,), i, dtype=np.float32)]] * n,
+                onetime_infos=[], infos=[{}] * n, n_step=n)
+
+
+def test_fifo_replay_trace_matches_reference(golden):
+    from surreal_b200.replay import FIFOReplay
+    f = golden('replay').js('fifo')
+    n, D, A = 3, 5, 2
+    lc, ec, sc = ppo_configs(D=D, A=A, n_step=n, stride=n, B=f['batch_size'], memory_size=f['memory_size'])
+    R = FIFOReplay(lc, ec, sc)
+    nxt = 0
+    for (op, k), tr in zip(f['script'], f['trace']):
+        if op == 'insert':
+            for _ in range(k):
+                R.insert(_window(nxt, n, D, A))
+                nxt += 1
+            assert [len(R), int(R.start_sample_condition())] == tr
+        else:
+            b = R.sample(k)
+            ids = b['rewards'][:, 0].cpu().numpy().astype(int).tolist()
+            assert ids == tr
+            assert b['obs']['low_dim']['flat_inputs'].shape == (k, n, D)
+            assert torch.allclose(b['obs_next']['low_dim']['flat_inputs'][:, 0, 0].cpu(), torch.tensor(tr, dtype=torch.float32) + 0.5)
+            assert b['persistent_infos'][0][:, 0, 0].cpu().numpy().astype(int).tolist() == tr
+            assert bool((b['dones'][:, -1] == 1).all()) and bool((b['dones'][:, 0] == 0).all())
+    with pytest.raises(IndexError):
+        while True:
+            R.sample(f['batch_size'])
+
+
+def test_uniform_replay_trace_matches_reference(golden):
+    from surreal_b200.replay import UniformReplay
+    u = golden('replay').js('uniform')
+    D, A = 4, 2
+    lc, ec, sc = ddpg_configs(D=D, A=A, B=8, memory_size=u['memory_size'], start=u['sampling_start_size'])
+    R = UniformReplay(lc, ec, sc)
+    random.seed(u['seed'])
+    nxt = 0
+    ob = lambda v: {'low_dim': {'flat_inputs': np.full((D,), v, dtype=np.float32)}}  # noqa: E731
+    for (op, k), tr in zip(u['script'], u['trace']):
+        if op == 'insert':
+            for _ in range(k):
+                R.insert({'obs': [ob(nxt), ob(nxt + 0.5)], 'action': np.full((A,), nxt / 1000.0), 'reward': float(nxt),
+                          'done': nxt % 2 == 0, 'info': {}})
+                nxt += 1
+            assert [len(R), int(R.start_sample_condition()), R._host_next] == tr
+        else:
+            b = R.sample(k)
+            assert b['rewards'][:, 0].cpu().numpy().astype(int).tolist() == tr
+            assert b['obs']['low_dim']['flat_inputs'][:, 0].cpu().numpy().astype(int).tolist() == tr
+            assert b['rewards'].shape == (k, 1) and b['dones'].shape == (k, 1)
+            assert b['dones'][:, 0].cpu().numpy().astype(int).tolist() == [int(t % 2 == 0) for t in tr]
+
+
+class ScriptedEnv:
+    """Deterministic device env: obs = global step id of that actor, reward = 0.25*g - 3, scripted episode ends."""
+    metadata = {}
+
+    def __init__(self, scripts, D=2, A=1):
+        self.scripts = [list(s) for s in scripts]
+        self.N, self.D, self.A = len(scripts), D, A
+        self.device = torch.device(DEV)
+        self.step_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.ep = [0] * self.N
+        self.t = [0] * self.N
+        self.g = [0] * self.N
+
+    def _obs(self):
+        return torch.tensor([[float(g)] * self.D for g in self.g], device=self.device)
+
+    def reset(self):
+        return {'low_dim': {'flat_inputs': self._obs()}}, {}
+
+    def step(self, action):
+        rew, done = [], []
+        for i in range(self.N):
+            self.t[i] += 1
+            self.g[i] += 1
+            rew.append(0.25 * self.g[i] - 3.0)
+            done.append(float(self.t[i] >= self.scripts[i][self.ep[i] % len(self.scripts[i])]))
+        obs_next = self._obs()
+        for i in range(self.N):
+            if done[i]:
+                self.ep[i] += 1
+                self.t[i] = 0
+        return ({'low_dim': {'flat_inputs': obs_next.clone()}}, torch.tensor(rew, device=self.device),
+                torch.tensor(done, device=self.device), {'obs_next': obs_next})
+
+
+@pytest.mark.parametrize('case_id', [0, 1, 2, 3])
+def test_window_staging_matches_reference_wrapper(golden, case_id):
+    """One actor, the exact scripts of the golden: windows (obs ids, obs_next, dones, action/pd/reward payload)."""
+    from surreal_b200.replay import FIFOReplay
+    from surreal_b200.env import ExpSenderWrapperMultiStepMovingWindowWithInfo as W
+    case = golden('window_multistep').js('cases')[case_id]
+    n, stride, ep_lens = case['n_step'], case['stride'], case['ep_lens']
+    lc, ec, sc = ppo_configs(D=2, A=1, n_step=n, stride=stride, B=1, memory_size=64)
+    R = FIFOReplay(lc, ec, sc)
+    env = ScriptedEnv([ep_lens])
+    w = W(env, lc, sc, replay=R)
+    w.reset()
+    for _ in range(sum(ep_lens)):
+        g = env.g[0]
+        p = int(w.stage_pos[0].item())
+        w.stage_act[0, p, 0] = float(g)                  # what sb200_ppo_sample_f32 stages for this step
+        w.stage_pd[0, p, 0] = float(g)
+        w.stage_pd[0, p, 1] = 1.0
+        w.step(torch.zeros(1, 1, device=DEV))
+    exp = case['windows']
+    assert len(R) == len(exp)
+    for e in exp:
+        b = R.sample(1)
+        assert b['obs']['low_dim']['flat_inputs'][0, :, 0].cpu().numpy().astype(int).tolist() == e['obs']
+        assert int(b['obs_next']['low_dim']['flat_inputs'][0, 0, 0].item()) == e['obs_next']
+        assert b['dones'][0].cpu().numpy().astype(bool).tolist() == e['dones']
+        assert b['actions'][0, :, 0].cpu().numpy().tolist() == e['actions']
+        assert b['persistent_infos'][0][0, :, 0].cpu().numpy().tolist() == e['pd0']
+        np.testing.assert_allclose(b['rewards'][0].cpu().numpy(), np.array(e['rewards'], dtype=np.float32), rtol=0, atol=0)
+
+
+def test_window_staging_many_actors_order_and_drop():
+    """Several actors with different episode scripts: arrival order is (step, actor); FIFO drops the oldest."""
+    from surreal_b200.replay import FIFOReplay
+    from surreal_b200.env import ExpSenderWrapperMultiStepMovingWindowWithInfo as W
+    n, stride = 4, 3
+    scripts = [[9, 5], [4, 11], [7], [6, 6, 2], [13]]
+    steps = 40
+    lc, ec, sc = ppo_configs(D=2, A=1, n_step=n, stride=stride, B=2, memory_size=12)
+    R = FIFOReplay(lc, ec, sc)
+    env = ScriptedEnv(scripts)
+    w = W(env, lc, sc, replay=R)
+    w.reset()
+    for _ in range(steps):
+        w.step(torch.zeros(len(scripts), 1, device=DEV))
+    # oracle: per-actor windows with their completion step, merged in (step, actor) order into a deque(maxlen=cap)
+    events = []
+    for a, sc_ in enumerate(scripts):
+        ep_lens, tot = [], 0
+        while tot < steps:
+            L = sc_[len(ep_lens) % len(sc_)]
+            ep_lens.append(min(L, steps - tot))
+            tot += L
+        # a truncated last episode must not emit a fake 'done'; only windows fully inside `steps` count
+        for obs_ids, nxt, dones in multistep_windows(ep_lens, n, stride):
+            if nxt <= steps:
+                events.append((nxt, a, obs_ids))
+    events.sort(key=lambda e: (e[0], e[1]))
+    q = OFIFO(12, 2)
+    for e in events:
+        q.insert(e)
+    st = R._read_state()
+    assert st['count'] == len(q) and st['total_in'] == len(events) and st['dropped'] == len(events) - len(q)
+    expect = list(q.q)
+    got = R.sample(len(q)) if len(q) <= 12 else None
+    ids = got['obs']['low_dim']['flat_inputs'][:, :, 0].cpu().numpy().astype(int).tolist()
+    assert ids == [e[2] for e in expect]
+
+
+@pytest.mark.parametrize('case_id', [0, 1, 2])
+def test_ssar_staging_matches_reference_wrapper(golden, case_id):
+    from surreal_b200.replay import UniformReplay
+    from surreal_b200.env import ExpSenderWrapperSSARNStepBootstrap as W
+    case = golden('window_ssar').js('cases')[case_id]
+    n, gamma, ep_lens = case['n_step'], case['gamma'], case['ep_lens']
+    lc, ec, sc = ddpg_configs(D=2, A=1, n_step=n, memory_size=64, start=0)
+    lc.algo.gamma = gamma
+    R = UniformReplay(lc, ec, sc)
+    env = ScriptedEnv([ep_lens])
+    w = W(env, lc, sc, replay=R)
+    w.reset()
+    for _ in range(sum(ep_lens)):
+        w.step(torch.full((1, 1), float(env.g[0]), device=DEV))
+    exp = case['records']
+    assert len(R) == len(exp)
+    k = len(exp)
+    assert R.r_obs[:k, 0].cpu().numpy().astype(int).tolist() == [e['obs'] for e in exp]
+    assert R.r_obs_next[:k, 0].cpu().numpy().astype(int).tolist() == [e['obs_next'] for e in exp]
+    assert R.r_act[:k, 0].cpu().numpy().tolist() == [e['action'] for e in exp]
+    assert R.r_done[:k].cpu().numpy().astype(bool).tolist() == [e['done'] for e in exp]
+    np.testing.assert_array_equal(R.r_rew[:k].cpu().numpy(), np.array([e['reward'] for e in exp], dtype=np.float32))
+    # and against the oracle model for a multi-actor run (slot = k-th emission in (step, actor) order)
+    got = ssar_nstep(ep_lens, n, gamma, lambda g: 0.25 * g - 3.0)
+    assert [(o, on) for o, on, *_ in got] == [(e['obs'], e['obs_next']) for e in exp]
+
+
+def test_ppo_agent_act_matches_reference(golden):
+    from surreal_b200.agent import PPOAgent
+    g = golden('ppo_act')
+    N = len(g['obs'])
+    lc, ec, sc = ppo_configs(D=11, A=3)
+    ec.num_envs = N
+    ag = PPOAgent(lc, ec, sc, 3, 'training')
+    ag.model.load_state_dict(ref_state_dict(g.sub('model/')))
+    ag.set_noise(np.full(N, float(g['noise'])))
+    action, info = ag.act({'low_dim': {'flat_inputs': g['obs']}}, eps=g['eps'])
+    assert action.dtype == np.float64 and action.shape == (N, 3)
+    np.testing.assert_allclose(info[1][0], g['pds'], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(action, g['actions'], rtol=0, atol=2e-6)
+    ag.agent_mode = 'eval_deterministic'
+    det = ag.act({'low_dim': {'flat_inputs': g['obs']}})
+    np.testing.assert_allclose(det, g['actions_det'], rtol=0, atol=2e-6)
+
+
+def test_engine_end_to_end_runs_and_is_consistent():
+    """replay -> learner -> agent through the launcher; windows the learner consumes are exactly what the
+    actors staged (behaviour pd recorded after noise scaling, FIFO order), parameters reach the agent only
+    at publish + fetch."""
+    from surreal_b200.launch import SurrealDefaultLauncher
+    from surreal_b200.agent import PPOAgent
+    from surreal_b200.learner import PPOLearner
+    from surreal_b200.replay import FIFOReplay
+    from surreal_b200.main.ppo_configs import make_synthetic_env_config
+    N, n = 64, 8
+    lc, ec, sc = ppo_configs(D=16, A=4, actor_h=(64, 48), critic_h=(64, 48), n_step=n, stride=n, B=N,
+                             memory_size=2 * N, exp_interval=N)
+    make_synthetic_env_config(ec, N, 16, 4, seed=3)
+    ec.limit_episode_length = 2 * n
+    sc.agent.fetch_parameter_interval = 1
+    la = SurrealDefaultLauncher(PPOAgent, PPOLearner, FIFOReplay, sc, ec, lc)
+    agent, replay, learner = la.setup_engine()
+    w0 = agent.model.actor.params.clone()
+    assert torch.equal(w0, learner.model.actor.params)            # initial publish + fetch
+    agent.main_loop(max_steps=n)
+    torch.cuda.synchronize()
+    assert len(replay) == N
+    pd_first = replay.r_pd[:N, 0].clone()
+    expect_std = torch.exp(agent.model.log_var)[None, :] * torch.exp(agent._log_noise)[:, None]
+    assert torch.allclose(pd_first[:, 4:], expect_std, rtol=1e-6)
+    assert float(replay.r_act[:N].abs().max()) <= 1.0
+    learner.main_loop()                                           # consumes the N windows, publishes (exp_interval)
+    assert len(replay) == 0 and learner.publisher.version == 2
+    assert not torch.equal(learner.model.actor.params, w0)
+    assert torch.equal(agent.model.actor.params, w0)              # actors still run the lagged snapshot
+    agent.main_loop(max_steps=1)                                  # fetch_parameter_interval = 1 -> pulls the new one
+    assert torch.equal(agent.model.actor.params, learner.model.actor.params)
+    st = learner.tensorplex.last
+    for k in ['_pol_kl', '_val_loss', '_surr_loss', '_entropy', 'grad_norm_actor', 'grad_norm_critic']:
+        assert k in st and np.isfinite(st[k])
