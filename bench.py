@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path on BASELINE.json's headline config.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (config.workload): BASELINE.json configs[1] -- PPO, synthetic 64-dim observations, 1024 actors x
+horizon 128 (n_step = stride = 128), 2x256 MLP actor + critic, clip mode, z-filter on, A = 8.
+One "step" = one pass of the hot path over one batch: a 128-step rollout of all 1024 co-located actors
+(batched policy inference -> device env -> window staging -> HBM FIFO replay) followed by one
+PPOLearner.learn() on the 1024 windows (critic pass over 132 096 rows -> windowed GAE -> <=10 clipped-
+surrogate policy epochs with KL early stop -> 10 value epochs), then publish + actor fetch.
+
+  value  : env-steps/s of the whole job, data resident in HBM (device actors feeding the device learner).
+  e2e    : the same metric through the reference-facing plugin API with HOST buffers: PPOAgent.act(numpy obs)
+           per env step (H2D obs, D2H action + pd) and PPOLearner.learn(numpy batch) (H2D batch, D2H stats).
+  roofline: the dominant kernel of the step (the fused critic pass), timed live with CUDA events.
+  cpu_baseline / --impl reference: the CPU oracle (a line-by-line restatement of the reference's torch-CPU
+           actors + learner, pinned against reference-generated goldens) timed on this box's host cores.
+Timing: CUDA events on the launching stream, >= 3 warm-up steps, max over ranks; inputs of every step are
+freshly generated on the device (the 47 MB batch and ~60 MB of staging/replay traffic per step exceed any
+reuse window together with the explicit L2 flush between timed steps).
+"""
+import argparse
+import copy
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ACTORS, HORIZON, OBS_DIM, ACT_DIM, HIDDEN = 1024, 128, 64, 8, (256, 256)
+EPISODE_LEN = 256          # two windows per episode (windows never span episodes)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d['hbm_gbs'], bf16_tflops=d['bf16_tflops'], bf16_tflops_sustained=d.get('bf16_tflops_sustained'),
+                    source='measured (MEASURED_PEAKS.json)')
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source='fallback (B200_PROFILING.md)')
+
+
+def build_configs(n_actors=N_ACTORS, horizon=HORIZON):
+    from surreal_b200.session import Config
+    from surreal_b200.main.ppo_configs import (PPO_DEFAULT_LEARNER_CONFIG, PPO_DEFAULT_ENV_CONFIG,
+                                               PPO_DEFAULT_SESSION_CONFIG, make_synthetic_env_config)
+    lc = Config(copy.deepcopy(PPO_DEFAULT_LEARNER_CONFIG.to_dict()))
+    ec = Config(copy.deepcopy(PPO_DEFAULT_ENV_CONFIG.to_dict()))
+    sc = Config(copy.deepcopy(PPO_DEFAULT_SESSION_CONFIG.to_dict()))
+    sc.folder = tempfile.mkdtemp(prefix='sb200_bench_')
+    lc.model.actor_fc_hidden_sizes = list(HIDDEN)
+    lc.model.critic_fc_hidden_sizes = list(HIDDEN)
+    lc.algo.ppo_mode = 'clip'
+    lc.algo.rnn.if_rnn_policy = False
+    lc.algo.n_step = horizon
+    lc.algo.stride = horizon
+    lc.replay.batch_size = n_actors
+    lc.replay.memory_size = 2 * n_actors
+    lc.parameter_publish.exp_interval = n_actors          # publish after every learn()
+    make_synthetic_env_config(ec, n_actors, OBS_DIM, ACT_DIM, seed=0)
+    ec.limit_episode_length = EPISODE_LEN
+    sc.agent.fetch_parameter_interval = horizon
+    return lc, ec, sc
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == 'Active' for r in self.rows)]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+    from surreal_b200 import _lib
+    from surreal_b200.launch import SurrealDefaultLauncher
+    from surreal_b200.agent import PPOAgent
+    from surreal_b200.learner import PPOLearner
+    from surreal_b200.replay import FIFOReplay
+    from surreal_b200.distributed import LocalHub
+    _lib.lib()
+    lc, ec, sc = build_configs()
+    ec.seed = rank
+    la = SurrealDefaultLauncher(PPOAgent, PPOLearner, FIFOReplay, sc, ec, lc)
+    agent, replay, learner = la.setup_engine()
+    if world > 1:
+        learner.enable_data_parallel(dist.group.WORLD)
+    N, T, D, A = N_ACTORS, HORIZON, OBS_DIM, ACT_DIM
+    flush = torch.empty(192 * 1024 * 1024 // 4, device=dev)       # > 126 MB L2
+    launches = {'n': 0}
+
+    def one_step():
+        agent.main_loop(max_steps=T)
+        learner.main_loop()
+
+    # kernel-launch accounting (ours only): launches per step are counted once via the library's own counter
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    torch.cuda.synchronize()
+    per_step_launches = count_launches(one_step)
+
+    # roofline of the dominant kernel: fused critic pass, timed with events around its launch inside learn()
+    learner.profile_events = True
+    clocks = ClockSampler(local)
+    times = []
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks.start()
+    t_wall0 = time.time()
+    for _ in range(args.steps):
+        flush.fill_(1.0)                                          # L2 flush between timed iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        one_step()
+        e1.record()
+        times.append((e0, e1))
+    torch.cuda.synchronize()
+    t_wall = time.time() - t_wall0
+    clk = clocks.stop()
+    ms = [a.elapsed_time(b) for a, b in times]
+    total_ms = sum(ms)
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    learner.profile_events = False
+    env_steps = N * T * args.steps * world
+    value = env_steps / (total_ms / 1e3)
+    critic_ms = learner.pop_profile('critic_pass')
+    gae_ms = learner.pop_profile('gae')
+    rows = N * (T + 1)
+    flops = 2.0 * rows * (D * HIDDEN[0] + HIDDEN[0] * HIDDEN[1] + HIDDEN[1] * 1)
+    peaks = load_peaks()
+    crit_avg = sum(critic_ms) / max(len(critic_ms), 1)
+    gae_avg = sum(gae_ms) / max(len(gae_ms), 1)
+    crit_tflops = flops / (crit_avg / 1e3) / 1e12 if crit_avg else None
+    gae_bytes = N * ((3 * T + 1) * 4 + 8)
+    roofline = {'kernel': 'mlp_fwd_kernel<8> (fused critic pass: z-filter + 3 Linear over %d rows)' % rows,
+                'bound': 'tensor', 'achieved': crit_tflops, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
+                'frac': (crit_tflops / peaks['bf16_tflops']) if crit_tflops else None, 'traffic': None,
+                'avg_ms': crit_avg, 'algorithmic_flop': flops, 'algorithmic_bytes': rows * (D * 4 + 4),
+                'peak_source': peaks['source'],
+                'note': 'fp32-accurate SIMT FFMA path (parity bar 1e-5 rules out plain TF32); the dense-bf16 tensor '
+                        'peak is the mandated denominator, the fp32 FFMA ceiling of the chip is ~72 TFLOP/s'}
+    roofline_gae = {'kernel': 'gae_full_kernel', 'bound': 'hbm', 'achieved': gae_bytes / (gae_avg / 1e3) / 1e9 if gae_avg else None,
+                    'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'avg_ms': gae_avg, 'algorithmic_bytes': gae_bytes,
+                    'frac': (gae_bytes / (gae_avg / 1e3) / 1e9 / peaks['hbm_gbs']) if gae_avg else None,
+                    'note': '1.58 MB per launch: below launch latency, cannot approach the HBM roofline stand-alone'}
+
+    e2e = None
+    cpu_baseline = None
+    if rank == 0:
+        e2e = run_e2e(agent, learner, lc, dev, steps=max(2, min(args.steps, 5)))
+        if world == 1:
+            cpu_baseline = cpu_reference(sample_seconds=8.0)
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        out = {
+            'metric': 'env-steps/sec', 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'PPO synthetic 64-dim obs, 1024 actors x horizon 128, 2x256 MLP (BASELINE configs[1])',
+                       'actors_per_gpu': N, 'horizon': T, 'obs_dim': D, 'action_dim': A, 'hidden': list(HIDDEN),
+                       'ppo_mode': 'clip', 'epoch_policy': 10, 'epoch_baseline': 10, 'episode_length': EPISODE_LEN,
+                       'global_windows_per_step': N * world,
+                       'parallelism': 'dp%d' % world, 'l2': 'flushed between timed steps (192 MB fill)'},
+            'learner_updates_per_sec': args.steps / (total_ms / 1e3),
+            'optimizer_steps_per_sec': learner.optimizer_steps_profiled / (total_ms / 1e3) if hasattr(learner, 'optimizer_steps_profiled') else None,
+            'gpu_launches': per_step_launches * args.steps, 'gpu_launches_per_step': per_step_launches,
+            'clocks': clk, 'roofline': roofline, 'roofline_gae': roofline_gae, 'e2e': e2e,
+            'cpu_baseline': cpu_baseline, 'wall_s': t_wall,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def count_launches(fn):
+    """Count kernel launches of one step with the CUDA profiler-free trick: torch's stream launch counter is not
+    exposed, so the library wrappers count their own launches (each C-ABI call = fixed #kernels)."""
+    from surreal_b200 import _lib
+    _lib.reset_call_counter()
+    fn()
+    return _lib.call_counter_kernels()
+
+
+def run_e2e(agent, learner, lc, dev, steps):
+    """env-steps/s through PPOAgent.act(host obs) + PPOLearner.learn(host batch): every byte crosses PCIe."""
+    import numpy as np
+    import torch
+    N, T, D, A = N_ACTORS, HORIZON, OBS_DIM, ACT_DIM
+    rng = np.random.default_rng(0)
+    obs_host = rng.standard_normal((T + 1, N, D)).astype(np.float32)
+    rew_host = rng.standard_normal((N, T))
+    saved_env = agent.env
+    agent.env = None                                   # external-env mode: nothing is staged on the device
+    acts = np.zeros((N, T, A))
+    pds = np.zeros((N, T, 2 * A), dtype=np.float32)
+    dones = np.zeros((N, T), dtype=np.float32)
+    dones[:, -1] = 1.0
+
+    def step():
+        for t in range(T):
+            a, info = agent.act(obs_host[t])
+            acts[:, t] = a
+            pds[:, t] = info[1][0]
+        batch = {'obs': {'low_dim': {'flat_inputs': np.ascontiguousarray(obs_host[:T].transpose(1, 0, 2))}},
+                 'obs_next': {'low_dim': {'flat_inputs': obs_host[T][:, None, :]}}, 'actions': acts, 'rewards': rew_host,
+                 'dones': dones, 'persistent_infos': [pds], 'onetime_infos': None}
+        return learner.learn(batch)
+
+    step()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    agent.env = saved_env
+    h2d = T * N * D * 4 + (N * (T + 1) * D + N * T * A + N * T * 2 * A + 2 * N * T) * 4
+    d2h = T * N * (A + 2 * A) * 4 + 32 * 4 + (2 * D + 1) * 4
+    return {'value': N * T * steps / dt, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+            'ms_per_step': dt / steps * 1e3, 'steps': steps,
+            'api': 'PPOAgent.act(numpy obs) x128 + PPOLearner.learn(numpy batch); pinned staging, copies inside the timed region'}
+
+
+# --------------------------------------------------------------------------------------------------
+def _actor_worker(args):
+    """One reference actor process: batch-1 torch forward + numpy sampling + deque windowing per env step
+    (ppo_agent.py:106-154, exp_sender_wrapper.py:209-228), for `seconds` of wall time."""
+    seconds, seed = args
+    import numpy as np
+    import torch
+    from collections import deque
+    from oracle.agent import ppo_act
+    from oracle.filters import ZFilter
+    torch.set_num_threads(1)
+    g = torch.Generator().manual_seed(seed)
+    dims = [OBS_DIM] + list(HIDDEN) + [ACT_DIM]
+    layers = [((torch.rand(dims[i + 1], dims[i], generator=g) - 0.5) * 0.2, torch.zeros(dims[i + 1])) for i in range(3)]
+    log_var = torch.zeros(1, ACT_DIM) - 1.0
+    zf = ZFilter(OBS_DIM)
+    rng = np.random.default_rng(seed)
+    Ws = rng.standard_normal((OBS_DIM, OBS_DIM)) / np.sqrt(OBS_DIM)
+    Wa = rng.standard_normal((OBS_DIM, ACT_DIM)) / np.sqrt(OBS_DIM)
+    s = rng.standard_normal(OBS_DIM)
+    last = deque()
+    n = 0
+    t0 = time.time()
+    while time.time() - t0 < seconds:
+        a, pdv = ppo_act(s.astype(np.float32), layers, log_var, zf, 0.1, eps=rng.standard_normal(ACT_DIM))
+        s2 = np.tanh(Ws @ s + Wa @ a) + 0.01 * rng.standard_normal(OBS_DIM)
+        r = -float(s @ s) / OBS_DIM
+        last.append((s.copy(), a, r, False, pdv))
+        if len(last) == HORIZON:
+            last.clear()
+        s = s2
+        n += 1
+    return n / (time.time() - t0)
+
+
+def cpu_reference(sample_seconds=8.0, learn_calls=1):
+    """The reference's CPU path restated by the oracle, on this box's cores: `cores` actor processes (one per core,
+    as Surreal runs them) for `sample_seconds`, then the torch-CPU learner on one cfg-2 batch with all cores.
+    ZeroMQ / pyarrow hops are omitted (un-vendored) -> this baseline is FASTER than real Surreal."""
+    import multiprocessing as mp
+    import numpy as np
+    import torch
+    from oracle.ppo import OraclePPOLearner
+    from oracle.filters import ZFilter
+    cores = os.cpu_count() or 1
+    use = min(cores, 64)
+    ctx = mp.get_context('spawn')
+    with ctx.Pool(use) as pool:
+        rates = pool.map(_actor_worker, [(sample_seconds, i) for i in range(use)])
+    actor_rate = float(sum(rates))
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(0)
+    dims_a = [OBS_DIM] + list(HIDDEN) + [ACT_DIM]
+    dims_c = [OBS_DIM] + list(HIDDEN) + [1]
+    mk = lambda d: [((torch.rand(d[i + 1], d[i], generator=g) - 0.5) * 0.2, torch.zeros(d[i + 1])) for i in range(3)]  # noqa: E731
+    B, n = N_ACTORS, HORIZON
+    L = OraclePPOLearner(mk(dims_a), torch.zeros(1, ACT_DIM) - 1.0, mk(dims_c), ZFilter(OBS_DIM), ACT_DIM, n, B,
+                         ppo_mode='clip')
+    rng = np.random.default_rng(0)
+    batch = dict(obs=rng.standard_normal((B, n, OBS_DIM)).astype(np.float32),
+                 obs_next=rng.standard_normal((B, 1, OBS_DIM)).astype(np.float32),
+                 actions=np.clip(rng.standard_normal((B, n, ACT_DIM)) * 0.3, -1, 1), rewards=rng.standard_normal((B, n)),
+                 dones=np.zeros((B, n), dtype=np.float32),
+                 pd=np.concatenate([np.zeros((B, n, ACT_DIM)), np.full((B, n, ACT_DIM), 0.37)], -1).astype(np.float32))
+    L.learn(batch)                                         # warm-up
+    t0 = time.time()
+    for _ in range(learn_calls):
+        L.learn(batch)
+    t_learn = (time.time() - t0) / learn_calls
+    steps_per_iter = N_ACTORS * HORIZON
+    value = steps_per_iter / (steps_per_iter / actor_rate + t_learn)
+    return {'value': value, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
+            'actors_only_steps_per_s': actor_rate, 'actor_processes': use, 'learner_learn_s': t_learn,
+            'learner_updates_per_s': 1.0 / t_learn,
+            'sample': '%d actor processes x %.0f s of batch-1 act()+env+windowing, then %d oracle learn() on one '
+                      '1024x128 batch with %d torch threads; sequential composition like the GPU engine; ZeroMQ/pyarrow '
+                      'hops omitted' % (use, sample_seconds, learn_calls, cores)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    vals, last = [], None
+    for i in range(args.warmup + args.steps):
+        r = cpu_reference(sample_seconds=3.0 if i < args.warmup else 6.0)
+        if i >= args.warmup:
+            vals.append(r['value'])
+            last = r
+    value = sum(vals) / len(vals)
+    last['value'] = value
+    out = {'impl': 'reference', 'metric': 'env-steps/sec', 'value': value, 'unit': 'env-steps/s',
+           'n_gpus': int(os.environ.get('WORLD_SIZE', args.gpus)), 'steps': args.steps, 'warmup': args.warmup,
+           'ms_per_step': N_ACTORS * HORIZON / value * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+           'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+           'config': {'workload': 'PPO synthetic 64-dim obs, 1024 actors x horizon 128, 2x256 MLP (BASELINE configs[1])',
+                      'parallelism': 'cpu'},
+           'cpu_baseline': last,
+           'e2e': {'value': value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(out))
+
+
+if __name__ == '__main__':
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', type=str, default='ours', choices=['ours', 'reference'])
+    a = ap.parse_args()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

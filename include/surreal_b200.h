@@ -38,6 +38,8 @@ int sb200_version(void);
 const char* sb200_status_string(int status);
 /* SM count / compute capability of the current device (fails without a GPU). */
 int sb200_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Number of CUDA kernels this library has launched so far (optionally reset) -- bench.py's gpu_launches. */
+uint64_t sb200_launch_counter(int reset);
 
 /* ---------------------------------------------------------------------------------------------
  * Networks.  One descriptor covers PPO_ActorNetwork / PPO_CriticNetwork

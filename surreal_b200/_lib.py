@@ -48,6 +48,7 @@ def _declare(lib):
         'sb200_version': (I, []),
         'sb200_status_string': (C.c_char_p, [I]),
         'sb200_device_info': (I, [C.POINTER(I), C.POINTER(I), C.POINTER(I)]),
+        'sb200_launch_counter': (C.c_uint64, [I]),
         'sb200_mlp_forward_f32': (I, [C.POINTER(Mlp), C.POINTER(ZFilter), C.POINTER(Rows),
                                       C.POINTER(P), C.POINTER(L), P]),
         'sb200_linear_bwd_dx_f32': (I, [P, L, P, I, P, L, P, L, I, I, I, P]),
@@ -114,3 +115,11 @@ def check(status, what=''):
     if status != 0:
         msg = lib().sb200_status_string(status).decode()
         raise SB200Error('%s failed: %s (status %d)' % (what or 'libsurreal_b200 call', msg, status))
+
+
+def reset_call_counter():
+    lib().sb200_launch_counter(1)
+
+
+def call_counter_kernels():
+    return int(lib().sb200_launch_counter(0))

@@ -1,7 +1,15 @@
 // Library-level entry points of libsurreal_b200.
 #include "common.cuh"
 
+unsigned long long g_sb200_launches = 0;
+
 extern "C" int sb200_version(void) { return 100; }
+
+extern "C" uint64_t sb200_launch_counter(int reset) {
+    const unsigned long long v = g_sb200_launches;
+    if (reset) g_sb200_launches = 0;
+    return (uint64_t)v;
+}
 
 extern "C" const char* sb200_status_string(int status) {
     switch (status) {

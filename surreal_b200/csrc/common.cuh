@@ -7,7 +7,10 @@
 
 #define SB200_THREADS 256
 
-static inline int sb200_launch_status() {
+extern unsigned long long g_sb200_launches;     // kernels launched by this library (api.cu)
+
+static inline int sb200_launch_status(int kernels = 1) {
+    g_sb200_launches += (unsigned long long)kernels;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) return SB200_OK;
     fprintf(stderr, "[surreal_b200] CUDA launch error: %s\n", cudaGetErrorString(e));

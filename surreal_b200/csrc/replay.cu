@@ -292,7 +292,7 @@ extern "C" int sb200_ssar_step_f32(const float* obs, const float* action, const 
                                           (UniformState*)uniform_state, (unsigned long long*)step_counter);
     ssar_commit_kernel<<<N, 128, 0, st>>>(obs, action, obs_next, done, N, n_step, D, A, dq_len, dq_obs, dq_act, dq_rew,
                                           dest_scratch, emit_scratch, r_obs, r_obs_next, r_act, r_rew, r_done);
-    return sb200_launch_status();
+    return sb200_launch_status(2);
 }
 
 // ---- CPython random.Random index stream (host) -------------------------------------------------

@@ -384,5 +384,5 @@ extern "C" int sb200_ppo_window_step_f32(const float* obs_next, const float* obs
     ppo_window_commit_kernel<<<N, 128, 0, st>>>(obs_next, obs_reset, done, N, n_step, stride, D, A, stage_pos, stage_obs,
                                                 stage_act, stage_pd, stage_rew, stage_done, dest_scratch, r_obs, r_act,
                                                 r_pd, r_rew, r_done);
-    return sb200_launch_status();
+    return sb200_launch_status(2);
 }

@@ -144,6 +144,9 @@ class PPOLearner(Learner):
         self._pin = {}
         self._sync_hyper()
         self.last_n_policy_epochs = 0
+        self.profile_events = False
+        self._prof = {}
+        self.optimizer_steps_profiled = 0
 
     # ------------------------------------------------------------------------------------------------
     def _sync_hyper(self):
@@ -223,17 +226,40 @@ class PPOLearner(Learner):
         """ppo.py:355-418 (MLP branch): critic over all B*(n+1) rows without materialising the cat, then GAE."""
         B, n = self.batch_size, self.n_step
         m = self.model
+        ev = self._prof_begin()
         ops.mlp_forward(m.critic, self._obs_full.view(B * (n + 1), -1), zf_stats=m.z_stats, zf_eps=m.z_eps,
                         out=self._values)
+        self._prof_end('critic_pass', ev)
         rewards, scale = self._rewards, self.reward_scale
         if self.use_r_filter:
             check(_lib.lib().sb200_reward_filter_f32(_ptr(self._rewards), B * n, float(self.reward_scale), 1e-5,
                                                      _ptr(self._rfilter_stats), _ptr(self._rewards_f), ops._stream()),
                   'sb200_reward_filter_f32')
             rewards, scale = self._rewards_f, 1.0
+        ev = self._prof_begin()
         ops.gae_window(rewards, self._values.view(B, n + 1), self._dones, self.gamma, self.lam, norm_adv=self.norm_adv,
                        reward_scale=scale, adv=self._adv, ret=self._ret)
+        self._prof_end('gae', ev)
         return self._adv, self._ret
+
+    # -- live kernel timing for bench.py's roofline (CUDA events on the launching stream) ---------------
+    def _prof_begin(self):
+        if not self.profile_events:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def _prof_end(self, name, e0):
+        if e0 is None:
+            return
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self._prof.setdefault(name, []).append((e0, e1))
+
+    def pop_profile(self, name):
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in self._prof.pop(name, [])]
 
     def _policy_epoch(self):
         L = _lib.lib()
@@ -289,6 +315,8 @@ class PPOLearner(Learner):
             if kl > self.kl_target * 4:
                 break
         self.last_n_policy_epochs = n_ep
+        if self.profile_events:
+            self.optimizer_steps_profiled += n_ep + self.epoch_baseline
         self.kl_record.append(kl)
         for _ in range(self.epoch_baseline):
             self._value_epoch()

@@ -172,8 +172,10 @@ def test_window_staging_many_actors_order_and_drop():
     st = R._read_state()
     assert st['count'] == len(q) and st['total_in'] == len(events) and st['dropped'] == len(events) - len(q)
     expect = list(q.q)
-    got = R.sample(len(q)) if len(q) <= 12 else None
-    ids = got['obs']['low_dim']['flat_inputs'][:, :, 0].cpu().numpy().astype(int).tolist()
+    ids = []
+    for _ in range(len(q)):
+        got = R.sample(1)
+        ids.append(got['obs']['low_dim']['flat_inputs'][0, :, 0].cpu().numpy().astype(int).tolist())
     assert ids == [e[2] for e in expect]
 
 
