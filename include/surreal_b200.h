@@ -35,6 +35,9 @@ extern "C" {
 #define SB200_MAX_LAYERS 4
 
 int sb200_version(void);
+/* One-time per-process setup on the current device (kernel attributes); fails on non-sm_100 devices.
+ * Must run before any compute entry (and before CUDA-graph capture). */
+int sb200_init(void);
 const char* sb200_status_string(int status);
 /* SM count / compute capability of the current device (fails without a GPU). */
 int sb200_device_info(int* sm_count, int* cc_major, int* cc_minor);
@@ -183,6 +186,31 @@ int sb200_clip_adam_f32(float* params, const float* grad, float* exp_avg, float*
                         const int* stop_flag, void* stream);
 /* target = target*(1-tau) + tau*src (soft target update, ddpg.py:410-418). */
 int sb200_soft_update_f32(float* target, const float* src, int64_t n, double tau, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * DDPG element-wise pieces (surreal/learner/ddpg.py:261-262,279,305,324-331,335-341); the networks run through
+ * sb200_mlp_forward_f32 (critic: aux_layer = 1 for cat(h, action)) and the backward / optimiser entries above. */
+#define SB200_DSTAT_ACTOR_LOSS 0
+#define SB200_DSTAT_CRITIC_LOSS 1
+#define SB200_DSTAT_ACTION_NORM 2
+#define SB200_DSTAT_REWARDS 3
+#define SB200_DSTAT_Q_TARGET 4
+#define SB200_DSTAT_Q_POLICY 5
+#define SB200_DSTAT_ACTION_ABSMAX 6   /* for the deferred `assert |a| <= 1` of ddpg.py:261-262 */
+size_t sb200_ddpg_workspace_bytes(int B);
+/* y = rewards + discount * q_next * (1 - dones), discount = gamma ** n_step. */
+int sb200_ddpg_target_f32(const float* rewards, const float* q_next, int64_t ldq, const float* dones,
+                          const float* actions, int64_t lda, int B, int A, double discount, float* y,
+                          float* stats, void* workspace, void* stream);
+/* MSE(q, y): dq = 2 (q - y) / B. */
+int sb200_ddpg_critic_loss_f32(const float* q, int64_t ldq, const float* y, int B, float* dq, int64_t ldd,
+                               float* stats, void* workspace, void* stream);
+/* actor loss -mean(q_pi): seeds dq = -1/B for the backward pass through the critic. */
+int sb200_ddpg_actor_seed_f32(const float* q_pi, int64_t ldq, int B, float* dq, int64_t ldd, float* stats,
+                              void* workspace, void* stream);
+/* dpre = dout * (1 - out^2). */
+int sb200_tanh_bwd_f32(const float* dout, int64_t ldo, const float* out, int64_t ldy, int B, int A,
+                       float* dpre, int64_t ldd, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Batched actors (one call serves all N co-located actors of a step).

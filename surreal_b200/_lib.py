@@ -46,6 +46,7 @@ def _declare(lib):
     P, I, L, D, F, S = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_float, C.c_size_t
     sig = {
         'sb200_version': (I, []),
+        'sb200_init': (I, []),
         'sb200_status_string': (C.c_char_p, [I]),
         'sb200_device_info': (I, [C.POINTER(I), C.POINTER(I), C.POINTER(I)]),
         'sb200_launch_counter': (C.c_uint64, [I]),
@@ -77,6 +78,11 @@ def _declare(lib):
         'sb200_mt19937_set_state_h': (I, [P, P, I]),
         'sb200_mt19937_get_state_h': (I, [P, P, C.POINTER(I)]),
         'sb200_mt19937_randint_fill_h': (I, [P, L, L, P]),
+        'sb200_ddpg_workspace_bytes': (S, [I]),
+        'sb200_ddpg_target_f32': (I, [P, P, L, P, P, L, I, I, D, P, P, P, P]),
+        'sb200_ddpg_critic_loss_f32': (I, [P, L, P, I, P, L, P, P, P]),
+        'sb200_ddpg_actor_seed_f32': (I, [P, L, I, P, L, P, P, P]),
+        'sb200_tanh_bwd_f32': (I, [P, L, P, L, I, I, P, L, P]),
         'sb200_optim_workspace_bytes': (S, []),
         'sb200_grad_reduce_norm_f32': (I, [P, L, I, P, L, P, P, P]),
         'sb200_clip_adam_f32': (I, [P, P, P, P, L, P, D, D, D, D, I, D, P, P, P, P]),
@@ -109,6 +115,17 @@ def lib():
         _lib = C.CDLL(LIB_PATH)
         _declare(_lib)
     return _lib
+
+
+_device_ready = False
+
+
+def ensure_device():
+    """sb200_init() once per process, on first use of a compute entry."""
+    global _device_ready
+    if not _device_ready:
+        check(lib().sb200_init(), 'sb200_init')
+        _device_ready = True
 
 
 def check(status, what=''):

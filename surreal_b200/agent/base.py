@@ -39,6 +39,7 @@ class Agent(metaclass=U.AutoInitializeMeta):
         self.actions_since_param_update = 0
         self.episodes_since_param_update = 0
         self.env = None
+        self._rollout_graphs = {}
 
     def _initialize(self):
         if self.agent_mode not in ['eval_deterministic_local', 'eval_stochastic_local']:
@@ -107,6 +108,27 @@ class Agent(metaclass=U.AutoInitializeMeta):
             self._obs, _ = env.reset()
         steps = max_steps if max_steps is not None else max(int(self.env_config.limit_episode_length), 1)
         obs = self._obs
+        if self._can_graph(obs):
+            # device-resident env: the whole chunk is ONE CUDA-graph submission (act -> env -> staging/replay kernels
+            # x steps).  Parameter fetches happen at chunk boundaries, at the configured cadence.
+            if self.agent_mode == 'training' and self._fetch_parameter_mode == 'step' and \
+                    self._fetch_parameter_tracker.track_increment(steps):
+                self.fetch_parameter()
+            if steps not in self._rollout_graphs:
+                from ..ops import GraphRunner
+                self._rollout_graphs[steps] = GraphRunner()
+
+            def body():
+                o = obs
+                for _ in range(steps):
+                    a = self.act(o)
+                    o, _, _, _ = env.step(a)
+            self._rollout_graphs[steps].run(body)
+            self.current_step += steps
+            self.cumulative_steps += steps * self.num_envs
+            self.actions_since_param_update += steps
+            self.post_episode()
+            return
         for _ in range(steps):
             self.pre_action(obs)
             action = self.act(obs)
@@ -115,6 +137,16 @@ class Agent(metaclass=U.AutoInitializeMeta):
             obs = obs_next
         self._obs = obs
         self.post_episode()
+
+    def _can_graph(self, obs):
+        """Graph capture needs every buffer of the step to live at a fixed device address: true for the in-tree
+        device env (its obs tensor is its state buffer), false for host envs."""
+        from ..ops import graphs_enabled
+        if not graphs_enabled() or not getattr(self.env, 'graph_safe', False):
+            return False
+        import torch
+        x = obs['low_dim']['flat_inputs'] if isinstance(obs, dict) else obs
+        return isinstance(x, torch.Tensor) and x.is_cuda
 
     def get_env(self):
         from ..env import SyntheticEnv

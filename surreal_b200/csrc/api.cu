@@ -21,6 +21,23 @@ extern "C" const char* sb200_status_string(int status) {
     }
 }
 
+int sb200_mlp_fwd_init();
+int sb200_gae_init();
+
+extern "C" int sb200_init(void) {
+    int dev = 0;
+    SB200_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    SB200_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) {
+        fprintf(stderr, "[surreal_b200] built for sm_100a (B200); found compute capability %d.%d\n", prop.major, prop.minor);
+        return SB200_ERR_UNSUPPORTED;
+    }
+    int rc = sb200_mlp_fwd_init();
+    if (rc != SB200_OK) return rc;
+    return sb200_gae_init();
+}
+
 extern "C" int sb200_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     int dev = 0;
     SB200_CUDA(cudaGetDevice(&dev));

@@ -49,7 +49,13 @@ __global__ void __launch_bounds__(GAE_WARPS * 32) gae_full_kernel(const float* _
                                                                    int norm_adv, float* __restrict__ adv,
                                                                    float* __restrict__ ret, GaeWs* ws) {
     __shared__ double sh[32];
+    extern __shared__ __align__(16) float tab[];       // [n] gamma^k, [n] lam^k (fp32 tables, ppo.py:373-374)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        tab[k] = pow_table(gamma_f, k);
+        tab[n + k] = pow_table(lam_f, k);
+    }
+    __syncthreads();
     const int b = blockIdx.x * GAE_WARPS + warp;
     if (b < B) {
         const float* r = rewards + (long long)b * n;
@@ -57,7 +63,7 @@ __global__ void __launch_bounds__(GAE_WARPS * 32) gae_full_kernel(const float* _
         const float* d = dones + (long long)b * n;
         double a_sum = 0.0, r_sum = 0.0;
         for (int k = lane; k < n; k += 32) {
-            const float g = pow_table(gamma_f, k), l = pow_table(lam_f, k);
+            const float g = tab[k], l = tab[n + k];
             const float rk = __fmul_rn(r[k], rscale);   // ppo.py:452 (x reward_scale, rounded to fp32)
             const float v0 = (k > 0) ? __fmul_rn(v[k], __fsub_rn(1.0f, d[k - 1])) : v[0];
             const float v1 = __fmul_rn(v[k + 1], __fsub_rn(1.0f, d[k]));
@@ -132,6 +138,11 @@ __global__ void __launch_bounds__(GAE_WARPS * 32) gae_horizon_kernel(const float
 
 }  // namespace
 
+int sb200_gae_init() {
+    SB200_CUDA(cudaFuncSetAttribute(gae_horizon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    return SB200_OK;
+}
+
 extern "C" size_t sb200_gae_workspace_bytes(int B, int n, int horizon) {
     (void)B; (void)n; (void)horizon;
     return sizeof(GaeWs);
@@ -147,17 +158,13 @@ extern "C" int sb200_gae_window_f32(const float* rewards, const float* values, c
     const int grid = (B + GAE_WARPS - 1) / GAE_WARPS;
     if (horizon == n) {
         const float gpn = (float)pow(gamma, (double)n);          // Python `gamma ** n_step` (double) -> fp32 scalar
-        gae_full_kernel<<<grid, GAE_WARPS * 32, 0, st>>>(rewards, values, dones, B, n, gamma_f, lam_f, gpn, (float)reward_scale, norm_adv,
+        SB200_REQUIRE((size_t)2 * n * sizeof(float) <= 48 * 1024);
+        gae_full_kernel<<<grid, GAE_WARPS * 32, (size_t)2 * n * sizeof(float), st>>>(rewards, values, dones, B, n, gamma_f, lam_f, gpn, (float)reward_scale, norm_adv,
                                                          adv, ret, (GaeWs*)workspace);
     } else {
         const float gph = (float)pow(gamma, (double)horizon);
         const size_t smem = (size_t)(2 * horizon + GAE_WARPS * (3 * n + 1)) * sizeof(float);
         SB200_REQUIRE(smem <= 200 * 1024);
-        static size_t configured = 0;
-        if (smem > 48 * 1024 && smem > configured) {
-            SB200_CUDA(cudaFuncSetAttribute(gae_horizon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
         gae_horizon_kernel<<<grid, GAE_WARPS * 32, smem, st>>>(rewards, values, dones, B, n, horizon, gamma_f, lam_f,
                                                              gph, (float)reward_scale, norm_adv, adv, ret, (GaeWs*)workspace);
     }

@@ -280,21 +280,27 @@ __global__ void __launch_bounds__(SB200_THREADS, 1) mlp_fwd_kernel(const __grid_
     }
 }
 
+constexpr size_t SMEM_BUDGET = 200 * 1024;
+
 template <int TM>
 int launch_fwd(const FwdParams& p, cudaStream_t st) {
     constexpr int BM = 8 * TM;
     const size_t smem = (size_t)(2 * BM * p.ldh + 2 * BK * PASS_N) * sizeof(float);
-    static size_t configured = 0;
-    if (smem > configured) {
-        SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
     const long long grid = (p.rows + BM - 1) / BM;
     mlp_fwd_kernel<TM><<<(unsigned)grid, SB200_THREADS, smem, st>>>(p);
     return sb200_launch_status();
 }
 
 }  // namespace
+
+// called once from sb200_init(): opt every instantiation into the full dynamic shared-memory budget
+int sb200_mlp_fwd_init() {
+    SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
+    SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
+    SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
+    SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
+    return SB200_OK;
+}
 
 extern "C" int sb200_mlp_forward_f32(const sb200_mlp* net, const sb200_zfilter* zf, const sb200_rows* in,
                                      float* const* save, const int64_t* ld_save, void* stream) {
@@ -342,7 +348,7 @@ extern "C" int sb200_mlp_forward_f32(const sb200_mlp* net, const sb200_zfilter* 
         }
     }
     p.ldh = round_up(maxw, BK) + 4;
-    const size_t budget = 200 * 1024;
+    const size_t budget = SMEM_BUDGET;
     auto fits = [&](int bm) { return (size_t)(2 * bm * p.ldh + 2 * BK * PASS_N) * 4 <= budget; };
     SB200_REQUIRE(fits(8));
     cudaStream_t st = (cudaStream_t)stream;

@@ -20,7 +20,8 @@ def _p(t):
 
 
 def _st():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    from ..ops import _stream
+    return _stream()
 
 
 class _WrapperBase:

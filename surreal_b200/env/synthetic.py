@@ -12,6 +12,7 @@ import torch
 
 from .. import _lib
 from .._lib import check
+from ..ops import _stream
 
 
 def _p(t):
@@ -20,6 +21,7 @@ def _p(t):
 
 class SyntheticEnv:
     metadata = {}
+    graph_safe = True          # obs IS the state buffer: fixed address, no host logic inside step()
 
     def __init__(self, num_envs, obs_dim=64, action_dim=8, limit_episode_length=200, seed=0, device=None):
         if not torch.cuda.is_available():
@@ -60,7 +62,7 @@ class SyntheticEnv:
         check(_lib.lib().sb200_synth_env_step_f32(
             _p(self.state), _p(action), _p(self.Ws), _p(self.Wa), self.N, self.D, self.A, self.max_steps,
             _p(self.ep_step), self.seed + 7, _p(self.step_counter), _p(self.obs_next), _p(self.reward), _p(self.done),
-            C.c_void_p(torch.cuda.current_stream().cuda_stream)), 'sb200_synth_env_step_f32')
+            _stream()), 'sb200_synth_env_step_f32')
         return {'low_dim': {'flat_inputs': self.state}}, self.reward, self.done, {'obs_next': self.obs_next}
 
     def close(self):

@@ -66,7 +66,11 @@ class Learner(metaclass=U.AutoInitializeMeta):
         if self._replay is None:
             raise RuntimeError('no replay attached: call learner.attach_replay(replay) (the ZeroMQ prefetcher '
                                'of the reference is collapsed to an in-process pull)')
-        batch = self._replay.sample(self.learner_config.replay.batch_size)
+        out = self.replay_out_buffers() if hasattr(self, 'replay_out_buffers') else None
+        if out is not None:
+            batch = self._replay.sample(self.learner_config.replay.batch_size, out=out)
+        else:
+            batch = self._replay.sample(self.learner_config.replay.batch_size)
         return self.preprocess(self._prefetcher_preprocess(batch))
 
     def fetch_iterator(self):

@@ -142,6 +142,9 @@ class PPOLearner(Learner):
         self._rfilter_stats = torch.tensor([1e-5, 0.0, 0.0], dtype=torch.float32, device=dev) \
             if self.use_r_filter else None
         self._pin = {}
+        self._gae_ws = torch.zeros(64, dtype=torch.uint8, device=dev)
+        self.use_cuda_graph = ops.graphs_enabled()
+        self._graph = ops.GraphRunner()
         self._sync_hyper()
         self.last_n_policy_epochs = 0
         self.profile_events = False
@@ -191,14 +194,19 @@ class PPOLearner(Learner):
         if pinfo is None:
             raise ValueError('PPO needs the behaviour policy in persistent_infos (ppo_agent.py:149)')
         full = batch.get('obs_full') if isinstance(batch, dict) else None
+        own = self._own
         if self._dev_ok(full, (B, n + 1, D)) and self._dev_ok(get('actions'), (B, n, A)) and \
                 self._dev_ok(pinfo[-1], (B, n, 2 * A)) and self._dev_ok(get('rewards'), (B, n)) and \
                 self._dev_ok(get('dones'), (B, n)):
-            self._obs_full, self._actions, self._pds = full, get('actions'), pinfo[-1]
-            self._rewards, self._dones = get('rewards'), get('dones')
+            # device batch (HBM replay).  When the replay gathered straight into our buffers (replay_out_buffers)
+            # there is nothing to do; foreign device tensors are copied device-to-device so that the captured
+            # CUDA graph always reads the same addresses.
+            for src, dst in ((full, own['obs_full']), (get('actions'), own['actions']), (pinfo[-1], own['pds']),
+                             (get('rewards'), own['rewards']), (get('dones'), own['dones'])):
+                if src.data_ptr() != dst.data_ptr():
+                    dst.copy_(src, non_blocking=True)
             self.last_h2d_bytes = 0
             return batch
-        own = self._own
         self._obs_full, self._actions, self._pds = own['obs_full'], own['actions'], own['pds']
         self._rewards, self._dones = own['rewards'], own['dones']
         obs, obs_next = self._low_dim(get('obs')), self._low_dim(get('obs_next'))
@@ -238,7 +246,7 @@ class PPOLearner(Learner):
             rewards, scale = self._rewards_f, 1.0
         ev = self._prof_begin()
         ops.gae_window(rewards, self._values.view(B, n + 1), self._dones, self.gamma, self.lam, norm_adv=self.norm_adv,
-                       reward_scale=scale, adv=self._adv, ret=self._ret)
+                       reward_scale=scale, adv=self._adv, ret=self._ret, ws=self._gae_ws)
         self._prof_end('gae', ev)
         return self._adv, self._ret
 
@@ -261,7 +269,12 @@ class PPOLearner(Learner):
         torch.cuda.synchronize()
         return [a.elapsed_time(b) for a, b in self._prof.pop(name, [])]
 
-    def _policy_epoch(self):
+    def replay_out_buffers(self):
+        """Buffers the HBM replay gathers a sampled batch into (zero extra copies, stable addresses)."""
+        o = self._own
+        return dict(obs_full=o['obs_full'], actions=o['actions'], pd=o['pds'], rewards=o['rewards'], dones=o['dones'])
+
+    def _policy_epoch(self, stop=None):
         L = _lib.lib()
         B, n, A, D = self.batch_size, self.n_step, self.action_dim, self.low_dim
         m, tr, st = self.model, self.actor_optim, ops._stream()
@@ -269,16 +282,16 @@ class PPOLearner(Learner):
         mode = 0 if self.ppo_mode == 'clip' else 1
         if mode == 1:
             check(L.sb200_ppo_kl_f32(_ptr(self._ref_pd), 2 * A, _ptr(mean), mean.stride(0), _ptr(m.log_var), B, A,
-                                     _ptr(self._stats), S['KL_PRE'], 0.0, None, _ptr(self._loss_ws), st),
+                                     _ptr(self._stats), S['KL_PRE'], 0.0, _ptr(stop), _ptr(self._loss_ws), st),
                   'sb200_ppo_kl_f32')
         dlog_var = tr.slabs[0, m.actor.extra_off:m.actor.extra_off + A]
         check(L.sb200_ppo_policy_loss_f32(mode, _ptr(mean), mean.stride(0), _ptr(m.log_var), _ptr(self._actions), n * A,
                                           _ptr(self._adv), _ptr(self._pds), n * 2 * A, _ptr(self._ref_pd), 2 * A, B, A,
                                           _ptr(self._hyper), float(self.eta), float(self.kl_target), _ptr(tr.d[-1]),
                                           tr.d[-1].stride(0), _ptr(dlog_var), _ptr(self._stats), _ptr(self._loss_ws),
-                                          None, st), 'sb200_ppo_policy_loss_f32')
+                                          _ptr(stop), st), 'sb200_ppo_policy_loss_f32')
         tr.backward()
-        tr.step(norm_out=self._stats[S['GN_ACTOR']:S['GN_ACTOR'] + 1])
+        tr.step(norm_out=self._stats[S['GN_ACTOR']:S['GN_ACTOR'] + 1], stop_flag=stop)
         # post-step KL(ref || current) (ppo.py:553-556)
         ops.mlp_forward(m.actor, self._obs_full, zf_stats=m.z_stats, zf_eps=m.z_eps, rows=B, ldx=(n + 1) * D, out=self._cur_mean)
         check(L.sb200_ppo_kl_f32(_ptr(self._ref_pd), 2 * A, _ptr(self._cur_mean), A, _ptr(m.log_var), B, A,
@@ -295,38 +308,61 @@ class PPOLearner(Learner):
         tr.backward()
         tr.step(norm_out=self._stats[S['GN_CRITIC']:S['GN_CRITIC'] + 1])
 
-    def _optimize(self):
-        """ppo.py:487-586."""
-        L = _lib.lib()
+    def _optimize_head(self):
         B, n, A, D = self.batch_size, self.n_step, self.action_dim, self.low_dim
-        m, ref, st = self.model, self.ref_target_model, ops._stream()
+        ref = self.ref_target_model
         self._gae_and_return()
         ops.mlp_forward(ref.actor, self._obs_full, zf_stats=ref.z_stats, zf_eps=ref.z_eps, rows=B, ldx=(n + 1) * D,
                         out=self._ref_mean)
         ops.make_pd(self._ref_mean, ref.log_var, B, A, self._ref_pd)
         self._stats.zero_()
         self._stop.zero_()
-        n_ep = 0
-        kl = 0.0
-        for _ in range(self.epoch_policy):
-            self._policy_epoch()
-            n_ep += 1
-            kl = float(self._stats[S['KL_POST']].item())          # one host sync per epoch (ppo.py:555-556)
-            if kl > self.kl_target * 4:
-                break
-        self.last_n_policy_epochs = n_ep
-        if self.profile_events:
-            self.optimizer_steps_profiled += n_ep + self.epoch_baseline
-        self.kl_record.append(kl)
+
+    def _optimize_tail(self):
+        L = _lib.lib()
+        B, n, A, D = self.batch_size, self.n_step, self.action_dim, self.low_dim
+        m, st = self.model, ops._stream()
         for _ in range(self.epoch_baseline):
             self._value_epoch()
         check(L.sb200_ppo_final_stats_f32(_ptr(self._cur_mean), A, _ptr(m.log_var), _ptr(self._actions), n * A,
                                           _ptr(self._pds), n * 2 * A, _ptr(self._ref_pd), 2 * A, B, A,
                                           _ptr(self._stats), _ptr(self._loss_ws), st), 'sb200_ppo_final_stats_f32')
         if self.use_z_filter:
-            ops.zfilter_update(self._obs_full, B, D, (n + 1) * D, m.z_stats)  # step-0 rows only, AFTER the updates (ppo.py:578)
+            # step-0 rows only, AFTER the updates (ppo.py:578)
+            ops.zfilter_update(self._obs_full, B, D, (n + 1) * D, m.z_stats)
+
+    def _optimize_device(self):
+        """The whole of ppo.py:487-586 as one fixed launch sequence (CUDA-graph body).  The KL early stop
+        (ppo.py:556) is a DEVICE flag: the post-step KL kernel raises it, and the loss / reduce / Adam / KL
+        kernels of the remaining policy epochs turn into no-ops -- same parameters and statistics as breaking
+        out of the loop, without a host round trip per epoch."""
+        self._optimize_head()
+        for _ in range(self.epoch_policy):
+            self._policy_epoch(stop=self._stop)
+        self._optimize_tail()
+
+    def _optimize(self):
+        """ppo.py:487-586."""
+        B, n, A, D = self.batch_size, self.n_step, self.action_dim, self.low_dim
+        m = self.model
+        if self.use_cuda_graph and not self.profile_events:
+            self._graph.run(self._optimize_device)
+        elif self.use_cuda_graph:
+            self._optimize_device()                               # same sequence, eager (per-kernel event timing)
+        else:
+            self._optimize_head()                                 # reference-style host loop: one sync per epoch
+            for _ in range(self.epoch_policy):
+                self._policy_epoch()
+                if float(self._stats[S['KL_POST']].item()) > self.kl_target * 4:
+                    break
+            self._optimize_tail()
         s = self._stats.cpu().numpy()                             # single D2H of all statistics
         self.last_d2h_bytes = s.nbytes
+        n_ep = int(round(float(s[S['EPOCHS']])))
+        self.last_n_policy_epochs = n_ep
+        self.kl_record.append(float(s[S['KL_POST']]))
+        if self.profile_events:
+            self.optimizer_steps_profiled += n_ep + self.epoch_baseline
         stats = {'_surr_loss': float(s[S['SURR']]), '_entropy': float(s[S['ENTROPY']])}
         if self.ppo_mode == 'clip':
             stats['_clip_surr_loss'] = float(s[S['LOSS']])

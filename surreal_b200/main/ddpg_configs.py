@@ -69,3 +69,44 @@ def ddpg_argparser():
     p.add_argument('--eval-batch', type=int, default=1)
     p.add_argument('--unit-test', action='store_true')
     return p
+
+
+class DDPGLauncher:
+    """DDPGLauncher of ddpg_configs.py:230-293 (constructed lazily so importing configs needs no GPU)."""
+
+    def __new__(cls, *a, **k):
+        from ..launch import SurrealDefaultLauncher
+        from ..agent import DDPGAgent
+        from ..learner import DDPGLearner
+        from ..replay import UniformReplay
+        from .ppo_configs import make_synthetic_env_config
+
+        class _DDPGLauncher(SurrealDefaultLauncher):
+            def __init__(self):
+                super().__init__(DDPGAgent, DDPGLearner, UniformReplay, DDPG_DEFAULT_SESSION_CONFIG.copy(),
+                                 DDPG_DEFAULT_ENV_CONFIG.copy(), DDPG_DEFAULT_LEARNER_CONFIG.copy())
+
+            def setup(self, argv):
+                args = ddpg_argparser().parse_args(args=argv)
+                dims = args.env.split(':')[1:] if ':' in args.env else []
+                D = int(dims[0]) if len(dims) > 0 else 64
+                A = int(dims[1]) if len(dims) > 1 else 8
+                make_synthetic_env_config(self.env_config, args.num_agents, D, A)
+                self.env_config.num_agents = args.num_agents
+                self.session_config.folder = args.experiment_folder
+                self.session_config.agent.num_gpus = args.agent_num_gpus
+                self.session_config.learner.num_gpus = args.num_gpus
+                if args.restore_folder is not None:
+                    self.session_config.checkpoint.restore = True
+                    self.session_config.checkpoint.restore_folder = args.restore_folder
+                self.agent_batch_size = args.agent_batch
+                self.eval_batch_size = args.eval_batch
+                if args.unit_test:
+                    self.learner_config.replay.sampling_start_size = 5
+                    self.learner_config.replay.replay_shards = 1
+                    self.session_config.ps.shards = 1
+        return _DDPGLauncher()
+
+
+def main():
+    DDPGLauncher().main()

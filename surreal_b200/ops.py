@@ -16,6 +16,7 @@ def _ru(v, m):
 
 
 def _stream():
+    _lib.ensure_device()
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -201,6 +202,13 @@ class MlpTrainer:
         return self.h[-1][:, :self.net.dims[-1]]
 
     def forward(self, x, zf_stats=None, zf_eps=1e-5, aux=None, rows=None, ldx=None):
+        if aux is not None and (aux.stride(0) % 4 != 0 or aux.data_ptr() % 16 != 0):
+            # the backward GEMMs read rows with 16-byte vector loads: re-home odd-width aux inputs once
+            if getattr(self, '_aux_pad', None) is None:
+                self._aux_pad = torch.zeros(self.M, _ru(self.net.aux_dim, 4), dtype=torch.float32,
+                                            device=self.net.device)
+            self._aux_pad[:, :self.net.aux_dim].copy_(aux[:, :self.net.aux_dim])
+            aux = self._aux_pad
         self.aux = aux
         mlp_forward(self.net, x, zf_stats=zf_stats, zf_eps=zf_eps, aux=aux, rows=rows, ldx=ldx,
                     saves=self.h, save_x=self.x_in)
@@ -231,6 +239,17 @@ class MlpTrainer:
                                                 ldw, _ptr(Xa), Xa.stride(0), _ptr(dX), dX.stride(0), M, N, K0, st),
                       'sb200_linear_bwd_dx_f32')
 
+    def backward_inputs(self, stop_layer=1):
+        """Only the dX chain from the last layer down to ``stop_layer`` (fills self.d[stop_layer-1 ...]); no weight
+        gradients -- the DDPG actor loss back-propagates THROUGH the critic without updating it."""
+        L, net, M = _lib.lib(), self.net, self.M
+        for l in reversed(range(stop_layer + 1, net.n_layers)):
+            lay = net.layout[l]
+            dY, Xa, dX = self.d[l], self.h[l - 1], self.d[l - 1]
+            check(L.sb200_linear_bwd_dx_f32(_ptr(dY), dY.stride(0), C.c_void_p(net.params.data_ptr() + 4 * lay['w']),
+                                            lay['ldw'], _ptr(Xa), Xa.stride(0), _ptr(dX), dX.stride(0), M, lay['N'],
+                                            net.dims[l], _stream()), 'sb200_linear_bwd_dx_f32')
+
     def grad_wrt_aux(self, l, out):
         """d loss / d aux input of layer l (the DDPG actor gradient dQ/da, ddpg.py:324-330)."""
         L, net = _lib.lib(), self.net
@@ -255,10 +274,35 @@ class MlpTrainer:
         self.lr.fill_(float(lr))
 
 
+class GraphRunner:
+    """Capture a fixed launch sequence once into a CUDA graph and replay it (B200: a launch-bound inner loop of
+    hundreds of small kernels becomes ONE submission).  Capture records without executing, so state is advanced
+    exactly once per call: the first call captures and immediately replays."""
+
+    def __init__(self):
+        self.graph = None
+
+    def run(self, fn):
+        if self.graph is None:
+            _lib.ensure_device()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            self.graph = g
+        self.graph.replay()
+
+
+def graphs_enabled():
+    import os
+    return os.environ.get('SB200_CUDA_GRAPH', '1') != '0'
+
+
 _gae_ws = {}
 
 
-def gae_window(rewards, values, dones, gamma, lam, horizon=None, norm_adv=True, reward_scale=1.0, adv=None, ret=None):
+def gae_window(rewards, values, dones, gamma, lam, horizon=None, norm_adv=True, reward_scale=1.0, adv=None, ret=None,
+               ws=None):
     """rewards [B,n], values [B,n+1] raw critic output, dones [B,n] -> (adv [B,E], ret [B,E])."""
     L = _lib.lib()
     _f32c(rewards), _f32c(values), _f32c(dones)
@@ -269,12 +313,14 @@ def gae_window(rewards, values, dones, gamma, lam, horizon=None, norm_adv=True, 
         adv = torch.empty(B, E, dtype=torch.float32, device=rewards.device)
     if ret is None:
         ret = torch.empty(B, E, dtype=torch.float32, device=rewards.device)
-    key = rewards.device
-    if key not in _gae_ws:
-        _gae_ws[key] = torch.zeros(max(16, L.sb200_gae_workspace_bytes(B, n, H)), dtype=torch.uint8,
-                                   device=rewards.device)
+    if ws is None:
+        key = rewards.device
+        if key not in _gae_ws:
+            _gae_ws[key] = torch.zeros(max(16, L.sb200_gae_workspace_bytes(B, n, H)), dtype=torch.uint8,
+                                       device=rewards.device)
+        ws = _gae_ws[key]
     check(L.sb200_gae_window_f32(_ptr(rewards), _ptr(values), _ptr(dones), B, n, H, float(gamma), float(lam),
-                                 float(reward_scale), int(bool(norm_adv)), _ptr(adv), _ptr(ret), _ptr(_gae_ws[key]),
+                                 float(reward_scale), int(bool(norm_adv)), _ptr(adv), _ptr(ret), _ptr(ws),
                                  _stream()), 'sb200_gae_window_f32')
     return adv, ret
 

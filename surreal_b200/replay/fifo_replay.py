@@ -23,7 +23,8 @@ def _p(t):
 
 
 def _st():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    from ..ops import _stream
+    return _stream()
 
 
 class FIFOReplay(Replay):
@@ -54,6 +55,7 @@ class FIFOReplay(Replay):
         self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._slots = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._pin = None
+        self.check_underflow = True
 
     # -- control block ---------------------------------------------------------------------------------
     def _read_state(self):
@@ -120,8 +122,8 @@ class FIFOReplay(Replay):
                               (self.r_done, out['dones'], n)):
             check(L.sb200_replay_gather_f32(_p(src), rec, _p(self._idx), None, batch_size, _p(dst), _st()),
                   'sb200_replay_gather_f32')
-        if int(self._status.item()) != 0:
-            raise IndexError('pop from a FIFO replay holding fewer than %d windows' % batch_size)
+        if self.check_underflow and int(self._status.item()) != 0:      # host sync; the engine polls
+            raise IndexError('pop from a FIFO replay holding fewer than %d windows' % batch_size)   # len() instead
         obs_full = out['obs_full']
         return {'obs': {'low_dim': {'flat_inputs': obs_full[:, :n, :]}},
                 'obs_next': {'low_dim': {'flat_inputs': obs_full[:, n:, :]}},

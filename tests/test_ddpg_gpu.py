@@ -1,0 +1,83 @@
+"""DDPGLearner / DDPGAgent (CUDA) vs goldens produced by the reference's own DDPGLearner._optimize / DDPGAgent.act."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import ddpg_configs, ref_state_dict
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('tag', ['hard', 'soft_clipcritic'])
+def test_ddpg_optimize_matches_reference(golden, tag):
+    from surreal_b200.learner import DDPGLearner
+    g = golden('ddpg_optimize_' + tag)
+    cfg, stats = g.js('cfg'), g.js('stats')
+    lc, ec, sc = ddpg_configs(D=cfg['D'], A=cfg['A'], actor_h=cfg['actor_h'], critic_h=cfg['critic_h'], B=cfg['B'],
+                              n_step=cfg['n_step'], target=cfg['target'], clip_critic=cfg['clip_critic'],
+                              lr_actor=cfg['lr_actor'], lr_critic=cfg['lr_critic'])
+    L = DDPGLearner(lc, ec, sc)
+    L.model.load_state_dict(ref_state_dict(g.sub('init/model/')))
+    L.model_target.load_state_dict(ref_state_dict(g.sub('init/target/')))
+    for it in range(3):
+        b = g.sub('it%d/' % it)
+        st = L.learn({'obs': {'low_dim': {'flat_inputs': b['obs']}}, 'obs_next': {'low_dim': {'flat_inputs': b['obs_next']}},
+                      'actions': b['actions'], 'rewards': b['rewards'], 'dones': b['dones']})
+        torch.cuda.synchronize()
+        for k, v in stats[it].items():
+            assert abs(st[k] - v) <= 1e-5 * max(1.0, abs(v)), '%s it%d: got %.9g expected %.9g' % (k, it, st[k], v)
+        for name, model in (('model', L.model), ('target', L.model_target)):
+            exp = ref_state_dict(g.sub('it%d/%s/' % (it, name)))
+            got = model.state_dict()
+            for k, e in exp.items():
+                d = float((got[k].cpu().reshape(e.shape) - e).abs().max())
+                assert d <= 2e-5, '%s %s it%d drift %.3e' % (name, k, it, d)      # lr_critic = 1e-3: 2% of one step
+
+
+def test_ddpg_agent_act_matches_reference(golden):
+    from surreal_b200.agent import DDPGAgent
+    g = golden('ddpg_act')
+    N = len(g['obs'])
+    lc, ec, sc = ddpg_configs(D=9, A=3)
+    ec.num_envs = N
+    ec.num_agents = 4
+    ag = DDPGAgent(lc, ec, sc, 0, 'training')
+    ag.model.load_state_dict(ref_state_dict(g.sub('model/')))
+    ag._sigma.fill_(float(g['sigma']))                       # every row of the fixture is agent 3 of 4
+    a = ag.act({'low_dim': {'flat_inputs': g['obs']}}, unit_noise=g['unit_noise'])
+    assert a.dtype == np.float32
+    np.testing.assert_allclose(a, g['actions'], rtol=0, atol=2e-6)
+    assert ag.sigma.tolist() == [0.0, 0.25, 0.5, 0.75, 1.0][:N] or N != 5
+
+
+def test_ddpg_engine_end_to_end():
+    """actors -> n-step SSAR staging -> UniformReplay ring -> CPython-exact sampling -> DDPGLearner."""
+    import random
+    from surreal_b200.launch import SurrealDefaultLauncher
+    from surreal_b200.agent import DDPGAgent
+    from surreal_b200.learner import DDPGLearner
+    from surreal_b200.replay import UniformReplay
+    from surreal_b200.main.ppo_configs import make_synthetic_env_config
+    N = 32
+    lc, ec, sc = ddpg_configs(D=12, A=4, actor_h=(48, 32), critic_h=(64, 48), B=64, n_step=3, memory_size=500, start=100)
+    make_synthetic_env_config(ec, N, 12, 4, seed=1)
+    ec.num_agents = N
+    ec.limit_episode_length = 20
+    la = SurrealDefaultLauncher(DDPGAgent, DDPGLearner, UniformReplay, sc, ec, lc)
+    agent, replay, learner = la.setup_engine()
+    agent.main_loop(max_steps=30)
+    torch.cuda.synchronize()
+    # every actor emits from its (n_step)-th step of an episode on: 20-step episodes -> 18 per episode
+    per_actor = 18 + (30 - 20 - 2)
+    assert len(replay) == min(500, N * per_actor)
+    assert replay.start_sample_condition()
+    random.seed(5)
+    expect_idx = [random.randint(0, len(replay) - 1) for _ in range(64)]
+    random.seed(5)
+    batch = replay.sample(64)
+    assert batch['indices'].tolist() == expect_idx
+    assert torch.equal(batch['actions'].cpu(), replay.r_act[torch.tensor(expect_idx)].cpu())
+    st = learner.learn(batch)
+    for k in ['actor_loss', 'critic_loss', 'Q_target', 'Q_policy', 'action_norm', 'rewards']:
+        assert np.isfinite(st[k])
+    assert float(replay.r_act.abs().max()) <= 1.0

@@ -1,0 +1,138 @@
+"""CPU-side tests of the product's HOST logic (no GPU): aggregators, CPython-exact index stream, trackers,
+checkpoint format, launcher argument handling."""
+import os
+import pickle
+import random
+
+import numpy as np
+import pytest
+import yaml
+
+
+def test_product_aggregators_match_reference(golden):
+    from surreal_b200.learner.aggregator import MultistepAggregatorWithInfo, SSARAggregator
+    g = golden('aggregate')
+    dt = g.js('dtypes')
+    obs_spec = {'low_dim': {'flat_inputs': (4,)}}
+    act_spec = {'dim': (2,), 'type': 'continuous'}
+    ob = lambda v: {'low_dim': {'flat_inputs': v}}  # noqa: E731
+    B, n = g['ms_in_obs'].shape[:2]
+    exps = [dict(obs=[ob(g['ms_in_obs'][b, k]) for k in range(n)], obs_next=ob(g['ms_in_obs_next'][b]),
+                 actions=list(g['ms_in_actions'][b]), rewards=[float(x) for x in g['ms_in_rewards'][b]],
+                 dones=[bool(x) for x in g['ms_in_dones'][b]],
+                 persistent_infos=[[g['ms_in_pd'][b, k]] for k in range(n)], onetime_infos=[], infos=[{}] * n, n_step=n)
+            for b in range(B)]
+    out = MultistepAggregatorWithInfo(obs_spec, act_spec).aggregate(exps)
+    got = dict(obs=out['obs']['low_dim']['flat_inputs'], obs_next=out['obs_next']['low_dim']['flat_inputs'],
+               actions=out['actions'], rewards=out['rewards'], dones=out['dones'], pd=out['persistent_infos'][0])
+    for k, v in got.items():
+        np.testing.assert_array_equal(v, g['ms_' + k])
+        assert str(v.dtype) == dt['ms_' + k]
+    assert out['onetime_infos'] is None
+    ss = [dict(obs=[ob(g['ss_in_obs'][b]), ob(g['ss_in_obs_next'][b])], action=g['ss_in_action'][b],
+               reward=float(g['ss_in_reward'][b]), done=bool(g['ss_in_done'][b]), info={}) for b in range(4)]
+    o2 = SSARAggregator(obs_spec, act_spec).aggregate(ss)
+    got = dict(obs=o2['obs']['low_dim']['flat_inputs'], obs_next=o2['obs_next']['low_dim']['flat_inputs'],
+               actions=o2['actions'], rewards=o2['rewards'], dones=o2['dones'])
+    for k, v in got.items():
+        np.testing.assert_array_equal(v, g['ss_' + k])
+        assert str(v.dtype) == dt['ss_' + k]
+    with pytest.raises(NotImplementedError):
+        SSARAggregator(obs_spec, {'dim': (2,), 'type': 'discrete'})
+
+
+def test_cpp_mt19937_reproduces_cpython_randint(golden):
+    """The C++ generator inside libsurreal_b200 (host code) == random.randint, and keeps the global stream in step."""
+    from surreal_b200.replay.uniform_replay import PyRandomStream
+    streams = golden('replay').js('streams')
+    for m, exp in streams.items():
+        if m.startswith('bigseed'):
+            rng, mm = random.Random(12345678901234567890), 1000
+        else:
+            rng, mm = random.Random(5), int(m)
+        out = np.empty(len(exp), dtype=np.int64)
+        PyRandomStream(rng).randint_fill(mm, len(exp), out)
+        assert out.tolist() == exp
+    random.seed(99)
+    a = [random.randint(0, 332) for _ in range(10)] + [random.random()]
+    random.seed(99)
+    out = np.empty(10, dtype=np.int64)
+    PyRandomStream().randint_fill(333, 10, out)
+    assert out.tolist() + [random.random()] == a
+
+
+def test_trackers_and_timers():
+    from surreal_b200.utils import PeriodicTracker, MovingAverageRecorder, AutoInitializeMeta
+    t = PeriodicTracker(3)
+    assert [t.track_increment() for _ in range(7)] == [False, False, True, False, False, True, False]
+    m = MovingAverageRecorder(0.5)
+    assert m.add_value(2.0) == 2.0 and abs(m.add_value(4.0) - (2.0 * 0.5 + 4.0) / 1.5) < 1e-12
+
+    class A(metaclass=AutoInitializeMeta):
+        def __init__(self):
+            self.order = ['init']
+
+        def _initialize(self):
+            self.order.append('initialize')
+
+    class B(A):
+        def __init__(self):
+            super().__init__()
+            self.order.append('sub-init')
+    assert B().order == ['init', 'sub-init', 'initialize']      # _initialize runs AFTER the most-derived __init__
+
+
+def test_checkpoint_format_and_roundtrip(tmp_path):
+    from surreal_b200.checkpoint import PeriodicCheckpoint
+
+    class Mod:
+        def __init__(self, v):
+            self.v = v
+
+        def state_dict(self):
+            return {'w': self.v}
+
+        def load_state_dict(self, sd):
+            self.v = sd['w']
+
+    class Obj:
+        pass
+    o = Obj()
+    o.model, o.current_iteration = Mod(1.5), 7
+    ck = PeriodicCheckpoint(str(tmp_path), 'learner', period=2, min_interval=0, tracked_obj=o,
+                            tracked_attrs=['model', 'current_iteration'], keep_history=2, keep_best=0)
+    assert ck.save(global_steps=1) is False and ck.save(global_steps=2) is True
+    o.model.v, o.current_iteration = 2.5, 9
+    ck.save(global_steps=3)
+    assert ck.save(global_steps=4) is True
+    o.model.v, o.current_iteration = 3.5, 11
+    ck.save(global_steps=5)
+    ck.save(global_steps=6)
+    meta = yaml.safe_load(open(tmp_path / 'metadata.learner.yml'))
+    assert meta['history_ckpt_files'] == ['learner.6.ckpt', 'learner.4.ckpt'] and meta['save_counter'] == 3
+    assert not os.path.exists(tmp_path / 'learner.2.ckpt')                      # keep_history = 2
+    data = pickle.load(open(tmp_path / 'learner.4.ckpt', 'rb'))
+    assert list(data.keys()) == ['model', 'current_iteration'] and data['model'] == {'w': 2.5}
+    o2 = Obj()
+    o2.model, o2.current_iteration = Mod(0.0), 0
+    ck2 = PeriodicCheckpoint(str(tmp_path), 'learner', period=1, tracked_obj=o2, tracked_attrs=None)
+    assert ck2.restore(target=1, mode='history').endswith('learner.4.ckpt')
+    assert (o2.model.v, o2.current_iteration) == (2.5, 9)
+    assert ck2.restore(target=5, mode='history') is None
+
+
+def test_launcher_component_parsing(tmp_path):
+    from surreal_b200.launch import Launcher
+
+    class L(Launcher):
+        def setup(self, args):
+            self.got_args = args
+
+        def launch(self, name):
+            return name
+    la = L()
+    assert la.main(['learner', '--', '--env', 'synthetic', '--num-agents', '4']) == 'learner'
+    assert la.got_args == ['--env', 'synthetic', '--num-agents', '4']
+    from surreal_b200.main.ppo_configs import ppo_argparser
+    a = ppo_argparser().parse_args(['--env', 'synthetic:64:8', '--num-agents', '1024', '--experiment-folder', str(tmp_path)])
+    assert a.num_agents == 1024 and a.unit_test is False

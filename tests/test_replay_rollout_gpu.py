@@ -241,8 +241,10 @@ def test_engine_end_to_end_runs_and_is_consistent():
     sc.agent.fetch_parameter_interval = 1
     la = SurrealDefaultLauncher(PPOAgent, PPOLearner, FIFOReplay, sc, ec, lc)
     agent, replay, learner = la.setup_engine()
+    # like the reference, PPO's first publish only happens after exp_interval experiences (ppo.py:633): until then
+    # the actors run their own initial weights
     w0 = agent.model.actor.params.clone()
-    assert torch.equal(w0, learner.model.actor.params)            # initial publish + fetch
+    assert learner.publisher.version == 0
     agent.main_loop(max_steps=n)
     torch.cuda.synchronize()
     assert len(replay) == N
@@ -251,7 +253,7 @@ def test_engine_end_to_end_runs_and_is_consistent():
     assert torch.allclose(pd_first[:, 4:], expect_std, rtol=1e-6)
     assert float(replay.r_act[:N].abs().max()) <= 1.0
     learner.main_loop()                                           # consumes the N windows, publishes (exp_interval)
-    assert len(replay) == 0 and learner.publisher.version == 2
+    assert len(replay) == 0 and learner.publisher.version == 1
     assert not torch.equal(learner.model.actor.params, w0)
     assert torch.equal(agent.model.actor.params, w0)              # actors still run the lagged snapshot
     agent.main_loop(max_steps=1)                                  # fetch_parameter_interval = 1 -> pulls the new one
