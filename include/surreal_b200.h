@@ -43,6 +43,8 @@ const char* sb200_status_string(int status);
 int sb200_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Number of CUDA kernels this library has launched so far (optionally reset) -- bench.py's gpu_launches. */
 uint64_t sb200_launch_counter(int reset);
+/* Account for kernels submitted through a replayed CUDA graph (counted once at capture time). */
+void sb200_launch_counter_add(uint64_t kernels);
 
 /* ---------------------------------------------------------------------------------------------
  * Networks.  One descriptor covers PPO_ActorNetwork / PPO_CriticNetwork
@@ -122,6 +124,11 @@ int sb200_make_pd_f32(const float* mean, int64_t ldm, const float* log_var, cons
 /* ZFilter.z_update (z_filter.py:44-57): stats = running_sum[D] | running_sumsq[D] | count[1], updated in place. */
 int sb200_zfilter_update_f32(const float* x, int64_t ldx, int64_t rows, int D, float* stats, void* stream);
 
+/* Global-batch statistics helpers for the data-parallel learner: moments3 = {sum, sum of squares, count} (fp64,
+ * summed over ranks by the caller); normalize applies (x-mean)/max(unbiased std, floor) (ppo.py:413-416). */
+int sb200_moments_f32(const float* x, int64_t n, double* moments3, void* stream);
+int sb200_normalize_f32(float* x, int64_t n, const double* moments3, double floor_value, void* stream);
+int sb200_add_f32(float* dst, const float* src, int64_t n, void* stream);
 /* RewardFilter as called from ppo.py:452-456: out = forward(rewards*reward_scale) with the current statistics,
  * then update (running_sumsq is OVERWRITTEN, reward_filter.py:42).  stats = count | running_sum | running_sumsq. */
 int sb200_reward_filter_f32(const float* rewards, int64_t n, double reward_scale, double eps, float* stats,
@@ -163,7 +170,13 @@ int sb200_ppo_policy_loss_f32(int mode, const float* mean, int64_t ldm, const fl
  * when the mean exceeds stop_threshold (> 0). */
 int sb200_ppo_kl_f32(const float* p0, int64_t ld0, const float* mean, int64_t ldm, const float* log_var,
                      int B, int A, float* stats, int stat_slot, double stop_threshold, int* stop_flag,
-                     void* workspace, void* stream);
+                     int defer, void* workspace, void* stream);
+/* Data-parallel split of the above: with defer != 0 sb200_ppo_kl_f32 only leaves the LOCAL mean KL as a double at
+ * byte offset sb200_ppo_loss_kl_offset() of the workspace; the caller averages it over ranks (NCCL) and then
+ * sb200_ppo_kl_apply publishes it to stats / raises the stop flag identically on every rank. */
+int sb200_ppo_kl_apply(void* workspace, float* stats, int stat_slot, double stop_threshold, int* stop_flag,
+                       void* stream);
+size_t sb200_ppo_loss_kl_offset(void);
 int sb200_value_loss_f32(const float* values, int64_t ldv, const float* returns, int B, float* dpre,
                          int64_t ldd, float* stats, void* workspace, void* stream);
 int sb200_ppo_final_stats_f32(const float* mean, int64_t ldm, const float* log_var, const float* actions,
@@ -173,13 +186,14 @@ int sb200_ppo_final_stats_f32(const float* mean, int64_t ldm, const float* log_v
 /* ---------------------------------------------------------------------------------------------
  * Optimiser over one flat parameter buffer (replaces clip_grad_norm_/clip_grad_value_ + torch.optim.Adam:
  * ppo.py:159-168,244-247,349-352; ddpg.py:145-165,309-310,332-333).
- *   grad_reduce_norm: grad[i] = sum_z slabs[z*slab_stride + i] (fixed order), global L2 norm and step += 1
- *                     into the workspace.
+ *   grad_reduce_norm: grad[i] = scale * sum_z slabs[z*slab_stride + i] (fixed order); global L2 norm (and
+ *                     step += 1 when bump_step) into the workspace.  Data-parallel learners call it twice around
+ *                     the NCCL all-reduce: (slabs -> grad, scale 1, no bump), (grad -> grad, 1/world, bump).
  *   clip_adam: clip_mode 0 none / 1 global norm (clip_value = max_norm) / 2 by value; lr is a DEVICE double.
  *   workspace: sb200_optim_workspace_bytes(), zero-initialised once (it holds the Adam step count). */
 size_t sb200_optim_workspace_bytes(void);
 int sb200_grad_reduce_norm_f32(const float* slabs, int64_t slab_stride, int splits, float* grad, int64_t n,
-                               void* workspace, const int* stop_flag, void* stream);
+                               double scale, int bump_step, void* workspace, const int* stop_flag, void* stream);
 int sb200_clip_adam_f32(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                         const double* lr, double beta1, double beta2, double eps, double weight_decay,
                         int clip_mode, double clip_value, void* workspace, float* norm_out,

@@ -50,6 +50,7 @@ def _declare(lib):
         'sb200_status_string': (C.c_char_p, [I]),
         'sb200_device_info': (I, [C.POINTER(I), C.POINTER(I), C.POINTER(I)]),
         'sb200_launch_counter': (C.c_uint64, [I]),
+        'sb200_launch_counter_add': (None, [C.c_uint64]),
         'sb200_mlp_forward_f32': (I, [C.POINTER(Mlp), C.POINTER(ZFilter), C.POINTER(Rows),
                                       C.POINTER(P), C.POINTER(L), P]),
         'sb200_linear_bwd_dx_f32': (I, [P, L, P, I, P, L, P, L, I, I, I, P]),
@@ -60,7 +61,12 @@ def _declare(lib):
         'sb200_gae_workspace_bytes': (S, [I, I, I]),
         'sb200_ppo_loss_workspace_bytes': (S, [I, I]),
         'sb200_ppo_policy_loss_f32': (I, [I, P, L, P, P, L, P, P, L, P, L, I, I, P, D, D, P, L, P, P, P, P, P]),
-        'sb200_ppo_kl_f32': (I, [P, L, P, L, P, I, I, P, I, D, P, P, P]),
+        'sb200_ppo_kl_f32': (I, [P, L, P, L, P, I, I, P, I, D, P, I, P, P]),
+        'sb200_ppo_kl_apply': (I, [P, P, I, D, P, P]),
+        'sb200_ppo_loss_kl_offset': (S, []),
+        'sb200_moments_f32': (I, [P, L, P, P]),
+        'sb200_normalize_f32': (I, [P, L, P, D, P]),
+        'sb200_add_f32': (I, [P, P, L, P]),
         'sb200_value_loss_f32': (I, [P, L, P, I, P, L, P, P, P]),
         'sb200_ppo_final_stats_f32': (I, [P, L, P, P, L, P, L, P, L, I, I, P, P, P]),
         'sb200_ppo_sample_f32': (I, [P, L, P, P, P, I, I, I, C.c_uint64, P, P, P, P, P, P, I, P]),
@@ -84,7 +90,7 @@ def _declare(lib):
         'sb200_ddpg_actor_seed_f32': (I, [P, L, I, P, L, P, P, P]),
         'sb200_tanh_bwd_f32': (I, [P, L, P, L, I, I, P, L, P]),
         'sb200_optim_workspace_bytes': (S, []),
-        'sb200_grad_reduce_norm_f32': (I, [P, L, I, P, L, P, P, P]),
+        'sb200_grad_reduce_norm_f32': (I, [P, L, I, P, L, D, I, P, P, P]),
         'sb200_clip_adam_f32': (I, [P, P, P, P, L, P, D, D, D, D, I, D, P, P, P, P]),
         'sb200_soft_update_f32': (I, [P, P, L, D, P]),
         'sb200_gae_window_f32': (I, [P, P, P, I, I, I, D, D, D, I, P, P, P, P]),

@@ -24,6 +24,8 @@ extern "C" const char* sb200_status_string(int status) {
 int sb200_mlp_fwd_init();
 int sb200_gae_init();
 
+extern "C" void sb200_launch_counter_add(uint64_t kernels) { g_sb200_launches += kernels; }
+
 extern "C" int sb200_init(void) {
     int dev = 0;
     SB200_CUDA(cudaGetDevice(&dev));

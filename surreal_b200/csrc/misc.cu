@@ -64,7 +64,60 @@ __global__ void __launch_bounds__(1024) reward_filter_kernel(const float* __rest
     }
 }
 
+// moments[0..1] = (sum, sum of squares) of x in fp64 -- the local half of a GLOBAL-batch advantage normalisation
+__global__ void __launch_bounds__(1024) moments_kernel(const float* __restrict__ x, long long n,
+                                                       double* __restrict__ moments) {
+    __shared__ double sh[32];
+    double s = 0.0, q = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = (double)x[i];
+        s += v;
+        q += v * v;
+    }
+    s = block_sum(s, sh);
+    q = block_sum(q, sh);
+    if (threadIdx.x == 0) {
+        moments[0] = s;
+        moments[1] = q;
+        moments[2] = (double)n;
+    }
+}
+
+// x = (x - mean) / max(unbiased_std, floor) from (sum, sumsq, count) moments (ppo.py:413-416 over the global batch)
+__global__ void normalize_kernel(float* __restrict__ x, long long n, const double* __restrict__ moments, float floor_) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double cnt = moments[2];
+    const double mean = moments[0] / cnt;
+    const double var = (moments[1] - moments[0] * moments[0] / cnt) / (cnt - 1.0);
+    const float mean_f = (float)mean, std_f = (float)sqrt(var > 0.0 ? var : 0.0);
+    x[i] = (x[i] - mean_f) / ((std_f > floor_) ? std_f : floor_);
+}
+
+__global__ void add_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __fadd_rn(dst[i], src[i]);
+}
+
 }  // namespace
+
+extern "C" int sb200_moments_f32(const float* x, int64_t n, double* moments3, void* stream) {
+    SB200_REQUIRE(x && moments3 && n >= 1);
+    moments_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, moments3);
+    return sb200_launch_status();
+}
+
+extern "C" int sb200_normalize_f32(float* x, int64_t n, const double* moments3, double floor_value, void* stream) {
+    SB200_REQUIRE(x && moments3 && n >= 1);
+    normalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, n, moments3, (float)floor_value);
+    return sb200_launch_status();
+}
+
+extern "C" int sb200_add_f32(float* dst, const float* src, int64_t n, void* stream) {
+    SB200_REQUIRE(dst && src && n >= 1);
+    add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dst, src, n);
+    return sb200_launch_status();
+}
 
 extern "C" int sb200_reward_filter_f32(const float* rewards, int64_t n, double reward_scale, double eps, float* stats,
                                        float* out, void* stream) {

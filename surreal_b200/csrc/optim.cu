@@ -23,13 +23,15 @@ struct OptWs {
 
 __global__ void __launch_bounds__(OT) grad_reduce_norm_kernel(const float* __restrict__ slabs, long long slab_stride,
                                                               int splits, float* __restrict__ grad, long long n,
-                                                              OptWs* ws, const int* __restrict__ stop) {
+                                                              float scale, int bump_step, OptWs* ws,
+                                                              const int* __restrict__ stop) {
     if (stop != nullptr && *stop) return;
     __shared__ double sh[32];
     double sq = 0.0;
     for (long long i = (long long)blockIdx.x * OT + threadIdx.x; i < n; i += (long long)gridDim.x * OT) {
         float g = slabs[i];
         for (int z = 1; z < splits; ++z) g += slabs[(long long)z * slab_stride + i];   // fixed order
+        if (scale != 1.0f) g = __fmul_rn(g, scale);
         grad[i] = g;
         sq += (double)g * (double)g;
     }
@@ -40,7 +42,7 @@ __global__ void __launch_bounds__(OT) grad_reduce_norm_kernel(const float* __res
             double acc = 0.0;
             for (unsigned int k = 0; k < gridDim.x; ++k) acc += ws->partial[k];
             ws->total_norm = (float)sqrt(acc);
-            ws->step += 1;
+            if (bump_step) ws->step += 1;
         }
     }
 }
@@ -101,10 +103,12 @@ inline int grid_for(long long n) {
 extern "C" size_t sb200_optim_workspace_bytes(void) { return sizeof(OptWs); }
 
 extern "C" int sb200_grad_reduce_norm_f32(const float* slabs, int64_t slab_stride, int splits, float* grad, int64_t n,
-                                          void* workspace, const int* stop_flag, void* stream) {
+                                          double scale, int bump_step, void* workspace, const int* stop_flag,
+                                          void* stream) {
     SB200_REQUIRE(slabs && grad && workspace && splits >= 1 && n >= 1);
     grad_reduce_norm_kernel<<<grid_for(n), OT, 0, (cudaStream_t)stream>>>(slabs, slab_stride, splits, grad, n,
-                                                                          (OptWs*)workspace, stop_flag);
+                                                                          (float)scale, bump_step, (OptWs*)workspace,
+                                                                          stop_flag);
     return sb200_launch_status();
 }
 

@@ -8,6 +8,7 @@
 // stats[] slots (fp32): see SB200_STAT_* in the header.
 #include "common.cuh"
 #include <math.h>
+#include <stddef.h>
 
 namespace {
 
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(LT) kl_kernel(const float* __restrict__ p0, lo
                                                 const float* __restrict__ mean, long long ldm,
                                                 const float* __restrict__ log_var, int B, int A,
                                                 float* __restrict__ stats, int slot, double stop_threshold,
-                                                int* __restrict__ stop, LossWs* ws) {
+                                                int* __restrict__ stop, LossWs* ws, int defer) {
     if (stop != nullptr && *stop) return;
     __shared__ double sh[32];
     __shared__ float s_sig[MAX_A];
@@ -189,11 +190,23 @@ __global__ void __launch_bounds__(LT) kl_kernel(const float* __restrict__ p0, lo
             for (unsigned int k = 0; k < gridDim.x; ++k) acc += ws->partial[k];
             const float klm = (float)(acc / (double)B);        // .mean() in fp32
             ws->kl_mean = (double)klm;
+            if (defer) return;                                 // data-parallel: all-reduce ws->kl_mean, then kl_apply
             if (stats != nullptr && slot >= 0) stats[slot] = klm;
             if (stop != nullptr && stop_threshold > 0.0 && (double)klm > stop_threshold) *stop = 1;
             if (stats != nullptr && slot == SB200_STAT_KL_POST) stats[SB200_STAT_EPOCHS] += 1.0f;
         }
     }
+}
+
+// second half of kl_kernel for the data-parallel learner (after the KL scalar was averaged over ranks)
+__global__ void kl_apply_kernel(LossWs* ws, float* __restrict__ stats, int slot, double stop_threshold,
+                                int* __restrict__ stop) {
+    if (stop != nullptr && *stop) return;
+    const float klm = (float)ws->kl_mean;
+    ws->kl_mean = (double)klm;
+    if (stats != nullptr && slot >= 0) stats[slot] = klm;
+    if (stop != nullptr && stop_threshold > 0.0 && (double)klm > stop_threshold) *stop = 1;
+    if (stats != nullptr && slot == SB200_STAT_KL_POST) stats[SB200_STAT_EPOCHS] += 1.0f;
 }
 
 // value loss: mean((v - ret)^2), dv = 2(v-ret)/B, explained variance (ppo.py:323-331)
@@ -305,13 +318,22 @@ extern "C" int sb200_ppo_policy_loss_f32(int mode, const float* mean, int64_t ld
 
 extern "C" int sb200_ppo_kl_f32(const float* p0, int64_t ld0, const float* mean, int64_t ldm, const float* log_var,
                                 int B, int A, float* stats, int stat_slot, double stop_threshold, int* stop_flag,
-                                void* workspace, void* stream) {
+                                int defer, void* workspace, void* stream) {
     SB200_REQUIRE(p0 && mean && log_var && workspace && B >= 1 && A >= 1 && A <= MAX_A);
     SB200_REQUIRE(stat_slot < SB200_STAT_COUNT);
     kl_kernel<<<nblocks(B), LT, 0, (cudaStream_t)stream>>>(p0, ld0, mean, ldm, log_var, B, A, stats, stat_slot,
-                                                          stop_threshold, stop_flag, (LossWs*)workspace);
+                                                          stop_threshold, stop_flag, (LossWs*)workspace, defer);
     return sb200_launch_status();
 }
+
+extern "C" int sb200_ppo_kl_apply(void* workspace, float* stats, int stat_slot, double stop_threshold, int* stop_flag,
+                                  void* stream) {
+    SB200_REQUIRE(workspace && stat_slot < SB200_STAT_COUNT);
+    kl_apply_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((LossWs*)workspace, stats, stat_slot, stop_threshold, stop_flag);
+    return sb200_launch_status();
+}
+
+extern "C" size_t sb200_ppo_loss_kl_offset(void) { return offsetof(LossWs, kl_mean); }
 
 extern "C" int sb200_value_loss_f32(const float* values, int64_t ldv, const float* returns, int B, float* dpre,
                                     int64_t ldd, float* stats, void* workspace, void* stream) {

@@ -145,6 +145,8 @@ class PPOLearner(Learner):
         self._gae_ws = torch.zeros(64, dtype=torch.uint8, device=dev)
         self.use_cuda_graph = ops.graphs_enabled()
         self._graph = ops.GraphRunner()
+        self.dp = None
+        self.epoch_history = []
         self._sync_hyper()
         self.last_n_policy_epochs = 0
         self.profile_events = False
@@ -245,8 +247,15 @@ class PPOLearner(Learner):
                   'sb200_reward_filter_f32')
             rewards, scale = self._rewards_f, 1.0
         ev = self._prof_begin()
-        ops.gae_window(rewards, self._values.view(B, n + 1), self._dones, self.gamma, self.lam, norm_adv=self.norm_adv,
+        local_norm = self.norm_adv and self.dp is None
+        ops.gae_window(rewards, self._values.view(B, n + 1), self._dones, self.gamma, self.lam, norm_adv=local_norm,
                        reward_scale=scale, adv=self._adv, ret=self._ret, ws=self._gae_ws)
+        if self.norm_adv and self.dp is not None:                 # statistics of the GLOBAL batch (ppo.py:413-416)
+            L = _lib.lib()
+            check(L.sb200_moments_f32(_ptr(self._adv), B, _ptr(self._moments), ops._stream()), 'sb200_moments_f32')
+            self.dp.sum_(self._moments)
+            check(L.sb200_normalize_f32(_ptr(self._adv), B, _ptr(self._moments), 1e-4, ops._stream()),
+                  'sb200_normalize_f32')
         self._prof_end('gae', ev)
         return self._adv, self._ret
 
@@ -281,9 +290,7 @@ class PPOLearner(Learner):
         mean = tr.forward(self._obs_full, zf_stats=m.z_stats, zf_eps=m.z_eps, rows=B, ldx=(n + 1) * D)
         mode = 0 if self.ppo_mode == 'clip' else 1
         if mode == 1:
-            check(L.sb200_ppo_kl_f32(_ptr(self._ref_pd), 2 * A, _ptr(mean), mean.stride(0), _ptr(m.log_var), B, A,
-                                     _ptr(self._stats), S['KL_PRE'], 0.0, _ptr(stop), _ptr(self._loss_ws), st),
-                  'sb200_ppo_kl_f32')
+            self._kl(mean, S['KL_PRE'], 0.0, stop)
         dlog_var = tr.slabs[0, m.actor.extra_off:m.actor.extra_off + A]
         check(L.sb200_ppo_policy_loss_f32(mode, _ptr(mean), mean.stride(0), _ptr(m.log_var), _ptr(self._actions), n * A,
                                           _ptr(self._adv), _ptr(self._pds), n * 2 * A, _ptr(self._ref_pd), 2 * A, B, A,
@@ -294,9 +301,43 @@ class PPOLearner(Learner):
         tr.step(norm_out=self._stats[S['GN_ACTOR']:S['GN_ACTOR'] + 1], stop_flag=stop)
         # post-step KL(ref || current) (ppo.py:553-556)
         ops.mlp_forward(m.actor, self._obs_full, zf_stats=m.z_stats, zf_eps=m.z_eps, rows=B, ldx=(n + 1) * D, out=self._cur_mean)
-        check(L.sb200_ppo_kl_f32(_ptr(self._ref_pd), 2 * A, _ptr(self._cur_mean), A, _ptr(m.log_var), B, A,
-                                 _ptr(self._stats), S['KL_POST'], 4.0 * self.kl_target, _ptr(self._stop),
+        self._kl(self._cur_mean, S['KL_POST'], 4.0 * self.kl_target, self._stop)
+
+    def _kl(self, mean, slot, threshold, stop):
+        """mean KL(ref || (mean, exp(log_var))) -> stats[slot]; raises the stop flag above `threshold`.  With a
+        data-parallel learner the scalar is averaged over ranks between the two halves."""
+        L = _lib.lib()
+        B, A, m, st = self.batch_size, self.action_dim, self.model, ops._stream()
+        dp = self.dp
+        check(L.sb200_ppo_kl_f32(_ptr(self._ref_pd), 2 * A, _ptr(mean), mean.stride(0), _ptr(m.log_var), B, A,
+                                 _ptr(self._stats), slot, float(threshold), _ptr(stop), 0 if dp is None else 1,
                                  _ptr(self._loss_ws), st), 'sb200_ppo_kl_f32')
+        if dp is not None:
+            dp.mean_(self._kl_scalar)
+            check(L.sb200_ppo_kl_apply(_ptr(self._loss_ws), _ptr(self._stats), slot, float(threshold), _ptr(stop), st),
+                  'sb200_ppo_kl_apply')
+
+    def enable_data_parallel(self, group=None):
+        """Shard the learner's batch over the ranks of `group`: this rank keeps its own actors / replay
+        shard / B local windows; gradients, advantage moments, the KL scalar, z-filter sums and statistics are
+        all-reduced.  Parameters start from rank 0's initialisation."""
+        from ..parallel import LearnerDP
+        if self.use_r_filter:
+            raise NotImplementedError('reward filter + data parallel')
+        self.dp = LearnerDP(group)
+        self.actor_optim.dp = self.dp
+        self.critic_optim.dp = self.dp
+        for mdl in (self.model, self.ref_target_model):
+            self.dp.broadcast_(mdl.actor.params)
+            self.dp.broadcast_(mdl.critic.params)
+            if mdl.z_stats is not None:
+                self.dp.broadcast_(mdl.z_stats)
+        off = _lib.lib().sb200_ppo_loss_kl_offset()
+        self._kl_scalar = self._loss_ws[off:off + 8].view(torch.float64)
+        self._moments = torch.zeros(3, dtype=torch.float64, device=self.device)
+        self._z_delta = torch.zeros_like(self.model.z_stats) if self.model.z_stats is not None else None
+        self._graph = ops.GraphRunner()
+        return self
 
     def _value_epoch(self):
         L = _lib.lib()
@@ -329,7 +370,15 @@ class PPOLearner(Learner):
                                           _ptr(self._stats), _ptr(self._loss_ws), st), 'sb200_ppo_final_stats_f32')
         if self.use_z_filter:
             # step-0 rows only, AFTER the updates (ppo.py:578)
-            ops.zfilter_update(self._obs_full, B, D, (n + 1) * D, m.z_stats)
+            if self.dp is None:
+                ops.zfilter_update(self._obs_full, B, D, (n + 1) * D, m.z_stats)
+            else:
+                self._z_delta.zero_()
+                ops.zfilter_update(self._obs_full, B, D, (n + 1) * D, self._z_delta)
+                self.dp.sum_(self._z_delta)
+                check(L.sb200_add_f32(_ptr(m.z_stats), _ptr(self._z_delta), 2 * D + 1, st), 'sb200_add_f32')
+        if self.dp is not None:
+            self.dp.mean_(self._stats)                            # every slot is a batch mean (or rank-invariant)
 
     def _optimize_device(self):
         """The whole of ppo.py:487-586 as one fixed launch sequence (CUDA-graph body).  The KL early stop
@@ -360,6 +409,7 @@ class PPOLearner(Learner):
         self.last_d2h_bytes = s.nbytes
         n_ep = int(round(float(s[S['EPOCHS']])))
         self.last_n_policy_epochs = n_ep
+        self.epoch_history.append(n_ep + self.epoch_baseline)
         self.kl_record.append(float(s[S['KL_POST']]))
         if self.profile_events:
             self.optimizer_steps_profiled += n_ep + self.epoch_baseline

@@ -263,8 +263,19 @@ class MlpTrainer:
     def step(self, norm_out=None, stop_flag=None):
         L, net = _lib.lib(), self.net
         st = _stream()
-        check(L.sb200_grad_reduce_norm_f32(_ptr(self.slabs), net.size, self.splits, _ptr(self.grad), net.size,
-                                           _ptr(self.ws), _ptr(stop_flag), st), 'sb200_grad_reduce_norm_f32')
+        dp = getattr(self, 'dp', None)
+        if dp is None:
+            check(L.sb200_grad_reduce_norm_f32(_ptr(self.slabs), net.size, self.splits, _ptr(self.grad), net.size,
+                                               1.0, 1, _ptr(self.ws), _ptr(stop_flag), st),
+                  'sb200_grad_reduce_norm_f32')
+        else:
+            # local slabs -> local grad; ONE flat all-reduce; average + global norm + step count
+            check(L.sb200_grad_reduce_norm_f32(_ptr(self.slabs), net.size, self.splits, _ptr(self.grad), net.size,
+                                               1.0, 0, _ptr(self.ws), None, st), 'sb200_grad_reduce_norm_f32')
+            dp.sum_(self.grad)
+            check(L.sb200_grad_reduce_norm_f32(_ptr(self.grad), net.size, 1, _ptr(self.grad), net.size,
+                                               1.0 / dp.world, 1, _ptr(self.ws), _ptr(stop_flag), st),
+                  'sb200_grad_reduce_norm_f32')
         check(L.sb200_clip_adam_f32(_ptr(net.params), _ptr(self.grad), _ptr(self.exp_avg), _ptr(self.exp_avg_sq),
                                     net.size, _ptr(self.lr), 0.9, 0.999, 1e-8, self.weight_decay, self.clip_mode,
                                     self.clip_value, _ptr(self.ws), _ptr(norm_out), _ptr(stop_flag), st),
@@ -281,16 +292,22 @@ class GraphRunner:
 
     def __init__(self):
         self.graph = None
+        self.kernels = 0
 
     def run(self, fn):
+        L = _lib.lib()
         if self.graph is None:
             _lib.ensure_device()
             torch.cuda.synchronize()
+            before = int(L.sb200_launch_counter(0))
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 fn()
+            self.kernels = int(L.sb200_launch_counter(0)) - before    # recorded, not yet executed
+            L.sb200_launch_counter_add(C.c_uint64(-self.kernels & 0xFFFFFFFFFFFFFFFF))
             self.graph = g
         self.graph.replay()
+        L.sb200_launch_counter_add(self.kernels)
 
 
 def graphs_enabled():

@@ -239,6 +239,7 @@ def test_engine_end_to_end_runs_and_is_consistent():
     make_synthetic_env_config(ec, N, 16, 4, seed=3)
     ec.limit_episode_length = 2 * n
     sc.agent.fetch_parameter_interval = 1
+    lc.parameter_publish.min_publish_interval = 0.0        # the reference throttles publishes to one per 0.3 s
     la = SurrealDefaultLauncher(PPOAgent, PPOLearner, FIFOReplay, sc, ec, lc)
     agent, replay, learner = la.setup_engine()
     # like the reference, PPO's first publish only happens after exp_interval experiences (ppo.py:633): until then
