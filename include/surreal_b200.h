@@ -242,7 +242,8 @@ int sb200_ddpg_noise_f32(const float* mean, int64_t ldm, const float* sigma, con
                          float* action, void* stream);
 /* Synthetic device-resident environment of the benchmark configs: s' = tanh(Ws s + Wa a) + 0.01 xi,
  * r = -|s|^2/D + 0.1 xi', done at max_steps (MaxStepWrapper, env/wrapper.py:142-163) with auto-reset.
- * state [N,D] is updated in place to what the agent observes next; obs_next is the true successor. */
+ * state [N,D] is updated in place to what the agent observes next; obs_next is the true successor.
+ * Ws / Wa are passed transposed (k-major): WsT [D][D] with WsT[k][d] = Ws[d][k], WaT [A][D]. */
 int sb200_synth_env_step_f32(float* state, const float* action, const float* Ws, const float* Wa, int N,
                              int D, int A, int max_steps, int* ep_step, uint64_t seed,
                              const uint64_t* step_counter, float* obs_next, float* reward, float* done,

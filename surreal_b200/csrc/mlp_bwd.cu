@@ -32,8 +32,10 @@ __global__ void __launch_bounds__(SB200_THREADS) bwd_dx_kernel(const float* __re
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
 
-    for (int n0 = 0; n0 < N; n0 += RK) {
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+    // global -> registers for chunk c+1 overlaps the FFMA work on chunk c (latency-bound at these sizes)
+    auto fetch = [&](int n0, float4& a, float4& b) {
+        a = make_float4(0.f, 0.f, 0.f, 0.f);
+        b = make_float4(0.f, 0.f, 0.f, 0.f);
         const int n = n0 + lc;
         if (m0 + lr < M && n < N) {
             const float* src = dY + (long long)(m0 + lr) * ldy + n;
@@ -46,9 +48,14 @@ __global__ void __launch_bounds__(SB200_THREADS) bwd_dx_kernel(const float* __re
             }
         }
         if (k0 + lr < K && n < ldw) b = *reinterpret_cast<const float4*>(W + (long long)(k0 + lr) * ldw + n);
+    };
+    float4 a, b;
+    fetch(0, a, b);
+    for (int n0 = 0; n0 < N; n0 += RK) {
         As[lc + 0][lr] = a.x; As[lc + 1][lr] = a.y; As[lc + 2][lr] = a.z; As[lc + 3][lr] = a.w;
         Bs[lc + 0][lr] = b.x; Bs[lc + 1][lr] = b.y; Bs[lc + 2][lr] = b.z; Bs[lc + 3][lr] = b.w;
         __syncthreads();
+        if (n0 + RK < N) fetch(n0 + RK, a, b);
 #pragma unroll
         for (int r = 0; r < RK; ++r) {
             const float4 av = *reinterpret_cast<const float4*>(&As[r][ty * 4]);
@@ -98,8 +105,9 @@ __global__ void __launch_bounds__(SB200_THREADS) bwd_dw_kernel(const float* __re
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
 
-    for (int mm = mb; mm < me; mm += RK) {
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto fetch = [&](int mm, float4& a, float4& b) {
+        a = make_float4(0.f, 0.f, 0.f, 0.f);
+        b = make_float4(0.f, 0.f, 0.f, 0.f);
         const int m = mm + lr;
         if (m < me) {
             const int k = k0 + lc;
@@ -125,9 +133,14 @@ __global__ void __launch_bounds__(SB200_THREADS) bwd_dw_kernel(const float* __re
                 }
             }
         }
+    };
+    float4 a, b;
+    fetch(mb, a, b);
+    for (int mm = mb; mm < me; mm += RK) {
         *reinterpret_cast<float4*>(&As[lr][lc]) = a;
         *reinterpret_cast<float4*>(&Bs[lr][lc]) = b;
         __syncthreads();
+        if (mm + RK < me) fetch(mm + RK, a, b);
 #pragma unroll
         for (int r = 0; r < RK; ++r) {
             const float4 av = *reinterpret_cast<const float4*>(&As[r][ty * 4]);

@@ -14,8 +14,9 @@
 
 namespace {
 
-constexpr int BK = 16;
 constexpr int PASS_N = 256;
+// k-chunk rows per cp.async stage: 16 for the big-tile (compute-bound) variants, 64 for the small-row-tile
+// variants whose wall time is a chain of L2 round trips (fewer, larger stages = fewer exposed latencies).
 
 struct FwdParams {
     const float* x;
@@ -40,6 +41,7 @@ struct FwdParams {
     float* save[SB200_MAX_LAYERS];
     long long ld_save[SB200_MAX_LAYERS];
     int ldh;
+    int scratch_floats;
 };
 
 __host__ __device__ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -50,7 +52,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
-template <int TM>
+template <int TM, int BK>
 __global__ void __launch_bounds__(SB200_THREADS, 1) mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
     constexpr int BM = 8 * TM;
     extern __shared__ __align__(16) float smem[];
@@ -217,6 +219,15 @@ __global__ void __launch_bounds__(SB200_THREADS, 1) mlp_fwd_kernel(const __grid_
         } else {
             // ------------------------------ narrow path: N <= 32 ------------------------------------
             // warp ty owns rows ty*TM..; lanes split k; 8 outputs at a time, shuffle-reduced.
+            // The head's weights (K x ldw floats, e.g. 8 KB) are staged once per CTA in the (idle) W stage.
+            const float* Wn = W;
+            if (K * ldw <= 2 * BK * PASS_N) {
+                for (int f = tid; f < (K * ldw) / 4; f += SB200_THREADS) cp_async16(Ws + f * 4, W + f * 4, 16);
+                cp_async_commit();
+                cp_async_wait<0>();
+                __syncthreads();
+                Wn = Ws;
+            }
             for (int i = 0; i < TM; ++i) {
                 const int m = ty * TM + i;
                 const long long r = row0 + m;
@@ -228,7 +239,7 @@ __global__ void __launch_bounds__(SB200_THREADS, 1) mlp_fwd_kernel(const __grid_
                     const bool second = (n8 + 4 < ldw);
                     for (int k = tx; k < K; k += 32) {
                         const float hv = hrow[k];
-                        const float* wr = W + (long long)k * ldw + n8;
+                        const float* wr = Wn + (long long)k * ldw + n8;
                         const float4 w0 = *reinterpret_cast<const float4*>(wr);
                         s[0] = fmaf(hv, w0.x, s[0]);
                         s[1] = fmaf(hv, w0.y, s[1]);
@@ -280,14 +291,192 @@ __global__ void __launch_bounds__(SB200_THREADS, 1) mlp_fwd_kernel(const __grid_
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// Skinny variant for small batches (rows <= ~2K: one env step of all actors, one learner minibatch).
+// There a forward is a chain of latency-bound steps, and the big-tile mapping re-reads every weight fragment
+// from shared memory in all 8 warps.  Here a CTA owns R = 8 rows and thread t owns output column n0 + t:
+// weights are read exactly once per CTA, coalesced (one 128-byte line per warp per k), straight from L2 with
+// a register double buffer of 8 k-steps (no shared-memory staging, no barriers inside a layer); the 8 input
+// rows are warp-broadcast LDS.128 along k.  Same ascending-k FFMA order as the tiled kernel => identical bits.
+constexpr int SK_R = 8;
+constexpr int SK_U = 8;      // k-steps per register stage
+
+__global__ void __launch_bounds__(SB200_THREADS, 2) mlp_fwd_skinny_kernel(const __grid_constant__ FwdParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int ldh = p.ldh;
+    float* Hin = smem;
+    float* Hout = smem + SK_R * ldh;
+    float* Wsc = smem + 2 * SK_R * ldh;                 // scratch: z-filter columns, then the narrow head's weights
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const long long row0 = (long long)blockIdx.x * SK_R;
+    const int K0 = p.dims[0];
+    if (p.zf != nullptr) {
+        const float cnt = p.zf[2 * K0];
+        for (int k = tid; k < K0; k += SB200_THREADS) {
+            const float mean = p.zf[k] / cnt;
+            const float var = p.zf[K0 + k] / cnt - mean * mean;
+            Wsc[k] = mean;
+            Wsc[K0 + k] = fmaxf(sqrtf(var), p.zf_eps);
+        }
+        __syncthreads();
+    }
+    {
+        const int in_w = K0 + (p.aux_layer == 0 ? p.aux_dim : 0);
+        const int in_wp = round_up(in_w, SK_U);
+        for (int idx = tid; idx < SK_R * in_wp; idx += SB200_THREADS) {
+            const int m = idx / in_wp, k = idx - m * in_wp;
+            const long long r = row0 + m;
+            float v = 0.0f;
+            if (r < p.rows) {
+                if (k < K0) {
+                    const float* src;
+                    if (p.win_n > 0) {
+                        const long long b = r / (p.win_n + 1);
+                        const int kk = (int)(r - b * (p.win_n + 1));
+                        src = (kk < p.win_n) ? p.x + (b * p.win_n + kk) * p.ldx : p.x_next + b * p.ldx;
+                    } else {
+                        src = p.x + r * p.ldx;
+                    }
+                    v = src[k];
+                    if (p.zf != nullptr) v = fminf(fmaxf((v - Wsc[k]) / Wsc[K0 + k], -5.0f), 5.0f);
+                } else if (k < in_w) {
+                    v = p.aux[r * p.aux_ld + (k - K0)];
+                }
+            }
+            Hin[m * ldh + k] = v;
+            if (p.save_x != nullptr && r < p.rows && k < K0) p.save_x[r * p.ld_save_x + k] = v;
+        }
+    }
+    __syncthreads();
+
+    for (int l = 0; l < p.n_layers; ++l) {
+        const int K = p.dims[l] + (p.aux_layer == l ? p.aux_dim : 0);
+        const int N = p.dims[l + 1];
+        const float* __restrict__ W = p.W[l];
+        const float* __restrict__ bias = p.b[l];
+        const int ldw = p.ldw[l];
+        const int act = p.act[l];
+        const bool last = (l == p.n_layers - 1);
+        float* sv = p.save[l];
+        const long long lds = p.ld_save[l];
+        if (N > 32) {
+            const int Kp = round_up(K, SK_U);
+            for (int n0 = 0; n0 < N; n0 += SB200_THREADS) {
+                const int n = n0 + tid;
+                const bool on = n < N;
+                float acc[SK_R];
+#pragma unroll
+                for (int r = 0; r < SK_R; ++r) acc[r] = 0.0f;
+                const float* wp = W + (on ? n : 0);
+                float w[SK_U], wn[SK_U];
+#pragma unroll
+                for (int u = 0; u < SK_U; ++u) w[u] = (on && u < K) ? __ldg(wp + (long long)u * ldw) : 0.0f;
+                for (int k0 = 0; k0 < Kp; k0 += SK_U) {
+#pragma unroll
+                    for (int u = 0; u < SK_U; ++u) {       // next stage in flight while this one is consumed
+                        const int k = k0 + SK_U + u;
+                        wn[u] = (on && k < K) ? __ldg(wp + (long long)k * ldw) : 0.0f;
+                    }
+#pragma unroll
+                    for (int r = 0; r < SK_R; ++r) {
+                        const float4 a0 = *reinterpret_cast<const float4*>(Hin + r * ldh + k0);
+                        const float4 a1 = *reinterpret_cast<const float4*>(Hin + r * ldh + k0 + 4);
+                        float t = acc[r];
+                        t = fmaf(a0.x, w[0], t); t = fmaf(a0.y, w[1], t); t = fmaf(a0.z, w[2], t); t = fmaf(a0.w, w[3], t);
+                        t = fmaf(a1.x, w[4], t); t = fmaf(a1.y, w[5], t); t = fmaf(a1.z, w[6], t); t = fmaf(a1.w, w[7], t);
+                        acc[r] = t;
+                    }
+#pragma unroll
+                    for (int u = 0; u < SK_U; ++u) w[u] = wn[u];
+                }
+                if (on) {
+                    const float bv = bias[n];
+#pragma unroll
+                    for (int r = 0; r < SK_R; ++r) {
+                        const float o = apply_act(acc[r] + bv, act);
+                        if (!last) Hout[r * ldh + n] = o;
+                        const long long rr = row0 + r;
+                        if (sv != nullptr && rr < p.rows) sv[rr * lds + n] = o;
+                    }
+                }
+            }
+        } else {
+            // narrow head: warp ty owns row ty; weights staged once in shared memory
+            const float* Wn = W;
+            __syncthreads();                               // Wsc may still hold z-filter columns in use
+            if (K * ldw <= p.scratch_floats) {
+                for (int f = tid; f < (K * ldw) / 4; f += SB200_THREADS) cp_async16(Wsc + f * 4, W + f * 4, 16);
+                cp_async_commit();
+                cp_async_wait<0>();
+                __syncthreads();
+                Wn = Wsc;
+            }
+            const int m = ty;                              // SK_R == number of warps
+            const long long r = row0 + m;
+            const float* hrow = Hin + m * ldh;
+            for (int n8 = 0; n8 < N; n8 += 8) {
+                float s8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s8[j] = 0.0f;
+                const bool second = (n8 + 4 < ldw);
+                for (int k = tx; k < K; k += 32) {
+                    const float hv = hrow[k];
+                    const float* wr = Wn + (long long)k * ldw + n8;
+                    const float4 w0 = *reinterpret_cast<const float4*>(wr);
+                    s8[0] = fmaf(hv, w0.x, s8[0]); s8[1] = fmaf(hv, w0.y, s8[1]);
+                    s8[2] = fmaf(hv, w0.z, s8[2]); s8[3] = fmaf(hv, w0.w, s8[3]);
+                    if (second) {
+                        const float4 w1 = *reinterpret_cast<const float4*>(wr + 4);
+                        s8[4] = fmaf(hv, w1.x, s8[4]); s8[5] = fmaf(hv, w1.y, s8[5]);
+                        s8[6] = fmaf(hv, w1.z, s8[6]); s8[7] = fmaf(hv, w1.w, s8[7]);
+                    }
+                }
+                float mine = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float t = warp_sum(s8[j]);
+                    if (tx == j) mine = t;
+                }
+                const int n = n8 + tx;
+                if (tx < 8 && n < N) {
+                    const float o = apply_act(mine + bias[n], act);
+                    if (!last) Hout[m * ldh + n] = o;
+                    if (sv != nullptr && r < p.rows) sv[r * lds + n] = o;
+                }
+            }
+        }
+        __syncthreads();
+        if (!last) {
+            const int auxd = (p.aux_layer == l + 1) ? p.aux_dim : 0;
+            const int wp2 = round_up(N + auxd, SK_U);
+            const int span = wp2 - N;
+            if (span > 0) {
+                for (int idx = tid; idx < SK_R * span; idx += SB200_THREADS) {
+                    const int m = idx / span, c = N + (idx - m * span);
+                    const long long r = row0 + m;
+                    float v = 0.0f;
+                    if (c < N + auxd && r < p.rows) v = p.aux[r * p.aux_ld + (c - N)];
+                    Hout[m * ldh + c] = v;
+                }
+            }
+            __syncthreads();
+            float* t = Hin;
+            Hin = Hout;
+            Hout = t;
+        }
+    }
+}
+
 constexpr size_t SMEM_BUDGET = 200 * 1024;
 
-template <int TM>
-int launch_fwd(const FwdParams& p, cudaStream_t st) {
+template <int TM, int BK>
+int launch_fwd(FwdParams p, int maxw, cudaStream_t st) {
     constexpr int BM = 8 * TM;
+    p.ldh = round_up(maxw, BK) + 4;
     const size_t smem = (size_t)(2 * BM * p.ldh + 2 * BK * PASS_N) * sizeof(float);
     const long long grid = (p.rows + BM - 1) / BM;
-    mlp_fwd_kernel<TM><<<(unsigned)grid, SB200_THREADS, smem, st>>>(p);
+    mlp_fwd_kernel<TM, BK><<<(unsigned)grid, SB200_THREADS, smem, st>>>(p);
     return sb200_launch_status();
 }
 
@@ -295,10 +484,13 @@ int launch_fwd(const FwdParams& p, cudaStream_t st) {
 
 // called once from sb200_init(): opt every instantiation into the full dynamic shared-memory budget
 int sb200_mlp_fwd_init() {
-    SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
-    SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
-    SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
-    SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
+    SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
+    SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
+    SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
+    SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
+    SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
+    SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
     return SB200_OK;
 }
 
@@ -309,6 +501,8 @@ extern "C" int sb200_mlp_forward_f32(const sb200_mlp* net, const sb200_zfilter* 
     SB200_REQUIRE(in->rows >= 0 && in->x != nullptr);
     if (in->rows == 0) return SB200_OK;
     FwdParams p;
+    p.scratch_floats = 0;
+    p.ldh = 0;
     p.x = in->x;
     p.x_next = in->x_next;
     p.ldx = in->ldx;
@@ -347,15 +541,35 @@ extern "C" int sb200_mlp_forward_f32(const sb200_mlp* net, const sb200_zfilter* 
             if (w > maxw) maxw = w;
         }
     }
-    p.ldh = round_up(maxw, BK) + 4;
     const size_t budget = SMEM_BUDGET;
-    auto fits = [&](int bm) { return (size_t)(2 * bm * p.ldh + 2 * BK * PASS_N) * 4 <= budget; };
-    SB200_REQUIRE(fits(8));
+    auto fits = [&](int bm, int bk) {
+        return (size_t)(2 * bm * (round_up(maxw, bk) + 4) + 2 * bk * PASS_N) * 4 <= budget;
+    };
+    SB200_REQUIRE(fits(8, 16));
     cudaStream_t st = (cudaStream_t)stream;
-    // largest row tile that still yields >= ~1 CTA per SM; small batches fall back to 16-row tiles
+    // small batches: skinny kernel (8 rows per CTA, weights streamed once per CTA from L2)
+    if (p.rows <= 2048) {
+        p.ldh = round_up(maxw, SK_U) + 4;
+        int scratch = 2 * net->dims[0];
+        for (int l = 0; l < net->n_layers; ++l)
+            if (net->dims[l + 1] <= 32) {
+                const int kl = (net->dims[l] + (p.aux_layer == l ? p.aux_dim : 0)) * net->ldw[l];
+                if (kl > scratch && kl <= 16384) scratch = kl;
+            }
+        p.scratch_floats = scratch;
+        const size_t smem = (size_t)(2 * SK_R * p.ldh + scratch) * sizeof(float);
+        if (smem <= 100 * 1024) {
+            const long long grid = (p.rows + SK_R - 1) / SK_R;
+            mlp_fwd_skinny_kernel<<<(unsigned)grid, SB200_THREADS, smem, st>>>(p);
+            return sb200_launch_status();
+        }
+    }
+    // largest row tile that still yields >= ~1 CTA per SM; small batches take 16-row tiles with 64-row W stages
     const long long want = 120;
-    if (fits(64) && (p.rows + 63) / 64 >= want) return launch_fwd<8>(p, st);
-    if (fits(32) && (p.rows + 31) / 32 >= want) return launch_fwd<4>(p, st);
-    if (fits(16)) return launch_fwd<2>(p, st);
-    return launch_fwd<1>(p, st);
+    if (fits(64, 16) && (p.rows + 63) / 64 >= want) return launch_fwd<8, 16>(p, maxw, st);
+    if (fits(32, 16) && (p.rows + 31) / 32 >= want) return launch_fwd<4, 16>(p, maxw, st);
+    if (fits(16, 64)) return launch_fwd<2, 64>(p, maxw, st);
+    if (fits(16, 16)) return launch_fwd<2, 16>(p, maxw, st);
+    if (fits(8, 64)) return launch_fwd<1, 64>(p, maxw, st);
+    return launch_fwd<1, 16>(p, maxw, st);
 }

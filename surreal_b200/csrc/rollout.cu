@@ -25,36 +25,38 @@ __global__ void __launch_bounds__(RT) ppo_sample_kernel(const float* __restrict_
                                                         const int* __restrict__ stage_pos,
                                                         float* __restrict__ stage_act,
                                                         float* __restrict__ stage_pd, int n_step) {
-    const int i = blockIdx.x * RT + threadIdx.x;
-    if (i >= N) return;
+    const int groups = (A + 3) >> 2;                      // one thread per (actor, 4 action dims)
+    const int t = blockIdx.x * RT + threadIdx.x;
+    if (t >= N * groups) return;
+    const int i = t / groups, j0 = (t - i * groups) * 4;
     const float sc = (log_noise != nullptr) ? expf(log_noise[i]) : 1.0f;
     const unsigned long long ctr = (step_ctr != nullptr) ? *step_ctr : 0ull;
     const int p = (stage_pos != nullptr) ? stage_pos[i] : 0;
-    for (int j0 = 0; j0 < A; j0 += 4) {
-        float z[4] = {0.f, 0.f, 0.f, 0.f};
-        if (!deterministic && eps == nullptr) {
-            const Philox4 r = philox4x32_10(seed, ctr, ((unsigned long long)i << 16) | (unsigned long long)(j0 >> 2));
-            const float2 a = box_muller(r.x, r.y), b = box_muller(r.z, r.w);
-            z[0] = a.x; z[1] = a.y; z[2] = b.x; z[3] = b.y;
+    float z[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!deterministic && eps == nullptr) {
+        const Philox4 r = philox4x32_10(seed, ctr, ((unsigned long long)i << 16) | (unsigned long long)(j0 >> 2));
+        const float2 a = box_muller(r.x, r.y), b = box_muller(r.z, r.w);
+        z[0] = a.x; z[1] = a.y; z[2] = b.x; z[3] = b.y;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int j = j0 + c;
+        if (j >= A) break;
+        const float mu = mean[(long long)i * ldm + j];
+        const float sd = __fmul_rn(expf(log_var[j]), sc);
+        float a = mu;
+        if (!deterministic) {
+            const float e = (eps != nullptr) ? eps[(long long)i * A + j] : z[c];
+            a = __fadd_rn(__fmul_rn(e, sd), mu);
         }
-        for (int c = 0; c < 4 && j0 + c < A; ++c) {
-            const int j = j0 + c;
-            const float mu = mean[(long long)i * ldm + j];
-            const float sd = __fmul_rn(expf(log_var[j]), sc);
-            float a = mu;
-            if (!deterministic) {
-                const float e = (eps != nullptr) ? eps[(long long)i * A + j] : z[c];
-                a = __fadd_rn(__fmul_rn(e, sd), mu);
-            }
-            a = fminf(fmaxf(a, -1.0f), 1.0f);
-            action[(long long)i * A + j] = a;
-            pd[(long long)i * 2 * A + j] = mu;
-            pd[(long long)i * 2 * A + A + j] = sd;
-            if (stage_act != nullptr) {
-                stage_act[((long long)i * n_step + p) * A + j] = a;
-                stage_pd[((long long)i * n_step + p) * 2 * A + j] = mu;
-                stage_pd[((long long)i * n_step + p) * 2 * A + A + j] = sd;
-            }
+        a = fminf(fmaxf(a, -1.0f), 1.0f);
+        action[(long long)i * A + j] = a;
+        pd[(long long)i * 2 * A + j] = mu;
+        pd[(long long)i * 2 * A + A + j] = sd;
+        if (stage_act != nullptr) {
+            stage_act[((long long)i * n_step + p) * A + j] = a;
+            stage_pd[((long long)i * n_step + p) * 2 * A + j] = mu;
+            stage_pd[((long long)i * n_step + p) * 2 * A + A + j] = sd;
         }
     }
 }
@@ -93,7 +95,8 @@ __global__ void __launch_bounds__(RT) ddpg_noise_kernel(const float* __restrict_
 // Synthetic environment of SURVEY §8(d) cfg 2/3/5, batched and device-resident:
 //   s' = tanh(Ws s + Wa a) + 0.01*xi,   r = -|s|^2 / D + 0.1*xi',   done when the episode reaches
 //   `max_steps` (MaxStepWrapper, env/wrapper.py:142-163); on done the state is re-drawn ~ N(0,1).
-// One block per 4 actors; Ws/Wa are read through L1/L2 (18 KB).  obs_next = the true successor (terminal
+// One block per 4 actors; the weights are passed TRANSPOSED (WsT [D][D], WaT [A][D]: k-major) so that the
+// threads of a warp read consecutive addresses; they stay L1/L2-resident (18 KB).  obs_next = the true successor (terminal
 // when done), state = what the agent observes next (reset when done).
 __global__ void __launch_bounds__(RT) synth_env_step_kernel(float* __restrict__ state, const float* __restrict__ action,
                                                             const float* __restrict__ Ws, const float* __restrict__ Wa,
@@ -132,11 +135,11 @@ __global__ void __launch_bounds__(RT) synth_env_step_kernel(float* __restrict__ 
         const int q = idx / D, d = idx - q * D;
         const int i = a0 + q;
         if (i >= N) continue;
-        float acc = 0.0f;
-        const float* ws = Ws + (long long)d * D;
-        for (int k = 0; k < D; ++k) acc = fmaf(ws[k], s_s[q * D + k], acc);
-        const float* wa = Wa + (long long)d * A;
-        for (int k = 0; k < A; ++k) acc = fmaf(wa[k], s_a[q * A + k], acc);
+        float acc = 0.0f;                                   // WsT / WaT are [k][d]: coalesced across d
+#pragma unroll 8
+        for (int k = 0; k < D; ++k) acc = fmaf(__ldg(Ws + (long long)k * D + d), s_s[q * D + k], acc);
+#pragma unroll 4
+        for (int k = 0; k < A; ++k) acc = fmaf(__ldg(Wa + (long long)k * D + d), s_a[q * A + k], acc);
         const Philox4 r = philox4x32_10(seed ^ 0x5851F42D4C957F2Dull, ctr, ((unsigned long long)i << 20) | (unsigned long long)d);
         const float2 g = box_muller(r.x, r.y);
         const float nxt = tanhf(acc) + 0.01f * g.x;
@@ -338,7 +341,7 @@ extern "C" int sb200_ppo_sample_f32(const float* mean, int64_t ldm, const float*
                                     float* stage_act, float* stage_pd, int n_step, void* stream) {
     SB200_REQUIRE(mean && log_var && action && pd && N >= 1 && A >= 1 && ldm >= A);
     SB200_REQUIRE(stage_act == nullptr || (stage_pos != nullptr && stage_pd != nullptr && n_step >= 1));
-    ppo_sample_kernel<<<(N + RT - 1) / RT, RT, 0, (cudaStream_t)stream>>>(
+    ppo_sample_kernel<<<(N * ((A + 3) / 4) + RT - 1) / RT, RT, 0, (cudaStream_t)stream>>>(
         mean, ldm, log_var, log_noise, eps, N, A, deterministic, (unsigned long long)seed,
         (const unsigned long long*)step_counter, action, pd, stage_pos, stage_act, stage_pd, n_step);
     return sb200_launch_status();

@@ -34,6 +34,7 @@ class SyntheticEnv:
         scale = 1.0 / (obs_dim ** 0.5)
         self.Ws = (torch.randn(obs_dim, obs_dim, generator=g) * scale).to(self.device)
         self.Wa = (torch.randn(obs_dim, action_dim, generator=g) * scale).to(self.device)
+        self.WsT, self.WaT = self.Ws.t().contiguous(), self.Wa.t().contiguous()     # kernel layout (k-major)
         self._g = torch.Generator().manual_seed(self.seed + 1)
         self.state = torch.zeros(num_envs, obs_dim, device=self.device)
         self.ep_step = torch.zeros(num_envs, dtype=torch.int32, device=self.device)
@@ -60,7 +61,7 @@ class SyntheticEnv:
         if isinstance(action, tuple):
             action = action[0]
         check(_lib.lib().sb200_synth_env_step_f32(
-            _p(self.state), _p(action), _p(self.Ws), _p(self.Wa), self.N, self.D, self.A, self.max_steps,
+            _p(self.state), _p(action), _p(self.WsT), _p(self.WaT), self.N, self.D, self.A, self.max_steps,
             _p(self.ep_step), self.seed + 7, _p(self.step_counter), _p(self.obs_next), _p(self.reward), _p(self.done),
             _stream()), 'sb200_synth_env_step_f32')
         return {'low_dim': {'flat_inputs': self.state}}, self.reward, self.done, {'obs_next': self.obs_next}

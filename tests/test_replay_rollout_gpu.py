@@ -262,3 +262,29 @@ def test_engine_end_to_end_runs_and_is_consistent():
     st = learner.tensorplex.last
     for k in ['_pol_kl', '_val_loss', '_surr_loss', '_entropy', 'grad_norm_actor', 'grad_norm_critic']:
         assert k in st and np.isfinite(st[k])
+
+
+def test_synthetic_env_dynamics_and_episode_cap():
+    """s' = tanh(Ws s + Wa a) + 0.01 xi, r = -|s|^2/D + 0.1 xi', done at the episode cap with auto-reset."""
+    from surreal_b200.env import SyntheticEnv
+    N, D, A, L = 257, 24, 5, 4
+    env = SyntheticEnv(N, D, A, limit_episode_length=L, seed=9)
+    obs, _ = env.reset()
+    s = obs['low_dim']['flat_inputs'].clone()
+    for t in range(1, 2 * L + 1):
+        a = torch.rand(N, A, device=DEV) * 2 - 1
+        obs2, r, d, info = env.step(a)
+        expect = torch.tanh(s @ env.Ws.t() + a @ env.Wa.t())
+        assert float((info['obs_next'] - expect).abs().max()) < 0.01 * 6
+        assert float((r - (-(s * s).sum(1) / D)).abs().max()) < 0.1 * 6
+        is_done = (t % L == 0)
+        assert bool((d == (1.0 if is_done else 0.0)).all())
+        nxt = obs2['low_dim']['flat_inputs']
+        if is_done:
+            assert abs(float(nxt.mean())) < 0.1 and abs(float(nxt.std()) - 1.0) < 0.1      # fresh N(0,1) states
+            assert bool((env.ep_step == 0).all())
+        else:
+            assert torch.equal(nxt, info['obs_next'])
+        s = nxt.clone()
+    noise = (info['obs_next'] - expect)
+    assert 0.005 < float(noise.std()) < 0.02
