@@ -337,6 +337,9 @@ class PPOLearner(Learner):
         self._moments = torch.zeros(3, dtype=torch.float64, device=self.device)
         self._z_delta = torch.zeros_like(self.model.z_stats) if self.model.z_stats is not None else None
         self._graph = ops.GraphRunner()
+        # NCCL collectives inside a captured graph are supported by torch, but stay opt-in until proven on the box
+        import os
+        self.dp_graph = os.environ.get('SB200_DP_GRAPH', '0') == '1'
         return self
 
     def _value_epoch(self):
@@ -394,7 +397,7 @@ class PPOLearner(Learner):
         """ppo.py:487-586."""
         B, n, A, D = self.batch_size, self.n_step, self.action_dim, self.low_dim
         m = self.model
-        if self.use_cuda_graph and not self.profile_events:
+        if self.use_cuda_graph and not self.profile_events and (self.dp is None or self.dp_graph):
             self._graph.run(self._optimize_device)
         elif self.use_cuda_graph:
             self._optimize_device()                               # same sequence, eager (per-kernel event timing)
