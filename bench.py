@@ -176,27 +176,49 @@ def run_ours(args):
     opt_steps = sum(learner.epoch_history[-args.steps:]) if hasattr(learner, 'epoch_history') else None
     # roofline of the dominant kernel (fused critic pass) and of the GAE kernel: separate, untimed-for-throughput
     # pass that runs learn() EAGERLY with CUDA events around those two launches (events cannot sit inside a graph)
-    learner.profile_events = True
-    for _ in range(5):
+    _lib.profile_calls(True)
+    learner.profile_events = True                                 # -> eager learn(), same launch sequence
+    os.environ['SB200_CUDA_GRAPH'] = '0'                          # -> eager rollout
+    n_prof = 3
+    for _ in range(n_prof):
         flush.fill_(1.0)
         one_step()
+    os.environ['SB200_CUDA_GRAPH'] = '1'
     learner.profile_events = False
-    critic_ms = learner.pop_profile('critic_pass')
-    gae_ms = learner.pop_profile('gae')
-    rows = N * (T + 1)
-    flops = 2.0 * rows * (D * HIDDEN[0] + HIDDEN[0] * HIDDEN[1] + HIDDEN[1] * 1)
+    calls = _lib.profile_calls(False)
+    learner.pop_profile('critic_pass'), learner.pop_profile('gae')
+    per_step = {k: (c / n_prof, ms / n_prof, ms / c) for k, (c, ms) in calls.items()}
+    total_kernel_ms = sum(v[1] for v in per_step.values())
+    breakdown = [{'call': k, 'launches_per_step': round(v[0], 1), 'ms_per_step': round(v[1], 4), 'avg_us': round(v[2] * 1e3, 2),
+                  'share': round(v[1] / total_kernel_ms, 4)}
+                 for k, v in sorted(per_step.items(), key=lambda kv: -kv[1][1])]
     peaks = load_peaks()
-    crit_avg = sum(critic_ms) / max(len(critic_ms), 1)
-    gae_avg = sum(gae_ms) / max(len(gae_ms), 1)
-    crit_tflops = flops / (crit_avg / 1e3) / 1e12 if crit_avg else None
+    rows = N * (T + 1)
+    w_params = D * HIDDEN[0] + HIDDEN[0] * HIDDEN[1]
+
+    def mlp_roof(key, nrows, out_dim, kernel):
+        if key not in per_step:
+            return None
+        avg_ms = per_step[key][2]
+        flop = 2.0 * nrows * (w_params + HIDDEN[1] * out_dim)
+        byts = nrows * (D * 4 + out_dim * 4) + (w_params + HIDDEN[1] * out_dim) * 4
+        ach = flop / (avg_ms / 1e3) / 1e12
+        return {'kernel': kernel, 'bound': 'tensor', 'achieved': ach, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
+                'frac': ach / peaks['bf16_tflops'], 'traffic': None, 'avg_ms': avg_ms, 'launches_per_step': per_step[key][0],
+                'share_of_step_kernel_time': per_step[key][1] / total_kernel_ms, 'algorithmic_flop': flop,
+                'algorithmic_bytes': byts, 'achieved_gbs': byts / (avg_ms / 1e3) / 1e9, 'peak_source': peaks['source'],
+                'note': 'fp32-accurate FFMA path (the 1e-5 parity bar rules out plain TF32); dense-bf16 tensor peak is the '
+                        'mandated denominator, the chip\'s fp32 FFMA ceiling is ~72 TFLOP/s'}
+    roof_small = mlp_roof('sb200_mlp_forward_f32[rows=%d]' % N, N, A, 'mlp_fwd_skinny_kernel (actor / learner forward on %d rows)' % N)
+    roof_critic = mlp_roof('sb200_mlp_forward_f32[rows=%d]' % rows, rows, 1,
+                           'mlp_fwd_kernel<8,16> (fused critic pass over %d rows)' % rows)
+    cands = [r for r in (roof_small, roof_critic) if r is not None]
+    roofline = max(cands, key=lambda r: r['share_of_step_kernel_time']) if cands else None
+    if roof_critic is not None and roofline is roof_critic:
+        roofline['traffic'] = 34260992        # dram__bytes_read+write of profiles/r01a_prof_critic.md (one ncu --set full capture)
+    gae_key = 'sb200_gae_window_f32'
+    gae_avg = per_step[gae_key][2] if gae_key in per_step else None
     gae_bytes = N * ((3 * T + 1) * 4 + 8)
-    roofline = {'kernel': 'mlp_fwd_kernel<8> (fused critic pass: z-filter + 3 Linear over %d rows)' % rows,
-                'bound': 'tensor', 'achieved': crit_tflops, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
-                'frac': (crit_tflops / peaks['bf16_tflops']) if crit_tflops else None, 'traffic': None,
-                'avg_ms': crit_avg, 'algorithmic_flop': flops, 'algorithmic_bytes': rows * (D * 4 + 4),
-                'peak_source': peaks['source'],
-                'note': 'fp32-accurate SIMT FFMA path (parity bar 1e-5 rules out plain TF32); the dense-bf16 tensor '
-                        'peak is the mandated denominator, the fp32 FFMA ceiling of the chip is ~72 TFLOP/s'}
     roofline_gae = {'kernel': 'gae_full_kernel', 'bound': 'hbm', 'achieved': gae_bytes / (gae_avg / 1e3) / 1e9 if gae_avg else None,
                     'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'avg_ms': gae_avg, 'algorithmic_bytes': gae_bytes,
                     'frac': (gae_bytes / (gae_avg / 1e3) / 1e9 / peaks['hbm_gbs']) if gae_avg else None,
@@ -223,7 +245,8 @@ def run_ours(args):
             'learner_updates_per_sec': args.steps / (total_ms / 1e3),
             'optimizer_steps_per_sec': (opt_steps * world / (total_ms / 1e3)) if opt_steps else None,
             'gpu_launches': per_step_launches * args.steps, 'gpu_launches_per_step': per_step_launches,
-            'clocks': clk, 'roofline': roofline, 'roofline_gae': roofline_gae, 'e2e': e2e,
+            'clocks': clk, 'roofline': roofline, 'roofline_critic_pass': roof_critic, 'roofline_gae': roofline_gae,
+            'kernel_breakdown': breakdown[:12], 'e2e': e2e,
             'cpu_baseline': cpu_baseline, 'wall_s': t_wall,
         }
         print(json.dumps(out))

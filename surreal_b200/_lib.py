@@ -111,8 +111,56 @@ def exported_symbols():
     return list(_declare(lib()).keys())
 
 
+class _ProfilingProxy:
+    """Wraps every C-ABI call between two CUDA events on the current stream (bench.py's live per-kernel timing;
+    only meaningful for eager launches -- events cannot sit inside a captured graph)."""
+
+    def __init__(self, real):
+        self._real = real
+        self.records = {}
+
+    def __getattr__(self, name):
+        fn = getattr(self._real, name)
+        if not name.endswith('_f32') and name not in ('sb200_fifo_pop', 'sb200_fifo_push', 'sb200_ppo_kl_apply'):
+            return fn
+        import torch
+
+        def wrapped(*args):
+            key = name
+            if name == 'sb200_mlp_forward_f32':
+                key = '%s[rows=%d]' % (name, int(args[2]._obj.rows))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*args)
+            e1.record()
+            self.records.setdefault(key, []).append((e0, e1))
+            return rc
+        return wrapped
+
+    def report(self):
+        import torch
+        torch.cuda.synchronize()
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in self.records.items()}
+
+
+_profiler = None
+
+
+def profile_calls(enable):
+    """Turn per-call CUDA-event timing on/off; returns the finished report when turning off."""
+    global _profiler
+    if enable:
+        _profiler = _ProfilingProxy(lib())
+        return None
+    rep = _profiler.report() if _profiler is not None else {}
+    _profiler = None
+    return rep
+
+
 def lib():
     global _lib
+    if _profiler is not None:
+        return _profiler
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise SB200Error(
