@@ -56,6 +56,7 @@ class PPOAgent(Agent):
         self._pd = torch.zeros(N, 2 * A, device=self.device)
         self._obs_dev = torch.zeros(N, D, device=self.device)
         self._obs_pin = None
+        self._out_pin = None
         self._counter = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.seed = 2 + 1000003 * int(agent_id)
 
@@ -76,8 +77,13 @@ class PPOAgent(Agent):
         if host:
             if self._obs_pin is None:
                 self._obs_pin = torch.empty(N, D, dtype=torch.float32, pin_memory=True)
-            self._obs_pin.numpy()[...] = np.asarray(x, dtype=np.float32).reshape(N, D)
-            self._obs_dev.copy_(self._obs_pin, non_blocking=True)
+            xt = torch.from_numpy(x) if (isinstance(x, np.ndarray) and x.dtype == np.float32 and
+                                         x.flags['C_CONTIGUOUS'] and x.flags['WRITEABLE']) else None
+            if xt is not None and xt.is_pinned():                  # observation already in pinned memory: DMA directly
+                self._obs_dev.copy_(xt.view(N, D), non_blocking=True)
+            else:
+                self._obs_pin.numpy()[...] = np.asarray(x, dtype=np.float32).reshape(N, D)
+                self._obs_dev.copy_(self._obs_pin, non_blocking=True)
             x = self._obs_dev
         x = x.reshape(N, D)
         m = self.model
@@ -97,8 +103,14 @@ class PPOAgent(Agent):
         if not staged and counter is self._counter:
             self._counter += 1
         if host:
-            action = self._action.cpu().numpy().astype(np.float64)
-            pd = self._pd.cpu().numpy()
+            if self._out_pin is None:
+                self._out_pin = (torch.empty(N, A, dtype=torch.float32, pin_memory=True),
+                                 torch.empty(N, 2 * A, dtype=torch.float32, pin_memory=True))
+            self._out_pin[0].copy_(self._action, non_blocking=True)
+            self._out_pin[1].copy_(self._pd, non_blocking=True)
+            torch.cuda.current_stream().synchronize()              # one sync for both D2H copies
+            action = self._out_pin[0].numpy().astype(np.float64)   # the reference hands the env float64 (ppo_net.py:83)
+            pd = self._out_pin[1].numpy().copy()
             if N == 1 and np.asarray(obs['low_dim'][next(iter(obs['low_dim']))] if isinstance(obs, dict) else obs).ndim == 1:
                 action, pd = action.reshape(-1), pd.reshape(-1)
         else:

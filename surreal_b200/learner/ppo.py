@@ -162,7 +162,7 @@ class PPOLearner(Learner):
         """numpy -> pinned staging -> device buffer (non-blocking); CUDA tensors are copied device-side."""
         if isinstance(arr, torch.Tensor):
             dst.copy_(arr.reshape(dst.shape), non_blocking=True)
-            return 0
+            return 0 if arr.is_cuda else dst.numel() * 4
         a = np.asarray(arr)
         if name not in self._pin:
             self._pin[name] = torch.empty(dst.shape, dtype=torch.float32, pin_memory=True)
@@ -211,9 +211,17 @@ class PPOLearner(Learner):
             return batch
         self._obs_full, self._actions, self._pds = own['obs_full'], own['actions'], own['pds']
         self._rewards, self._dones = own['rewards'], own['dones']
-        obs, obs_next = self._low_dim(get('obs')), self._low_dim(get('obs_next'))
         nbytes = 0
-        if isinstance(obs, torch.Tensor):
+        if isinstance(full, torch.Tensor) and not full.is_cuda and tuple(full.shape) == (B, n + 1, D):
+            # host batch already in the working layout (ideally pinned): one DMA, no staging copy
+            own['obs_full'].copy_(full, non_blocking=True)
+            nbytes += own['obs_full'].numel() * 4
+            obs = None
+        else:
+            obs, obs_next = self._low_dim(get('obs')), self._low_dim(get('obs_next'))
+        if obs is None:
+            pass
+        elif isinstance(obs, torch.Tensor):
             own['obs_full'][:, :n].copy_(obs.reshape(B, n, D), non_blocking=True)
             own['obs_full'][:, n:].copy_(obs_next.reshape(B, 1, D), non_blocking=True)
         else:
