@@ -138,15 +138,26 @@ def run_ours(args):
     flush = torch.empty(192 * 1024 * 1024 // 4, device=dev)       # > 126 MB L2
     launches = {'n': 0}
 
-    def one_step():
+    from surreal_b200.launch import PipelinedEngine
+    eng = None
+    if not args.sequential:
+        # actors and learner on two concurrent CUDA streams (Surreal's async actor / learner processes on one GPU)
+        eng = PipelinedEngine(agent, replay, learner, T)
+        eng.prime()
+
+    def seq_step():
         agent.main_loop(max_steps=T)
         learner.main_loop()
+
+    one_step = eng.step if eng is not None else seq_step
+    tstream = eng.sL if eng is not None else torch.cuda.current_stream()
 
     # kernel-launch accounting (ours only): launches per step are counted once via the library's own counter
     for _ in range(max(args.warmup, 3)):
         one_step()
     torch.cuda.synchronize()
     per_step_launches = count_launches(one_step)
+    torch.cuda.synchronize()
 
     clocks = ClockSampler(local)
     times = []
@@ -156,11 +167,13 @@ def run_ours(args):
     clocks.start()
     t_wall0 = time.time()
     for _ in range(args.steps):
-        flush.fill_(1.0)                                          # L2 flush between timed iterations
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        with torch.cuda.stream(tstream):
+            flush.fill_(1.0)                                      # L2 flush between timed iterations
+            e0.record()
         one_step()
-        e1.record()
+        with torch.cuda.stream(tstream):
+            e1.record()
         times.append((e0, e1))
     torch.cuda.synchronize()
     t_wall = time.time() - t_wall0
@@ -182,7 +195,7 @@ def run_ours(args):
     n_prof = 3
     for _ in range(n_prof):
         flush.fill_(1.0)
-        one_step()
+        seq_step()                                                # sequential + eager: one CUDA-event pair per call
     os.environ['SB200_CUDA_GRAPH'] = '1'
     learner.profile_events = False
     calls = _lib.profile_calls(False)
@@ -250,13 +263,14 @@ def run_ours(args):
                        'actors_per_gpu': N, 'horizon': T, 'obs_dim': D, 'action_dim': A, 'hidden': list(HIDDEN),
                        'ppo_mode': 'clip', 'epoch_policy': 10, 'epoch_baseline': 10, 'episode_length': EPISODE_LEN,
                        'global_windows_per_step': N * world,
-                       'parallelism': 'dp%d' % world, 'l2': 'flushed between timed steps (192 MB fill)'},
+                       'parallelism': 'dp%d' % world, 'l2': 'flushed between timed steps (192 MB fill)',
+                       'engine': 'sequential' if eng is None else 'pipelined: actors (stream A) overlap the learner (stream L), one-iteration policy lag'},
             'learner_updates_per_sec': args.steps / (total_ms / 1e3),
             'optimizer_steps_per_sec': (opt_steps * world / (total_ms / 1e3)) if opt_steps else None,
             'gpu_launches': per_step_launches * args.steps, 'gpu_launches_per_step': per_step_launches,
             'clocks': clk, 'roofline': roofline, 'roofline_critic_pass': roof_critic, 'roofline_gae': roofline_gae,
             'kernel_breakdown': breakdown[:12], 'e2e': e2e,
-            'cpu_baseline': cpu_baseline, 'wall_s': t_wall,
+            'cpu_baseline': cpu_baseline, 'wall_s': t_wall, 'wall_env_steps_per_s': env_steps / t_wall / world * world,
         }
         print(json.dumps(out))
     if world > 1:
@@ -436,6 +450,7 @@ if __name__ == '__main__':
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', type=str, default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--sequential', action='store_true', help='rollout then learn on one stream (no actor/learner overlap)')
     ap.add_argument('--lite', action='store_true', help='skip the e2e and CPU-baseline legs (profiling runs under ncu)')
     a = ap.parse_args()
     if a.impl == 'reference':

@@ -49,7 +49,14 @@ class ParameterPublisher:
         snap = {}
         for name, m in self._module_dict.items():
             if hasattr(m, 'flat_state'):       # flat device buffers: a publish is a handful of D2D copies
-                snap[name] = {'__flat__': {k: v.detach().clone() for k, v in m.flat_state().items()}}
+                old = (self._snapshot or {}).get(name, {}).get('__flat__')
+                cur = m.flat_state()
+                if old is not None and old.keys() == cur.keys() and all(old[k].shape == cur[k].shape for k in cur):
+                    for k, v in cur.items():       # persistent snapshot buffers: stable addresses, no allocator
+                        old[k].copy_(v)            # traffic; cross-stream ordering is the engine's job (events)
+                    snap[name] = {'__flat__': old}
+                else:
+                    snap[name] = {'__flat__': {k: v.detach().clone() for k, v in cur.items()}}
             else:
                 snap[name] = {k: v.detach().clone() for k, v in m.state_dict().items()}
         self._snapshot = snap

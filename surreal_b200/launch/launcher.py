@@ -37,6 +37,77 @@ class Launcher:
         pass
 
 
+class PipelinedEngine:
+    """Actors and learner as two concurrent CUDA streams of ONE process (the B200 form of Surreal's asynchronous
+    actor / learner processes): while the learner works on batch k, the actors already roll out batch k+1 with the
+    weights published after batch k-1 -- exactly the policy lag Surreal's actors run with (docs/ppo.md:16).
+
+      stream A:  [wait pop_k, pub]  rollout_{k+1} .........................  -> roll_{k+1}
+      stream L:  [wait roll_k] pop+gather_k -> pop_k | learn_k (CUDA graph) ... publish -> pub
+
+    The rollout is a chain of small latency-bound kernels that occupies a handful of SMs; the learner's kernels fill
+    the rest, so the step time tends to max(rollout, learn) instead of their sum.  Ordering between the streams is
+    carried by events only (FIFO control block: push happens-before pop happens-before next push; parameter
+    snapshot: publish happens-before fetch happens-before next publish)."""
+
+    def __init__(self, agent, replay, learner, rollout_steps):
+        import torch
+        self.torch = torch
+        self.agent, self.replay, self.learner, self.T = agent, replay, learner, rollout_steps
+        self.sA, self.sL = torch.cuda.Stream(), torch.cuda.Stream()
+        self.ev_roll = self.ev_pop = self.ev_pub = self.ev_fetch = None
+        self.iterations = 0
+        cur = torch.cuda.current_stream()
+        self.sA.wait_stream(cur)
+        self.sL.wait_stream(cur)
+
+    def _rollout(self):
+        torch = self.torch
+        with torch.cuda.stream(self.sA):
+            if self.ev_pop is not None:
+                self.sA.wait_event(self.ev_pop)
+            if self.ev_pub is not None:
+                self.sA.wait_event(self.ev_pub)
+            self.agent.main_loop(max_steps=self.T)          # parameter fetch (if due) + T batched env steps
+            self.ev_fetch = torch.cuda.Event()
+            self.ev_fetch.record(self.sA)
+            self.ev_roll = torch.cuda.Event()
+            self.ev_roll.record(self.sA)
+
+    def prime(self):
+        """First rollout (nothing to overlap with yet)."""
+        self._rollout()
+
+    def step(self):
+        """One learner iteration, overlapped with the actors' next rollout.  Returns the learner statistics."""
+        torch = self.torch
+        L = self.learner
+        with torch.cuda.stream(self.sL):
+            self.sL.wait_event(self.ev_roll)
+            if not self.replay.start_sample_condition():
+                raise RuntimeError('replay under-filled: rollout_steps too small for one learner batch')
+            data = L.fetch_batch()                           # pop + gather into the learner's buffers
+            self.ev_pop = torch.cuda.Event()
+            self.ev_pop.record(self.sL)
+        self._rollout()                                      # enqueue rollout k+1 BEFORE blocking on learn k
+        with torch.cuda.stream(self.sL):
+            with L.learn_timer.time():
+                stats = L.learn(data)                        # graph replay + one statistics read-back
+            if self.ev_fetch is not None:
+                self.sL.wait_event(self.ev_fetch)            # the snapshot buffers may still be read by a fetch
+            if L.should_publish_parameter():
+                L.publish_parameter(L.current_iter, message='batch ' + str(L.current_iter))
+            self.ev_pub = torch.cuda.Event()
+            self.ev_pub.record(self.sL)
+            L.iter_timer.lap()
+            L.current_iter += 1
+        self.iterations += 1
+        return stats
+
+    def drain(self):
+        self.torch.cuda.synchronize()
+
+
 class SurrealDefaultLauncher(Launcher):
     def __init__(self, agent_class, learner_class, replay_class, session_config, env_config, learner_config,
                  eval_mode='eval_stochastic', agent_batch_size=8, eval_batch_size=8, render=False):
@@ -90,12 +161,24 @@ class SurrealDefaultLauncher(Launcher):
         self.agent.main_setup(env)
         return self.agent, self.replay, self.learner
 
-    def run_engine(self, iterations=None, rollout_steps=None):
-        """Alternate a rollout chunk of all co-located actors with as many learner iterations as the replay
-        can feed (Surreal's actors and learner run concurrently in separate processes; on one GPU the two
-        phases share the device and are time-sliced)."""
+    def run_engine(self, iterations=None, rollout_steps=None, pipelined=None):
+        """Run actors + learner.  pipelined (default when one rollout chunk yields exactly one learner batch):
+        PipelinedEngine -- actors and learner on two concurrent streams.  Otherwise alternate a rollout chunk with
+        as many learner iterations as the replay can feed."""
         agent, replay, learner = self.setup_engine()
         T = rollout_steps or self.learner_config.algo.stride
+        n, stride = self.learner_config.algo.n_step, self.learner_config.algo.stride
+        one_batch_per_chunk = (n == stride == T and agent.num_envs == self.learner_config.replay.batch_size and
+                               hasattr(learner, 'replay_out_buffers'))
+        if pipelined is None:
+            pipelined = one_batch_per_chunk
+        if pipelined:
+            eng = PipelinedEngine(agent, replay, learner, T)
+            eng.prime()
+            while iterations is None or eng.iterations < iterations:
+                eng.step()
+            eng.drain()
+            return learner
         it = 0
         while iterations is None or it < iterations:
             agent.main_loop(max_steps=T)

@@ -288,3 +288,35 @@ def test_synthetic_env_dynamics_and_episode_cap():
         s = nxt.clone()
     noise = (info['obs_next'] - expect)
     assert 0.005 < float(noise.std()) < 0.02
+
+
+def test_pipelined_engine_matches_sequential_semantics():
+    """Two-stream PipelinedEngine: every window is consumed exactly once, in arrival order, and the learner's
+    statistics are finite; parameters reach the actors one publish late (the documented policy lag)."""
+    from surreal_b200.launch import SurrealDefaultLauncher, PipelinedEngine
+    from surreal_b200.agent import PPOAgent
+    from surreal_b200.learner import PPOLearner
+    from surreal_b200.replay import FIFOReplay
+    from surreal_b200.main.ppo_configs import make_synthetic_env_config
+    N, n = 128, 8
+    lc, ec, sc = ppo_configs(D=16, A=4, actor_h=(64, 48), critic_h=(64, 48), n_step=n, stride=n, B=N,
+                             memory_size=2 * N, exp_interval=N)
+    make_synthetic_env_config(ec, N, 16, 4, seed=5)
+    ec.limit_episode_length = 2 * n
+    sc.agent.fetch_parameter_interval = n
+    lc.parameter_publish.min_publish_interval = 0.0
+    la = SurrealDefaultLauncher(PPOAgent, PPOLearner, FIFOReplay, sc, ec, lc)
+    agent, replay, learner = la.setup_engine()
+    eng = PipelinedEngine(agent, replay, learner, n)
+    eng.prime()
+    versions = []
+    for k in range(6):
+        st = eng.step()
+        assert all(np.isfinite(v) for v in st.values())
+        versions.append(learner.publisher.version)
+    eng.drain()
+    s = replay._read_state()
+    assert s['total_in'] == 7 * N and s['total_out'] == 6 * N and s['count'] == N and s['dropped'] == 0
+    assert versions == [1, 2, 3, 4, 5, 6]
+    assert agent._ps_client._last_version in (5, 6)               # one publish behind the learner at most
+    assert learner.current_iteration == 6
