@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(SB200_THREADS, 1) mlp_fwd_kernel(const __grid_
 // from shared memory in all 8 warps.  Here a CTA owns R = 8 rows and thread t owns output column n0 + t:
 // weights are read exactly once per CTA, coalesced (one 128-byte line per warp per k), straight from L2 with
 // a register double buffer of 8 k-steps (no shared-memory staging, no barriers inside a layer); the 8 input
-// rows are warp-broadcast LDS.128 along k.  Same ascending-k FFMA order as the tiled kernel => identical bits.
+// rows are warp-broadcast LDS.128 along k.  Each CTA starts its k loop at a rotated offset (see below).
 constexpr int SK_R = 8;
 constexpr int SK_U = 8;      // k-steps per register stage
 
@@ -370,13 +370,26 @@ __global__ void __launch_bounds__(SB200_THREADS, 2) mlp_fwd_skinny_kernel(const 
                 for (int r = 0; r < SK_R; ++r) acc[r] = 0.0f;
                 const float* wp = W + (on ? n : 0);
                 float w[SK_U], wn[SK_U];
+                // Every CTA needs the SAME weight rows.  Walking k in lock-step would make all ~128 CTAs hit the
+                // same few L2 lines at the same instant (slice hot-spotting, measured: ~3x slower), so each CTA
+                // starts its k loop at a different, SK_U-aligned offset and wraps around.  The summation ORDER of
+                // a row therefore depends on its CTA index only (deterministic run to run).
+                const int nst = Kp / SK_U;
+                const int rot = (int)(((unsigned)blockIdx.x * 5u) % (unsigned)nst) * SK_U;
 #pragma unroll
-                for (int u = 0; u < SK_U; ++u) w[u] = (on && u < K) ? __ldg(wp + (long long)u * ldw) : 0.0f;
-                for (int k0 = 0; k0 < Kp; k0 += SK_U) {
+                for (int u = 0; u < SK_U; ++u) {
+                    const int k = rot + u;
+                    w[u] = (on && k < K) ? __ldg(wp + (long long)k * ldw) : 0.0f;
+                }
+                for (int it = 0; it < nst; ++it) {
+                    int k0 = rot + it * SK_U;
+                    if (k0 >= Kp) k0 -= Kp;
+                    int k1 = k0 + SK_U;
+                    if (k1 >= Kp) k1 -= Kp;
 #pragma unroll
                     for (int u = 0; u < SK_U; ++u) {       // next stage in flight while this one is consumed
-                        const int k = k0 + SK_U + u;
-                        wn[u] = (on && k < K) ? __ldg(wp + (long long)k * ldw) : 0.0f;
+                        const int k = k1 + u;
+                        wn[u] = (on && it + 1 < nst && k < K) ? __ldg(wp + (long long)k * ldw) : 0.0f;
                     }
 #pragma unroll
                     for (int r = 0; r < SK_R; ++r) {
