@@ -71,13 +71,14 @@ class DDPGLearner(Learner):
         self.actor_update_time = U.TimeRecorder()
         f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.device)  # noqa: E731
         self._own = dict(obs=f(B, D), obs_next=f(B, D), actions=f(B, A), rewards=f(B, 1), dones=f(B, 1))
-        self._b = dict(self._own)
         self._pi_t, self._q_t, self._y = f(B, A), f(B, 1), f(B)
         self._dA = f(B, ops._ru(A, 4))
         self._stats = f(16)
         self._ws = torch.zeros(_lib.lib().sb200_ddpg_workspace_bytes(B), dtype=torch.uint8, device=self.device)
         self._pin = {}
         self.check_action_range = True
+        self.use_cuda_graph = ops.graphs_enabled()
+        self._graph = ops.GraphRunner()
 
     # ------------------------------------------------------------------------------------------------
     def preprocess(self, batch):
@@ -90,13 +91,11 @@ class DDPGLearner(Learner):
         nbytes = 0
         for k, v in src.items():
             dst = self._own[k]
-            if isinstance(v, torch.Tensor) and v.is_cuda and v.dtype == torch.float32 and v.is_contiguous() \
-                    and tuple(v.shape) == tuple(dst.shape):
-                self._b[k] = v
-                continue
-            self._b[k] = dst
             if isinstance(v, torch.Tensor):
-                dst.copy_(v.reshape(dst.shape), non_blocking=True)
+                if v.data_ptr() != dst.data_ptr():                # foreign tensors are copied in: the captured graph
+                    dst.copy_(v.reshape(dst.shape), non_blocking=True)   # always reads the same addresses
+                    if not v.is_cuda:
+                        nbytes += dst.numel() * 4
                 continue
             if k not in self._pin:
                 self._pin[k] = torch.empty(dst.shape, dtype=torch.float32, pin_memory=True)
@@ -109,38 +108,47 @@ class DDPGLearner(Learner):
     def replay_out_buffers(self):
         return self._own
 
-    def _optimize(self):
+    def _optimize_device(self):
+        """ddpg.py:244-333 as one fixed launch sequence (CUDA-graph body; no host round trip inside)."""
         L = _lib.lib()
         B, A = self.batch_size, self.action_dim
         m, mt, st = self.model, self.model_target, ops._stream()
-        b = self._b
+        b = self._own
         obs, obs_next, actions, rewards, dones = b['obs'], b['obs_next'], b['actions'], b['rewards'], b['dones']
+        ops.mlp_forward(mt.actor, obs_next, out=self._pi_t)                              # ddpg.py:266
+        ops.mlp_forward(mt.critic, obs_next, aux=self._pi_t, out=self._q_t)
+        check(L.sb200_ddpg_target_f32(_ptr(rewards), _ptr(self._q_t), 1, _ptr(dones), _ptr(actions), A, B, A,
+                                      float(pow(self.discount_factor, self.n_step)), _ptr(self._y),
+                                      _ptr(self._stats), _ptr(self._ws), st), 'sb200_ddpg_target_f32')
+        ct = self.critic_optim
+        q = ct.forward(obs, aux=actions)                                                # Q(s_t, a_t)
+        check(L.sb200_ddpg_critic_loss_f32(_ptr(q), q.stride(0), _ptr(self._y), B, _ptr(ct.d[-1]),
+                                           ct.d[-1].stride(0), _ptr(self._stats), _ptr(self._ws), st),
+              'sb200_ddpg_critic_loss_f32')
+        ct.backward()
+        ct.step()
+        at = self.actor_optim
+        a_pi = at.forward(obs)
+        q_pi = ct.forward(obs, aux=at.h[-1])                  # through the UPDATED critic (ddpg.py:324-327)
+        check(L.sb200_ddpg_actor_seed_f32(_ptr(q_pi), q_pi.stride(0), B, _ptr(ct.d[-1]), ct.d[-1].stride(0),
+                                          _ptr(self._stats), _ptr(self._ws), st), 'sb200_ddpg_actor_seed_f32')
+        ct.backward_inputs(stop_layer=1)
+        ct.grad_wrt_aux(1, self._dA)
+        check(L.sb200_tanh_bwd_f32(_ptr(self._dA), self._dA.stride(0), _ptr(a_pi), a_pi.stride(0), B, A,
+                                   _ptr(at.d[-1]), at.d[-1].stride(0), st), 'sb200_tanh_bwd_f32')
+        at.backward()
+        at.step()
+        if self.target_update_type == 'soft':                                           # ddpg.py:410-418
+            for t, s_ in ((mt.actor, m.actor), (mt.critic, m.critic)):
+                check(L.sb200_soft_update_f32(_ptr(t.params), _ptr(s_.params), t.size, float(self.target_update_tau),
+                                              st), 'sb200_soft_update_f32')
+
+    def _optimize(self):
         with self.forward_time.time():
-            ops.mlp_forward(mt.actor, obs_next, out=self._pi_t)                              # ddpg.py:266
-            ops.mlp_forward(mt.critic, obs_next, aux=self._pi_t, out=self._q_t)
-            check(L.sb200_ddpg_target_f32(_ptr(rewards), _ptr(self._q_t), 1, _ptr(dones), _ptr(actions), A, B, A,
-                                          float(pow(self.discount_factor, self.n_step)), _ptr(self._y),
-                                          _ptr(self._stats), _ptr(self._ws), st), 'sb200_ddpg_target_f32')
-            ct = self.critic_optim
-            q = ct.forward(obs, aux=actions)                                                # Q(s_t, a_t)
-        with self.critic_update_time.time():
-            check(L.sb200_ddpg_critic_loss_f32(_ptr(q), q.stride(0), _ptr(self._y), B, _ptr(ct.d[-1]),
-                                               ct.d[-1].stride(0), _ptr(self._stats), _ptr(self._ws), st),
-                  'sb200_ddpg_critic_loss_f32')
-            ct.backward()
-            ct.step()
-        with self.actor_update_time.time():
-            at = self.actor_optim
-            a_pi = at.forward(obs)
-            q_pi = ct.forward(obs, aux=at.h[-1])              # through the UPDATED critic (ddpg.py:324-327)
-            check(L.sb200_ddpg_actor_seed_f32(_ptr(q_pi), q_pi.stride(0), B, _ptr(ct.d[-1]), ct.d[-1].stride(0),
-                                              _ptr(self._stats), _ptr(self._ws), st), 'sb200_ddpg_actor_seed_f32')
-            ct.backward_inputs(stop_layer=1)
-            ct.grad_wrt_aux(1, self._dA)
-            check(L.sb200_tanh_bwd_f32(_ptr(self._dA), self._dA.stride(0), _ptr(a_pi), a_pi.stride(0), B, A,
-                                       _ptr(at.d[-1]), at.d[-1].stride(0), st), 'sb200_tanh_bwd_f32')
-            at.backward()
-            at.step()
+            if self.use_cuda_graph:
+                self._graph.run(self._optimize_device)
+            else:
+                self._optimize_device()
         s = self._stats.cpu().numpy()
         self.last_d2h_bytes = s.nbytes
         if self.check_action_range and s[DS['ABSMAX']] > 1.0:
@@ -151,7 +159,11 @@ class DDPGLearner(Learner):
                  'performance/forward_time': self.forward_time.avg,
                  'performance/critic_update_time': self.critic_update_time.avg,
                  'performance/actor_update_time': self.actor_update_time.avg}
-        self._target_update()
+        if self.target_update_type == 'hard':                     # host-side counter (ddpg.py:419-428)
+            self.target_update_counter += 1
+            if self.target_update_counter % self.target_update_interval == 0:
+                self.model_target.actor.params.copy_(self.model.actor.params)
+                self.model_target.critic.params.copy_(self.model.critic.params)
         return stats
 
     def learn(self, batch):

@@ -196,6 +196,9 @@ class MlpTrainer:
         self.h = [z(M, _ru(n, 4)) for n in net.dims[1:]]          # post-activation outputs
         self.d = [z(M, _ru(n, 4)) for n in net.dims[1:]]          # gradients w.r.t. pre-activations
         self.aux = None
+        self._aux_pad = None
+        if net.aux_layer >= 0 and net.aux_dim % 4 != 0:       # pre-allocated: nothing may allocate during graph capture
+            self._aux_pad = z(M, _ru(net.aux_dim, 4))
 
     @property
     def out(self):
@@ -204,7 +207,7 @@ class MlpTrainer:
     def forward(self, x, zf_stats=None, zf_eps=1e-5, aux=None, rows=None, ldx=None):
         if aux is not None and (aux.stride(0) % 4 != 0 or aux.data_ptr() % 16 != 0):
             # the backward GEMMs read rows with 16-byte vector loads: re-home odd-width aux inputs once
-            if getattr(self, '_aux_pad', None) is None:
+            if self._aux_pad is None:
                 self._aux_pad = torch.zeros(self.M, _ru(self.net.aux_dim, 4), dtype=torch.float32,
                                             device=self.net.device)
             self._aux_pad[:, :self.net.aux_dim].copy_(aux[:, :self.net.aux_dim])
