@@ -11,6 +11,7 @@
 // 35-84 and the z-filter of z_filter.py:59-79.  Algorithmic HBM bytes per row: 4*D read + saved
 // activations written (critic pass: 4 bytes); weights are L2-resident.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -53,7 +54,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 template <int TM, int BK>
-__global__ void __launch_bounds__(SB200_THREADS, 1) mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
+__global__ void __launch_bounds__(SB200_THREADS, (TM <= 4 && BK == 16) ? 2 : 1) mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
     constexpr int BM = 8 * TM;
     extern __shared__ __align__(16) float smem[];
     const int ldh = p.ldh;
@@ -561,7 +562,8 @@ extern "C" int sb200_mlp_forward_f32(const sb200_mlp* net, const sb200_zfilter* 
     SB200_REQUIRE(fits(8, 16));
     cudaStream_t st = (cudaStream_t)stream;
     // small batches: skinny kernel (8 rows per CTA, weights streamed once per CTA from L2)
-    if (p.rows <= 2048) {
+    static const int no_skinny = [] { const char* e = getenv("SB200_NO_SKINNY"); return e ? atoi(e) : 0; }();
+    if (p.rows <= 2048 && !no_skinny) {
         p.ldh = round_up(maxw, SK_U) + 4;
         int scratch = 2 * net->dims[0];
         for (int l = 0; l < net->n_layers; ++l)
@@ -577,6 +579,12 @@ extern "C" int sb200_mlp_forward_f32(const sb200_mlp* net, const sb200_zfilter* 
             return sb200_launch_status();
         }
     }
+    // tuning override for experiments (tools/bench_kernels.py): SB200_FWD_TM = 8 | 4 | 2 | 1
+    static const int force_tm = [] { const char* e = getenv("SB200_FWD_TM"); return e ? atoi(e) : 0; }();
+    if (force_tm == 8 && fits(64, 16)) return launch_fwd<8, 16>(p, maxw, st);
+    if (force_tm == 4 && fits(32, 16)) return launch_fwd<4, 16>(p, maxw, st);
+    if (force_tm == 2 && fits(16, 64)) return launch_fwd<2, 64>(p, maxw, st);
+    if (force_tm == 1 && fits(8, 64)) return launch_fwd<1, 64>(p, maxw, st);
     // largest row tile that still yields >= ~1 CTA per SM; small batches take 16-row tiles with 64-row W stages
     const long long want = 120;
     if (fits(64, 16) && (p.rows + 63) / 64 >= want) return launch_fwd<8, 16>(p, maxw, st);
