@@ -302,6 +302,7 @@ __global__ void __launch_bounds__(SB200_THREADS, (TM <= 4 && BK == 16) ? 2 : 1) 
 // rows are warp-broadcast LDS.128 along k.  Each CTA starts its k loop at a rotated offset (see below).
 constexpr int SK_R = 8;
 constexpr int SK_U = 8;      // k-steps per register stage
+constexpr int SK_D = 4;      // register stages in flight
 
 __global__ void __launch_bounds__(SB200_THREADS, 2) mlp_fwd_skinny_kernel(const __grid_constant__ FwdParams p) {
     extern __shared__ __align__(16) float smem[];
@@ -324,7 +325,7 @@ __global__ void __launch_bounds__(SB200_THREADS, 2) mlp_fwd_skinny_kernel(const 
     }
     {
         const int in_w = K0 + (p.aux_layer == 0 ? p.aux_dim : 0);
-        const int in_wp = round_up(in_w, SK_U);
+        const int in_wp = round_up(in_w, SK_U * SK_D);
         for (int idx = tid; idx < SK_R * in_wp; idx += SB200_THREADS) {
             const int m = idx / in_wp, k = idx - m * in_wp;
             const long long r = row0 + m;
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(SB200_THREADS, 2) mlp_fwd_skinny_kernel(const 
         float* sv = p.save[l];
         const long long lds = p.ld_save[l];
         if (N > 32) {
-            const int Kp = round_up(K, SK_U);
+            const int Kp = round_up(K, SK_U * SK_D);
             for (int n0 = 0; n0 < N; n0 += SB200_THREADS) {
                 const int n = n0 + tid;
                 const bool on = n < N;
@@ -370,39 +371,43 @@ __global__ void __launch_bounds__(SB200_THREADS, 2) mlp_fwd_skinny_kernel(const 
 #pragma unroll
                 for (int r = 0; r < SK_R; ++r) acc[r] = 0.0f;
                 const float* wp = W + (on ? n : 0);
-                float w[SK_U], wn[SK_U];
-                // Every CTA needs the SAME weight rows.  Walking k in lock-step would make all ~128 CTAs hit the
-                // same few L2 lines at the same instant (slice hot-spotting, measured: ~3x slower), so each CTA
-                // starts its k loop at a different, SK_U-aligned offset and wraps around.  The summation ORDER of
-                // a row therefore depends on its CTA index only (deterministic run to run).
-                const int nst = Kp / SK_U;
-                const int rot = (int)(((unsigned)blockIdx.x * 5u) % (unsigned)nst) * SK_U;
+                // Register ring of SK_D stages x SK_U k-steps: ~24 weight loads per thread stay in flight, enough to
+                // cover the L2 round trip (a single look-ahead stage left every iteration exposed to ~1 us of latency).
+                // Every CTA needs the SAME weight rows; each starts its k loop at a different stage and wraps around
+                // so that the CTAs do not hit the same L2 lines in lock-step.  The summation order of a row therefore
+                // depends on its CTA index only (deterministic run to run).
+                float w[SK_D][SK_U];
+                const int nst = Kp / SK_U;                         // multiple of SK_D (Kp is padded to SK_U*SK_D)
+                const int rot = (int)(((unsigned)blockIdx.x * 5u) % (unsigned)nst);
+                auto stage_k0 = [&](int it) { int s_ = rot + it; if (s_ >= nst) s_ -= nst; return s_ * SK_U; };
+                auto load_stage = [&](float (&dst)[SK_U], int it) {
+                    const int k0 = stage_k0(it);
 #pragma unroll
-                for (int u = 0; u < SK_U; ++u) {
-                    const int k = rot + u;
-                    w[u] = (on && k < K) ? __ldg(wp + (long long)k * ldw) : 0.0f;
-                }
-                for (int it = 0; it < nst; ++it) {
-                    int k0 = rot + it * SK_U;
-                    if (k0 >= Kp) k0 -= Kp;
-                    int k1 = k0 + SK_U;
-                    if (k1 >= Kp) k1 -= Kp;
-#pragma unroll
-                    for (int u = 0; u < SK_U; ++u) {       // next stage in flight while this one is consumed
-                        const int k = k1 + u;
-                        wn[u] = (on && it + 1 < nst && k < K) ? __ldg(wp + (long long)k * ldw) : 0.0f;
+                    for (int u = 0; u < SK_U; ++u) {
+                        const int k = k0 + u;
+                        dst[u] = (on && it < nst && k < K) ? __ldg(wp + (long long)k * ldw) : 0.0f;
                     }
+                };
+                auto consume = [&](const float (&ws)[SK_U], int it) {
+                    const int k0 = stage_k0(it);
 #pragma unroll
                     for (int r = 0; r < SK_R; ++r) {
                         const float4 a0 = *reinterpret_cast<const float4*>(Hin + r * ldh + k0);
                         const float4 a1 = *reinterpret_cast<const float4*>(Hin + r * ldh + k0 + 4);
                         float t = acc[r];
-                        t = fmaf(a0.x, w[0], t); t = fmaf(a0.y, w[1], t); t = fmaf(a0.z, w[2], t); t = fmaf(a0.w, w[3], t);
-                        t = fmaf(a1.x, w[4], t); t = fmaf(a1.y, w[5], t); t = fmaf(a1.z, w[6], t); t = fmaf(a1.w, w[7], t);
+                        t = fmaf(a0.x, ws[0], t); t = fmaf(a0.y, ws[1], t); t = fmaf(a0.z, ws[2], t); t = fmaf(a0.w, ws[3], t);
+                        t = fmaf(a1.x, ws[4], t); t = fmaf(a1.y, ws[5], t); t = fmaf(a1.z, ws[6], t); t = fmaf(a1.w, ws[7], t);
                         acc[r] = t;
                     }
+                };
 #pragma unroll
-                    for (int u = 0; u < SK_U; ++u) w[u] = wn[u];
+                for (int d = 0; d < SK_D - 1; ++d) load_stage(w[d], d);
+                for (int it = 0; it < nst; it += SK_D) {
+#pragma unroll
+                    for (int d = 0; d < SK_D; ++d) {
+                        load_stage(w[(d + SK_D - 1) % SK_D], it + d + SK_D - 1);
+                        consume(w[d], it + d);
+                    }
                 }
                 if (on) {
                     const float bv = bias[n];
@@ -463,7 +468,7 @@ __global__ void __launch_bounds__(SB200_THREADS, 2) mlp_fwd_skinny_kernel(const 
         __syncthreads();
         if (!last) {
             const int auxd = (p.aux_layer == l + 1) ? p.aux_dim : 0;
-            const int wp2 = round_up(N + auxd, SK_U);
+            const int wp2 = round_up(N + auxd, SK_U * SK_D);
             const int span = wp2 - N;
             if (span > 0) {
                 for (int idx = tid; idx < SK_R * span; idx += SB200_THREADS) {
@@ -564,7 +569,7 @@ extern "C" int sb200_mlp_forward_f32(const sb200_mlp* net, const sb200_zfilter* 
     // small batches: skinny kernel (8 rows per CTA, weights streamed once per CTA from L2)
     static const int no_skinny = [] { const char* e = getenv("SB200_NO_SKINNY"); return e ? atoi(e) : 0; }();
     if (p.rows <= 2048 && !no_skinny) {
-        p.ldh = round_up(maxw, SK_U) + 4;
+        p.ldh = round_up(maxw, SK_U * SK_D) + 4;
         int scratch = 2 * net->dims[0];
         for (int l = 0; l < net->n_layers; ++l)
             if (net->dims[l + 1] <= 32) {
