@@ -90,6 +90,10 @@ typedef struct {
  * ddpg_net.py:63-91. */
 int sb200_mlp_forward_f32(const sb200_mlp* net, const sb200_zfilter* zf, const sb200_rows* in,
                           float* const* save, const int64_t* ld_save, void* stream);
+/* Numerics of the wide layers of sb200_mlp_forward_f32: 1 (default) = tensor-core mma.sync TF32 with the 3xTF32
+ * error-compensated split (fp32-level accuracy, ~1e-6 relative); 0 = fp32 FFMA kernels.  Env SB200_MMA overrides
+ * the initial value. */
+int sb200_set_forward_mode(int mode);
 
 /* Backward of one Linear layer (kernel layout), replacing torch autograd in ppo.py:242,347 and
  * ddpg.py:306,330.

@@ -47,6 +47,7 @@ def _declare(lib):
     sig = {
         'sb200_version': (I, []),
         'sb200_init': (I, []),
+        'sb200_set_forward_mode': (I, [I]),
         'sb200_status_string': (C.c_char_p, [I]),
         'sb200_device_info': (I, [C.POINTER(I), C.POINTER(I), C.POINTER(I)]),
         'sb200_launch_counter': (C.c_uint64, [I]),

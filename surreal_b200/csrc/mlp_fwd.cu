@@ -487,6 +487,12 @@ __global__ void __launch_bounds__(SB200_THREADS, 2) mlp_fwd_skinny_kernel(const 
     }
 }
 
+}  // namespace
+
+#include "mlp_fwd_mma.cuh"
+
+namespace {
+
 constexpr size_t SMEM_BUDGET = 200 * 1024;
 
 template <int TM, int BK>
@@ -501,8 +507,18 @@ int launch_fwd(FwdParams p, int maxw, cudaStream_t st) {
 
 }  // namespace
 
+int g_forward_mode = [] { const char* e = getenv("SB200_MMA"); return e ? atoi(e) : 1; }();
+
+extern "C" int sb200_set_forward_mode(int mode) {
+    if (mode != 0 && mode != 1) return SB200_ERR_ARG;
+    g_forward_mode = mode;
+    return SB200_OK;
+}
+
 // called once from sb200_init(): opt every instantiation into the full dynamic shared-memory budget
 int sb200_mlp_fwd_init() {
+    SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
+    SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
     SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
     SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
@@ -567,6 +583,11 @@ extern "C" int sb200_mlp_forward_f32(const sb200_mlp* net, const sb200_zfilter* 
     SB200_REQUIRE(fits(8, 16));
     cudaStream_t st = (cudaStream_t)stream;
     // small batches: skinny kernel (8 rows per CTA, weights streamed once per CTA from L2)
+    // default numerics: tensor-core 3xTF32 (fp32-level accuracy, ~1e-6 rel); SB200_MMA=0 selects the pure-FFMA kernels
+    if (g_forward_mode == 1) {
+        int rc = (p.rows <= 4096) ? launch_fwd_mma<1>(p, maxw, net, st) : launch_fwd_mma<4>(p, maxw, net, st);
+        if (rc != SB200_ERR_UNSUPPORTED) return rc;
+    }
     static const int no_skinny = [] { const char* e = getenv("SB200_NO_SKINNY"); return e ? atoi(e) : 0; }();
     if (p.rows <= 2048 && !no_skinny) {
         p.ldh = round_up(maxw, SK_U * SK_D) + 4;
@@ -592,6 +613,9 @@ extern "C" int sb200_mlp_forward_f32(const sb200_mlp* net, const sb200_zfilter* 
     if (force_tm == 1 && fits(8, 64)) return launch_fwd<1, 64>(p, maxw, st);
     // largest row tile that still yields >= ~1 CTA per SM; small batches take 16-row tiles with 64-row W stages
     const long long want = 120;
+    // measured on B200 (tools/bench_kernels.py critic): 32-row tiles at 2 CTAs/SM (16 warps hide the LDS->FFMA
+    // dependency chains) beat 64-row tiles at 1 CTA/SM: 800 us vs 914 us on the 132 096-row critic pass
+    if (fits(32, 16) && (p.rows + 31) / 32 >= 2 * want) return launch_fwd<4, 16>(p, maxw, st);
     if (fits(64, 16) && (p.rows + 63) / 64 >= want) return launch_fwd<8, 16>(p, maxw, st);
     if (fits(32, 16) && (p.rows + 31) / 32 >= want) return launch_fwd<4, 16>(p, maxw, st);
     if (fits(16, 64)) return launch_fwd<2, 64>(p, maxw, st);
