@@ -90,6 +90,17 @@ typedef struct {
  * ddpg_net.py:63-91. */
 int sb200_mlp_forward_f32(const sb200_mlp* net, const sb200_zfilter* zf, const sb200_rows* in,
                           float* const* save, const int64_t* ld_save, void* stream);
+/* Small-batch inference on PRE-PACKED weights (the actors' per-step policy forward, ppo_agent.py:138-141 /
+ * ddpg_agent.py:170-176): pack once per parameter version, then every step's forward reads the weights in
+ * mma-fragment order, already split for 3xTF32, and a 2-CTA cluster shares each 16-row tile.
+ *   pack_floats: size of `packed` in floats (0: this architecture is not supported -- use sb200_mlp_forward_f32;
+ *     supported = every layer but the last wider than 32 outputs).
+ *   pack_tf32: (re)builds `packed` from net->W.  Must be re-run after ANY change of the parameters.
+ *   forward_packed: out[rows][ld_out] = network output; same numerics class as forward mode 1. */
+size_t sb200_mlp_pack_floats(const sb200_mlp* net);
+int sb200_mlp_pack_tf32(const sb200_mlp* net, float* packed, void* stream);
+int sb200_mlp_forward_packed_f32(const sb200_mlp* net, const float* packed, const sb200_zfilter* zf,
+                                 const sb200_rows* in, float* out, int64_t ld_out, void* stream);
 /* Numerics of the wide layers of sb200_mlp_forward_f32: 1 (default) = tensor-core mma.sync TF32 with the 3xTF32
  * error-compensated split (fp32-level accuracy, ~1e-6 relative); 0 = fp32 FFMA kernels.  Env SB200_MMA overrides
  * the initial value. */
@@ -241,6 +252,16 @@ int sb200_ppo_sample_f32(const float* mean, int64_t ldm, const float* log_var, c
                          const float* eps, int N, int A, int deterministic, uint64_t seed,
                          const uint64_t* step_counter, float* action, float* pd, const int* stage_pos,
                          float* stage_act, float* stage_pd, int n_step, void* stream);
+/*   ppo_sample_assign: ppo_sample fused with the slot assignment of ppo_window_step for the windows this step
+ *     completes (it depends only on the deque lengths, so it can precede the env step): writes dest[N]
+ *     (slot | -1 not complete | -2 complete but dropped), advances fifo_state and *step_counter (+1, after every
+ *     block has drawn with the old value).  Follow with ppo_window_step(slots_assigned=1) or
+ *     synth_env_window_step. */
+int sb200_ppo_sample_assign_f32(const float* mean, int64_t ldm, const float* log_var, const float* log_noise,
+                                const float* eps, int N, int A, int deterministic, uint64_t seed,
+                                uint64_t* step_counter, float* action, float* pd, const int* stage_pos,
+                                float* stage_act, float* stage_pd, int n_step, void* fifo_state, int* dest,
+                                void* stream);
 int sb200_ddpg_noise_f32(const float* mean, int64_t ldm, const float* sigma, const float* unit_noise, int N,
                          int A, int deterministic, uint64_t seed, const uint64_t* step_counter,
                          float* action, void* stream);
@@ -252,6 +273,15 @@ int sb200_synth_env_step_f32(float* state, const float* action, const float* Ws,
                              int D, int A, int max_steps, int* ep_step, uint64_t seed,
                              const uint64_t* step_counter, float* obs_next, float* reward, float* done,
                              void* stream);
+/* synth_env_step fused with the commit half of ppo_window_step (dest from ppo_sample_assign): the successor
+ * state is staged straight from shared memory.  One launch per rollout step instead of three. */
+int sb200_synth_env_window_step_f32(float* state, const float* action, const float* Ws, const float* Wa, int N,
+                                    int D, int A, int max_steps, int* ep_step, uint64_t seed,
+                                    const uint64_t* step_counter, float* obs_next, float* reward, float* done,
+                                    int n_step, int stride, int* stage_pos, float* stage_obs, float* stage_act,
+                                    float* stage_pd, float* stage_rew, float* stage_done, const int* dest,
+                                    float* r_obs, float* r_act, float* r_pd, float* r_rew, float* r_done,
+                                    void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Experience staging + HBM replay.
@@ -270,7 +300,7 @@ int sb200_ppo_window_step_f32(const float* obs_next, const float* obs_reset, con
                               int* stage_pos, float* stage_obs, float* stage_act, float* stage_pd,
                               float* stage_rew, float* stage_done, int* dest_scratch, void* fifo_state,
                               float* r_obs, float* r_act, float* r_pd, float* r_rew, float* r_done,
-                              uint64_t* step_counter, void* stream);
+                              uint64_t* step_counter, int slots_assigned, void* stream);
 int sb200_fifo_pop(void* fifo_state, int batch, int* idx, int* status, void* stream);
 int sb200_fifo_push(void* fifo_state, int k, int* slots, void* stream);
 int sb200_replay_gather_f32(const float* src, int64_t record_floats, const int* idx32, const int64_t* idx64,

@@ -54,6 +54,9 @@ def _declare(lib):
         'sb200_launch_counter_add': (None, [C.c_uint64]),
         'sb200_mlp_forward_f32': (I, [C.POINTER(Mlp), C.POINTER(ZFilter), C.POINTER(Rows),
                                       C.POINTER(P), C.POINTER(L), P]),
+        'sb200_mlp_pack_floats': (S, [C.POINTER(Mlp)]),
+        'sb200_mlp_pack_tf32': (I, [C.POINTER(Mlp), P, P]),
+        'sb200_mlp_forward_packed_f32': (I, [C.POINTER(Mlp), P, C.POINTER(ZFilter), C.POINTER(Rows), P, L, P]),
         'sb200_linear_bwd_dx_f32': (I, [P, L, P, I, P, L, P, L, I, I, I, P]),
         'sb200_linear_bwd_dw_f32': (I, [P, L, P, L, P, P, L, I, I, I, I, I, P]),
         'sb200_make_pd_f32': (I, [P, L, P, P, I, I, P, L, P]),
@@ -74,7 +77,10 @@ def _declare(lib):
         'sb200_ddpg_noise_f32': (I, [P, L, P, P, I, I, I, C.c_uint64, P, P, P]),
         'sb200_synth_env_step_f32': (I, [P, P, P, P, I, I, I, I, P, C.c_uint64, P, P, P, P, P]),
         'sb200_fifo_state_bytes': (S, []),
-        'sb200_ppo_window_step_f32': (I, [P, P, P, P, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P]),
+        'sb200_ppo_window_step_f32': (I, [P, P, P, P, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, P, P, I, P]),
+        'sb200_ppo_sample_assign_f32': (I, [P, L, P, P, P, I, I, I, C.c_uint64, P, P, P, P, P, P, I, P, P, P]),
+        'sb200_synth_env_window_step_f32': (I, [P, P, P, P, I, I, I, I, P, C.c_uint64, P, P, P, P, I, I,
+                                                P, P, P, P, P, P, P, P, P, P, P, P, P]),
         'sb200_fifo_pop': (I, [P, I, P, P, P]),
         'sb200_fifo_push': (I, [P, I, P, P]),
         'sb200_replay_gather_f32': (I, [P, L, P, P, I, P, P]),
@@ -122,7 +128,8 @@ class _ProfilingProxy:
 
     def __getattr__(self, name):
         fn = getattr(self._real, name)
-        if not name.endswith('_f32') and name not in ('sb200_fifo_pop', 'sb200_fifo_push', 'sb200_ppo_kl_apply'):
+        if not name.endswith('_f32') and name not in ('sb200_fifo_pop', 'sb200_fifo_push', 'sb200_ppo_kl_apply',
+                                                      'sb200_mlp_pack_tf32'):
             return fn
         import torch
 
@@ -130,6 +137,8 @@ class _ProfilingProxy:
             key = name
             if name == 'sb200_mlp_forward_f32':
                 key = '%s[rows=%d]' % (name, int(args[2]._obj.rows))
+            elif name == 'sb200_mlp_forward_packed_f32':
+                key = '%s[rows=%d]' % (name, int(args[3]._obj.rows))
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             rc = fn(*args)

@@ -40,6 +40,7 @@ class Agent(metaclass=U.AutoInitializeMeta):
         self.episodes_since_param_update = 0
         self.env = None
         self._rollout_graphs = {}
+        self._in_chunk = False                 # True while main_loop() records / runs a multi-step chunk
 
     def _initialize(self):
         if self.agent_mode not in ['eval_deterministic_local', 'eval_stochastic_local']:
@@ -120,9 +121,16 @@ class Agent(metaclass=U.AutoInitializeMeta):
 
             def body():
                 o = obs
-                for _ in range(steps):
-                    a = self.act(o)
-                    o, _, _, _ = env.step(a)
+                packed = getattr(self, '_packed', None)
+                if packed is not None:
+                    packed.refresh()                   # weights are fixed inside a chunk: pack them once, here
+                self._in_chunk = True
+                try:
+                    for _ in range(steps):
+                        a = self.act(o)
+                        o, _, _, _ = env.step(a)
+                finally:
+                    self._in_chunk = False
             self._rollout_graphs[steps].run(body)
             self.current_step += steps
             self.cumulative_steps += steps * self.num_envs

@@ -56,6 +56,7 @@ class DDPGAgent(Agent):
         A, D = self.action_dim, self.model.input_dim
         self._sigma = torch.tensor(self.sigma, dtype=torch.float32, device=self.device)
         self._mean = torch.zeros(N, A, device=self.device)
+        self._packed = ops.PackedWeights(self.model.actor)          # per-step inference copy of the policy weights
         self._action = torch.zeros(N, A, device=self.device)
         self._obs_dev = torch.zeros(N, D, device=self.device)
         self._obs_pin = None
@@ -75,7 +76,12 @@ class DDPGAgent(Agent):
             self._obs_dev.copy_(self._obs_pin, non_blocking=True)
             x = self._obs_dev
         x = x.reshape(N, D)
-        ops.mlp_forward(self.model.actor, x, out=self._mean)
+        if self._packed.supported and x.stride(1) == 1:
+            if not self._in_chunk:
+                self._packed.refresh()                             # inside a chunk: refreshed once, at its top
+            ops.mlp_forward_packed(self._packed, x, out=self._mean)
+        else:
+            ops.mlp_forward(self.model.actor, x, out=self._mean)
         det = self.agent_mode in ['eval_deterministic', 'eval_deterministic_local']
         env = self.env
         counter = env.step_counter if (env is not None and hasattr(env, 'step_counter')) else self._counter

@@ -52,6 +52,7 @@ class PPOAgent(Agent):
         A, D = self.action_dim, self.model.low_dim
         self._log_noise = torch.tensor(self.noise, dtype=torch.float32, device=self.device)
         self._mean = torch.zeros(N, A, device=self.device)
+        self._packed = ops.PackedWeights(self.model.actor)          # per-step inference copy of the policy weights
         self._action = torch.zeros(N, A, device=self.device)
         self._pd = torch.zeros(N, 2 * A, device=self.device)
         self._obs_dev = torch.zeros(N, D, device=self.device)
@@ -87,7 +88,12 @@ class PPOAgent(Agent):
             x = self._obs_dev
         x = x.reshape(N, D)
         m = self.model
-        ops.mlp_forward(m.actor, x, zf_stats=m.z_stats, zf_eps=m.z_eps, out=self._mean)
+        if self._packed.supported and x.stride(1) == 1:
+            if not self._in_chunk:
+                self._packed.refresh()                             # inside a chunk: refreshed once, at its top
+            ops.mlp_forward_packed(self._packed, x, zf_stats=m.z_stats, zf_eps=m.z_eps, out=self._mean)
+        else:
+            ops.mlp_forward(m.actor, x, zf_stats=m.z_stats, zf_eps=m.z_eps, out=self._mean)
         det = self.agent_mode in ['eval_deterministic', 'eval_deterministic_local']
         env = self.env
         staged = self.agent_mode == 'training' and isinstance(env, ExpSenderWrapperMultiStepMovingWindowWithInfo)
@@ -95,11 +101,19 @@ class PPOAgent(Agent):
         eps_dev = None
         if eps is not None:
             eps_dev = torch.as_tensor(np.asarray(eps, dtype=np.float32).reshape(N, A)).to(self.device)
-        check(_lib.lib().sb200_ppo_sample_f32(
-            _p(self._mean), A, _p(m.log_var), _p(self._log_noise), _p(eps_dev), N, A, int(det), self.seed, _p(counter),
-            _p(self._action), _p(self._pd), _p(env.stage_pos) if staged else None,
-            _p(env.stage_act) if staged else None, _p(env.stage_pd) if staged else None,
-            env.n_step if staged else 1, ops._stream()), 'sb200_ppo_sample_f32')
+        if staged and counter is not self._counter and env.fuse_launches:
+            # sampling + this step's replay-slot assignment + step-counter advance in one launch
+            fifo_state, dest = env.slot_assignment_args()
+            check(_lib.lib().sb200_ppo_sample_assign_f32(
+                _p(self._mean), A, _p(m.log_var), _p(self._log_noise), _p(eps_dev), N, A, int(det), self.seed,
+                _p(counter), _p(self._action), _p(self._pd), _p(env.stage_pos), _p(env.stage_act), _p(env.stage_pd),
+                env.n_step, _p(fifo_state), _p(dest), ops._stream()), 'sb200_ppo_sample_assign_f32')
+        else:
+            check(_lib.lib().sb200_ppo_sample_f32(
+                _p(self._mean), A, _p(m.log_var), _p(self._log_noise), _p(eps_dev), N, A, int(det), self.seed,
+                _p(counter), _p(self._action), _p(self._pd), _p(env.stage_pos) if staged else None,
+                _p(env.stage_act) if staged else None, _p(env.stage_pd) if staged else None,
+                env.n_step if staged else 1, ops._stream()), 'sb200_ppo_sample_f32')
         if not staged and counter is self._counter:
             self._counter += 1
         if host:

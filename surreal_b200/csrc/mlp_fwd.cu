@@ -490,6 +490,7 @@ __global__ void __launch_bounds__(SB200_THREADS, 2) mlp_fwd_skinny_kernel(const 
 }  // namespace
 
 #include "mlp_fwd_mma.cuh"
+#include "mlp_fwd_pk.cuh"
 
 namespace {
 
@@ -519,6 +520,7 @@ extern "C" int sb200_set_forward_mode(int mode) {
 int sb200_mlp_fwd_init() {
     SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
     SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
+    SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_pk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
     SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
@@ -529,13 +531,12 @@ int sb200_mlp_fwd_init() {
     return SB200_OK;
 }
 
-extern "C" int sb200_mlp_forward_f32(const sb200_mlp* net, const sb200_zfilter* zf, const sb200_rows* in,
-                                     float* const* save, const int64_t* ld_save, void* stream) {
+// Validates the descriptors and fills the kernel parameter block; *maxw = widest layer input.
+static int fill_fwd_params(const sb200_mlp* net, const sb200_zfilter* zf, const sb200_rows* in, float* const* save,
+                           const int64_t* ld_save, FwdParams& p, int* maxw_out) {
     SB200_REQUIRE(net != nullptr && in != nullptr);
     SB200_REQUIRE(net->n_layers >= 1 && net->n_layers <= SB200_MAX_LAYERS);
     SB200_REQUIRE(in->rows >= 0 && in->x != nullptr);
-    if (in->rows == 0) return SB200_OK;
-    FwdParams p;
     p.scratch_floats = 0;
     p.ldh = 0;
     p.x = in->x;
@@ -576,6 +577,98 @@ extern "C" int sb200_mlp_forward_f32(const sb200_mlp* net, const sb200_zfilter* 
             if (w > maxw) maxw = w;
         }
     }
+    *maxw_out = maxw;
+    return SB200_OK;
+}
+
+// ---- packed small-batch inference path (mlp_fwd_pk.cuh) --------------------------------------------------------
+static long long pack_layer_floats(const sb200_mlp* net, int l) {
+    if (net->dims[l + 1] <= 32) return 0;
+    const int K = net->dims[l] + (net->aux_layer == l ? net->aux_dim : 0);
+    return (long long)((K + 7) / 8) * ((net->dims[l + 1] + 7) / 8) * 32 * 4;
+}
+
+// wide layers first, at most one narrow layer and only as the last one
+static bool pack_supported(const sb200_mlp* net) {
+    if (net == nullptr || net->n_layers < 1 || net->n_layers > SB200_MAX_LAYERS) return false;
+    for (int l = 0; l + 1 < net->n_layers; ++l)
+        if (net->dims[l + 1] <= 32) return false;
+    return true;
+}
+
+extern "C" size_t sb200_mlp_pack_floats(const sb200_mlp* net) {
+    if (!pack_supported(net)) return 0;
+    long long tot = 0;
+    for (int l = 0; l < net->n_layers; ++l) tot += pack_layer_floats(net, l);
+    return (size_t)(tot > 0 ? tot : 4);
+}
+
+extern "C" int sb200_mlp_pack_tf32(const sb200_mlp* net, float* packed, void* stream) {
+    SB200_REQUIRE(packed != nullptr && pack_supported(net) && (((uintptr_t)packed) & 15) == 0);
+    long long off = 0;
+    int launches = 0;
+    for (int l = 0; l < net->n_layers; ++l) {
+        const long long fl = pack_layer_floats(net, l);
+        if (fl == 0) continue;
+        const int K = net->dims[l] + (net->aux_layer == l ? net->aux_dim : 0);
+        const long long items = fl / 4;
+        mlp_pack_tf32_kernel<<<(unsigned)((items + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+            net->W[l], K, net->dims[l + 1], net->ldw[l], reinterpret_cast<float4*>(packed + off));
+        off += fl;
+        ++launches;
+    }
+    return sb200_launch_status(launches > 0 ? launches : 1);
+}
+
+extern "C" int sb200_mlp_forward_packed_f32(const sb200_mlp* net, const float* packed, const sb200_zfilter* zf,
+                                            const sb200_rows* in, float* out, int64_t ld_out, void* stream) {
+    SB200_REQUIRE(packed != nullptr && out != nullptr && (((uintptr_t)packed) & 15) == 0);
+    if (!pack_supported(net)) return SB200_ERR_UNSUPPORTED;
+    PkParams pp;
+    int maxw = 0;
+    const int rc = fill_fwd_params(net, zf, in, nullptr, nullptr, pp.f, &maxw);
+    if (rc != SB200_OK) return rc;
+    if (in->rows == 0) return SB200_OK;
+    SB200_REQUIRE(in->save_x == nullptr && ld_out >= net->dims[net->n_layers]);
+    long long off = 0;
+    int ldp = 4, head = 0;
+    for (int l = 0; l < SB200_MAX_LAYERS; ++l) {
+        pp.P[l] = nullptr;
+        if (l >= net->n_layers) continue;
+        const long long fl = pack_layer_floats(net, l);
+        const int K = net->dims[l] + (net->aux_layer == l ? net->aux_dim : 0);
+        if (fl > 0) {
+            pp.P[l] = packed + off;
+            off += fl;
+        } else {
+            ldp = round_up(K, 4) + 4;
+            head = K * net->ldw[l];
+        }
+    }
+    pp.out = out;
+    pp.ld_out = ld_out;
+    pp.nst_max = (round_up(maxw, 8)) / 8;
+    pp.ldp = ldp;
+    const int zf_floats = (pp.f.zf != nullptr) ? 2 * net->dims[0] : 0;
+    int scratch = zf_floats + ((head <= 16384) ? head : 0);
+    scratch = round_up(scratch > 0 ? scratch : 4, 4);
+    pp.f.scratch_floats = scratch;
+    const size_t smem = (size_t)(4 * pp.nst_max * 128 + 16 * ldp + scratch) * sizeof(float);
+    if (smem > 200 * 1024) return SB200_ERR_UNSUPPORTED;
+    const long long clusters = (in->rows + 15) / 16;
+    mlp_fwd_pk_kernel<<<(unsigned)(2 * clusters), SB200_THREADS, smem, (cudaStream_t)stream>>>(pp);
+    return sb200_launch_status();
+}
+
+extern "C" int sb200_mlp_forward_f32(const sb200_mlp* net, const sb200_zfilter* zf, const sb200_rows* in,
+                                     float* const* save, const int64_t* ld_save, void* stream) {
+    FwdParams p;
+    int maxw = 0;
+    {
+        const int rc = fill_fwd_params(net, zf, in, save, ld_save, p, &maxw);
+        if (rc != SB200_OK) return rc;
+    }
+    if (in->rows == 0) return SB200_OK;
     const size_t budget = SMEM_BUDGET;
     auto fits = [&](int bm, int bk) {
         return (size_t)(2 * bm * (round_up(maxw, bk) + 4) + 2 * bk * PASS_N) * 4 <= budget;

@@ -10,24 +10,23 @@ namespace {
 
 constexpr int RT = 256;
 
+struct FifoState;
+__device__ void assign_window_slots(int N, int n_step, const int* __restrict__ stage_pos, int* __restrict__ dest,
+                                    FifoState* fifo);
+__device__ unsigned int* fifo_ticket(FifoState* fifo);
+
 // ------------------------------------------------------------------------------------------------
 // PPOAgent.act after the network (ppo_agent.py:138-149): pd = [mean | exp(log_var)*exp(noise_i)],
 // action = clip(eps*std + mean, -1, 1) (or the mean when deterministic).  eps: injected N(0,1) draws
 // [N,A] or NULL -> Philox4x32-10 keyed by (seed, step counter, actor).  Also writes the step's action
 // and pd rows into the window staging area at the actor's current deque position.
-__global__ void __launch_bounds__(RT) ppo_sample_kernel(const float* __restrict__ mean, long long ldm,
-                                                        const float* __restrict__ log_var,
-                                                        const float* __restrict__ log_noise,
-                                                        const float* __restrict__ eps, int N, int A,
-                                                        int deterministic, unsigned long long seed,
-                                                        const unsigned long long* __restrict__ step_ctr,
-                                                        float* __restrict__ action, float* __restrict__ pd,
-                                                        const int* __restrict__ stage_pos,
-                                                        float* __restrict__ stage_act,
-                                                        float* __restrict__ stage_pd, int n_step) {
-    const int groups = (A + 3) >> 2;                      // one thread per (actor, 4 action dims)
-    const int t = blockIdx.x * RT + threadIdx.x;
-    if (t >= N * groups) return;
+__device__ __forceinline__ void sample_one(const float* __restrict__ mean, long long ldm,
+                                           const float* __restrict__ log_var, const float* __restrict__ log_noise,
+                                           const float* __restrict__ eps, int N, int A, int deterministic,
+                                           unsigned long long seed, const unsigned long long* step_ctr,
+                                           float* __restrict__ action, float* __restrict__ pd,
+                                           const int* __restrict__ stage_pos, float* __restrict__ stage_act,
+                                           float* __restrict__ stage_pd, int n_step, int t, int groups) {
     const int i = t / groups, j0 = (t - i * groups) * 4;
     const float sc = (log_noise != nullptr) ? expf(log_noise[i]) : 1.0f;
     const unsigned long long ctr = (step_ctr != nullptr) ? *step_ctr : 0ull;
@@ -58,6 +57,32 @@ __global__ void __launch_bounds__(RT) ppo_sample_kernel(const float* __restrict_
             stage_pd[((long long)i * n_step + p) * 2 * A + j] = mu;
             stage_pd[((long long)i * n_step + p) * 2 * A + A + j] = sd;
         }
+    }
+}
+
+__global__ void __launch_bounds__(RT) ppo_sample_kernel(const float* __restrict__ mean, long long ldm,
+                                                        const float* __restrict__ log_var,
+                                                        const float* __restrict__ log_noise,
+                                                        const float* __restrict__ eps, int N, int A,
+                                                        int deterministic, unsigned long long seed,
+                                                        const unsigned long long* step_ctr,
+                                                        float* __restrict__ action, float* __restrict__ pd,
+                                                        const int* __restrict__ stage_pos,
+                                                        float* __restrict__ stage_act,
+                                                        float* __restrict__ stage_pd, int n_step,
+                                                        FifoState* fifo, int* __restrict__ dest,
+                                                        unsigned long long* step_ctr_mut) {
+    const int groups = (A + 3) >> 2;                      // one thread per (actor, 4 action dims)
+    const int t = blockIdx.x * RT + threadIdx.x;
+    if (t < N * groups) sample_one(mean, ldm, log_var, log_noise, eps, N, A, deterministic, seed, step_ctr, action, pd,
+                                   stage_pos, stage_act, stage_pd, n_step, t, groups);
+    if (fifo != nullptr) {
+        // Fused slot assignment for the windows this step completes (it needs only the deque lengths): block 0,
+        // while the other blocks sample.  The LAST block to finish advances the shared step counter, after
+        // every block has read it.
+        if (blockIdx.x == 0) assign_window_slots(N, n_step, stage_pos, dest, fifo);
+        if (last_block_ticket(fifo_ticket(fifo), gridDim.x) && threadIdx.x == 0 && step_ctr_mut != nullptr)
+            *step_ctr_mut += 1ull;
     }
 }
 
@@ -98,19 +123,17 @@ __global__ void __launch_bounds__(RT) ddpg_noise_kernel(const float* __restrict_
 // One block per 4 actors; the weights are passed TRANSPOSED (WsT [D][D], WaT [A][D]: k-major) so that the
 // threads of a warp read consecutive addresses; they stay L1/L2-resident (18 KB).  obs_next = the true successor (terminal
 // when done), state = what the agent observes next (reset when done).
-__global__ void __launch_bounds__(RT) synth_env_step_kernel(float* __restrict__ state, const float* __restrict__ action,
-                                                            const float* __restrict__ Ws, const float* __restrict__ Wa,
-                                                            int N, int D, int A, int max_steps,
-                                                            int* __restrict__ ep_step, unsigned long long seed,
-                                                            const unsigned long long* __restrict__ step_ctr,
-                                                            float* __restrict__ obs_next, float* __restrict__ reward,
-                                                            float* __restrict__ done) {
-    extern __shared__ float sm[];                  // [4][D] states, [4][A] actions, [4] reward partials
+// Block-level body (RT threads, 4 actors).  s_n / s_z (optional) receive the successor and the next observed
+// state of the block's actors, s_rew / s_dn their reward and done flag.
+__device__ void synth_env_block(float* __restrict__ state, const float* __restrict__ action,
+                                const float* __restrict__ Ws, const float* __restrict__ Wa, int N, int D, int A,
+                                int max_steps, int* __restrict__ ep_step, unsigned long long seed,
+                                const unsigned long long* __restrict__ step_ctr, float* __restrict__ obs_next,
+                                float* __restrict__ reward, float* __restrict__ done, float* s_s, float* s_a,
+                                float* s_q, float* s_n, float* s_z, float* s_rew, float* s_dn,
+                                unsigned long long ctr_bias) {
     const int per = 4;
     const int a0 = blockIdx.x * per;
-    float* s_s = sm;
-    float* s_a = sm + per * D;
-    __shared__ float s_r[4][8];
     const int tid = threadIdx.x;
     for (int idx = tid; idx < per * D; idx += RT) {
         const int q = idx / D, d = idx - q * D;
@@ -121,14 +144,16 @@ __global__ void __launch_bounds__(RT) synth_env_step_kernel(float* __restrict__ 
         s_a[idx] = (a0 + q < N) ? action[(long long)(a0 + q) * A + j] : 0.0f;
     }
     __syncthreads();
-    const unsigned long long ctr = (step_ctr != nullptr) ? *step_ctr : 0ull;
+    // ctr_bias = -1 in the fused rollout, where the sampling kernel has already advanced the counter: both launch
+    // sequences then draw the same noise for the same step
+    const unsigned long long ctr = ((step_ctr != nullptr) ? *step_ctr : 0ull) + ctr_bias;
     // reward: -|s|^2/D (+ noise), one warp per actor (warps 0..3)
     const int warp = tid >> 5, lane = tid & 31;
     if (warp < per) {
         float q = 0.0f;
         for (int d = lane; d < D; d += 32) q += s_s[warp * D + d] * s_s[warp * D + d];
         q = warp_sum(q);
-        if (lane == 0) s_r[warp][0] = q;
+        if (lane == 0) s_q[warp] = q;
     }
     __syncthreads();
     for (int idx = tid; idx < per * D; idx += RT) {
@@ -145,11 +170,21 @@ __global__ void __launch_bounds__(RT) synth_env_step_kernel(float* __restrict__ 
         const float nxt = tanhf(acc) + 0.01f * g.x;
         const int t = ep_step[i] + 1;
         const bool dn = (max_steps > 0) && (t >= max_steps);
+        const float st = dn ? box_muller(r.z, r.w).x : nxt;
         obs_next[(long long)i * D + d] = nxt;
-        state[(long long)i * D + d] = dn ? box_muller(r.z, r.w).x : nxt;
+        state[(long long)i * D + d] = st;
+        if (s_n != nullptr) {
+            s_n[idx] = nxt;
+            s_z[idx] = st;
+        }
         if (d == 0) {
-            reward[i] = -s_r[q][0] / (float)D + 0.1f * g.y;
+            const float rw = -s_q[q] / (float)D + 0.1f * g.y;
+            reward[i] = rw;
             done[i] = dn ? 1.0f : 0.0f;
+            if (s_rew != nullptr) {
+                s_rew[q] = rw;
+                s_dn[q] = dn ? 1.0f : 0.0f;
+            }
         }
     }
     __syncthreads();
@@ -162,11 +197,24 @@ __global__ void __launch_bounds__(RT) synth_env_step_kernel(float* __restrict__ 
     }
 }
 
+__global__ void __launch_bounds__(RT) synth_env_step_kernel(float* __restrict__ state, const float* __restrict__ action,
+                                                            const float* __restrict__ Ws, const float* __restrict__ Wa,
+                                                            int N, int D, int A, int max_steps,
+                                                            int* __restrict__ ep_step, unsigned long long seed,
+                                                            const unsigned long long* __restrict__ step_ctr,
+                                                            float* __restrict__ obs_next, float* __restrict__ reward,
+                                                            float* __restrict__ done) {
+    extern __shared__ float sm[];                  // [4][D] states, [4][A] actions
+    __shared__ float s_q[4];
+    synth_env_block(state, action, Ws, Wa, N, D, A, max_steps, ep_step, seed, step_ctr, obs_next, reward, done, sm,
+                    sm + 4 * D, s_q, nullptr, nullptr, nullptr, nullptr, 0ull);
+}
+
 // ------------------------------------------------------------------------------------------------
 // ExpSenderWrapperMultiStepMovingWindowWithInfo._step (exp_sender_wrapper.py:209-228), batched.
-// Phase 1 (single block, ordered): append (reward, done) at the actor's deque position, detect windows
-// that reached n_step, assign FIFO slots in (step, actor) order with drop-oldest at `capacity`
-// (fifo_replay.py:27), advance the RNG/step counter.
+// Slot assignment (one block, ordered): detect the deques that reach n_step with this step's append and give
+// them FIFO slots in (step, actor) order with drop-oldest at `capacity` (fifo_replay.py:27).  It depends only
+// on the deque lengths, so it can run before the environment has stepped (fused into the sampling kernel).
 struct FifoState {
     int head;        // physical index of the oldest window
     int count;       // windows currently queued
@@ -174,29 +222,24 @@ struct FifoState {
     int dropped;     // windows silently dropped so far (diagnostic)
     long long total_in;
     long long total_out;
+    unsigned int ticket;   // last-block ticket of the fused sampling kernel (self-resetting)
+    int pad_;
 };
 
-__global__ void __launch_bounds__(1024) ppo_window_flags_kernel(const float* __restrict__ reward,
-                                                                const float* __restrict__ done, int N, int n_step,
-                                                                int* __restrict__ stage_pos,
-                                                                float* __restrict__ stage_rew,
-                                                                float* __restrict__ stage_done,
-                                                                int* __restrict__ dest, FifoState* fifo,
-                                                                unsigned long long* step_ctr) {
+constexpr int SLOT_NONE = -1;      // deque not full after this step
+constexpr int SLOT_DROPPED = -2;   // window completes but falls straight out of the deque(maxlen)
+
+// dest[i] <- physical slot | SLOT_NONE | SLOT_DROPPED; advances the queue.  Called by all threads of ONE block.
+__device__ void assign_window_slots(int N, int n_step, const int* __restrict__ stage_pos, int* __restrict__ dest,
+                                    FifoState* fifo) {
     __shared__ int warp_tot[32];
     __shared__ int warp_excl[32];
     __shared__ int chunk_total;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
     int base = 0;                                  // windows completed by actors before this chunk
-    for (int i0 = 0; i0 < N; i0 += 1024) {
+    for (int i0 = 0; i0 < N; i0 += nt) {
         const int i = i0 + tid;
-        int flag = 0;
-        if (i < N) {
-            const int p = stage_pos[i];
-            stage_rew[(long long)i * n_step + p] = reward[i];
-            stage_done[(long long)i * n_step + p] = done[i];
-            flag = (p + 1 == n_step) ? 1 : 0;
-        }
+        const int flag = (i < N && stage_pos[i] + 1 == n_step) ? 1 : 0;
         int incl = flag;                           // inclusive scan inside the warp (actor order)
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -206,7 +249,7 @@ __global__ void __launch_bounds__(1024) ppo_window_flags_kernel(const float* __r
         if (lane == 31) warp_tot[warp] = incl;
         __syncthreads();
         if (warp == 0) {
-            const int w = warp_tot[lane];
+            const int w = (lane < nw) ? warp_tot[lane] : 0;
             int wi = w;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -217,7 +260,7 @@ __global__ void __launch_bounds__(1024) ppo_window_flags_kernel(const float* __r
             if (lane == 31) chunk_total = wi;
         }
         __syncthreads();
-        if (i < N) dest[i] = flag ? (base + warp_excl[warp] + incl - flag) : -1;
+        if (i < N) dest[i] = flag ? (base + warp_excl[warp] + incl - flag) : SLOT_NONE;
         base += chunk_total;
         __syncthreads();
     }
@@ -225,14 +268,14 @@ __global__ void __launch_bounds__(1024) ppo_window_flags_kernel(const float* __r
     const int K = base;
     const int cap = fifo->capacity;
     const int head = fifo->head, count = fifo->count;
-    for (int i = tid; i < N; i += 1024) {
+    __syncthreads();
+    for (int i = tid; i < N; i += nt) {
         const int r = dest[i];
         if (r >= 0) {
             // more arrivals than the deque holds: the earliest of THIS step fall out immediately
-            dest[i] = (K > cap && r < K - cap) ? -1 : (int)(((long long)head + count + r) % cap);
+            dest[i] = (K > cap && r < K - cap) ? SLOT_DROPPED : (int)(((long long)head + count + r) % cap);
         }
     }
-    __syncthreads();
     if (tid == 0) {
         int nc = count + K, nh = head, dr = 0;
         if (nc > cap) {                       // deque(maxlen): the oldest entries fall out
@@ -244,15 +287,111 @@ __global__ void __launch_bounds__(1024) ppo_window_flags_kernel(const float* __r
         fifo->count = nc;
         fifo->dropped += dr;
         fifo->total_in += K;
-        if (step_ctr != nullptr) *step_ctr += 1ull;
     }
 }
 
-// Phase 2: one block per actor.  Writes obs_next at deque position p+1; if the window completed, copies it
-// into the replay slot (coalesced float4 where aligned) and pops `stride` items; if the episode ended,
-// clears the deque (exp_sender_wrapper.py:204-207) and seeds position 0 with the reset observation.
+__device__ unsigned int* fifo_ticket(FifoState* fifo) { return &fifo->ticket; }
+
+__global__ void __launch_bounds__(1024) ppo_window_slots_kernel(int N, int n_step, const int* __restrict__ stage_pos,
+                                                                int* __restrict__ dest, FifoState* fifo,
+                                                                unsigned long long* step_ctr) {
+    assign_window_slots(N, n_step, stage_pos, dest, fifo);
+    if (threadIdx.x == 0 && step_ctr != nullptr) *step_ctr += 1ull;
+}
+
+__device__ __forceinline__ void copy_floats(float* __restrict__ dst, const float* __restrict__ src, int count, int g,
+                                            int G) {
+    if (((count & 3) == 0) && ((((uintptr_t)dst) | ((uintptr_t)src)) & 15) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (int k = g; k < (count >> 2); k += G) d4[k] = s4[k];
+    } else {
+        for (int k = g; k < count; k += G) dst[k] = src[k];
+    }
+}
+
+// Commit of one actor's step by a group of G threads (g = index inside the group).  Appends (reward, done) at
+// deque position p and obs_next at p+1; if the window completed, copies it into its replay slot and pops
+// `stride` items; if the episode ended, clears the deque (exp_sender_wrapper.py:204-207) and seeds position 0
+// with the reset observation.  Barriers are block-wide and executed by EVERY thread (valid or not).
+__device__ void commit_actor(bool valid, int i, int g, int G, const float* __restrict__ next_row,
+                             const float* __restrict__ reset_row, float rew, float dn, int n_step, int stride, int D,
+                             int A, int* __restrict__ stage_pos, float* __restrict__ stage_obs,
+                             float* __restrict__ stage_act, float* __restrict__ stage_pd,
+                             float* __restrict__ stage_rew, float* __restrict__ stage_done,
+                             const int* __restrict__ dest, float* __restrict__ r_obs, float* __restrict__ r_act,
+                             float* __restrict__ r_pd, float* __restrict__ r_rew, float* __restrict__ r_done) {
+    const long long ii = valid ? i : 0;
+    const int p = valid ? stage_pos[ii] : 0;
+    float* so = stage_obs + ii * (n_step + 1) * D;
+    float* sa = stage_act + ii * n_step * A;
+    float* sp = stage_pd + ii * n_step * 2 * A;
+    float* sr = stage_rew + ii * n_step;
+    float* sd = stage_done + ii * n_step;
+    if (valid) {
+        for (int d = g; d < D; d += G) so[(long long)(p + 1) * D + d] = next_row[d];
+        if (g == 0) {
+            sr[p] = rew;
+            sd[p] = dn;
+        }
+    }
+    __syncthreads();
+    int len = p + 1;
+    const int slot = valid ? dest[ii] : SLOT_NONE;
+    const bool complete = (slot != SLOT_NONE);               // len == n_step
+    if (slot >= 0) {                                         // ship the window
+        copy_floats(r_obs + (long long)slot * (n_step + 1) * D, so, (n_step + 1) * D, g, G);
+        copy_floats(r_act + (long long)slot * n_step * A, sa, n_step * A, g, G);
+        copy_floats(r_pd + (long long)slot * n_step * 2 * A, sp, n_step * 2 * A, g, G);
+        copy_floats(r_rew + (long long)slot * n_step, sr, n_step, g, G);
+        copy_floats(r_done + (long long)slot * n_step, sd, n_step, g, G);
+    }
+    __syncthreads();
+    const int pop = min(stride, n_step);                     // uniform: every completing deque holds n_step items
+    const int keep = n_step - pop;
+    if (keep > 0) {                                          // overlapping windows: slide the deque down
+        for (int k0 = 0; k0 < (keep + 1) * D; k0 += G) {
+            const int k = k0 + g;
+            const bool on = complete && k < (keep + 1) * D;
+            float v = 0.f;
+            if (on) v = so[(long long)pop * D + k];
+            __syncthreads();
+            if (on) so[k] = v;
+            __syncthreads();
+        }
+        for (int k0 = 0; k0 < keep * 2 * A; k0 += G) {
+            const int k = k0 + g;
+            float va = 0.f, vp = 0.f;
+            if (complete && k < keep * A) va = sa[(long long)pop * A + k];
+            if (complete && k < keep * 2 * A) vp = sp[(long long)pop * 2 * A + k];
+            __syncthreads();
+            if (complete && k < keep * A) sa[k] = va;
+            if (complete && k < keep * 2 * A) sp[k] = vp;
+            __syncthreads();
+        }
+        for (int k0 = 0; k0 < keep; k0 += G) {
+            const int k = k0 + g;
+            float vr = 0.f, vd = 0.f;
+            if (complete && k < keep) { vr = sr[pop + k]; vd = sd[pop + k]; }
+            __syncthreads();
+            if (complete && k < keep) { sr[k] = vr; sd[k] = vd; }
+            __syncthreads();
+        }
+    } else if (complete) {
+        for (int d = g; d < D; d += G) so[d] = next_row[d];                 // obs_next -> next window's first obs
+    }
+    if (complete) len = keep;
+    __syncthreads();
+    if (valid && dn > 0.5f) {                                // episode over: deque cleared, new episode's first obs
+        for (int d = g; d < D; d += G) so[d] = reset_row[d];
+        len = 0;
+    }
+    if (valid && g == 0) stage_pos[ii] = len;
+}
+
 __global__ void __launch_bounds__(128) ppo_window_commit_kernel(const float* __restrict__ obs_next,
                                                                 const float* __restrict__ obs_reset,
+                                                                const float* __restrict__ reward,
                                                                 const float* __restrict__ done, int N, int n_step,
                                                                 int stride, int D, int A,
                                                                 int* __restrict__ stage_pos,
@@ -266,71 +405,38 @@ __global__ void __launch_bounds__(128) ppo_window_commit_kernel(const float* __r
                                                                 float* __restrict__ r_pd, float* __restrict__ r_rew,
                                                                 float* __restrict__ r_done) {
     const int i = blockIdx.x;
+    commit_actor(true, i, threadIdx.x, blockDim.x, obs_next + (long long)i * D, obs_reset + (long long)i * D, reward[i],
+                 done[i], n_step, stride, D, A, stage_pos, stage_obs, stage_act, stage_pd, stage_rew, stage_done, dest,
+                 r_obs, r_act, r_pd, r_rew, r_done);
+}
+
+// Fused environment step + window commit for the device-resident synthetic env: the successor state never
+// leaves shared memory before it is staged.  One block per 4 actors, 64 threads per actor in the commit.
+__global__ void __launch_bounds__(RT) synth_env_window_step_kernel(
+    float* __restrict__ state, const float* __restrict__ action, const float* __restrict__ Ws,
+    const float* __restrict__ Wa, int N, int D, int A, int max_steps, int* __restrict__ ep_step,
+    unsigned long long seed, const unsigned long long* __restrict__ step_ctr, float* __restrict__ obs_next,
+    float* __restrict__ reward, float* __restrict__ done, int n_step, int stride, int* __restrict__ stage_pos,
+    float* __restrict__ stage_obs, float* __restrict__ stage_act, float* __restrict__ stage_pd,
+    float* __restrict__ stage_rew, float* __restrict__ stage_done, const int* __restrict__ dest,
+    float* __restrict__ r_obs, float* __restrict__ r_act, float* __restrict__ r_pd, float* __restrict__ r_rew,
+    float* __restrict__ r_done) {
+    extern __shared__ float sm[];                  // [4][D] states, [4][A] actions, [4][D] successor, [4][D] reset
+    const int per = 4;
+    const int a0 = blockIdx.x * per;
+    float* s_s = sm;
+    float* s_a = sm + per * D;
+    float* s_n = s_a + per * A;
+    float* s_z = s_n + per * D;
+    __shared__ float s_q[4], s_rew[4], s_dn[4];
     const int tid = threadIdx.x;
-    const int p = stage_pos[i];
-    float* so = stage_obs + (long long)i * (n_step + 1) * D;
-    float* sa = stage_act + (long long)i * n_step * A;
-    float* sp = stage_pd + (long long)i * n_step * 2 * A;
-    float* sr = stage_rew + (long long)i * n_step;
-    float* sd = stage_done + (long long)i * n_step;
-    for (int d = tid; d < D; d += blockDim.x) so[(long long)(p + 1) * D + d] = obs_next[(long long)i * D + d];
+    synth_env_block(state, action, Ws, Wa, N, D, A, max_steps, ep_step, seed, step_ctr, obs_next, reward, done, s_s, s_a,
+                    s_q, s_n, s_z, s_rew, s_dn, ~0ull);
     __syncthreads();
-    int len = p + 1;
-    const int slot = dest[i];
-    if (slot >= 0) {                                         // len == n_step: ship the window
-        float* o = r_obs + (long long)slot * (n_step + 1) * D;
-        for (int k = tid; k < (n_step + 1) * D; k += blockDim.x) o[k] = so[k];
-        float* a = r_act + (long long)slot * n_step * A;
-        for (int k = tid; k < n_step * A; k += blockDim.x) a[k] = sa[k];
-        float* q = r_pd + (long long)slot * n_step * 2 * A;
-        for (int k = tid; k < n_step * 2 * A; k += blockDim.x) q[k] = sp[k];
-        float* r = r_rew + (long long)slot * n_step;
-        float* dn = r_done + (long long)slot * n_step;
-        for (int k = tid; k < n_step; k += blockDim.x) {
-            r[k] = sr[k];
-            dn[k] = sd[k];
-        }
-        __syncthreads();
-        const int pop = min(stride, len);
-        const int keep = len - pop;
-        if (keep > 0) {                                      // overlapping windows: slide the deque down
-            for (int k0 = 0; k0 < (keep + 1) * D; k0 += blockDim.x) {
-                const int k = k0 + tid;
-                float v = 0.f;
-                if (k < (keep + 1) * D) v = so[(long long)pop * D + k];
-                __syncthreads();
-                if (k < (keep + 1) * D) so[k] = v;
-                __syncthreads();
-            }
-            for (int k0 = 0; k0 < keep * 2 * A; k0 += blockDim.x) {
-                const int k = k0 + tid;
-                float va = 0.f, vp = 0.f;
-                if (k < keep * A) va = sa[(long long)pop * A + k];
-                if (k < keep * 2 * A) vp = sp[(long long)pop * 2 * A + k];
-                __syncthreads();
-                if (k < keep * A) sa[k] = va;
-                if (k < keep * 2 * A) sp[k] = vp;
-                __syncthreads();
-            }
-            for (int k0 = 0; k0 < keep; k0 += blockDim.x) {
-                const int k = k0 + tid;
-                float vr = 0.f, vd = 0.f;
-                if (k < keep) { vr = sr[pop + k]; vd = sd[pop + k]; }
-                __syncthreads();
-                if (k < keep) { sr[k] = vr; sd[k] = vd; }
-                __syncthreads();
-            }
-        } else {
-            for (int d = tid; d < D; d += blockDim.x) so[d] = so[(long long)len * D + d];   // obs_next -> next obs
-        }
-        len = keep;
-    }
-    __syncthreads();
-    if (done[i] > 0.5f) {                                    // episode over: deque cleared, new episode's first obs
-        for (int d = tid; d < D; d += blockDim.x) so[d] = obs_reset[(long long)i * D + d];
-        len = 0;
-    }
-    if (tid == 0) stage_pos[i] = len;
+    const int q = tid >> 6, g = tid & 63;
+    const int i = a0 + q;
+    commit_actor(i < N, i, g, 64, s_n + q * D, s_z + q * D, s_rew[q], s_dn[q], n_step, stride, D, A, stage_pos, stage_obs,
+                 stage_act, stage_pd, stage_rew, stage_done, dest, r_obs, r_act, r_pd, r_rew, r_done);
 }
 
 }  // namespace
@@ -343,7 +449,22 @@ extern "C" int sb200_ppo_sample_f32(const float* mean, int64_t ldm, const float*
     SB200_REQUIRE(stage_act == nullptr || (stage_pos != nullptr && stage_pd != nullptr && n_step >= 1));
     ppo_sample_kernel<<<(N * ((A + 3) / 4) + RT - 1) / RT, RT, 0, (cudaStream_t)stream>>>(
         mean, ldm, log_var, log_noise, eps, N, A, deterministic, (unsigned long long)seed,
-        (const unsigned long long*)step_counter, action, pd, stage_pos, stage_act, stage_pd, n_step);
+        (const unsigned long long*)step_counter, action, pd, stage_pos, stage_act, stage_pd, n_step, nullptr, nullptr,
+        nullptr);
+    return sb200_launch_status();
+}
+
+extern "C" int sb200_ppo_sample_assign_f32(const float* mean, int64_t ldm, const float* log_var,
+                                           const float* log_noise, const float* eps, int N, int A, int deterministic,
+                                           uint64_t seed, uint64_t* step_counter, float* action, float* pd,
+                                           const int* stage_pos, float* stage_act, float* stage_pd, int n_step,
+                                           void* fifo_state, int* dest, void* stream) {
+    SB200_REQUIRE(mean && log_var && action && pd && N >= 1 && A >= 1 && ldm >= A);
+    SB200_REQUIRE(stage_pos && stage_act && stage_pd && n_step >= 1 && fifo_state && dest && step_counter);
+    ppo_sample_kernel<<<(N * ((A + 3) / 4) + RT - 1) / RT, RT, 0, (cudaStream_t)stream>>>(
+        mean, ldm, log_var, log_noise, eps, N, A, deterministic, (unsigned long long)seed,
+        (const unsigned long long*)step_counter, action, pd, stage_pos, stage_act, stage_pd, n_step,
+        (FifoState*)fifo_state, dest, (unsigned long long*)step_counter);
     return sb200_launch_status();
 }
 
@@ -370,6 +491,29 @@ extern "C" int sb200_synth_env_step_f32(float* state, const float* action, const
     return sb200_launch_status();
 }
 
+static bool env_smem_ok(int D, int A, bool fused) {
+    return (size_t)(4 * (D + A) + (fused ? 8 * D : 0)) * sizeof(float) <= 40 * 1024;
+}
+
+extern "C" int sb200_synth_env_window_step_f32(float* state, const float* action, const float* Ws, const float* Wa,
+                                               int N, int D, int A, int max_steps, int* ep_step, uint64_t seed,
+                                               const uint64_t* step_counter, float* obs_next, float* reward,
+                                               float* done, int n_step, int stride, int* stage_pos, float* stage_obs,
+                                               float* stage_act, float* stage_pd, float* stage_rew, float* stage_done,
+                                               const int* dest, float* r_obs, float* r_act, float* r_pd, float* r_rew,
+                                               float* r_done, void* stream) {
+    SB200_REQUIRE(state && action && Ws && Wa && ep_step && obs_next && reward && done);
+    SB200_REQUIRE(stage_pos && stage_obs && stage_act && stage_pd && stage_rew && stage_done && dest);
+    SB200_REQUIRE(r_obs && r_act && r_pd && r_rew && r_done);
+    SB200_REQUIRE(N >= 1 && D >= 1 && A >= 1 && n_step >= 1 && stride >= 1 && env_smem_ok(D, A, true));
+    const size_t smem = (size_t)(4 * (D + A) + 8 * D) * sizeof(float);
+    synth_env_window_step_kernel<<<(N + 3) / 4, RT, smem, (cudaStream_t)stream>>>(
+        state, action, Ws, Wa, N, D, A, max_steps, ep_step, (unsigned long long)seed,
+        (const unsigned long long*)step_counter, obs_next, reward, done, n_step, stride, stage_pos, stage_obs, stage_act,
+        stage_pd, stage_rew, stage_done, dest, r_obs, r_act, r_pd, r_rew, r_done);
+    return sb200_launch_status();
+}
+
 extern "C" size_t sb200_fifo_state_bytes(void) { return sizeof(FifoState); }
 
 extern "C" int sb200_ppo_window_step_f32(const float* obs_next, const float* obs_reset, const float* reward,
@@ -377,15 +521,16 @@ extern "C" int sb200_ppo_window_step_f32(const float* obs_next, const float* obs
                                          int* stage_pos, float* stage_obs, float* stage_act, float* stage_pd,
                                          float* stage_rew, float* stage_done, int* dest_scratch, void* fifo_state,
                                          float* r_obs, float* r_act, float* r_pd, float* r_rew, float* r_done,
-                                         uint64_t* step_counter, void* stream) {
+                                         uint64_t* step_counter, int slots_assigned, void* stream) {
     SB200_REQUIRE(obs_next && obs_reset && reward && done && stage_pos && stage_obs && stage_act && stage_pd);
     SB200_REQUIRE(stage_rew && stage_done && dest_scratch && fifo_state && r_obs && r_act && r_pd && r_rew && r_done);
     SB200_REQUIRE(N >= 1 && n_step >= 1 && stride >= 1 && D >= 1 && A >= 1);
     cudaStream_t st = (cudaStream_t)stream;
-    ppo_window_flags_kernel<<<1, 1024, 0, st>>>(reward, done, N, n_step, stage_pos, stage_rew, stage_done, dest_scratch,
-                                                (FifoState*)fifo_state, (unsigned long long*)step_counter);
-    ppo_window_commit_kernel<<<N, 128, 0, st>>>(obs_next, obs_reset, done, N, n_step, stride, D, A, stage_pos, stage_obs,
-                                                stage_act, stage_pd, stage_rew, stage_done, dest_scratch, r_obs, r_act,
-                                                r_pd, r_rew, r_done);
-    return sb200_launch_status(2);
+    if (!slots_assigned)
+        ppo_window_slots_kernel<<<1, 1024, 0, st>>>(N, n_step, stage_pos, dest_scratch, (FifoState*)fifo_state,
+                                                    (unsigned long long*)step_counter);
+    ppo_window_commit_kernel<<<N, 128, 0, st>>>(obs_next, obs_reset, reward, done, N, n_step, stride, D, A, stage_pos,
+                                                stage_obs, stage_act, stage_pd, stage_rew, stage_done, dest_scratch,
+                                                r_obs, r_act, r_pd, r_rew, r_done);
+    return sb200_launch_status(slots_assigned ? 1 : 2);
 }

@@ -120,6 +120,46 @@ def zfilter_desc(stats, eps=1e-5):
     return z
 
 
+class PackedWeights:
+    """Per-step inference copy of a FlatNet's weights in tensor-core fragment order (sb200_mlp_pack_tf32), for
+    mlp_forward_packed.  The owner calls ``refresh()`` whenever the parameters may have changed -- the agents do
+    it at every parameter fetch and at the top of every rollout chunk, so a pack can never outlive its version."""
+
+    def __init__(self, net):
+        self.net = net
+        d = net.desc()
+        n = int(_lib.lib().sb200_mlp_pack_floats(C.byref(d)))
+        self.supported = n > 0
+        self.buf = torch.zeros(max(n, 4), dtype=torch.float32, device=net.device) if self.supported else None
+
+    def refresh(self):
+        if self.supported:
+            d = self.net.desc()
+            check(_lib.lib().sb200_mlp_pack_tf32(C.byref(d), _ptr(self.buf), _stream()), 'sb200_mlp_pack_tf32')
+        return self
+
+
+def mlp_forward_packed(packed, x, zf_stats=None, zf_eps=1e-5, aux=None, out=None):
+    """Small-batch inference forward on pre-packed weights; x: [rows, D] contiguous-row CUDA tensor."""
+    net = packed.net
+    assert packed.supported and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    r = Rows()
+    r.x, r.x_next, r.ldx, r.rows, r.win_n = x.data_ptr(), None, x.stride(0), x.shape[0], 0
+    if net.aux_layer >= 0:
+        assert aux is not None and aux.is_cuda and aux.stride(-1) == 1
+        r.aux, r.aux_ld = aux.data_ptr(), aux.stride(0)
+    else:
+        r.aux, r.aux_ld = None, 0
+    r.save_x, r.ld_save_x = None, 0
+    if out is None:
+        out = torch.empty(x.shape[0], net.dims[-1], dtype=torch.float32, device=x.device)
+    zf = zfilter_desc(zf_stats, zf_eps)
+    d = net.desc()
+    check(_lib.lib().sb200_mlp_forward_packed_f32(C.byref(d), _ptr(packed.buf), C.byref(zf), C.byref(r), _ptr(out),
+                                                  out.stride(0), _stream()), 'sb200_mlp_forward_packed_f32')
+    return out
+
+
 def mlp_forward(net, x, zf_stats=None, zf_eps=1e-5, x_next=None, win_n=0, aux=None, save_all=False,
                 params=None, out=None, rows=None, ldx=None, saves=None, save_x=None):
     """Run the fused forward.

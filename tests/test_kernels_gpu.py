@@ -73,6 +73,53 @@ def test_mlp_forward_matches_oracle(dims, rows, zf):
         assert_close_scale(o, e, 1e-5, 'layer %d' % l)
 
 
+@pytest.mark.parametrize('dims,rows,zf,aux', [
+    ([64, 256, 256, 8], 1024, True, None),      # cfg2 actor: one env step of all actors
+    ([64, 256, 256, 8], 1000, True, None),      # rows not a multiple of the 16-row cluster tile
+    ([17, 300, 200, 6], 333, True, None),       # reference default hidden sizes: odd K, n-tiles not a pass multiple
+    ([33, 100, 52, 40], 50, False, None),       # wide LAST layer (written straight to global memory)
+    ([10, 400, 300, 1], 77, False, (1, 4)),     # DDPG critic: action concatenated into layer 1
+    ([10, 44, 36, 3], 21, False, (1, 5)),       # aux columns sharing a k-step with the previous layer's tail
+    ([12, 64, 5], 9, True, (0, 3)),             # aux on the input layer, 2-layer net
+])
+def test_mlp_forward_packed_matches_oracle(dims, rows, zf, aux):
+    """Small-batch inference on pre-packed fragment-order weights (2-CTA cluster, DSMEM exchange)."""
+    from surreal_b200 import ops
+    gen = torch.Generator().manual_seed(sum(dims) + rows)
+    aux_layer, aux_dim = aux if aux is not None else (-1, 0)
+    layers = _rand_layers(dims, gen, aux_layer=aux_layer, aux_dim=aux_dim)
+    acts = [ops.ACT_RELU] * (len(dims) - 2) + [ops.ACT_TANH if dims[-1] > 1 else ops.ACT_NONE]
+    x = torch.randn(rows, dims[0], generator=gen) * 2 + 0.5
+    a = torch.rand(rows, max(aux_dim, 1), generator=gen) * 2 - 1
+    ozf, stats = None, None
+    if zf:
+        ozf = OZFilter(dims[0])
+        ozf.update(torch.randn(200, dims[0], generator=gen) * 1.7 + 0.4)
+        stats = torch.cat([ozf.running_sum, ozf.running_sumsq, ozf.count]).to(_dev())
+    net = ops.FlatNet(dims, acts, _dev(), aux_layer=aux_layer, aux_dim=aux_dim).load_layers(layers)
+    pk = ops.PackedWeights(net)
+    assert pk.supported
+    pk.refresh()
+    out = ops.mlp_forward_packed(pk, x.to(_dev()), zf_stats=stats, aux=a.to(_dev()) if aux is not None else None)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        h = ozf.forward(x) if zf else x
+        for l, (w, b) in enumerate(layers):
+            if l == aux_layer:
+                h = torch.cat([h, a], 1)
+            h = torch.nn.functional.linear(h, w, b)
+            h = torch.relu(h) if acts[l] == ops.ACT_RELU else (torch.tanh(h) if acts[l] == ops.ACT_TANH else h)
+    assert out.shape == h.shape
+    assert_close_scale(out, h, 1e-5, 'packed forward')
+    # a re-pack after a parameter change is picked up; an architecture with a narrow hidden layer is declined
+    net.params.mul_(0.5)
+    pk.refresh()
+    out2 = ops.mlp_forward_packed(pk, x.to(_dev()), zf_stats=stats, aux=a.to(_dev()) if aux is not None else None)
+    ref2 = ops.mlp_forward(net, x.to(_dev()), zf_stats=stats, aux=a.to(_dev()) if aux is not None else None)
+    assert_close_scale(out2, ref2, 1e-5, 'packed vs tiled after re-pack')
+    assert not ops.PackedWeights(ops.FlatNet([8, 16, 64, 2], [ops.ACT_RELU] * 3, _dev())).supported
+
+
 def test_mlp_forward_window_rows_and_aux():
     """virtual cat([obs, obs_next]) row mapping (ppo.py:376-383) and the DDPG critic's cat(h, action)."""
     from surreal_b200 import ops

@@ -320,3 +320,41 @@ def test_pipelined_engine_matches_sequential_semantics():
     assert versions == [1, 2, 3, 4, 5, 6]
     assert agent._ps_client._last_version in (5, 6)               # one publish behind the learner at most
     assert learner.current_iteration == 6
+
+
+@pytest.mark.parametrize('n,stride,cap_extra', [(8, 8, 40), (6, 4, 40), (4, 4, -30)])
+def test_fused_rollout_launches_match_unfused(n, stride, cap_extra):
+    """sample+slot-assignment and env+commit fused launches (3 per step) against the 5-launch sequence: identical
+    actions, staging and FIFO contents, including overlapping windows, episode ends and a queue that overflows
+    inside ONE step (more completing actors than capacity)."""
+    from surreal_b200.agent import PPOAgent
+    from surreal_b200.replay import FIFOReplay
+    from surreal_b200.env import SyntheticEnv
+    N, D, A, T = 50, 12, 3, 37
+    out = []
+    for fuse in (True, False):
+        lc, ec, sc = ppo_configs(D=D, A=A, actor_h=(40, 36), critic_h=(40, 36), n_step=n, stride=stride, B=8,
+                                 memory_size=N + cap_extra)
+        ec.num_envs = N
+        R = FIFOReplay(lc, ec, sc)
+        ag = PPOAgent(lc, ec, sc, 1, 'training')
+        torch.manual_seed(5)
+        ag.model.actor.params.copy_(torch.randn_like(ag.model.actor.params) * 0.2)
+        env = SyntheticEnv(N, D, A, limit_episode_length=11, seed=4)
+        ag.env = w = ag.prepare_env_agent(env)
+        w.fuse_launches = fuse
+        obs, _ = w.reset()
+        acts = []
+        for _ in range(T):
+            a = ag.act(obs)
+            acts.append(a[0].clone())
+            obs, _, _, _ = w.step(a)
+        torch.cuda.synchronize()
+        out.append(dict(acts=torch.stack(acts), state=R._read_state(), pos=w.stage_pos.clone(), so=w.stage_obs.clone(),
+                        r_obs=R.r_obs.clone(), r_act=R.r_act.clone(), r_pd=R.r_pd.clone(), r_rew=R.r_rew.clone(),
+                        r_done=R.r_done.clone(), ctr=int(env.step_counter.item())))
+    f, u = out
+    assert f['state'] == u['state'] and f['ctr'] == u['ctr'] == T
+    assert f['state']['total_in'] > 0 and (cap_extra > 0 or f['state']['dropped'] > 0)
+    for k in ['acts', 'pos', 'r_obs', 'r_act', 'r_pd', 'r_rew', 'r_done']:
+        assert torch.equal(f[k], u[k]), k

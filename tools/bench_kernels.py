@@ -74,6 +74,23 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             print(json.dumps(dict(kernel='actor_forward_in_graph', rows=rows, us_per_launch=e0.elapsed_time(e1) * 1e3 / 320, **tag)))
+            pk = ops.PackedWeights(a).refresh()
+            med, mn = timeit(lambda: ops.mlp_forward_packed(pk, x, zf_stats=zs, out=out), reps=200)
+            print(json.dumps(dict(kernel='actor_forward_packed', rows=rows, median_us=med, min_us=mn, tflops=flop / med / 1e6)))
+            gr = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(gr):
+                for _ in range(64):
+                    ops.mlp_forward_packed(pk, x, zf_stats=zs, out=out)
+            gr.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                gr.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            print(json.dumps(dict(kernel='actor_forward_packed_in_graph', rows=rows, us_per_launch=e0.elapsed_time(e1) * 1e3 / 320)))
 
 
 if __name__ == '__main__':
