@@ -220,12 +220,16 @@ def run_ours(args):
                 'frac': ach / peaks['bf16_tflops'], 'traffic': None, 'avg_ms': avg_ms, 'launches_per_step': per_step[key][0],
                 'share_of_step_kernel_time': per_step[key][1] / total_kernel_ms, 'algorithmic_flop': flop,
                 'algorithmic_bytes': byts, 'achieved_gbs': byts / (avg_ms / 1e3) / 1e9, 'peak_source': peaks['source'],
-                'note': 'fp32-accurate FFMA path (the 1e-5 parity bar rules out plain TF32); dense-bf16 tensor peak is the '
-                        'mandated denominator, the chip\'s fp32 FFMA ceiling is ~72 TFLOP/s'}
-    roof_small = mlp_roof('sb200_mlp_forward_f32[rows=%d]' % N, N, A, 'mlp_fwd_skinny_kernel (actor / learner forward on %d rows)' % N)
+                'note': 'fp32-accurate 3xTF32 tensor-core path (the 1e-5 parity bar rules out plain TF32/bf16: every '
+                        'product costs 3 mma); dense-bf16 tensor peak is the mandated denominator.  At %d rows the '
+                        'kernel is a chain of dependent latencies, not a throughput problem' % nrows}
+    roof_small = mlp_roof('sb200_mlp_forward_packed_f32[rows=%d]' % N, N, A,
+                          'mlp_fwd_pk_kernel (per-env-step policy forward of %d actors, 2-CTA clusters)' % N)
+    roof_mb = mlp_roof('sb200_mlp_forward_f32[rows=%d]' % N, N, A,
+                       'mlp_fwd_mma_kernel<1> (learner minibatch forward on %d rows)' % N)
     roof_critic = mlp_roof('sb200_mlp_forward_f32[rows=%d]' % rows, rows, 1,
-                           'mlp_fwd_kernel<8,16> (fused critic pass over %d rows)' % rows)
-    cands = [r for r in (roof_small, roof_critic) if r is not None]
+                           'mlp_fwd_mma_kernel<4> (fused critic pass over %d rows)' % rows)
+    cands = [r for r in (roof_small, roof_mb, roof_critic) if r is not None]
     roofline = max(cands, key=lambda r: r['share_of_step_kernel_time']) if cands else None
     if roof_critic is not None and roofline is roof_critic:
         roofline['traffic'] = 34260992        # dram__bytes_read+write of profiles/r01a_prof_critic.md (one ncu --set full capture)

@@ -520,7 +520,7 @@ extern "C" int sb200_set_forward_mode(int mode) {
 int sb200_mlp_fwd_init() {
     SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
     SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
-    SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_pk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_pk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
     SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
     SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
@@ -585,78 +585,101 @@ static int fill_fwd_params(const sb200_mlp* net, const sb200_zfilter* zf, const 
 static long long pack_layer_floats(const sb200_mlp* net, int l) {
     if (net->dims[l + 1] <= 32) return 0;
     const int K = net->dims[l] + (net->aux_layer == l ? net->aux_dim : 0);
-    return (long long)((K + 7) / 8) * ((net->dims[l + 1] + 7) / 8) * 32 * 4;
+    return (long long)PK_CS * pk_nst(K) * pk_ntl(net->dims[l + 1]) * 64;
 }
 
-// wide layers first, at most one narrow layer and only as the last one
-static bool pack_supported(const sb200_mlp* net) {
+// Shared-memory plan of mlp_fwd_pk_kernel (floats); false when the architecture does not fit one SM.
+static bool pack_plan(const sb200_mlp* net, bool zf, PkParams* pp, size_t* smem_bytes) {
     if (net == nullptr || net->n_layers < 1 || net->n_layers > SB200_MAX_LAYERS) return false;
     for (int l = 0; l + 1 < net->n_layers; ++l)
-        if (net->dims[l + 1] <= 32) return false;
+        if (net->dims[l + 1] <= 32) return false;        // wide layers first, a narrow layer only as the last one
+    long long off = 0;
+    int ldp = 4, head = 0;
+    int offW[SB200_MAX_LAYERS] = {0}, offA[SB200_MAX_LAYERS] = {0};
+    for (int l = 0; l < net->n_layers; ++l) {
+        const int K = net->dims[l] + (net->aux_layer == l ? net->aux_dim : 0);
+        if (net->dims[l + 1] > 32) {
+            offW[l] = (int)off;
+            off += pack_layer_floats(net, l) / PK_CS;
+            offA[l] = (int)off;
+            off += 2LL * PK_MT * pk_nst(K) * 128;
+        } else {
+            ldp = round_up(K, 4) + 4;
+            head = K * net->ldw[l];
+        }
+    }
+    const int offHp = (int)off;
+    off += (long long)PK_ROWS * ldp;
+    const int zf_floats = zf ? round_up(2 * net->dims[0], 4) : 0;
+    const int scratch = round_up(zf_floats + ((head <= 16384) ? head : 0) + 4, 4);
+    const int offScratch = (int)off;
+    off += scratch;
+    if ((size_t)off * sizeof(float) > 225 * 1024) return false;
+    if (pp != nullptr) {
+        for (int l = 0; l < SB200_MAX_LAYERS; ++l) {
+            pp->offW[l] = offW[l];
+            pp->offA[l] = offA[l];
+        }
+        pp->offHp = offHp;
+        pp->offScratch = offScratch;
+        pp->ldp = ldp;
+        pp->f.scratch_floats = scratch;
+    }
+    if (smem_bytes != nullptr) *smem_bytes = (size_t)off * sizeof(float);
     return true;
 }
 
 extern "C" size_t sb200_mlp_pack_floats(const sb200_mlp* net) {
-    if (!pack_supported(net)) return 0;
+    if (!pack_plan(net, true, nullptr, nullptr)) return 0;
     long long tot = 0;
     for (int l = 0; l < net->n_layers; ++l) tot += pack_layer_floats(net, l);
     return (size_t)(tot > 0 ? tot : 4);
 }
 
 extern "C" int sb200_mlp_pack_tf32(const sb200_mlp* net, float* packed, void* stream) {
-    SB200_REQUIRE(packed != nullptr && pack_supported(net) && (((uintptr_t)packed) & 15) == 0);
+    SB200_REQUIRE(packed != nullptr && (((uintptr_t)packed) & 15) == 0);
+    if (!pack_plan(net, true, nullptr, nullptr)) return SB200_ERR_UNSUPPORTED;
     long long off = 0;
     int launches = 0;
     for (int l = 0; l < net->n_layers; ++l) {
         const long long fl = pack_layer_floats(net, l);
         if (fl == 0) continue;
         const int K = net->dims[l] + (net->aux_layer == l ? net->aux_dim : 0);
-        const long long items = fl / 4;
+        const long long items = fl / 2;
         mlp_pack_tf32_kernel<<<(unsigned)((items + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-            net->W[l], K, net->dims[l + 1], net->ldw[l], reinterpret_cast<float4*>(packed + off));
+            net->W[l], K, net->dims[l + 1], net->ldw[l], reinterpret_cast<float2*>(packed + off));
         off += fl;
         ++launches;
     }
-    return sb200_launch_status(launches > 0 ? launches : 1);
+    if (launches == 0) return SB200_OK;
+    return sb200_launch_status(launches);
 }
 
 extern "C" int sb200_mlp_forward_packed_f32(const sb200_mlp* net, const float* packed, const sb200_zfilter* zf,
                                             const sb200_rows* in, float* out, int64_t ld_out, void* stream) {
     SB200_REQUIRE(packed != nullptr && out != nullptr && (((uintptr_t)packed) & 15) == 0);
-    if (!pack_supported(net)) return SB200_ERR_UNSUPPORTED;
     PkParams pp;
     int maxw = 0;
     const int rc = fill_fwd_params(net, zf, in, nullptr, nullptr, pp.f, &maxw);
     if (rc != SB200_OK) return rc;
+    size_t smem = 0;
+    if (!pack_plan(net, pp.f.zf != nullptr, &pp, &smem)) return SB200_ERR_UNSUPPORTED;
     if (in->rows == 0) return SB200_OK;
     SB200_REQUIRE(in->save_x == nullptr && ld_out >= net->dims[net->n_layers]);
     long long off = 0;
-    int ldp = 4, head = 0;
     for (int l = 0; l < SB200_MAX_LAYERS; ++l) {
         pp.P[l] = nullptr;
         if (l >= net->n_layers) continue;
         const long long fl = pack_layer_floats(net, l);
-        const int K = net->dims[l] + (net->aux_layer == l ? net->aux_dim : 0);
         if (fl > 0) {
             pp.P[l] = packed + off;
             off += fl;
-        } else {
-            ldp = round_up(K, 4) + 4;
-            head = K * net->ldw[l];
         }
     }
     pp.out = out;
     pp.ld_out = ld_out;
-    pp.nst_max = (round_up(maxw, 8)) / 8;
-    pp.ldp = ldp;
-    const int zf_floats = (pp.f.zf != nullptr) ? 2 * net->dims[0] : 0;
-    int scratch = zf_floats + ((head <= 16384) ? head : 0);
-    scratch = round_up(scratch > 0 ? scratch : 4, 4);
-    pp.f.scratch_floats = scratch;
-    const size_t smem = (size_t)(4 * pp.nst_max * 128 + 16 * ldp + scratch) * sizeof(float);
-    if (smem > 200 * 1024) return SB200_ERR_UNSUPPORTED;
-    const long long clusters = (in->rows + 15) / 16;
-    mlp_fwd_pk_kernel<<<(unsigned)(2 * clusters), SB200_THREADS, smem, (cudaStream_t)stream>>>(pp);
+    const long long clusters = (in->rows + PK_ROWS - 1) / PK_ROWS;
+    mlp_fwd_pk_kernel<<<(unsigned)(PK_CS * clusters), SB200_THREADS, smem, (cudaStream_t)stream>>>(pp);
     return sb200_launch_status();
 }
 

@@ -1,16 +1,18 @@
 // Inference forward for SMALL batches (one env step of all co-located actors: ~1K rows) on pre-packed weights.
 //
-// At this size the forward is a chain of dependent latencies, not a throughput problem; ncu on the two earlier
-// variants (profiles/r01c_small_forward.md) showed 2 warps per scheduler each retiring one instruction every
-// ~5 cycles, 70 % of them address arithmetic, operand splitting and shared-memory reads.  This kernel shortens
-// the per-warp chain ~8x:
-//   * weights are packed ONCE per parameter version (sb200_mlp_pack_tf32) into mma.m16n8k8 B-fragment order,
-//     already split into the 3xTF32 pair (hi, lo): one coalesced 16-byte load per lane per (k-step, n-tile)
-//     replaces 2 scalar loads + 6 conversion instructions;
-//   * activations are kept in shared memory in A-fragment order, already split: one LDS.128 for hi, one for lo;
-//   * a thread-block CLUSTER of 2 CTAs owns 16 rows; each CTA computes half of a layer's output columns and
-//     stores them into BOTH CTAs' shared memory (distributed shared memory), so 1024 rows occupy 128 SMs with
-//     no duplicated tensor work, one cluster barrier per layer.
+// At this size the forward is a chain of dependent latencies, not a throughput problem.  ncu on the earlier
+// variants (profiles/r01c_small_forward.md): two warps per scheduler, each retiring one instruction per ~5
+// cycles, every CTA pulling ALL the weights (330 KB) through a register ring that keeps only ~24 KB in flight
+// per SM -- the L2 round trip, not bandwidth or math, sets the time.  This kernel attacks exactly that:
+//   * a thread-block CLUSTER of 4 CTAs owns 32 rows; each CTA computes a QUARTER of every layer's output
+//     columns, so it needs only a quarter of the weights (~80 KB for 64-256-256), and it fetches that slice
+//     with cp.async in one burst at kernel entry -- the whole slice is in flight at once and then RESIDENT in
+//     shared memory; 1024 rows occupy 128 SMs and total L2->SM traffic drops 4x;
+//   * the CTAs exchange layer outputs through distributed shared memory (st.shared::cluster into all four
+//     copies), one cluster barrier per layer;
+//   * weights are packed once per parameter version (sb200_mlp_pack_tf32) into mma.m16n8k8 B-fragment order
+//     ({b0, b1} per lane: one conflict-free LDS.64 per k-step), activations are stored in A-fragment order and
+//     already split for 3xTF32 (one LDS.128 for hi, one for lo, shared by all 8 warps).
 // Numerics: the same 3xTF32 error-compensated products as mlp_fwd_mma.cuh (fp32-level accuracy); the main
 // (hi*hi) and correction terms accumulate in separate registers to halve the dependent mma chain.
 #pragma once
@@ -20,16 +22,24 @@ namespace {
 
 namespace cg = cooperative_groups;
 
+constexpr int PK_CS = 4;                // CTAs per cluster (column split)
+constexpr int PK_MT = 2;                // 16-row m-tiles per cluster
+constexpr int PK_ROWS = 16 * PK_MT;     // rows per cluster
+
 struct PkParams {
     FwdParams f;
-    const float* P[SB200_MAX_LAYERS];   // packed weights of layer l (NULL for narrow layers)
+    const float* P[SB200_MAX_LAYERS];   // packed weights of wide layer l (NULL for the narrow head)
+    int offW[SB200_MAX_LAYERS];         // shared-memory offsets (floats): resident weight slice of layer l
+    int offA[SB200_MAX_LAYERS];         //   A-fragment planes (hi | lo) holding the INPUT of wide layer l
+    int offHp;                          //   plain row-major input of the narrow head [PK_ROWS][ldp]
+    int offScratch;                     //   z-filter columns, then the head's weights
+    int ldp;
     float* out;
     long long ld_out;
-    int nst_max;                        // k-steps of the widest activation
-    int ldp;                            // row stride of the plain (row-major) activation copy
 };
 
-constexpr int PK_RING = 4;              // k-steps of B fragments in flight per warp
+__host__ __device__ inline int pk_nst(int K) { return (K + 7) >> 3; }
+__host__ __device__ inline int pk_ntl(int N) { return (((N + 7) >> 3) + PK_CS - 1) / PK_CS; }   // n-tiles per CTA
 
 __device__ __forceinline__ void mma_tf32u(float (&d)[4], const uint4& a, unsigned b0, unsigned b1) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
@@ -37,61 +47,85 @@ __device__ __forceinline__ void mma_tf32u(float (&d)[4], const uint4& a, unsigne
                  : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
 }
 
-// position of element (row m of 16, column k) inside an A-fragment plane: [k/8][lane = (m%8)*4 + k%4][slot]
-__device__ __forceinline__ int afrag_index(int m, int k) {
-    const int kk = k & 7;
-    return ((k >> 3) * 32 + (m & 7) * 4 + (kk & 3)) * 4 + ((m >> 3) & 1) + ((kk >> 2) << 1);
+// distributed shared memory: address of CTA `rank`'s copy of a local shared-memory location, and a store to it
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_v4(unsigned addr, const float4& v) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
 }
 
-// Pack kernel: P[((s*NT + nt)*32 + lane)] = {hi(b0), hi(b1), lo(b0), lo(b1)},  b0 = W[8s + t][8nt + g],
-// b1 = W[8s + t + 4][8nt + g]  (g = lane / 4, t = lane % 4), zero outside [K) x [N).
+// position of element (row m of PK_ROWS, column k) inside an A-fragment plane of a layer with `nst` k-steps:
+// [m/16][k/8][lane = (m%8)*4 + k%4][slot = (m%16 >= 8) + 2*(k%8 >= 4)]
+__device__ __forceinline__ int afrag_index(int m, int k, int nst) {
+    const int kk = k & 7;
+    return ((((m >> 4) * nst + (k >> 3)) * 32 + (m & 7) * 4 + (kk & 3)) << 2) + ((m >> 3) & 1) + ((kk >> 2) << 1);
+}
+
+// Pack kernel: P[((c*nst + s)*NTL + j)*32 + lane] = {b0, b1},  b0 = W[8s + t][8(c*NTL + j) + g],
+// b1 = W[8s + t + 4][same column]  (g = lane / 4, t = lane % 4), zero outside [K) x [N): CTA c's slice is contiguous.
 __global__ void __launch_bounds__(256) mlp_pack_tf32_kernel(const float* __restrict__ W, int K, int N, int ldw,
-                                                            float4* __restrict__ P) {
-    const int NT = (N + 7) >> 3, nst = (K + 7) >> 3;
+                                                            float2* __restrict__ P) {
+    const int nst = pk_nst(K), NTL = pk_ntl(N);
     const int idx = blockIdx.x * 256 + threadIdx.x;
-    if (idx >= nst * NT * 32) return;
-    const int lane = idx & 31, nt = (idx >> 5) % NT, s = (idx >> 5) / NT;
+    if (idx >= PK_CS * nst * NTL * 32) return;
+    const int lane = idx & 31;
+    int q = idx >> 5;
+    const int j = q % NTL;
+    q /= NTL;
+    const int s = q % nst, c = q / nst;
     const int g = lane >> 2, t = lane & 3;
-    const int n = nt * 8 + g, k0 = s * 8 + t, k1 = k0 + 4;
+    const int n = (c * NTL + j) * 8 + g, k0 = s * 8 + t, k1 = k0 + 4;
     const float b0 = (n < N && k0 < K) ? W[(long long)k0 * ldw + n] : 0.0f;
     const float b1 = (n < N && k1 < K) ? W[(long long)k1 * ldw + n] : 0.0f;
-    unsigned h0, l0, h1, l1;
-    split_tf32(b0, h0, l0);
-    split_tf32(b1, h1, l1);
-    P[idx] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
+    P[idx] = make_float2(b0, b1);
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SB200_THREADS, 2)
+__global__ void __cluster_dims__(PK_CS, 1, 1) __launch_bounds__(SB200_THREADS, 1)
     mlp_fwd_pk_kernel(const __grid_constant__ PkParams pp) {
     const FwdParams& p = pp.f;
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned crank = cluster.block_rank();
     extern __shared__ __align__(16) float smem[];
-    const int plane = pp.nst_max * 128;                 // floats per A-fragment plane
-    // [buf 0: hi | lo][buf 1: hi | lo][plain rows 16 x ldp][scratch]
-    float* Hp = smem + 4 * plane;
-    float* Wsc = Hp + 16 * pp.ldp;
-    float* rsmem = cluster.map_shared_rank(smem, crank ^ 1u);
+    const unsigned smem_base = smem_u32(smem);
+    unsigned peer_base[PK_CS - 1];                      // the three OTHER CTAs' copies of smem[0]
+#pragma unroll
+    for (int c = 1; c < PK_CS; ++c) peer_base[c - 1] = mapa_u32(smem_base, (crank + (unsigned)c) % PK_CS);
+    float* Hp = smem + pp.offHp;
+    float* Wsc = smem + pp.offScratch;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const long long row0 = (long long)(blockIdx.x >> 1) * 16;
+    const long long row0 = (long long)(blockIdx.x / PK_CS) * PK_ROWS;
     const int K0 = p.dims[0];
 
-    // prefetch the narrow head's weights (used last) while the wide layers run
-    int head_l = -1;
-    for (int l = 0; l < p.n_layers; ++l)
-        if (p.dims[l + 1] <= 32) head_l = l;
-    const int zf_floats = (p.zf != nullptr) ? 2 * K0 : 0;
+    // ---- one burst: this CTA's weight slices of every wide layer + the head's weights -> shared memory.
+    // group 0 = first layer (needed first), group 1 = everything else.
+    const int zf_floats = (p.zf != nullptr) ? round_up(2 * K0, 4) : 0;
     float* Whead = Wsc + zf_floats;
     bool head_staged = false;
-    if (head_l >= 0) {
-        const int kl = (p.dims[head_l] + (p.aux_layer == head_l ? p.aux_dim : 0)) * p.ldw[head_l];
-        if (zf_floats + kl <= p.scratch_floats) {
-            for (int f = tid; f < kl / 4; f += SB200_THREADS) cp_async16(Whead + f * 4, p.W[head_l] + f * 4, 16);
-            head_staged = true;
+    for (int l = 0; l < p.n_layers; ++l) {
+        const int K = p.dims[l] + (p.aux_layer == l ? p.aux_dim : 0);
+        const int N = p.dims[l + 1];
+        if (N > 32) {
+            const int slice = pk_nst(K) * pk_ntl(N) * 64;                 // floats
+            const float* src = pp.P[l] + (long long)crank * slice;
+            float* dst = smem + pp.offW[l];
+            for (int f = tid; f < slice / 4; f += SB200_THREADS) cp_async16(dst + f * 4, src + f * 4, 16);
+        } else {
+            const int kl = K * p.ldw[l];
+            if (zf_floats + kl <= p.scratch_floats) {
+                for (int f = tid; f < kl / 4; f += SB200_THREADS) cp_async16(Whead + f * 4, p.W[l] + f * 4, 16);
+                head_staged = true;
+            }
         }
-        cp_async_commit();
+        if (l == 0) cp_async_commit();
     }
+    cp_async_commit();
+
     if (p.zf != nullptr) {
         const float cnt = p.zf[2 * K0];
         for (int k = tid; k < K0; k += SB200_THREADS) {
@@ -102,14 +136,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SB200_THREADS, 2)
         }
         __syncthreads();
     }
-    int cur = 0;
-    {   // input rows -> fragment order (both CTAs of the cluster stage all 16 rows)
+    {   // input rows -> fragment order (every CTA of the cluster stages all PK_ROWS rows: 8 KB, cheaper than an exchange)
         const int in_w = K0 + (p.aux_layer == 0 ? p.aux_dim : 0);
         const int in_wp = round_up(in_w, 8);
         const bool first_narrow = (p.dims[1] <= 32);
-        float* Ahi = smem;
-        float* Alo = smem + plane;
-        for (int idx = tid; idx < 16 * in_wp; idx += SB200_THREADS) {
+        const int nst0 = in_wp >> 3;
+        float* Ahi = smem + pp.offA[0];
+        float* Alo = Ahi + PK_MT * nst0 * 128;
+        for (int idx = tid; idx < PK_ROWS * in_wp; idx += SB200_THREADS) {
             const int m = idx / in_wp, k = idx - m * in_wp;
             const long long r = row0 + m;
             float v = 0.0f;
@@ -134,13 +168,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SB200_THREADS, 2)
             } else {
                 unsigned hi, lo;
                 split_tf32(v, hi, lo);
-                const int a = afrag_index(m, k);
+                const int a = afrag_index(m, k, nst0);
                 Ahi[a] = __uint_as_float(hi);
                 Alo[a] = __uint_as_float(lo);
             }
         }
     }
-    cluster.sync();                                    // also: the peer CTA has started (its smem is addressable)
+    cp_async_wait<1>();                                // first layer's weights have landed (this thread's copies)
+    cluster.sync();                                    // ... everyone's; and every peer CTA is running (DSMEM is live)
 
     for (int l = 0; l < p.n_layers; ++l) {
         const int K = p.dims[l] + (p.aux_layer == l ? p.aux_dim : 0);
@@ -149,91 +184,105 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SB200_THREADS, 2)
         const int act = p.act[l];
         const bool last = (l == p.n_layers - 1);
         if (N > 32) {
-            const int nst = (K + 7) >> 3;
-            const int NT = (N + 7) >> 3, half = (NT + 1) >> 1;
-            const int nt_lo = (int)crank * half, nt_hi = min(NT, nt_lo + half);
-            const uint4* Ahi = reinterpret_cast<const uint4*>(smem + cur * 2 * plane);
-            const uint4* Alo = reinterpret_cast<const uint4*>(smem + cur * 2 * plane + plane);
-            float* Ohi = smem + (cur ^ 1) * 2 * plane;
-            float* Olo = Ohi + plane;
+            const int nst = pk_nst(K), NTL = pk_ntl(N);
+            const uint4* Ahi = reinterpret_cast<const uint4*>(smem + pp.offA[l]);
+            const uint4* Alo = Ahi + PK_MT * nst * 32;
+            const float2* Wl = reinterpret_cast<const float2*>(smem + pp.offW[l]);
             const bool next_narrow = !last && (p.dims[l + 2] <= 32);
             const int auxd = (!last && p.aux_layer == l + 1) ? p.aux_dim : 0;
-            const long long roff = rsmem - smem;       // the same offset addresses the peer CTA's copy
-            for (int pass0 = nt_lo; pass0 < nt_hi; pass0 += 16) {
-                const int nt0 = pass0 + warp * 2;
-                if (nt0 >= nt_hi) continue;            // warp-uniform; no block barrier inside the pass loop
-                const bool two = (nt0 + 1 < nt_hi);
-                float accM[2][4], accC[2][4];
+            const int kp_next = round_up(N + auxd, 8);
+            const int nst_next = kp_next >> 3;
+            float* Ohi = (last || next_narrow) ? smem : smem + pp.offA[l + 1];   // only used when the next layer is wide
+            float* Olo = Ohi + PK_MT * nst_next * 128;
+            for (int j = warp; j < NTL; j += 8) {                          // warp-uniform; no block barrier inside
+                float accM[PK_MT][4], accC[PK_MT][4];
 #pragma unroll
-                for (int j = 0; j < 2; ++j)
+                for (int mt = 0; mt < PK_MT; ++mt)
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) accM[j][c] = accC[j][c] = 0.0f;
-                const float4* bp = reinterpret_cast<const float4*>(pp.P[l]) + ((long long)nt0 * 32 + lane);
-                const long long sstride = (long long)NT * 32;
-                float4 ring[PK_RING][2];
-                auto load_stage = [&](float4 (&dst)[2], int s) {
-                    if (s < nst) {
-                        dst[0] = __ldg(bp + s * sstride);
-                        dst[1] = two ? __ldg(bp + s * sstride + 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int c = 0; c < 4; ++c) accM[mt][c] = accC[mt][c] = 0.0f;
+                const float2* bp = Wl + (long long)j * 32 + lane;
+#pragma unroll 4
+                for (int s = 0; s < nst; ++s) {
+                    const float2 b = bp[(long long)s * NTL * 32];
+                    unsigned bh0, bl0, bh1, bl1;
+                    split_tf32(b.x, bh0, bl0);
+                    split_tf32(b.y, bh1, bl1);
+#pragma unroll
+                    for (int mt = 0; mt < PK_MT; ++mt) {
+                        const uint4 ah = Ahi[(mt * nst + s) * 32 + lane];
+                        const uint4 al = Alo[(mt * nst + s) * 32 + lane];
+                        mma_tf32u(accC[mt], al, bh0, bh1);
+                        mma_tf32u(accC[mt], ah, bl0, bl1);
+                        mma_tf32u(accM[mt], ah, bh0, bh1);
                     }
-                };
+                }
+                // epilogue: c0,c1 -> (row g, cols 2t, 2t+1); c2,c3 -> (row g+8, same cols).  The warp owns ALL 8 columns
+                // of next-layer k-step `nt` for all rows: it writes them into its own CTA's copy with scalar stores, then
+                // pushes the finished 512-byte chunks to the three peers with 16-byte DSMEM stores (scalar remote stores
+                // cost ~1 SM-to-SM transaction each and dominated the first version of this kernel).
+                const int nt = (int)crank * NTL + j;
+                const bool keep = !last && (nt * 8 < kp_next);
 #pragma unroll
-                for (int d = 0; d < PK_RING - 1; ++d) load_stage(ring[d], d);
-                for (int s0 = 0; s0 < nst; s0 += PK_RING) {
+                for (int mt = 0; mt < PK_MT; ++mt) {
 #pragma unroll
-                    for (int d = 0; d < PK_RING; ++d) {
-                        const int s = s0 + d;
-                        load_stage(ring[(d + PK_RING - 1) % PK_RING], s + PK_RING - 1);
-                        if (s < nst) {
-                            const uint4 ah = Ahi[s * 32 + lane];
-                            const uint4 al = Alo[s * 32 + lane];
-#pragma unroll
-                            for (int j = 0; j < 2; ++j) {
-                                const float4 b = ring[d][j];
-                                mma_tf32u(accC[j], al, __float_as_uint(b.x), __float_as_uint(b.y));
-                                mma_tf32u(accC[j], ah, __float_as_uint(b.z), __float_as_uint(b.w));
-                                mma_tf32u(accM[j], ah, __float_as_uint(b.x), __float_as_uint(b.y));
+                    for (int c = 0; c < 4; ++c) {
+                        const int m = mt * 16 + g + 8 * (c >> 1);
+                        const int n = nt * 8 + 2 * t + (c & 1);
+                        const long long r = row0 + m;
+                        float v = 0.0f;
+                        if (n < N) v = apply_act(accM[mt][c] + accC[mt][c] + bias[n], act);
+                        else if (n < N + auxd && r < p.rows) v = p.aux[r * p.aux_ld + (n - N)];
+                        if (last) {
+                            if (n < N && r < p.rows) pp.out[r * pp.ld_out + n] = v;
+                        } else if (keep) {
+                            if (next_narrow) {
+                                Hp[m * pp.ldp + n] = v;
+                            } else {
+                                unsigned hi, lo;
+                                split_tf32(v, hi, lo);
+                                const int a = afrag_index(m, n, nst_next);
+                                Ohi[a] = __uint_as_float(hi);
+                                Olo[a] = __uint_as_float(lo);
                             }
                         }
                     }
                 }
-                // epilogue: c0,c1 -> (row g, cols 2t, 2t+1); c2,c3 -> (row g+8, same cols)
+                if (keep) {
+                    __syncwarp();
+                    if (next_narrow) {                                     // 32 rows x 8 columns: lane = row, 2 x float4
+                        const float* q = Hp + lane * pp.ldp + nt * 8;
+                        const float4 v0 = *reinterpret_cast<const float4*>(q);
+                        const float4 v1 = *reinterpret_cast<const float4*>(q + 4);
+                        const unsigned off = smem_u32(q) - smem_base;
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    if (j == 1 && !two) break;
-                    const int nt = nt0 + j;
+                        for (int cc = 1; cc < PK_CS; ++cc) {
+                            const unsigned pb = peer_base[cc - 1] + off;
+                            st_cluster_v4(pb, v0);
+                            st_cluster_v4(pb + 16, v1);
+                        }
+                    } else {                                               // (hi, lo) x m-tile: 128 floats each
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int m = g + 8 * (c >> 1);
-                        const int n = nt * 8 + 2 * t + (c & 1);
-                        const long long r = row0 + m;
-                        float v = 0.0f;
-                        if (n < N) v = apply_act(accM[j][c] + accC[j][c] + bias[n], act);
-                        else if (n < N + auxd && r < p.rows) v = p.aux[r * p.aux_ld + (n - N)];
-                        if (last) {
-                            if (n < N && r < p.rows) pp.out[r * pp.ld_out + n] = v;
-                        } else if (next_narrow) {
-                            float* q = Hp + m * pp.ldp + n;
-                            *q = v;
-                            *(q + roff) = v;
-                        } else {
-                            unsigned hi, lo;
-                            split_tf32(v, hi, lo);
-                            const int a = afrag_index(m, n);
-                            Ohi[a] = __uint_as_float(hi);
-                            Olo[a] = __uint_as_float(lo);
-                            *(Ohi + a + roff) = __uint_as_float(hi);
-                            *(Olo + a + roff) = __uint_as_float(lo);
+                        for (int mt = 0; mt < PK_MT; ++mt) {
+                            const int a = ((mt * nst_next + nt) * 32 + lane) * 4;
+                            const float4 vh = *reinterpret_cast<const float4*>(Ohi + a);
+                            const float4 vl = *reinterpret_cast<const float4*>(Olo + a);
+                            const unsigned oh = smem_u32(Ohi + a) - smem_base, ol = smem_u32(Olo + a) - smem_base;
+#pragma unroll
+                            for (int cc = 1; cc < PK_CS; ++cc) {
+                                const unsigned pb = peer_base[cc - 1];
+                                st_cluster_v4(pb + oh, vh);
+                                st_cluster_v4(pb + ol, vl);
+                            }
                         }
                     }
                 }
             }
             if (!last) {
-                // columns past this layer's last n-tile (aux concatenation / padding of the next layer's K): local copy
-                const int kp_next = round_up(N + auxd, 8);
-                const int span = kp_next - NT * 8;
-                for (int idx = tid; idx < 16 * span; idx += SB200_THREADS) {
-                    const int m = idx / span, k = NT * 8 + (idx - m * span);
+                // columns past the cluster's last n-tile (aux concatenation wider than the tile padding): local copy
+                const int covered = PK_CS * NTL * 8;
+                const int span = kp_next - covered;
+                for (int idx = tid; idx < PK_ROWS * span; idx += SB200_THREADS) {
+                    const int m = idx / span, k = covered + (idx - m * span);
                     const long long r = row0 + m;
                     float v = 0.0f;
                     if (k < N + auxd && r < p.rows) v = p.aux[r * p.aux_ld + (k - N)];
@@ -242,13 +291,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SB200_THREADS, 2)
                     } else {
                         unsigned hi, lo;
                         split_tf32(v, hi, lo);
-                        const int a = afrag_index(m, k);
+                        const int a = afrag_index(m, k, nst_next);
                         Ohi[a] = __uint_as_float(hi);
                         Olo[a] = __uint_as_float(lo);
                     }
                 }
+                cp_async_wait<0>();                    // the remaining weight slices (issued at entry) have landed
                 cluster.sync();
-                cur ^= 1;
             }
         } else {
             // narrow head (<= 32 outputs): fp32 dot products on the plain activation copy; CTA c owns rows 8c..8c+7
@@ -262,7 +311,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SB200_THREADS, 2)
             for (int n8 = 0; n8 < N; n8 += 8) {
                 float s8[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) s8[j] = 0.0f;
+                for (int jj = 0; jj < 8; ++jj) s8[jj] = 0.0f;
                 const bool second = (n8 + 4 < ldw);
                 for (int k = lane; k < K; k += 32) {
                     const float hv = hrow[k];
@@ -278,16 +327,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SB200_THREADS, 2)
                 }
                 float mine = 0.0f;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float tt = warp_sum(s8[j]);
-                    if (lane == j) mine = tt;
+                for (int jj = 0; jj < 8; ++jj) {
+                    const float tt = warp_sum(s8[jj]);
+                    if (lane == jj) mine = tt;
                 }
                 const int n = n8 + lane;
                 if (lane < 8 && n < N && r < p.rows) pp.out[r * pp.ld_out + n] = apply_act(mine + bias[n], act);
             }
         }
     }
-    cluster.sync();                                    // no CTA may exit while its peer can still write into it
+    cluster.sync();                                    // no CTA may exit while a peer can still write into it
 }
 
 }  // namespace

@@ -18,6 +18,8 @@ struct FifoState {          // must match rollout.cu
     int dropped;
     long long total_in;
     long long total_out;
+    unsigned int ticket;     // used by the fused sampling kernel (rollout.cu)
+    int pad_;
 };
 
 // pop `batch` oldest windows: idx[k] = physical slot of the k-th oldest (fifo_replay.py:37-39).

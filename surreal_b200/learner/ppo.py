@@ -7,6 +7,7 @@ Same constructor, config keys, method names, statistics names and control flow a
 numpy (copied through pinned memory) or CUDA tensors (zero copy).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -139,11 +140,14 @@ class PPOLearner(Learner):
         self._stop = torch.zeros(1, dtype=torch.int32, device=dev)
         L = _lib.lib()
         self._loss_ws = torch.zeros(L.sb200_ppo_loss_workspace_bytes(B, A), dtype=torch.uint8, device=dev)
+        self._loss_ws_v = torch.zeros_like(self._loss_ws)     # the value branch runs concurrently with the policy branch
+        self._side_stream = None
         self._rfilter_stats = torch.tensor([1e-5, 0.0, 0.0], dtype=torch.float32, device=dev) \
             if self.use_r_filter else None
         self._pin = {}
         self._gae_ws = torch.zeros(64, dtype=torch.uint8, device=dev)
         self.use_cuda_graph = ops.graphs_enabled()
+        self.parallel_branches = os.environ.get("SB200_PPO_FORK", "1") != "0"   # policy || value epochs
         self._graph = ops.GraphRunner()
         self.dp = None
         self.epoch_history = []
@@ -291,11 +295,15 @@ class PPOLearner(Learner):
         o = self._own
         return dict(obs_full=o['obs_full'], actions=o['actions'], pd=o['pds'], rewards=o['rewards'], dones=o['dones'])
 
-    def _policy_epoch(self, stop=None):
+    def _policy_epoch(self, stop=None, fresh=True):
+        """One policy epoch (ppo.py:523-556).  The post-step forward that measures KL(ref || new) runs on the same
+        inputs and parameters as the NEXT epoch's training forward, so it is done once, with saved activations:
+        ``fresh=False`` reuses it."""
         L = _lib.lib()
         B, n, A, D = self.batch_size, self.n_step, self.action_dim, self.low_dim
         m, tr, st = self.model, self.actor_optim, ops._stream()
-        mean = tr.forward(self._obs_full, zf_stats=m.z_stats, zf_eps=m.z_eps, rows=B, ldx=(n + 1) * D)
+        mean = tr.forward(self._obs_full, zf_stats=m.z_stats, zf_eps=m.z_eps, rows=B, ldx=(n + 1) * D) if fresh \
+            else tr.out
         mode = 0 if self.ppo_mode == 'clip' else 1
         if mode == 1:
             self._kl(mean, S['KL_PRE'], 0.0, stop)
@@ -308,7 +316,7 @@ class PPOLearner(Learner):
         tr.backward()
         tr.step(norm_out=self._stats[S['GN_ACTOR']:S['GN_ACTOR'] + 1], stop_flag=stop)
         # post-step KL(ref || current) (ppo.py:553-556)
-        ops.mlp_forward(m.actor, self._obs_full, zf_stats=m.z_stats, zf_eps=m.z_eps, rows=B, ldx=(n + 1) * D, out=self._cur_mean)
+        self._cur_mean = tr.forward(self._obs_full, zf_stats=m.z_stats, zf_eps=m.z_eps, rows=B, ldx=(n + 1) * D)
         self._kl(self._cur_mean, S['KL_POST'], 4.0 * self.kl_target, self._stop)
 
     def _kl(self, mean, slot, threshold, stop):
@@ -356,7 +364,7 @@ class PPOLearner(Learner):
         m, tr, st = self.model, self.critic_optim, ops._stream()
         v = tr.forward(self._obs_full, zf_stats=m.z_stats, zf_eps=m.z_eps, rows=B, ldx=(n + 1) * D)
         check(L.sb200_value_loss_f32(_ptr(v), v.stride(0), _ptr(self._ret), B, _ptr(tr.d[-1]), tr.d[-1].stride(0),
-                                     _ptr(self._stats), _ptr(self._loss_ws), st), 'sb200_value_loss_f32')
+                                     _ptr(self._stats), _ptr(self._loss_ws_v), st), 'sb200_value_loss_f32')
         tr.backward()
         tr.step(norm_out=self._stats[S['GN_CRITIC']:S['GN_CRITIC'] + 1])
 
@@ -370,13 +378,15 @@ class PPOLearner(Learner):
         self._stats.zero_()
         self._stop.zero_()
 
-    def _optimize_tail(self):
+    def _optimize_tail(self, value_done=False):
         L = _lib.lib()
         B, n, A, D = self.batch_size, self.n_step, self.action_dim, self.low_dim
         m, st = self.model, ops._stream()
-        for _ in range(self.epoch_baseline):
-            self._value_epoch()
-        check(L.sb200_ppo_final_stats_f32(_ptr(self._cur_mean), A, _ptr(m.log_var), _ptr(self._actions), n * A,
+        if not value_done:
+            for _ in range(self.epoch_baseline):
+                self._value_epoch()
+        check(L.sb200_ppo_final_stats_f32(_ptr(self._cur_mean), self._cur_mean.stride(0), _ptr(m.log_var),
+                                          _ptr(self._actions), n * A,
                                           _ptr(self._pds), n * 2 * A, _ptr(self._ref_pd), 2 * A, B, A,
                                           _ptr(self._stats), _ptr(self._loss_ws), st), 'sb200_ppo_final_stats_f32')
         if self.use_z_filter:
@@ -397,9 +407,24 @@ class PPOLearner(Learner):
         kernels of the remaining policy epochs turn into no-ops -- same parameters and statistics as breaking
         out of the loop, without a host round trip per epoch."""
         self._optimize_head()
-        for _ in range(self.epoch_policy):
-            self._policy_epoch(stop=self._stop)
-        self._optimize_tail()
+        # The value epochs (critic, returns) and the policy epochs (actor, advantages) share nothing but read-only
+        # inputs: they run as two concurrent branches (a fork / join inside the captured graph), so the step costs
+        # max(policy chain, value chain) instead of their sum.  With a data-parallel learner both branches would
+        # issue collectives on one communicator, so that case stays sequential.
+        fork = self.dp is None and self.parallel_branches and not self.profile_events
+        if fork:
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(device=self.device)
+            main, side = torch.cuda.current_stream(), self._side_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                for _ in range(self.epoch_baseline):
+                    self._value_epoch()
+        for e in range(self.epoch_policy):
+            self._policy_epoch(stop=self._stop, fresh=(e == 0))
+        if fork:
+            main.wait_stream(side)
+        self._optimize_tail(value_done=fork)
 
     def _optimize(self):
         """ppo.py:487-586."""
@@ -411,8 +436,8 @@ class PPOLearner(Learner):
             self._optimize_device()                               # same sequence, eager (per-kernel event timing)
         else:
             self._optimize_head()                                 # reference-style host loop: one sync per epoch
-            for _ in range(self.epoch_policy):
-                self._policy_epoch()
+            for e in range(self.epoch_policy):
+                self._policy_epoch(fresh=(e == 0))
                 if float(self._stats[S['KL_POST']].item()) > self.kl_target * 4:
                     break
             self._optimize_tail()

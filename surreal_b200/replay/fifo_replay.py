@@ -48,8 +48,9 @@ class FIFOReplay(Replay):
         self.r_obs, self.r_act, self.r_pd = f(C_, n + 1, D), f(C_, n, A), f(C_, n, 2 * A)
         self.r_rew, self.r_done = f(C_, n), f(C_, n)
         L = _lib.lib()
-        assert L.sb200_fifo_state_bytes() == 32
-        self.state = torch.zeros(8, dtype=torch.int32, device=self.device)
+        nb = int(L.sb200_fifo_state_bytes())                    # {head, count, capacity, dropped, int64 in, out, ...}
+        assert nb >= 32 and nb % 4 == 0
+        self.state = torch.zeros(nb // 4, dtype=torch.int32, device=self.device)
         self.state[2] = self.capacity
         self._idx = torch.zeros(max(self.batch_size, 1), dtype=torch.int32, device=self.device)
         self._status = torch.zeros(1, dtype=torch.int32, device=self.device)

@@ -78,12 +78,13 @@ def test_mlp_forward_matches_oracle(dims, rows, zf):
     ([64, 256, 256, 8], 1000, True, None),      # rows not a multiple of the 16-row cluster tile
     ([17, 300, 200, 6], 333, True, None),       # reference default hidden sizes: odd K, n-tiles not a pass multiple
     ([33, 100, 52, 40], 50, False, None),       # wide LAST layer (written straight to global memory)
-    ([10, 400, 300, 1], 77, False, (1, 4)),     # DDPG critic: action concatenated into layer 1
+    ([10, 200, 120, 1], 77, False, (1, 4)),     # DDPG-critic shape: action concatenated into layer 1
+    ([64, 300, 200, 8], 130, False, None),      # DDPG actor of configs[2]
     ([10, 44, 36, 3], 21, False, (1, 5)),       # aux columns sharing a k-step with the previous layer's tail
     ([12, 64, 5], 9, True, (0, 3)),             # aux on the input layer, 2-layer net
 ])
 def test_mlp_forward_packed_matches_oracle(dims, rows, zf, aux):
-    """Small-batch inference on pre-packed fragment-order weights (2-CTA cluster, DSMEM exchange)."""
+    """Small-batch inference on pre-packed fragment-order weights (4-CTA cluster, resident weight slices, DSMEM)."""
     from surreal_b200 import ops
     gen = torch.Generator().manual_seed(sum(dims) + rows)
     aux_layer, aux_dim = aux if aux is not None else (-1, 0)
@@ -118,6 +119,8 @@ def test_mlp_forward_packed_matches_oracle(dims, rows, zf, aux):
     ref2 = ops.mlp_forward(net, x.to(_dev()), zf_stats=stats, aux=a.to(_dev()) if aux is not None else None)
     assert_close_scale(out2, ref2, 1e-5, 'packed vs tiled after re-pack')
     assert not ops.PackedWeights(ops.FlatNet([8, 16, 64, 2], [ops.ACT_RELU] * 3, _dev())).supported
+    # a weight slice that does not fit one SM's shared memory is declined too (callers use the tiled forward)
+    assert not ops.PackedWeights(ops.FlatNet([64, 1024, 1024, 8], [ops.ACT_RELU] * 3, _dev())).supported
 
 
 def test_mlp_forward_window_rows_and_aux():

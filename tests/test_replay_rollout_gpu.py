@@ -340,6 +340,7 @@ def test_fused_rollout_launches_match_unfused(n, stride, cap_extra):
         ag = PPOAgent(lc, ec, sc, 1, 'training')
         torch.manual_seed(5)
         ag.model.actor.params.copy_(torch.randn_like(ag.model.actor.params) * 0.2)
+        ag.set_noise(np.linspace(-0.5, 0.5, N))                   # the per-actor exploration constant is drawn at random
         env = SyntheticEnv(N, D, A, limit_episode_length=11, seed=4)
         ag.env = w = ag.prepare_env_agent(env)
         w.fuse_launches = fuse
