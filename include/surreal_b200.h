@@ -283,6 +283,60 @@ int sb200_synth_env_window_step_f32(float* state, const float* action, const flo
                                     float* r_obs, float* r_act, float* r_pd, float* r_rew, float* r_done,
                                     void* stream);
 
+/* Persistent rollout: T steps of policy forward -> sample -> synthetic env step -> window staging for ALL N
+ * actors in ONE launch (a 4-CTA cluster owns 32 actors for the whole chunk; the policy weights stay resident in
+ * shared memory, layer outputs cross CTAs through distributed shared memory).  Replaces T x (ppo_sample_assign +
+ * synth_env_window_step + the policy forward), i.e. the actor main loop of surreal/agent/base.py:224-271 for a
+ * device-resident env.  Same sampling / env arithmetic and Philox keys as the per-step entries.
+ *   Completed windows are written to a per-actor OUTBOX (o_*: [N*W] records in the replay's record layout,
+ *   ev_step [N*W] = chunk-relative completion step, ev_count [N]); W >= T / stride + 2.
+ *   rollout_commit then assigns FIFO slots in the reference's (step, actor) arrival order, copies the windows into
+ *   the replay ring, advances fifo_state and *step_counter (+T).  scratch: sb200_ppo_rollout_scratch_ints() ints.
+ *   rollout_supported: 1 when `net` (2 hidden layers whose widths are multiples of 16, head <= 32, D % 4 == 0,
+ *   D <= 128) fits the shared-memory plan; otherwise use the per-step entries. */
+typedef struct {
+    const sb200_mlp* net;               /* policy: D -> H1 -> H2 -> A */
+    const float* zf_stats;              /* NULL: no z-filter */
+    float zf_eps;
+    const float* log_var;               /* [A] */
+    const float* log_noise;             /* [N] or NULL */
+    uint64_t agent_seed;
+    int deterministic;
+    float* state;                       /* [N][D] env state = next observation, updated in place */
+    const float* WsT;                   /* [D][D] k-major */
+    const float* WaT;                   /* [A][D] k-major */
+    int* ep_step;                       /* [N] */
+    int max_steps;
+    uint64_t env_seed;
+    float* action;                      /* outputs of the LAST step, like the per-step entries leave them */
+    float* pd;
+    float* obs_next;
+    float* reward;
+    float* done;
+    int* stage_pos;                     /* window staging, see ppo_window_step */
+    float* stage_obs;
+    float* stage_act;
+    float* stage_pd;
+    float* stage_rew;
+    float* stage_done;
+    float* o_obs;                       /* outbox */
+    float* o_act;
+    float* o_pd;
+    float* o_rew;
+    float* o_done;
+    int* ev_step;
+    int* ev_count;
+    int W;
+    int N, D, A, n_step, stride, T;
+    const uint64_t* step_counter;       /* read only; rollout_commit advances it */
+} sb200_ppo_rollout;
+int sb200_ppo_rollout_supported(const sb200_mlp* net, int D, int A);
+size_t sb200_ppo_rollout_scratch_ints(int N, int W, int T);
+int sb200_ppo_rollout_f32(const sb200_ppo_rollout* args, void* stream);
+int sb200_ppo_rollout_commit_f32(const sb200_ppo_rollout* args, int* scratch, void* fifo_state, float* r_obs,
+                                 float* r_act, float* r_pd, float* r_rew, float* r_done, uint64_t* step_counter,
+                                 void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Experience staging + HBM replay.
  *   ppo_window_step: ExpSenderWrapperMultiStepMovingWindowWithInfo._step (exp_sender_wrapper.py:209-228) for N

@@ -23,6 +23,7 @@ extern "C" const char* sb200_status_string(int status) {
 
 int sb200_mlp_fwd_init();
 int sb200_gae_init();
+int sb200_rollout_fused_init();
 
 extern "C" void sb200_launch_counter_add(uint64_t kernels) { g_sb200_launches += kernels; }
 
@@ -37,7 +38,9 @@ extern "C" int sb200_init(void) {
     }
     int rc = sb200_mlp_fwd_init();
     if (rc != SB200_OK) return rc;
-    return sb200_gae_init();
+    rc = sb200_gae_init();
+    if (rc != SB200_OK) return rc;
+    return sb200_rollout_fused_init();
 }
 
 extern "C" int sb200_device_info(int* sm_count, int* cc_major, int* cc_minor) {

@@ -5,15 +5,12 @@
 // All per-actor control state (deque length, episode step, RNG counter) lives in HBM so that a whole
 // T-step rollout is a fixed launch sequence (CUDA-graph capturable) with no host round trip.
 #include "common.cuh"
+#include "rollout_dev.cuh"
 
 namespace {
 
 constexpr int RT = 256;
 
-struct FifoState;
-__device__ void assign_window_slots(int N, int n_step, const int* __restrict__ stage_pos, int* __restrict__ dest,
-                                    FifoState* fifo);
-__device__ unsigned int* fifo_ticket(FifoState* fifo);
 
 // ------------------------------------------------------------------------------------------------
 // PPOAgent.act after the network (ppo_agent.py:138-149): pd = [mean | exp(log_var)*exp(noise_i)],
@@ -210,183 +207,11 @@ __global__ void __launch_bounds__(RT) synth_env_step_kernel(float* __restrict__ 
                     sm + 4 * D, s_q, nullptr, nullptr, nullptr, nullptr, 0ull);
 }
 
-// ------------------------------------------------------------------------------------------------
-// ExpSenderWrapperMultiStepMovingWindowWithInfo._step (exp_sender_wrapper.py:209-228), batched.
-// Slot assignment (one block, ordered): detect the deques that reach n_step with this step's append and give
-// them FIFO slots in (step, actor) order with drop-oldest at `capacity` (fifo_replay.py:27).  It depends only
-// on the deque lengths, so it can run before the environment has stepped (fused into the sampling kernel).
-struct FifoState {
-    int head;        // physical index of the oldest window
-    int count;       // windows currently queued
-    int capacity;    // memory_size + 3
-    int dropped;     // windows silently dropped so far (diagnostic)
-    long long total_in;
-    long long total_out;
-    unsigned int ticket;   // last-block ticket of the fused sampling kernel (self-resetting)
-    int pad_;
-};
-
-constexpr int SLOT_NONE = -1;      // deque not full after this step
-constexpr int SLOT_DROPPED = -2;   // window completes but falls straight out of the deque(maxlen)
-
-// dest[i] <- physical slot | SLOT_NONE | SLOT_DROPPED; advances the queue.  Called by all threads of ONE block.
-__device__ void assign_window_slots(int N, int n_step, const int* __restrict__ stage_pos, int* __restrict__ dest,
-                                    FifoState* fifo) {
-    __shared__ int warp_tot[32];
-    __shared__ int warp_excl[32];
-    __shared__ int chunk_total;
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-    int base = 0;                                  // windows completed by actors before this chunk
-    for (int i0 = 0; i0 < N; i0 += nt) {
-        const int i = i0 + tid;
-        const int flag = (i < N && stage_pos[i] + 1 == n_step) ? 1 : 0;
-        int incl = flag;                           // inclusive scan inside the warp (actor order)
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) warp_tot[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            const int w = (lane < nw) ? warp_tot[lane] : 0;
-            int wi = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= o) wi += t;
-            }
-            warp_excl[lane] = wi - w;
-            if (lane == 31) chunk_total = wi;
-        }
-        __syncthreads();
-        if (i < N) dest[i] = flag ? (base + warp_excl[warp] + incl - flag) : SLOT_NONE;
-        base += chunk_total;
-        __syncthreads();
-    }
-    // translate ranks into physical slots; advance the queue
-    const int K = base;
-    const int cap = fifo->capacity;
-    const int head = fifo->head, count = fifo->count;
-    __syncthreads();
-    for (int i = tid; i < N; i += nt) {
-        const int r = dest[i];
-        if (r >= 0) {
-            // more arrivals than the deque holds: the earliest of THIS step fall out immediately
-            dest[i] = (K > cap && r < K - cap) ? SLOT_DROPPED : (int)(((long long)head + count + r) % cap);
-        }
-    }
-    if (tid == 0) {
-        int nc = count + K, nh = head, dr = 0;
-        if (nc > cap) {                       // deque(maxlen): the oldest entries fall out
-            dr = nc - cap;
-            nh = (int)(((long long)head + dr) % cap);
-            nc = cap;
-        }
-        fifo->head = nh;
-        fifo->count = nc;
-        fifo->dropped += dr;
-        fifo->total_in += K;
-    }
-}
-
-__device__ unsigned int* fifo_ticket(FifoState* fifo) { return &fifo->ticket; }
-
 __global__ void __launch_bounds__(1024) ppo_window_slots_kernel(int N, int n_step, const int* __restrict__ stage_pos,
                                                                 int* __restrict__ dest, FifoState* fifo,
                                                                 unsigned long long* step_ctr) {
     assign_window_slots(N, n_step, stage_pos, dest, fifo);
     if (threadIdx.x == 0 && step_ctr != nullptr) *step_ctr += 1ull;
-}
-
-__device__ __forceinline__ void copy_floats(float* __restrict__ dst, const float* __restrict__ src, int count, int g,
-                                            int G) {
-    if (((count & 3) == 0) && ((((uintptr_t)dst) | ((uintptr_t)src)) & 15) == 0) {
-        const float4* s4 = reinterpret_cast<const float4*>(src);
-        float4* d4 = reinterpret_cast<float4*>(dst);
-        for (int k = g; k < (count >> 2); k += G) d4[k] = s4[k];
-    } else {
-        for (int k = g; k < count; k += G) dst[k] = src[k];
-    }
-}
-
-// Commit of one actor's step by a group of G threads (g = index inside the group).  Appends (reward, done) at
-// deque position p and obs_next at p+1; if the window completed, copies it into its replay slot and pops
-// `stride` items; if the episode ended, clears the deque (exp_sender_wrapper.py:204-207) and seeds position 0
-// with the reset observation.  Barriers are block-wide and executed by EVERY thread (valid or not).
-__device__ void commit_actor(bool valid, int i, int g, int G, const float* __restrict__ next_row,
-                             const float* __restrict__ reset_row, float rew, float dn, int n_step, int stride, int D,
-                             int A, int* __restrict__ stage_pos, float* __restrict__ stage_obs,
-                             float* __restrict__ stage_act, float* __restrict__ stage_pd,
-                             float* __restrict__ stage_rew, float* __restrict__ stage_done,
-                             const int* __restrict__ dest, float* __restrict__ r_obs, float* __restrict__ r_act,
-                             float* __restrict__ r_pd, float* __restrict__ r_rew, float* __restrict__ r_done) {
-    const long long ii = valid ? i : 0;
-    const int p = valid ? stage_pos[ii] : 0;
-    float* so = stage_obs + ii * (n_step + 1) * D;
-    float* sa = stage_act + ii * n_step * A;
-    float* sp = stage_pd + ii * n_step * 2 * A;
-    float* sr = stage_rew + ii * n_step;
-    float* sd = stage_done + ii * n_step;
-    if (valid) {
-        for (int d = g; d < D; d += G) so[(long long)(p + 1) * D + d] = next_row[d];
-        if (g == 0) {
-            sr[p] = rew;
-            sd[p] = dn;
-        }
-    }
-    __syncthreads();
-    int len = p + 1;
-    const int slot = valid ? dest[ii] : SLOT_NONE;
-    const bool complete = (slot != SLOT_NONE);               // len == n_step
-    if (slot >= 0) {                                         // ship the window
-        copy_floats(r_obs + (long long)slot * (n_step + 1) * D, so, (n_step + 1) * D, g, G);
-        copy_floats(r_act + (long long)slot * n_step * A, sa, n_step * A, g, G);
-        copy_floats(r_pd + (long long)slot * n_step * 2 * A, sp, n_step * 2 * A, g, G);
-        copy_floats(r_rew + (long long)slot * n_step, sr, n_step, g, G);
-        copy_floats(r_done + (long long)slot * n_step, sd, n_step, g, G);
-    }
-    __syncthreads();
-    const int pop = min(stride, n_step);                     // uniform: every completing deque holds n_step items
-    const int keep = n_step - pop;
-    if (keep > 0) {                                          // overlapping windows: slide the deque down
-        for (int k0 = 0; k0 < (keep + 1) * D; k0 += G) {
-            const int k = k0 + g;
-            const bool on = complete && k < (keep + 1) * D;
-            float v = 0.f;
-            if (on) v = so[(long long)pop * D + k];
-            __syncthreads();
-            if (on) so[k] = v;
-            __syncthreads();
-        }
-        for (int k0 = 0; k0 < keep * 2 * A; k0 += G) {
-            const int k = k0 + g;
-            float va = 0.f, vp = 0.f;
-            if (complete && k < keep * A) va = sa[(long long)pop * A + k];
-            if (complete && k < keep * 2 * A) vp = sp[(long long)pop * 2 * A + k];
-            __syncthreads();
-            if (complete && k < keep * A) sa[k] = va;
-            if (complete && k < keep * 2 * A) sp[k] = vp;
-            __syncthreads();
-        }
-        for (int k0 = 0; k0 < keep; k0 += G) {
-            const int k = k0 + g;
-            float vr = 0.f, vd = 0.f;
-            if (complete && k < keep) { vr = sr[pop + k]; vd = sd[pop + k]; }
-            __syncthreads();
-            if (complete && k < keep) { sr[k] = vr; sd[k] = vd; }
-            __syncthreads();
-        }
-    } else if (complete) {
-        for (int d = g; d < D; d += G) so[d] = next_row[d];                 // obs_next -> next window's first obs
-    }
-    if (complete) len = keep;
-    __syncthreads();
-    if (valid && dn > 0.5f) {                                // episode over: deque cleared, new episode's first obs
-        for (int d = g; d < D; d += G) so[d] = reset_row[d];
-        len = 0;
-    }
-    if (valid && g == 0) stage_pos[ii] = len;
 }
 
 __global__ void __launch_bounds__(128) ppo_window_commit_kernel(const float* __restrict__ obs_next,
@@ -406,8 +231,8 @@ __global__ void __launch_bounds__(128) ppo_window_commit_kernel(const float* __r
                                                                 float* __restrict__ r_done) {
     const int i = blockIdx.x;
     commit_actor(true, i, threadIdx.x, blockDim.x, obs_next + (long long)i * D, obs_reset + (long long)i * D, reward[i],
-                 done[i], n_step, stride, D, A, stage_pos, stage_obs, stage_act, stage_pd, stage_rew, stage_done, dest,
-                 r_obs, r_act, r_pd, r_rew, r_done);
+                 done[i], n_step, stride, D, A, stage_pos + i, dest[i], stage_obs, stage_act, stage_pd, stage_rew,
+                 stage_done, r_obs, r_act, r_pd, r_rew, r_done);
 }
 
 // Fused environment step + window commit for the device-resident synthetic env: the successor state never
@@ -435,8 +260,9 @@ __global__ void __launch_bounds__(RT) synth_env_window_step_kernel(
     __syncthreads();
     const int q = tid >> 6, g = tid & 63;
     const int i = a0 + q;
-    commit_actor(i < N, i, g, 64, s_n + q * D, s_z + q * D, s_rew[q], s_dn[q], n_step, stride, D, A, stage_pos, stage_obs,
-                 stage_act, stage_pd, stage_rew, stage_done, dest, r_obs, r_act, r_pd, r_rew, r_done);
+    commit_actor(i < N, i, g, 64, s_n + q * D, s_z + q * D, s_rew[q], s_dn[q], n_step, stride, D, A, stage_pos + min(i, N - 1),
+                 (i < N) ? dest[i] : SLOT_NONE, stage_obs, stage_act, stage_pd, stage_rew, stage_done, r_obs, r_act, r_pd,
+                 r_rew, r_done);
 }
 
 }  // namespace

@@ -1,0 +1,579 @@
+// Persistent rollout kernel: T env steps of ALL co-located actors in ONE launch.
+//
+// The per-step launch sequence (policy forward -> sample -> env step -> window staging) is bound by fixed costs:
+// every launch re-fetches the policy weights from L2 (a chain of dependent round trips, profiles/r01c) and pays
+// launch + drain; 128 steps x 3 launches cost ~4.3 ms per rollout for ~0.2 ms of arithmetic.  Actors are
+// independent of one another, so the loop over time can move INSIDE the kernel:
+//   * a thread-block cluster of 4 CTAs owns 32 actors for the whole chunk;
+//   * each CTA keeps a QUARTER of every hidden layer's weights resident in shared memory for all T steps (fetched
+//     once with cp.async) and computes that quarter of the layer's columns for the cluster's 32 rows (fp32 FFMA,
+//     thread = 1 row x 4 columns); layer outputs are exchanged through distributed shared memory (16-byte
+//     st.shared::cluster pushes into all four copies) with one cluster barrier per layer;
+//   * each CTA then finishes ITS 8 actors: head, sampling, environment step, window staging -- one warp per actor,
+//     observations / env state never leave shared memory between steps;
+//   * finished windows go to a per-actor outbox with their completion step; sb200_ppo_rollout_commit_f32 assigns
+//     FIFO slots in the reference's (step, actor) arrival order afterwards and copies them into the replay ring.
+// Sampling and environment arithmetic (and their Philox keys) are those of rollout.cu, so both paths draw the
+// same noise; the policy forward is fp32 FFMA (the per-step path uses 3xTF32 tensor-core products; both are
+// fp32-accurate, they differ by rounding order only).
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+#include "rollout_dev.cuh"
+
+namespace {
+
+namespace cg = cooperative_groups;
+
+constexpr int RF_CS = 4;            // CTAs per cluster
+constexpr int RF_ROWS = 32;         // actors per cluster
+constexpr int RF_OWN = RF_ROWS / RF_CS;
+constexpr int RF_THREADS = 512;     // 16 warps: thread (ty = row 0..31, tx = column quad 0..15)
+
+struct RfParams {
+    const float* W[3];
+    const float* b[3];
+    int ldw[3];
+    int act[3];
+    int D, H1, H2, A;
+    const float* zf;
+    float zf_eps;
+    const float* log_var;
+    const float* log_noise;
+    unsigned long long agent_seed;
+    int deterministic;
+    float* state;
+    const float* WsT;
+    const float* WaT;
+    int* ep_step;
+    int max_steps;
+    unsigned long long env_seed;
+    float* action;
+    float* pd;
+    float* obs_next;
+    float* reward;
+    float* done;
+    int* stage_pos;
+    float* stage_obs;
+    float* stage_act;
+    float* stage_pd;
+    float* stage_rew;
+    float* stage_done;
+    float* o_obs;
+    float* o_act;
+    float* o_pd;
+    float* o_rew;
+    float* o_done;
+    int* ev_step;
+    int* ev_count;
+    int Wout;                       // outbox entries per actor
+    int N, n_step, stride, T;
+    const unsigned long long* step_ctr;
+    // shared-memory plan (float offsets)
+    int oW1, oW2, oWh, oB, oX0, oH1, oH2, oZf, oEnv, oS, oNext, oAct;
+    int ldx0, ldh1, ldh2;
+};
+
+__device__ __forceinline__ float rf_act(float v, int act) {
+    if (act == SB200_ACT_RELU) return fmaxf(v, 0.0f);
+    if (act == SB200_ACT_TANH) return tanhf(v);
+    return v;
+}
+
+__device__ __forceinline__ unsigned rf_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned rf_mapa(unsigned addr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void rf_st_cluster_v4(unsigned addr, const float4& v) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+// One hidden layer for the cluster's 32 rows, this CTA's Nc columns: out[ty][col0 + 4c4 ..] = act(x[ty] . Ws + b),
+// stored locally and pushed to the three peers.  Xin [32][ldin] and Ws [K][Nc] live in shared memory; K % 4 == 0.
+__device__ __forceinline__ void rf_layer(const float* __restrict__ Xin, int ldin, int K, const float* __restrict__ Ws,
+                                         int Nc, const float* __restrict__ bias_s, int act, float* __restrict__ Hout,
+                                         int ldout, int col0, unsigned smem_base, const unsigned (&peer_base)[RF_CS - 1]) {
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const float* xr = Xin + ty * ldin;
+    for (int c4 = tx; c4 < (Nc >> 2); c4 += 16) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* wp = Ws + c4 * 4;
+#pragma unroll 2
+        for (int k = 0; k < K; k += 4) {
+            const float4 a = *reinterpret_cast<const float4*>(xr + k);
+            const float4 w0 = *reinterpret_cast<const float4*>(wp + (k + 0) * Nc);
+            const float4 w1 = *reinterpret_cast<const float4*>(wp + (k + 1) * Nc);
+            const float4 w2 = *reinterpret_cast<const float4*>(wp + (k + 2) * Nc);
+            const float4 w3 = *reinterpret_cast<const float4*>(wp + (k + 3) * Nc);
+            acc.x = fmaf(a.x, w0.x, acc.x); acc.y = fmaf(a.x, w0.y, acc.y); acc.z = fmaf(a.x, w0.z, acc.z); acc.w = fmaf(a.x, w0.w, acc.w);
+            acc.x = fmaf(a.y, w1.x, acc.x); acc.y = fmaf(a.y, w1.y, acc.y); acc.z = fmaf(a.y, w1.z, acc.z); acc.w = fmaf(a.y, w1.w, acc.w);
+            acc.x = fmaf(a.z, w2.x, acc.x); acc.y = fmaf(a.z, w2.y, acc.y); acc.z = fmaf(a.z, w2.z, acc.z); acc.w = fmaf(a.z, w2.w, acc.w);
+            acc.x = fmaf(a.w, w3.x, acc.x); acc.y = fmaf(a.w, w3.y, acc.y); acc.z = fmaf(a.w, w3.z, acc.z); acc.w = fmaf(a.w, w3.w, acc.w);
+        }
+        const float4 bv = *reinterpret_cast<const float4*>(bias_s + c4 * 4);
+        float4 o;
+        o.x = rf_act(acc.x + bv.x, act);
+        o.y = rf_act(acc.y + bv.y, act);
+        o.z = rf_act(acc.z + bv.z, act);
+        o.w = rf_act(acc.w + bv.w, act);
+        float* q = Hout + ty * ldout + col0 + c4 * 4;
+        *reinterpret_cast<float4*>(q) = o;
+        const unsigned off = rf_smem_u32(q) - smem_base;
+#pragma unroll
+        for (int c = 0; c < RF_CS - 1; ++c) rf_st_cluster_v4(peer_base[c] + off, o);
+    }
+}
+
+__global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
+    ppo_rollout_kernel(const __grid_constant__ RfParams p) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned crank = cluster.block_rank();
+    extern __shared__ __align__(16) float smem[];
+    const unsigned smem_base = rf_smem_u32(smem);
+    unsigned peer_base[RF_CS - 1];
+#pragma unroll
+    for (int c = 1; c < RF_CS; ++c) peer_base[c - 1] = rf_mapa(smem_base, (crank + (unsigned)c) % RF_CS);
+    __shared__ int s_pos[RF_OWN], s_ep[RF_OWN], s_cnt[RF_OWN];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int D = p.D, H1 = p.H1, H2 = p.H2, A = p.A;
+    const int Nc1 = H1 / RF_CS, Nc2 = H2 / RF_CS;
+    const int ldwh = p.ldw[2];
+    float* W1s = smem + p.oW1;          // [D][Nc1]
+    float* W2s = smem + p.oW2;          // [H1][Nc2]
+    float* Whs = smem + p.oWh;          // [H2][ldwh]
+    float* B1s = smem + p.oB;           // [Nc1] | [Nc2] | [ldwh]
+    float* B2s = B1s + Nc1;
+    float* Bhs = B2s + Nc2;
+    float* X0 = smem + p.oX0;           // [32][ldx0]  z-filtered observations of the cluster's actors
+    float* Hb1 = smem + p.oH1;          // [32][ldh1]
+    float* Hb2 = smem + p.oH2;          // [32][ldh2]
+    float* Zm = smem + p.oZf;           // [D] mean | [D] std
+    float* Zs = Zm + D;
+    float* EWs = smem + p.oEnv;         // [D][D] | [A][D]   (k-major)
+    float* EWa = EWs + D * D;
+    float* S = smem + p.oS;             // [8][D]   env state of the owned actors (what they observe next)
+    float* Nx = smem + p.oNext;         // [8][D]   true successor of the step
+    float* Ac = smem + p.oAct;          // [8][A]   sampled actions
+    const long long row0 = (long long)(blockIdx.x / RF_CS) * RF_ROWS;
+
+    // ---- one-time loads: weight slices, biases, env matrices (cp.async burst), z-filter columns, actor state
+    for (int f = tid; f < D * (Nc1 >> 2); f += RF_THREADS) {
+        const int k = f / (Nc1 >> 2), q = f - k * (Nc1 >> 2);
+        cp_async16(W1s + k * Nc1 + q * 4, p.W[0] + (long long)k * p.ldw[0] + crank * Nc1 + q * 4, 16);
+    }
+    for (int f = tid; f < H1 * (Nc2 >> 2); f += RF_THREADS) {
+        const int k = f / (Nc2 >> 2), q = f - k * (Nc2 >> 2);
+        cp_async16(W2s + k * Nc2 + q * 4, p.W[1] + (long long)k * p.ldw[1] + crank * Nc2 + q * 4, 16);
+    }
+    for (int f = tid; f < (H2 * ldwh) >> 2; f += RF_THREADS) cp_async16(Whs + f * 4, p.W[2] + f * 4, 16);
+    for (int f = tid; f < (D * D) >> 2; f += RF_THREADS) cp_async16(EWs + f * 4, p.WsT + f * 4, 16);
+    for (int f = tid; f < (A * D) >> 2; f += RF_THREADS) cp_async16(EWa + f * 4, p.WaT + f * 4, 16);
+    cp_async_commit();
+    for (int n = tid; n < Nc1; n += RF_THREADS) B1s[n] = p.b[0][crank * Nc1 + n];
+    for (int n = tid; n < Nc2; n += RF_THREADS) B2s[n] = p.b[1][crank * Nc2 + n];
+    for (int n = tid; n < ldwh; n += RF_THREADS) Bhs[n] = (n < A) ? p.b[2][n] : 0.0f;
+    if (p.zf != nullptr) {
+        const float cnt = p.zf[2 * D];
+        for (int k = tid; k < D; k += RF_THREADS) {
+            const float mean = p.zf[k] / cnt;
+            const float var = p.zf[D + k] / cnt - mean * mean;
+            Zm[k] = mean;
+            Zs[k] = fmaxf(sqrtf(var), p.zf_eps);
+        }
+    }
+    if (tid < RF_OWN) {
+        const long long i = row0 + crank * RF_OWN + tid;
+        s_pos[tid] = (i < p.N) ? p.stage_pos[i] : 0;
+        s_ep[tid] = (i < p.N) ? p.ep_step[i] : 0;
+        s_cnt[tid] = 0;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < RF_ROWS * D; idx += RF_THREADS) {       // all 32 rows: every CTA needs the full input
+        const int m = idx / D, k = idx - m * D;
+        const long long i = row0 + m;
+        float v = (i < p.N) ? p.state[i * D + k] : 0.0f;
+        const int own = m - (int)crank * RF_OWN;
+        if (own >= 0 && own < RF_OWN) S[own * D + k] = v;
+        if (p.zf != nullptr) v = fminf(fmaxf((v - Zm[k]) / Zs[k], -5.0f), 5.0f);
+        X0[m * p.ldx0 + k] = (i < p.N) ? v : 0.0f;
+    }
+    const unsigned long long ctr0 = (p.step_ctr != nullptr) ? *p.step_ctr : 0ull;
+    cp_async_wait<0>();
+    cluster.sync();                                   // weights landed; every peer is running (DSMEM is live)
+
+    const int own = warp;                             // warps 0..7: one owned actor each
+    const bool owner = own < RF_OWN;
+    const int m_own = (int)crank * RF_OWN + own;
+    const long long i_own = row0 + m_own;
+    const bool valid = owner && (i_own < p.N);
+    const float sc = (valid && p.log_noise != nullptr) ? expf(p.log_noise[i_own]) : 1.0f;
+
+    for (int t = 0; t < p.T; ++t) {
+        const unsigned long long ctr = ctr0 + (unsigned long long)t;
+        const bool final_step = (t == p.T - 1);
+        rf_layer(X0, p.ldx0, D, W1s, Nc1, B1s, p.act[0], Hb1, p.ldh1, (int)crank * Nc1, smem_base, peer_base);
+        cluster.sync();
+        rf_layer(Hb1, p.ldh1, H1, W2s, Nc2, B2s, p.act[1], Hb2, p.ldh2, (int)crank * Nc2, smem_base, peer_base);
+        cluster.sync();
+
+        float rew = 0.0f, dn = 0.0f;
+        int slot = SLOT_NONE;
+        if (owner) {
+            // ---- head: mean[j] (j < A) ends up in lane j of chunk j / 8
+            const float* hrow = Hb2 + m_own * p.ldh2;
+            const int pos = s_pos[own];
+            for (int n8 = 0; n8 < A; n8 += 8) {
+                float s8[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) s8[jj] = 0.0f;
+                const bool second = (n8 + 4 < ldwh);
+                for (int k = lane; k < H2; k += 32) {
+                    const float hv = hrow[k];
+                    const float* wr = Whs + k * ldwh + n8;
+                    const float4 w0 = *reinterpret_cast<const float4*>(wr);
+                    s8[0] = fmaf(hv, w0.x, s8[0]); s8[1] = fmaf(hv, w0.y, s8[1]);
+                    s8[2] = fmaf(hv, w0.z, s8[2]); s8[3] = fmaf(hv, w0.w, s8[3]);
+                    if (second) {
+                        const float4 w1 = *reinterpret_cast<const float4*>(wr + 4);
+                        s8[4] = fmaf(hv, w1.x, s8[4]); s8[5] = fmaf(hv, w1.y, s8[5]);
+                        s8[6] = fmaf(hv, w1.z, s8[6]); s8[7] = fmaf(hv, w1.w, s8[7]);
+                    }
+                }
+                float mine = 0.0f;
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    const float tt = warp_sum(s8[jj]);
+                    if (lane == jj) mine = tt;
+                }
+                const int j = n8 + lane;
+                if (lane < 8 && j < A) {
+                    // ---- PPOAgent.act after the network (ppo_agent.py:138-149), same arithmetic and Philox keys as
+                    // sample_one() in rollout.cu
+                    const float mu = rf_act(mine + Bhs[j], p.act[2]);
+                    const float sd = __fmul_rn(expf(p.log_var[j]), sc);
+                    float a = mu;
+                    if (!p.deterministic) {
+                        const Philox4 r = philox4x32_10(p.agent_seed, ctr, ((unsigned long long)i_own << 16) | (unsigned long long)(j >> 2));
+                        const float2 z01 = box_muller(r.x, r.y), z23 = box_muller(r.z, r.w);
+                        const int c = j & 3;
+                        const float e = (c == 0) ? z01.x : (c == 1) ? z01.y : (c == 2) ? z23.x : z23.y;
+                        a = __fadd_rn(__fmul_rn(e, sd), mu);
+                    }
+                    a = fminf(fmaxf(a, -1.0f), 1.0f);
+                    Ac[own * A + j] = a;
+                    if (valid) {
+                        p.stage_act[((long long)i_own * p.n_step + pos) * A + j] = a;
+                        p.stage_pd[((long long)i_own * p.n_step + pos) * 2 * A + j] = mu;
+                        p.stage_pd[((long long)i_own * p.n_step + pos) * 2 * A + A + j] = sd;
+                        if (final_step) {
+                            p.action[i_own * A + j] = a;
+                            p.pd[i_own * 2 * A + j] = mu;
+                            p.pd[i_own * 2 * A + A + j] = sd;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- environment step (synth_env_block of rollout.cu, one warp per actor)
+            float* s = S + own * D;
+            float q = 0.0f;
+            for (int d = lane; d < D; d += 32) q += s[d] * s[d];
+            q = warp_sum(q);
+            const int ep = s_ep[own] + 1;
+            const bool is_done = (p.max_steps > 0) && (ep >= p.max_steps);
+            dn = is_done ? 1.0f : 0.0f;
+            float nxt_v[4], st_v[4];                       // D <= 128: up to 4 elements per lane
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int d = lane + 32 * u;
+                nxt_v[u] = st_v[u] = 0.0f;
+                if (d < D) {
+                    float acc = 0.0f;
+#pragma unroll 8
+                    for (int k = 0; k < D; ++k) acc = fmaf(EWs[k * D + d], s[k], acc);
+#pragma unroll 4
+                    for (int k = 0; k < A; ++k) acc = fmaf(EWa[k * D + d], Ac[own * A + k], acc);
+                    const Philox4 r = philox4x32_10(p.env_seed ^ 0x5851F42D4C957F2Dull, ctr,
+                                                    ((unsigned long long)i_own << 20) | (unsigned long long)d);
+                    const float2 gz = box_muller(r.x, r.y);
+                    const float nxt = tanhf(acc) + 0.01f * gz.x;
+                    nxt_v[u] = nxt;
+                    st_v[u] = is_done ? box_muller(r.z, r.w).x : nxt;
+                    if (d == 0) rew = -q / (float)D + 0.1f * gz.y;
+                }
+            }
+            rew = __shfl_sync(0xffffffffu, rew, 0);
+            __syncwarp();                                   // every lane has finished reading s[] before it is replaced
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int d = lane + 32 * u;
+                if (d < D) {
+                    Nx[own * D + d] = nxt_v[u];
+                    s[d] = st_v[u];
+                    if (valid && final_step) p.obs_next[i_own * D + d] = nxt_v[u];
+                }
+            }
+            if (lane == 0) {
+                s_ep[own] = is_done ? 0 : ep;
+                if (valid && final_step) {
+                    p.reward[i_own] = rew;
+                    p.done[i_own] = dn;
+                }
+                if (valid && s_pos[own] + 1 == p.n_step) {  // this step completes a window -> next outbox entry
+                    const int w = s_cnt[own];
+                    if (w < p.Wout) {
+                        slot = (int)(i_own * p.Wout + w);
+                        p.ev_step[slot] = t;
+                        s_cnt[own] = w + 1;
+                    } else {
+                        slot = SLOT_DROPPED;
+                    }
+                }
+            }
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+        }
+        __syncthreads();
+        // ---- window staging (block-wide barriers inside: every warp calls; only owners do work)
+        commit_actor(valid, (int)i_own, lane, 32, Nx + (owner ? own : 0) * D, S + (owner ? own : 0) * D, rew, dn, p.n_step,
+                     p.stride, D, A, s_pos + (owner ? own : 0), slot, p.stage_obs, p.stage_act, p.stage_pd, p.stage_rew,
+                     p.stage_done, p.o_obs, p.o_act, p.o_pd, p.o_rew, p.o_done);
+        // ---- next observation -> z-filter -> every CTA's input tile
+        if (owner) {
+            const int q4 = lane;                            // D / 4 <= 32 float4 per row
+            if (q4 < (D >> 2)) {
+                float4 v = *reinterpret_cast<const float4*>(S + own * D + q4 * 4);
+                if (i_own >= p.N) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.zf != nullptr) {
+                    const float4 zm = *reinterpret_cast<const float4*>(Zm + q4 * 4);
+                    const float4 zs = *reinterpret_cast<const float4*>(Zs + q4 * 4);
+                    v.x = fminf(fmaxf((v.x - zm.x) / zs.x, -5.0f), 5.0f);
+                    v.y = fminf(fmaxf((v.y - zm.y) / zs.y, -5.0f), 5.0f);
+                    v.z = fminf(fmaxf((v.z - zm.z) / zs.z, -5.0f), 5.0f);
+                    v.w = fminf(fmaxf((v.w - zm.w) / zs.w, -5.0f), 5.0f);
+                    if (i_own >= p.N) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                float* qx = X0 + m_own * p.ldx0 + q4 * 4;
+                *reinterpret_cast<float4*>(qx) = v;
+                const unsigned off = rf_smem_u32(qx) - smem_base;
+#pragma unroll
+                for (int c = 0; c < RF_CS - 1; ++c) rf_st_cluster_v4(peer_base[c] + off, v);
+            }
+        }
+        cluster.sync();
+    }
+
+    // ---- write the per-actor control state back
+    if (valid) {
+        for (int d = lane; d < D; d += 32) p.state[i_own * D + d] = S[own * D + d];
+        if (lane == 0) {
+            p.stage_pos[i_own] = s_pos[own];
+            p.ep_step[i_own] = s_ep[own];
+            p.ev_count[i_own] = s_cnt[own];
+        }
+    }
+}
+
+// ---- post-pass 1 (one block): rank the chunk's window completions in (step, actor) order, give them FIFO slots
+// with drop-oldest at capacity (fifo_replay.py:27), advance the queue and the shared step counter.
+__global__ void __launch_bounds__(1024) ppo_rollout_rank_kernel(const int* __restrict__ ev_step,
+                                                                const int* __restrict__ ev_count, int N, int W, int T,
+                                                                int* __restrict__ bitmap, int* __restrict__ base,
+                                                                int* __restrict__ ev_slot, FifoState* fifo,
+                                                                unsigned long long* step_ctr) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int words = (N + 31) >> 5;
+    __shared__ int s_total;
+    for (int x = tid; x < T * words; x += nt) bitmap[x] = 0;
+    for (int x = tid; x <= T; x += nt) base[x] = 0;
+    __syncthreads();
+    for (int e = tid; e < N * W; e += nt) {
+        const int i = e / W, w = e - i * W;
+        if (w < ev_count[i]) {
+            const int t = ev_step[e];
+            atomicOr(&bitmap[t * words + (i >> 5)], 1 << (i & 31));
+            atomicAdd(&base[t + 1], 1);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {                                   // T is a few hundred at most: a serial prefix is negligible
+        int run = 0;
+        for (int t = 0; t <= T; ++t) {
+            run += base[t];
+            base[t] = run;
+        }
+        s_total = run;
+    }
+    __syncthreads();
+    const int K = s_total;
+    const int cap = fifo->capacity, head = fifo->head, count = fifo->count;
+    for (int e = tid; e < N * W; e += nt) {
+        const int i = e / W, w = e - i * W;
+        int out = SLOT_NONE;
+        if (w < ev_count[i]) {
+            const int t = ev_step[e];
+            int r = base[t];
+            const int* bm = bitmap + t * words;
+            for (int x = 0; x < (i >> 5); ++x) r += __popc(bm[x]);
+            r += __popc(bm[i >> 5] & ((1u << (i & 31)) - 1u));
+            out = (K > cap && r < K - cap) ? SLOT_DROPPED : (int)(((long long)head + count + r) % cap);
+        }
+        ev_slot[e] = out;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int nc = count + K, nh = head, dr = 0;
+        if (nc > cap) {
+            dr = nc - cap;
+            nh = (int)(((long long)head + dr) % cap);
+            nc = cap;
+        }
+        fifo->head = nh;
+        fifo->count = nc;
+        fifo->dropped += dr;
+        fifo->total_in += K;
+        if (step_ctr != nullptr) *step_ctr += (unsigned long long)T;
+    }
+}
+
+// ---- post-pass 2: one block per outbox entry, pure copy into the replay ring
+__global__ void __launch_bounds__(256) ppo_rollout_copy_kernel(const int* __restrict__ ev_slot, int n_step, int D, int A,
+                                                               const float* __restrict__ o_obs,
+                                                               const float* __restrict__ o_act,
+                                                               const float* __restrict__ o_pd,
+                                                               const float* __restrict__ o_rew,
+                                                               const float* __restrict__ o_done,
+                                                               float* __restrict__ r_obs, float* __restrict__ r_act,
+                                                               float* __restrict__ r_pd, float* __restrict__ r_rew,
+                                                               float* __restrict__ r_done) {
+    const long long e = blockIdx.x;
+    const int slot = ev_slot[e];
+    if (slot < 0) return;
+    const int g = threadIdx.x, G = blockDim.x;
+    copy_floats(r_obs + (long long)slot * (n_step + 1) * D, o_obs + e * (n_step + 1) * D, (n_step + 1) * D, g, G);
+    copy_floats(r_act + (long long)slot * n_step * A, o_act + e * n_step * A, n_step * A, g, G);
+    copy_floats(r_pd + (long long)slot * n_step * 2 * A, o_pd + e * n_step * 2 * A, n_step * 2 * A, g, G);
+    copy_floats(r_rew + (long long)slot * n_step, o_rew + e * n_step, n_step, g, G);
+    copy_floats(r_done + (long long)slot * n_step, o_done + e * n_step, n_step, g, G);
+}
+
+bool rf_plan(const sb200_mlp* net, int D, int A, RfParams* p, size_t* smem_bytes) {
+    if (net == nullptr || net->n_layers != 3 || net->aux_layer >= 0) return false;
+    const int H1 = net->dims[1], H2 = net->dims[2];
+    if (net->dims[0] != D || net->dims[3] != A) return false;
+    if (D % 4 != 0 || D > 128 || A < 1 || A > 32 || H1 % 16 != 0 || H2 % 16 != 0) return false;
+    const int Nc1 = H1 / RF_CS, Nc2 = H2 / RF_CS, ldwh = net->ldw[2];
+    long long off = 0;
+    auto take = [&](long long n) { const long long o = off; off += (n + 3) / 4 * 4; return (int)o; };
+    const int oW1 = take((long long)D * Nc1), oW2 = take((long long)H1 * Nc2), oWh = take((long long)H2 * ldwh);
+    const int oB = take(Nc1 + Nc2 + ldwh);
+    const int ldx0 = D + 4, ldh1 = H1 + 4, ldh2 = H2 + 4;
+    const int oX0 = take(RF_ROWS * ldx0), oH1 = take(RF_ROWS * ldh1), oH2 = take(RF_ROWS * ldh2);
+    const int oZf = take(2 * D), oEnv = take((long long)D * D + A * D);
+    const int oS = take(RF_OWN * D), oNext = take(RF_OWN * D), oAct = take(RF_OWN * A);
+    if ((size_t)off * sizeof(float) > 220 * 1024) return false;
+    if (p != nullptr) {
+        p->oW1 = oW1; p->oW2 = oW2; p->oWh = oWh; p->oB = oB; p->oX0 = oX0; p->oH1 = oH1; p->oH2 = oH2;
+        p->oZf = oZf; p->oEnv = oEnv; p->oS = oS; p->oNext = oNext; p->oAct = oAct;
+        p->ldx0 = ldx0; p->ldh1 = ldh1; p->ldh2 = ldh2;
+        p->D = D; p->H1 = H1; p->H2 = H2; p->A = A;
+    }
+    if (smem_bytes != nullptr) *smem_bytes = (size_t)off * sizeof(float);
+    return true;
+}
+
+}  // namespace
+
+int sb200_rollout_fused_init() {
+    SB200_CUDA(cudaFuncSetAttribute(ppo_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    return SB200_OK;
+}
+
+extern "C" int sb200_ppo_rollout_supported(const sb200_mlp* net, int D, int A) {
+    return rf_plan(net, D, A, nullptr, nullptr) ? 1 : 0;
+}
+
+extern "C" size_t sb200_ppo_rollout_scratch_ints(int N, int W, int T) {
+    // bitmap [T][ceil(N/32)] | base [T+1] | ev_slot [N*W]
+    return (size_t)T * ((N + 31) / 32) + (size_t)(T + 1) + (size_t)N * W;
+}
+
+extern "C" int sb200_ppo_rollout_f32(const sb200_ppo_rollout* a, void* stream) {
+    SB200_REQUIRE(a != nullptr && a->net != nullptr);
+    RfParams p;
+    size_t smem = 0;
+    if (!rf_plan(a->net, a->D, a->A, &p, &smem)) return SB200_ERR_UNSUPPORTED;
+    SB200_REQUIRE(a->N >= 1 && a->T >= 1 && a->n_step >= 1 && a->stride >= 1 && a->W >= 1);
+    SB200_REQUIRE(a->state && a->WsT && a->WaT && a->ep_step && a->action && a->pd && a->obs_next && a->reward && a->done);
+    SB200_REQUIRE(a->log_var && a->stage_pos && a->stage_obs && a->stage_act && a->stage_pd && a->stage_rew && a->stage_done);
+    SB200_REQUIRE(a->o_obs && a->o_act && a->o_pd && a->o_rew && a->o_done && a->ev_step && a->ev_count);
+    for (int l = 0; l < 3; ++l) {
+        p.W[l] = a->net->W[l];
+        p.b[l] = a->net->b[l];
+        p.ldw[l] = a->net->ldw[l];
+        p.act[l] = a->net->act[l];
+        SB200_REQUIRE(p.W[l] != nullptr && p.b[l] != nullptr && p.ldw[l] % 4 == 0 && (((uintptr_t)p.W[l]) & 15) == 0);
+    }
+    SB200_REQUIRE((((uintptr_t)a->WsT) & 15) == 0 && (((uintptr_t)a->WaT) & 15) == 0 && (((uintptr_t)a->state) & 15) == 0);
+    p.zf = a->zf_stats;
+    p.zf_eps = a->zf_eps;
+    p.log_var = a->log_var;
+    p.log_noise = a->log_noise;
+    p.agent_seed = a->agent_seed;
+    p.deterministic = a->deterministic;
+    p.state = a->state;
+    p.WsT = a->WsT;
+    p.WaT = a->WaT;
+    p.ep_step = a->ep_step;
+    p.max_steps = a->max_steps;
+    p.env_seed = a->env_seed;
+    p.action = a->action;
+    p.pd = a->pd;
+    p.obs_next = a->obs_next;
+    p.reward = a->reward;
+    p.done = a->done;
+    p.stage_pos = a->stage_pos;
+    p.stage_obs = a->stage_obs;
+    p.stage_act = a->stage_act;
+    p.stage_pd = a->stage_pd;
+    p.stage_rew = a->stage_rew;
+    p.stage_done = a->stage_done;
+    p.o_obs = a->o_obs;
+    p.o_act = a->o_act;
+    p.o_pd = a->o_pd;
+    p.o_rew = a->o_rew;
+    p.o_done = a->o_done;
+    p.ev_step = a->ev_step;
+    p.ev_count = a->ev_count;
+    p.Wout = a->W;
+    p.N = a->N;
+    p.n_step = a->n_step;
+    p.stride = a->stride;
+    p.T = a->T;
+    p.step_ctr = (const unsigned long long*)a->step_counter;
+    const long long clusters = ((long long)a->N + RF_ROWS - 1) / RF_ROWS;
+    ppo_rollout_kernel<<<(unsigned)(clusters * RF_CS), RF_THREADS, smem, (cudaStream_t)stream>>>(p);
+    return sb200_launch_status();
+}
+
+extern "C" int sb200_ppo_rollout_commit_f32(const sb200_ppo_rollout* a, int* scratch, void* fifo_state, float* r_obs,
+                                            float* r_act, float* r_pd, float* r_rew, float* r_done,
+                                            uint64_t* step_counter, void* stream) {
+    SB200_REQUIRE(a != nullptr && scratch != nullptr && fifo_state != nullptr);
+    SB200_REQUIRE(r_obs && r_act && r_pd && r_rew && r_done && step_counter);
+    SB200_REQUIRE(a->N >= 1 && a->T >= 1 && a->W >= 1 && a->ev_step && a->ev_count);
+    const int words = (a->N + 31) / 32;
+    int* bitmap = scratch;
+    int* base = bitmap + (size_t)a->T * words;
+    int* ev_slot = base + (a->T + 1);
+    cudaStream_t st = (cudaStream_t)stream;
+    ppo_rollout_rank_kernel<<<1, 1024, 0, st>>>(a->ev_step, a->ev_count, a->N, a->W, a->T, bitmap, base, ev_slot,
+                                                (FifoState*)fifo_state, (unsigned long long*)step_counter);
+    ppo_rollout_copy_kernel<<<(unsigned)((long long)a->N * a->W), 256, 0, st>>>(
+        ev_slot, a->n_step, a->D, a->A, a->o_obs, a->o_act, a->o_pd, a->o_rew, a->o_done, r_obs, r_act, r_pd, r_rew,
+        r_done);
+    return sb200_launch_status(2);
+}
