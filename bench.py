@@ -229,7 +229,27 @@ def run_ours(args):
                        'mlp_fwd_mma_kernel<1> (learner minibatch forward on %d rows)' % N)
     roof_critic = mlp_roof('sb200_mlp_forward_f32[rows=%d]' % rows, rows, 1,
                            'mlp_fwd_mma_kernel<4> (fused critic pass over %d rows)' % rows)
-    cands = [r for r in (roof_small, roof_mb, roof_critic) if r is not None]
+    roof_roll = None
+    rk = 'sb200_ppo_rollout_f32'
+    if rk in per_step:
+        avg_ms = per_step[rk][2]
+        flop = 2.0 * N * T * (w_params + HIDDEN[1] * A + D * (D + A))          # policy forward + env step, all T steps
+        byts = N * T * (D + 3 * A + 2) * 4 + 2 * N * ((T + 1) * D + 3 * T * A + 2 * T) * 4   # staging writes + window copy
+        ach = flop / (avg_ms / 1e3) / 1e12
+        ffma_peak = 148 * 128 * 2 * 1.9e9 / 1e12
+        roof_roll = {'kernel': 'ppo_rollout_kernel (persistent: %d env steps of %d actors per launch; 4-CTA clusters, '
+                               'resident weights, DSMEM exchange)' % (T, N),
+                     'bound': 'tensor', 'achieved': ach, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
+                     'frac': ach / peaks['bf16_tflops'], 'traffic': None, 'avg_ms': avg_ms,
+                     'launches_per_step': per_step[rk][0], 'share_of_step_kernel_time': per_step[rk][1] / total_kernel_ms,
+                     'algorithmic_flop': flop, 'algorithmic_bytes': byts, 'achieved_gbs': byts / (avg_ms / 1e3) / 1e9,
+                     'fp32_ffma_peak_tflops': ffma_peak, 'frac_of_fp32_ffma_peak': ach / ffma_peak,
+                     'peak_source': peaks['source'],
+                     'note': 'fp32 FFMA by necessity (1e-5 parity with the fp32 reference); the dense-bf16 tensor peak is '
+                             'the mandated denominator, the fp32 FFMA ceiling (148 SMs x 128 lanes x 2 x 1.9 GHz) the '
+                             'meaningful one.  Per step the kernel is a dependent chain: layer -> cluster barrier -> '
+                             'layer -> cluster barrier -> head/sample/env -> cluster barrier'}
+    cands = [r for r in (roof_roll, roof_small, roof_mb, roof_critic) if r is not None]
     roofline = max(cands, key=lambda r: r['share_of_step_kernel_time']) if cands else None
     if roof_critic is not None and roofline is roof_critic:
         roofline['traffic'] = 34260992        # dram__bytes_read+write of profiles/r01a_prof_critic.md (one ncu --set full capture)
@@ -273,7 +293,7 @@ def run_ours(args):
             'optimizer_steps_per_sec': (opt_steps * world / (total_ms / 1e3)) if opt_steps else None,
             'gpu_launches': per_step_launches * args.steps, 'gpu_launches_per_step': per_step_launches,
             'clocks': clk, 'roofline': roofline, 'roofline_critic_pass': roof_critic, 'roofline_gae': roofline_gae,
-            'kernel_breakdown': breakdown[:12], 'e2e': e2e,
+            'roofline_rollout': roof_roll, 'kernel_breakdown': breakdown[:12], 'e2e': e2e,
             'cpu_baseline': cpu_baseline, 'wall_s': t_wall, 'wall_env_steps_per_s': env_steps / t_wall / world * world,
         }
         print(json.dumps(out))

@@ -29,6 +29,20 @@ class Mlp(C.Structure):
                 ('aux_dim', C.c_int)]
 
 
+class PPORollout(C.Structure):
+    """sb200_ppo_rollout (include/surreal_b200.h)."""
+    _fields_ = [('net', C.POINTER(Mlp)), ('zf_stats', C.c_void_p), ('zf_eps', C.c_float), ('log_var', C.c_void_p),
+                ('log_noise', C.c_void_p), ('agent_seed', C.c_uint64), ('deterministic', C.c_int),
+                ('state', C.c_void_p), ('WsT', C.c_void_p), ('WaT', C.c_void_p), ('ep_step', C.c_void_p),
+                ('max_steps', C.c_int), ('env_seed', C.c_uint64), ('action', C.c_void_p), ('pd', C.c_void_p),
+                ('obs_next', C.c_void_p), ('reward', C.c_void_p), ('done', C.c_void_p), ('stage_pos', C.c_void_p),
+                ('stage_obs', C.c_void_p), ('stage_act', C.c_void_p), ('stage_pd', C.c_void_p),
+                ('stage_rew', C.c_void_p), ('stage_done', C.c_void_p), ('o_obs', C.c_void_p), ('o_act', C.c_void_p),
+                ('o_pd', C.c_void_p), ('o_rew', C.c_void_p), ('o_done', C.c_void_p), ('ev_step', C.c_void_p),
+                ('ev_count', C.c_void_p), ('W', C.c_int), ('N', C.c_int), ('D', C.c_int), ('A', C.c_int),
+                ('n_step', C.c_int), ('stride', C.c_int), ('T', C.c_int), ('step_counter', C.c_void_p)]
+
+
 class ZFilter(C.Structure):
     _fields_ = [('stats', C.c_void_p), ('eps', C.c_float)]
 
@@ -57,6 +71,10 @@ def _declare(lib):
         'sb200_mlp_pack_floats': (S, [C.POINTER(Mlp)]),
         'sb200_mlp_pack_tf32': (I, [C.POINTER(Mlp), P, P]),
         'sb200_mlp_forward_packed_f32': (I, [C.POINTER(Mlp), P, C.POINTER(ZFilter), C.POINTER(Rows), P, L, P]),
+        'sb200_ppo_rollout_supported': (I, [C.POINTER(Mlp), I, I]),
+        'sb200_ppo_rollout_scratch_ints': (S, [I, I, I]),
+        'sb200_ppo_rollout_f32': (I, [C.POINTER(PPORollout), P]),
+        'sb200_ppo_rollout_commit_f32': (I, [C.POINTER(PPORollout), P, P, P, P, P, P, P, P, P]),
         'sb200_linear_bwd_dx_f32': (I, [P, L, P, I, P, L, P, L, I, I, I, P]),
         'sb200_linear_bwd_dw_f32': (I, [P, L, P, L, P, P, L, I, I, I, I, I, P]),
         'sb200_make_pd_f32': (I, [P, L, P, P, I, I, P, L, P]),

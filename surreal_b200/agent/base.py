@@ -109,17 +109,22 @@ class Agent(metaclass=U.AutoInitializeMeta):
             self._obs, _ = env.reset()
         steps = max_steps if max_steps is not None else max(int(self.env_config.limit_episode_length), 1)
         obs = self._obs
-        if self._can_graph(obs):
-            # device-resident env: the whole chunk is ONE CUDA-graph submission (act -> env -> staging/replay kernels
-            # x steps).  Parameter fetches happen at chunk boundaries, at the configured cadence.
+        if self._device_resident(obs):
+            # device-resident env: the whole chunk is a fixed launch sequence with no host logic inside -- ONE
+            # persistent kernel where the policy / env allow it, else act -> env -> staging kernels x steps -- submitted
+            # as one CUDA graph (SB200_CUDA_GRAPH=0: the same launches, eagerly).  Parameter fetches happen at chunk
+            # boundaries, at the configured cadence.
+            from ..ops import GraphRunner, graphs_enabled
             if self.agent_mode == 'training' and self._fetch_parameter_mode == 'step' and \
                     self._fetch_parameter_tracker.track_increment(steps):
                 self.fetch_parameter()
-            if steps not in self._rollout_graphs:
-                from ..ops import GraphRunner
-                self._rollout_graphs[steps] = GraphRunner()
+            persistent = hasattr(self, 'rollout_chunk') and self.rollout_chunk_supported()
+            if persistent:
+                env.rollout_outbox(steps)              # allocate outside graph capture
 
             def body():
+                if persistent and self.rollout_chunk(steps):
+                    return                             # whole chunk = one persistent kernel + the commit pass
                 o = obs
                 packed = getattr(self, '_packed', None)
                 if packed is not None:
@@ -131,7 +136,12 @@ class Agent(metaclass=U.AutoInitializeMeta):
                         o, _, _, _ = env.step(a)
                 finally:
                     self._in_chunk = False
-            self._rollout_graphs[steps].run(body)
+            if graphs_enabled():
+                if steps not in self._rollout_graphs:
+                    self._rollout_graphs[steps] = GraphRunner()
+                self._rollout_graphs[steps].run(body)
+            else:
+                body()
             self.current_step += steps
             self.cumulative_steps += steps * self.num_envs
             self.actions_since_param_update += steps
@@ -146,11 +156,10 @@ class Agent(metaclass=U.AutoInitializeMeta):
         self._obs = obs
         self.post_episode()
 
-    def _can_graph(self, obs):
-        """Graph capture needs every buffer of the step to live at a fixed device address: true for the in-tree
+    def _device_resident(self, obs):
+        """The chunked path needs every buffer of the step to live at a fixed device address: true for the in-tree
         device env (its obs tensor is its state buffer), false for host envs."""
-        from ..ops import graphs_enabled
-        if not graphs_enabled() or not getattr(self.env, 'graph_safe', False):
+        if not getattr(self.env, 'graph_safe', False):
             return False
         import torch
         x = obs['low_dim']['flat_inputs'] if isinstance(obs, dict) else obs

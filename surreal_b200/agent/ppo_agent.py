@@ -135,6 +135,55 @@ class PPOAgent(Agent):
             time.sleep(self.env_config.sleep_time)
         return action, [[], [pd]]
 
+    def rollout_chunk_supported(self):
+        """True when ``steps`` consecutive act -> env.step -> staging iterations can run as the persistent rollout
+        kernel (sb200_ppo_rollout_f32): training mode, the in-tree device env behind the window wrapper, and a policy
+        that fits the kernel's shared-memory plan."""
+        import os
+        from ..env import SyntheticEnv
+        env = self.env
+        if self.agent_mode != 'training' or os.environ.get('SB200_PERSISTENT_ROLLOUT', '1') == '0':
+            return False
+        if not isinstance(env, ExpSenderWrapperMultiStepMovingWindowWithInfo) or not env.persistent_rollout:
+            return False
+        if type(env.env) is not SyntheticEnv:
+            return False
+        d = self.model.actor.desc()
+        return bool(_lib.lib().sb200_ppo_rollout_supported(C.byref(d), self.model.low_dim, self.action_dim))
+
+    def rollout_chunk(self, steps):
+        """``steps`` iterations of the actor loop (agent/base.py:244-262) in one launch + the ordered commit pass."""
+        w = self.env
+        e, r, m = w.env, w.replay, self.model
+        ob = w.rollout_outbox(steps)
+        if ob is None:
+            return False
+        a = _lib.PPORollout()
+        d = m.actor.desc()
+        a.net = C.pointer(d)
+        a.zf_stats = m.z_stats.data_ptr() if m.z_stats is not None else None
+        a.zf_eps = float(m.z_eps)
+        a.log_var, a.log_noise = m.log_var.data_ptr(), self._log_noise.data_ptr()
+        a.agent_seed, a.deterministic = self.seed, 0
+        a.state, a.WsT, a.WaT, a.ep_step = e.state.data_ptr(), e.WsT.data_ptr(), e.WaT.data_ptr(), e.ep_step.data_ptr()
+        a.max_steps, a.env_seed = e.max_steps, e.seed + 7
+        a.action, a.pd = self._action.data_ptr(), self._pd.data_ptr()
+        a.obs_next, a.reward, a.done = e.obs_next.data_ptr(), e.reward.data_ptr(), e.done.data_ptr()
+        a.stage_pos, a.stage_obs, a.stage_act = w.stage_pos.data_ptr(), w.stage_obs.data_ptr(), w.stage_act.data_ptr()
+        a.stage_pd, a.stage_rew, a.stage_done = w.stage_pd.data_ptr(), w.stage_rew.data_ptr(), w.stage_done.data_ptr()
+        a.o_obs, a.o_act, a.o_pd = ob['o_obs'].data_ptr(), ob['o_act'].data_ptr(), ob['o_pd'].data_ptr()
+        a.o_rew, a.o_done = ob['o_rew'].data_ptr(), ob['o_done'].data_ptr()
+        a.ev_step, a.ev_count, a.W = ob['ev_step'].data_ptr(), ob['ev_count'].data_ptr(), ob['W']
+        a.N, a.D, a.A = self.num_envs, m.low_dim, self.action_dim
+        a.n_step, a.stride, a.T = w.n_step, w.stride, int(steps)
+        a.step_counter = e.step_counter.data_ptr()
+        L, st = _lib.lib(), ops._stream()
+        check(L.sb200_ppo_rollout_f32(C.byref(a), st), 'sb200_ppo_rollout_f32')
+        check(L.sb200_ppo_rollout_commit_f32(C.byref(a), _p(ob['scratch']), _p(r.state), _p(r.r_obs), _p(r.r_act),
+                                             _p(r.r_pd), _p(r.r_rew), _p(r.r_done), _p(e.step_counter), st),
+              'sb200_ppo_rollout_commit_f32')
+        return True
+
     def module_dict(self):
         return {'ppo': self.model}
 

@@ -61,6 +61,8 @@ class ExpSenderWrapperMultiStepMovingWindowWithInfo(_WrapperBase):
         self._dest = torch.zeros(N, dtype=torch.int32, device=self.device)
         self._slots_ready = False      # the agent's sampling kernel already assigned this step's replay slots
         self.fuse_launches = True      # sample+assign / env+commit: 3 launches per step instead of 5 (same results)
+        self.persistent_rollout = True  # device env + supported policy: whole chunks in ONE launch (agent.rollout_chunk)
+        self._outbox = {}
         r = self.replay
         assert (r.n_step, r.D, r.A) == (n, D, A), 'replay record shape does not match the env / n_step'
 
@@ -69,6 +71,26 @@ class ExpSenderWrapperMultiStepMovingWindowWithInfo(_WrapperBase):
         self.stage_pos.zero_()                                     # deque.clear() (exp_sender_wrapper.py:204-207)
         self.stage_obs[:, 0].copy_(obs['low_dim']['flat_inputs'])
         return obs, info
+
+    def rollout_outbox(self, T):
+        """Buffers of the persistent rollout kernel for chunks of T steps: per-actor outbox of finished windows (in
+        the replay's record layout), their completion steps, and the commit pass's scratch.  None when the outbox
+        would not be worth its memory (tiny strides)."""
+        key = int(T)
+        if key in self._outbox:
+            return self._outbox[key]
+        N, n, D, A = self.N, self.n_step, self.D, self.A
+        W = T // self.stride + 2
+        rec_bytes = 4 * ((n + 1) * D + n * A + n * 2 * A + 2 * n)
+        ob = None
+        if N * W * rec_bytes <= 4 << 30:
+            f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.device)  # noqa: E731
+            z = lambda k: torch.zeros(k, dtype=torch.int32, device=self.device)      # noqa: E731
+            ob = dict(W=W, o_obs=f(N * W, n + 1, D), o_act=f(N * W, n, A), o_pd=f(N * W, n, 2 * A), o_rew=f(N * W, n),
+                      o_done=f(N * W, n), ev_step=z(N * W), ev_count=z(N),
+                      scratch=z(int(_lib.lib().sb200_ppo_rollout_scratch_ints(N, W, T))))
+        self._outbox[key] = ob
+        return ob
 
     def slot_assignment_args(self):
         """For PPOAgent.act: (fifo_state, dest) of sb200_ppo_sample_assign_f32, which folds this step's slot

@@ -359,3 +359,70 @@ def test_fused_rollout_launches_match_unfused(n, stride, cap_extra):
     assert f['state']['total_in'] > 0 and (cap_extra > 0 or f['state']['dropped'] > 0)
     for k in ['acts', 'pos', 'r_obs', 'r_act', 'r_pd', 'r_rew', 'r_done']:
         assert torch.equal(f[k], u[k]), k
+
+
+def _rollout_pair(n, stride, cap_extra, zero_head, T, N=50, D=12, A=3):
+    """Run the same chunk through the persistent rollout kernel and through the per-step launch sequence."""
+    from surreal_b200.agent import PPOAgent
+    from surreal_b200.replay import FIFOReplay
+    from surreal_b200.env import SyntheticEnv
+    out = []
+    for persistent in (True, False):
+        lc, ec, sc = ppo_configs(D=D, A=A, actor_h=(48, 32), critic_h=(48, 32), n_step=n, stride=stride, B=8,
+                                 memory_size=N + cap_extra)
+        ec.num_envs = N
+        R = FIFOReplay(lc, ec, sc)
+        ag = PPOAgent(lc, ec, sc, 1, 'training')
+        torch.manual_seed(5)
+        ag.model.actor.params.copy_(torch.randn_like(ag.model.actor.params) * 0.2)
+        if zero_head:                                             # mean == tanh(0) == 0 on both paths: bitwise comparable
+            ag.model.actor.W(2).zero_()
+            ag.model.actor.b(2).zero_()
+        ag.model.z_stats.copy_(torch.cat([torch.linspace(-3, 3, D) * 10, torch.linspace(1, 2, D) * 40,
+                                          torch.tensor([10.0])]).to(DEV))
+        ag.set_noise(np.linspace(-0.5, 0.5, N))
+        env = SyntheticEnv(N, D, A, limit_episode_length=11, seed=4)
+        ag.env = w = ag.prepare_env_agent(env)
+        obs, _ = w.reset()
+        if persistent:
+            assert ag.rollout_chunk_supported()
+            for t0 in range(0, T, 8):                             # several chunks: state carries over between launches
+                assert ag.rollout_chunk(min(8, T - t0))
+        else:
+            for _ in range(T):
+                a = ag.act(obs)
+                obs, _, _, _ = w.step(a)
+        torch.cuda.synchronize()
+        out.append(dict(state=R._read_state(), ctr=int(env.step_counter.item()), pos=w.stage_pos.clone(),
+                        ep=env.ep_step.clone(), env_state=env.state.clone(), act=ag._action.clone(), pd=ag._pd.clone(),
+                        rew=env.reward.clone(), done=env.done.clone(), obs_next=env.obs_next.clone(),
+                        r_obs=R.r_obs.clone(), r_act=R.r_act.clone(), r_pd=R.r_pd.clone(), r_rew=R.r_rew.clone(),
+                        r_done=R.r_done.clone(), so=w.stage_obs.clone(), sa=w.stage_act.clone()))
+    return out
+
+
+@pytest.mark.parametrize('n,stride,cap_extra', [(8, 8, 40), (6, 4, 40), (4, 4, -30), (5, 2, 100)])
+def test_persistent_rollout_matches_per_step_bitwise(n, stride, cap_extra):
+    """One persistent launch per chunk vs T x (forward, sample, env+commit): with a zero policy head both paths
+    produce mean == 0 exactly, so sampling, env dynamics, window staging (overlapping windows, episode ends),
+    outbox -> FIFO ordering in (step, actor) order and drop-oldest must agree bit for bit."""
+    p, s = _rollout_pair(n, stride, cap_extra, zero_head=True, T=29)
+    assert p['state'] == s['state'] and p['ctr'] == s['ctr'] == 29
+    assert p['state']['total_in'] > 0 and (cap_extra > 0 or p['state']['dropped'] > 0)
+    for k in ['pos', 'ep', 'env_state', 'act', 'pd', 'rew', 'done', 'obs_next', 'r_obs', 'r_act', 'r_pd', 'r_rew',
+              'r_done', 'sa']:
+        assert torch.equal(p[k], s[k]), k
+
+
+def test_persistent_rollout_policy_forward_close():
+    """Same comparison with a live policy head: the cluster FFMA forward and the per-step tensor-core forward agree
+    to fp32 rounding, so trajectories stay within a small tolerance and every discrete quantity is identical."""
+    p, s = _rollout_pair(8, 8, 40, zero_head=False, T=16)
+    assert p['state'] == s['state'] and torch.equal(p['pos'], s['pos']) and torch.equal(p['ep'], s['ep'])
+    assert torch.equal(p['r_done'], s['r_done'])
+    A = 3
+    d0 = (p['r_pd'][:, 0, :A] - s['r_pd'][:, 0, :A]).abs().max()           # first step: identical inputs
+    assert float(d0) <= 1e-5, float(d0)
+    assert float(p['r_pd'][:, 0, :A].abs().max()) > 0.05                       # ... and a non-trivial policy output
+    for k in ['r_obs', 'r_act', 'r_pd', 'r_rew', 'env_state']:
+        assert float((p[k] - s[k]).abs().max()) <= 2e-3, (k, float((p[k] - s[k]).abs().max()))
