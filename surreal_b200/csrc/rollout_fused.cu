@@ -70,7 +70,7 @@ struct RfParams {
     int N, n_step, stride, T;
     const unsigned long long* step_ctr;
     // shared-memory plan (float offsets)
-    int oW1, oW2, oWh, oB, oX0, oH1, oH2, oZf, oEnv, oS, oNext, oAct;
+    int oW1, oW2, oWh, oB, oX0, oH1, oH2, oPart, oZf, oEnv, oS, oNext, oAct;
     int ldx0, ldh1, ldh2;
 };
 
@@ -91,39 +91,84 @@ __device__ __forceinline__ void rf_st_cluster_v4(unsigned addr, const float4& v)
                  : "memory");
 }
 
-// One hidden layer for the cluster's 32 rows, this CTA's Nc columns: out[ty][col0 + 4c4 ..] = act(x[ty] . Ws + b),
-// stored locally and pushed to the three peers.  Xin [32][ldin] and Ws [K][Nc] live in shared memory; K % 4 == 0.
+// One hidden layer for the cluster's 32 rows, this CTA's Nc columns: out[row][col0 + c] = act(x[row] . Ws[:, c] + b).
+// Xin [32][ldin] and Ws [K][Nc] live in shared memory; K % 4 == 0.
+//   Thread tile 4 rows x 4 columns (16 accumulators): with the first version's 1 x 4 tile every 16 FFMA needed 5
+//   LDS.128 and the layer was bound by shared-memory bandwidth (ncu: mio_throttle + short_scoreboard, 60 % of the
+//   kernel); 4 x 4 needs 8 LDS.128 per 64 FFMA.  The 512 threads form 4 groups of 128 that split K; the partial
+//   tiles are summed in a fixed order (deterministic) through `Part` [4][32][Nc].
+//   ALL_ROWS: the result is stored in every CTA's copy of Hout [32][ldout] (input of the next hidden layer);
+//   otherwise each row goes only to the CTA that owns the actor, into its Hout [8][ldout] (input of the head).
+template <bool ALL_ROWS>
 __device__ __forceinline__ void rf_layer(const float* __restrict__ Xin, int ldin, int K, const float* __restrict__ Ws,
                                          int Nc, const float* __restrict__ bias_s, int act, float* __restrict__ Hout,
-                                         int ldout, int col0, unsigned smem_base, const unsigned (&peer_base)[RF_CS - 1]) {
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const float* xr = Xin + ty * ldin;
-    for (int c4 = tx; c4 < (Nc >> 2); c4 += 16) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                                         int ldout, int col0, float* __restrict__ Part, unsigned smem_base,
+                                         unsigned crank) {
+    const int tid = threadIdx.x;
+    const int q = tid >> 7, t128 = tid & 127, ty = t128 >> 4, tx = t128 & 15;
+    const int kq = (((K >> 2) + 3) >> 2) << 2;               // k span of one group (multiple of 4)
+    const int k_lo = q * kq, k_hi = min(K, k_lo + kq);
+    const int nq = Nc >> 2;
+    for (int c4 = tx; c4 < nq; c4 += 16) {
+        float acc[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
+        const float* xr = Xin + (ty * 4) * ldin;
         const float* wp = Ws + c4 * 4;
 #pragma unroll 2
-        for (int k = 0; k < K; k += 4) {
-            const float4 a = *reinterpret_cast<const float4*>(xr + k);
+        for (int k = k_lo; k < k_hi; k += 4) {
+            float4 a[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) a[r] = *reinterpret_cast<const float4*>(xr + r * ldin + k);
             const float4 w0 = *reinterpret_cast<const float4*>(wp + (k + 0) * Nc);
             const float4 w1 = *reinterpret_cast<const float4*>(wp + (k + 1) * Nc);
             const float4 w2 = *reinterpret_cast<const float4*>(wp + (k + 2) * Nc);
             const float4 w3 = *reinterpret_cast<const float4*>(wp + (k + 3) * Nc);
-            acc.x = fmaf(a.x, w0.x, acc.x); acc.y = fmaf(a.x, w0.y, acc.y); acc.z = fmaf(a.x, w0.z, acc.z); acc.w = fmaf(a.x, w0.w, acc.w);
-            acc.x = fmaf(a.y, w1.x, acc.x); acc.y = fmaf(a.y, w1.y, acc.y); acc.z = fmaf(a.y, w1.z, acc.z); acc.w = fmaf(a.y, w1.w, acc.w);
-            acc.x = fmaf(a.z, w2.x, acc.x); acc.y = fmaf(a.z, w2.y, acc.y); acc.z = fmaf(a.z, w2.z, acc.z); acc.w = fmaf(a.z, w2.w, acc.w);
-            acc.x = fmaf(a.w, w3.x, acc.x); acc.y = fmaf(a.w, w3.y, acc.y); acc.z = fmaf(a.w, w3.z, acc.z); acc.w = fmaf(a.w, w3.w, acc.w);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                acc[r][0] = fmaf(a[r].x, w0.x, acc[r][0]); acc[r][1] = fmaf(a[r].x, w0.y, acc[r][1]);
+                acc[r][2] = fmaf(a[r].x, w0.z, acc[r][2]); acc[r][3] = fmaf(a[r].x, w0.w, acc[r][3]);
+                acc[r][0] = fmaf(a[r].y, w1.x, acc[r][0]); acc[r][1] = fmaf(a[r].y, w1.y, acc[r][1]);
+                acc[r][2] = fmaf(a[r].y, w1.z, acc[r][2]); acc[r][3] = fmaf(a[r].y, w1.w, acc[r][3]);
+                acc[r][0] = fmaf(a[r].z, w2.x, acc[r][0]); acc[r][1] = fmaf(a[r].z, w2.y, acc[r][1]);
+                acc[r][2] = fmaf(a[r].z, w2.z, acc[r][2]); acc[r][3] = fmaf(a[r].z, w2.w, acc[r][3]);
+                acc[r][0] = fmaf(a[r].w, w3.x, acc[r][0]); acc[r][1] = fmaf(a[r].w, w3.y, acc[r][1]);
+                acc[r][2] = fmaf(a[r].w, w3.z, acc[r][2]); acc[r][3] = fmaf(a[r].w, w3.w, acc[r][3]);
+            }
         }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            *reinterpret_cast<float4*>(Part + ((q * RF_ROWS + ty * 4 + r) * Nc + c4 * 4)) =
+                make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < RF_ROWS * nq; idx += RF_THREADS) {
+        const int row = idx / nq, c4 = idx - row * nq;
+        const float* pp = Part + row * Nc + c4 * 4;
+        const float4 p0 = *reinterpret_cast<const float4*>(pp);
+        const float4 p1 = *reinterpret_cast<const float4*>(pp + RF_ROWS * Nc);
+        const float4 p2 = *reinterpret_cast<const float4*>(pp + 2 * RF_ROWS * Nc);
+        const float4 p3 = *reinterpret_cast<const float4*>(pp + 3 * RF_ROWS * Nc);
         const float4 bv = *reinterpret_cast<const float4*>(bias_s + c4 * 4);
         float4 o;
-        o.x = rf_act(acc.x + bv.x, act);
-        o.y = rf_act(acc.y + bv.y, act);
-        o.z = rf_act(acc.z + bv.z, act);
-        o.w = rf_act(acc.w + bv.w, act);
-        float* q = Hout + ty * ldout + col0 + c4 * 4;
-        *reinterpret_cast<float4*>(q) = o;
-        const unsigned off = rf_smem_u32(q) - smem_base;
+        o.x = rf_act(((p0.x + p1.x) + (p2.x + p3.x)) + bv.x, act);
+        o.y = rf_act(((p0.y + p1.y) + (p2.y + p3.y)) + bv.y, act);
+        o.z = rf_act(((p0.z + p1.z) + (p2.z + p3.z)) + bv.z, act);
+        o.w = rf_act(((p0.w + p1.w) + (p2.w + p3.w)) + bv.w, act);
+        if (ALL_ROWS) {
+            float* qd = Hout + row * ldout + col0 + c4 * 4;
+            *reinterpret_cast<float4*>(qd) = o;
+            const unsigned off = rf_smem_u32(qd) - smem_base;
 #pragma unroll
-        for (int c = 0; c < RF_CS - 1; ++c) rf_st_cluster_v4(peer_base[c] + off, o);
+            for (int c = 1; c < RF_CS; ++c) rf_st_cluster_v4(rf_mapa(smem_base, (crank + (unsigned)c) % RF_CS) + off, o);
+        } else {
+            const unsigned owner = (unsigned)(row / RF_OWN);
+            float* qd = Hout + (row - (int)owner * RF_OWN) * ldout + col0 + c4 * 4;
+            if (owner == crank) *reinterpret_cast<float4*>(qd) = o;
+            else rf_st_cluster_v4(rf_mapa(smem_base, owner) + (rf_smem_u32(qd) - smem_base), o);
+        }
     }
 }
 
@@ -150,7 +195,8 @@ __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
     float* Bhs = B2s + Nc2;
     float* X0 = smem + p.oX0;           // [32][ldx0]  z-filtered observations of the cluster's actors
     float* Hb1 = smem + p.oH1;          // [32][ldh1]
-    float* Hb2 = smem + p.oH2;          // [32][ldh2]
+    float* Hb2 = smem + p.oH2;          // [8][ldh2]   last hidden layer, owned actors only
+    float* Part = smem + p.oPart;       // [4][32][max(Nc1, Nc2)] k-split partial tiles
     float* Zm = smem + p.oZf;           // [D] mean | [D] std
     float* Zs = Zm + D;
     float* EWs = smem + p.oEnv;         // [D][D] | [A][D]   (k-major)
@@ -215,16 +261,16 @@ __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
     for (int t = 0; t < p.T; ++t) {
         const unsigned long long ctr = ctr0 + (unsigned long long)t;
         const bool final_step = (t == p.T - 1);
-        rf_layer(X0, p.ldx0, D, W1s, Nc1, B1s, p.act[0], Hb1, p.ldh1, (int)crank * Nc1, smem_base, peer_base);
+        rf_layer<true>(X0, p.ldx0, D, W1s, Nc1, B1s, p.act[0], Hb1, p.ldh1, (int)crank * Nc1, Part, smem_base, crank);
         cluster.sync();
-        rf_layer(Hb1, p.ldh1, H1, W2s, Nc2, B2s, p.act[1], Hb2, p.ldh2, (int)crank * Nc2, smem_base, peer_base);
+        rf_layer<false>(Hb1, p.ldh1, H1, W2s, Nc2, B2s, p.act[1], Hb2, p.ldh2, (int)crank * Nc2, Part, smem_base, crank);
         cluster.sync();
 
         float rew = 0.0f, dn = 0.0f;
         int slot = SLOT_NONE;
         if (owner) {
             // ---- head: mean[j] (j < A) ends up in lane j of chunk j / 8
-            const float* hrow = Hb2 + m_own * p.ldh2;
+            const float* hrow = Hb2 + own * p.ldh2;
             const int pos = s_pos[own];
             for (int n8 = 0; n8 < A; n8 += 8) {
                 float s8[8];
@@ -471,12 +517,13 @@ bool rf_plan(const sb200_mlp* net, int D, int A, RfParams* p, size_t* smem_bytes
     const int oW1 = take((long long)D * Nc1), oW2 = take((long long)H1 * Nc2), oWh = take((long long)H2 * ldwh);
     const int oB = take(Nc1 + Nc2 + ldwh);
     const int ldx0 = D + 4, ldh1 = H1 + 4, ldh2 = H2 + 4;
-    const int oX0 = take(RF_ROWS * ldx0), oH1 = take(RF_ROWS * ldh1), oH2 = take(RF_ROWS * ldh2);
+    const int oX0 = take(RF_ROWS * ldx0), oH1 = take(RF_ROWS * ldh1), oH2 = take(RF_OWN * ldh2);
+    const int oPart = take(4LL * RF_ROWS * (Nc1 > Nc2 ? Nc1 : Nc2));
     const int oZf = take(2 * D), oEnv = take((long long)D * D + A * D);
     const int oS = take(RF_OWN * D), oNext = take(RF_OWN * D), oAct = take(RF_OWN * A);
-    if ((size_t)off * sizeof(float) > 220 * 1024) return false;
+    if ((size_t)off * sizeof(float) > 224 * 1024) return false;
     if (p != nullptr) {
-        p->oW1 = oW1; p->oW2 = oW2; p->oWh = oWh; p->oB = oB; p->oX0 = oX0; p->oH1 = oH1; p->oH2 = oH2;
+        p->oW1 = oW1; p->oW2 = oW2; p->oWh = oWh; p->oB = oB; p->oX0 = oX0; p->oH1 = oH1; p->oH2 = oH2; p->oPart = oPart;
         p->oZf = oZf; p->oEnv = oEnv; p->oS = oS; p->oNext = oNext; p->oAct = oAct;
         p->ldx0 = ldx0; p->ldh1 = ldh1; p->ldh2 = ldh2;
         p->D = D; p->H1 = H1; p->H2 = H2; p->A = A;
@@ -488,7 +535,7 @@ bool rf_plan(const sb200_mlp* net, int D, int A, RfParams* p, size_t* smem_bytes
 }  // namespace
 
 int sb200_rollout_fused_init() {
-    SB200_CUDA(cudaFuncSetAttribute(ppo_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    SB200_CUDA(cudaFuncSetAttribute(ppo_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     return SB200_OK;
 }
 
