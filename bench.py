@@ -187,6 +187,19 @@ def run_ours(args):
     env_steps = N * T * args.steps * world
     value = env_steps / (total_ms / 1e3)
     opt_steps = sum(learner.epoch_history[-args.steps:]) if hasattr(learner, 'epoch_history') else None
+    # the two halves of a step in isolation (graph-replayed, sequential, device-timed): explains the pipelined number
+    phase = {'rollout': [], 'learn': []}
+    for _ in range(5):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        agent.main_loop(max_steps=T)
+        ev[1].record()
+        learner.main_loop()
+        ev[2].record()
+        torch.cuda.synchronize()
+        phase['rollout'].append(ev[0].elapsed_time(ev[1]))
+        phase['learn'].append(ev[1].elapsed_time(ev[2]))
+    phase_ms = {k: sorted(v)[len(v) // 2] for k, v in phase.items()}
     # roofline of the dominant kernel (fused critic pass) and of the GAE kernel: separate, untimed-for-throughput
     # pass that runs learn() EAGERLY with CUDA events around those two launches (events cannot sit inside a graph)
     _lib.profile_calls(True)
@@ -293,7 +306,7 @@ def run_ours(args):
             'optimizer_steps_per_sec': (opt_steps * world / (total_ms / 1e3)) if opt_steps else None,
             'gpu_launches': per_step_launches * args.steps, 'gpu_launches_per_step': per_step_launches,
             'clocks': clk, 'roofline': roofline, 'roofline_critic_pass': roof_critic, 'roofline_gae': roofline_gae,
-            'roofline_rollout': roof_roll, 'kernel_breakdown': breakdown[:12], 'e2e': e2e,
+            'phase_ms_sequential': phase_ms, 'roofline_rollout': roof_roll, 'kernel_breakdown': breakdown[:12], 'e2e': e2e,
             'cpu_baseline': cpu_baseline, 'wall_s': t_wall, 'wall_env_steps_per_s': env_steps / t_wall / world * world,
         }
         print(json.dumps(out))

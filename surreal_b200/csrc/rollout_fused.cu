@@ -70,7 +70,7 @@ struct RfParams {
     int N, n_step, stride, T;
     const unsigned long long* step_ctr;
     // shared-memory plan (float offsets)
-    int oW1, oW2, oWh, oB, oX0, oH1, oH2, oPart, oZf, oEnv, oS, oNext, oAct;
+    int oW1, oW2, oWh, oB, oX0, oH1, oH2, oPart, oZf, oEnv, oS, oNext, oAct, oPre;
     int ldx0, ldh1, ldh2;
 };
 
@@ -203,7 +203,14 @@ __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
     float* EWa = EWs + D * D;
     float* S = smem + p.oS;             // [8][D]   env state of the owned actors (what they observe next)
     float* Nx = smem + p.oNext;         // [8][D]   true successor of the step
-    float* Ac = smem + p.oAct;          // [8][A]   sampled actions
+    float* Ac = smem + p.oAct;          // [8][A]   sampled actions | means | std | N(0,1) draws
+    float* Mu = Ac + RF_OWN * A;
+    float* Sd = Mu + RF_OWN * A;
+    float* Zn = Sd + RF_OWN * A;
+    float* Eacc = smem + p.oPre;        // [8][D] Ws.s | [8][D] env noise | [8][D] reset draws | [16] |s|^2, reward noise
+    float* Egx = Eacc + RF_OWN * D;
+    float* Erz = Egx + RF_OWN * D;
+    float* Eq = Erz + RF_OWN * D;
     const long long row0 = (long long)(blockIdx.x / RF_CS) * RF_ROWS;
 
     // ---- one-time loads: weight slices, biases, env matrices (cp.async burst), z-filter columns, actor state
@@ -257,6 +264,8 @@ __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
     const long long i_own = row0 + m_own;
     const bool valid = owner && (i_own < p.N);
     const float sc = (valid && p.log_noise != nullptr) ? expf(p.log_noise[i_own]) : 1.0f;
+    if (owner && lane < A) Sd[own * A + lane] = __fmul_rn(expf(p.log_var[lane]), sc);     // constant over the chunk
+    __syncthreads();
 
     for (int t = 0; t < p.T; ++t) {
         const unsigned long long ctr = ctr0 + (unsigned long long)t;
@@ -268,10 +277,11 @@ __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
 
         float rew = 0.0f, dn = 0.0f;
         int slot = SLOT_NONE;
+        // ---- phase 1, two halves of the CTA in parallel.  Owner warps 0..7: the head.  Helper warps 8..15 (one per
+        // owned actor): everything of the step that does not depend on the action -- the exploration draws, Ws.s, the
+        // env noise, |s|^2 -- so that the serial chain after the head is a handful of instructions.
         if (owner) {
-            // ---- head: mean[j] (j < A) ends up in lane j of chunk j / 8
             const float* hrow = Hb2 + own * p.ldh2;
-            const int pos = s_pos[own];
             for (int n8 = 0; n8 < A; n8 += 8) {
                 float s8[8];
 #pragma unroll
@@ -296,72 +306,77 @@ __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
                     if (lane == jj) mine = tt;
                 }
                 const int j = n8 + lane;
-                if (lane < 8 && j < A) {
-                    // ---- PPOAgent.act after the network (ppo_agent.py:138-149), same arithmetic and Philox keys as
-                    // sample_one() in rollout.cu
-                    const float mu = rf_act(mine + Bhs[j], p.act[2]);
-                    const float sd = __fmul_rn(expf(p.log_var[j]), sc);
-                    float a = mu;
-                    if (!p.deterministic) {
-                        const Philox4 r = philox4x32_10(p.agent_seed, ctr, ((unsigned long long)i_own << 16) | (unsigned long long)(j >> 2));
-                        const float2 z01 = box_muller(r.x, r.y), z23 = box_muller(r.z, r.w);
-                        const int c = j & 3;
-                        const float e = (c == 0) ? z01.x : (c == 1) ? z01.y : (c == 2) ? z23.x : z23.y;
-                        a = __fadd_rn(__fmul_rn(e, sd), mu);
-                    }
-                    a = fminf(fmaxf(a, -1.0f), 1.0f);
-                    Ac[own * A + j] = a;
-                    if (valid) {
-                        p.stage_act[((long long)i_own * p.n_step + pos) * A + j] = a;
-                        p.stage_pd[((long long)i_own * p.n_step + pos) * 2 * A + j] = mu;
-                        p.stage_pd[((long long)i_own * p.n_step + pos) * 2 * A + A + j] = sd;
-                        if (final_step) {
-                            p.action[i_own * A + j] = a;
-                            p.pd[i_own * 2 * A + j] = mu;
-                            p.pd[i_own * 2 * A + A + j] = sd;
-                        }
+                if (lane < 8 && j < A) Mu[own * A + j] = rf_act(mine + Bhs[j], p.act[2]);
+            }
+        } else {
+            const int h = warp - RF_OWN;                       // helper of owned actor h
+            const long long ih = row0 + (int)crank * RF_OWN + h;
+            const float* sh = S + h * D;
+            float q = 0.0f;
+            for (int d = lane; d < D; d += 32) q += sh[d] * sh[d];
+            q = warp_sum(q);
+            const bool h_done = (p.max_steps > 0) && (s_ep[h] + 1 >= p.max_steps);
+            for (int d = lane; d < D; d += 32) {
+                float acc = 0.0f;                              // WsT is [k][d]: conflict-free across lanes
+#pragma unroll 8
+                for (int k = 0; k < D; ++k) acc = fmaf(EWs[k * D + d], sh[k], acc);
+                const Philox4 r = philox4x32_10(p.env_seed ^ 0x5851F42D4C957F2Dull, ctr,
+                                                ((unsigned long long)ih << 20) | (unsigned long long)d);
+                const float2 gz = box_muller(r.x, r.y);
+                Eacc[h * D + d] = acc;
+                Egx[h * D + d] = gz.x;
+                Erz[h * D + d] = h_done ? box_muller(r.z, r.w).x : 0.0f;
+                if (d == 0) {
+                    Eq[2 * h] = q;
+                    Eq[2 * h + 1] = gz.y;
+                }
+            }
+            if (!p.deterministic && lane < A) {                // PPOAgent.act's N(0,1) draws: keys of sample_one()
+                const int j = lane;
+                const Philox4 r = philox4x32_10(p.agent_seed, ctr, ((unsigned long long)ih << 16) | (unsigned long long)(j >> 2));
+                const float2 z01 = box_muller(r.x, r.y), z23 = box_muller(r.z, r.w);
+                const int c = j & 3;
+                Zn[h * A + j] = (c == 0) ? z01.x : (c == 1) ? z01.y : (c == 2) ? z23.x : z23.y;
+            }
+        }
+        __syncthreads();
+        // ---- phase 2 (owner warps): action, env step, bookkeeping -- same arithmetic, operand order and Philox keys as
+        // sample_one() / synth_env_block() of rollout.cu
+        if (owner) {
+            const int pos = s_pos[own];
+            if (lane < A) {
+                const int j = lane;
+                const float mu = Mu[own * A + j];
+                const float sd = Sd[own * A + j];
+                float a = mu;
+                if (!p.deterministic) a = __fadd_rn(__fmul_rn(Zn[own * A + j], sd), mu);
+                a = fminf(fmaxf(a, -1.0f), 1.0f);
+                Ac[own * A + j] = a;
+                if (valid) {
+                    p.stage_act[((long long)i_own * p.n_step + pos) * A + j] = a;
+                    p.stage_pd[((long long)i_own * p.n_step + pos) * 2 * A + j] = mu;
+                    p.stage_pd[((long long)i_own * p.n_step + pos) * 2 * A + A + j] = sd;
+                    if (final_step) {
+                        p.action[i_own * A + j] = a;
+                        p.pd[i_own * 2 * A + j] = mu;
+                        p.pd[i_own * 2 * A + A + j] = sd;
                     }
                 }
             }
             __syncwarp();
-            // ---- environment step (synth_env_block of rollout.cu, one warp per actor)
-            float* s = S + own * D;
-            float q = 0.0f;
-            for (int d = lane; d < D; d += 32) q += s[d] * s[d];
-            q = warp_sum(q);
+            float* sown = S + own * D;
             const int ep = s_ep[own] + 1;
             const bool is_done = (p.max_steps > 0) && (ep >= p.max_steps);
             dn = is_done ? 1.0f : 0.0f;
-            float nxt_v[4], st_v[4];                       // D <= 128: up to 4 elements per lane
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int d = lane + 32 * u;
-                nxt_v[u] = st_v[u] = 0.0f;
-                if (d < D) {
-                    float acc = 0.0f;
-#pragma unroll 8
-                    for (int k = 0; k < D; ++k) acc = fmaf(EWs[k * D + d], s[k], acc);
+            rew = -Eq[2 * own] / (float)D + 0.1f * Eq[2 * own + 1];
+            for (int d = lane; d < D; d += 32) {
+                float acc = Eacc[own * D + d];
 #pragma unroll 4
-                    for (int k = 0; k < A; ++k) acc = fmaf(EWa[k * D + d], Ac[own * A + k], acc);
-                    const Philox4 r = philox4x32_10(p.env_seed ^ 0x5851F42D4C957F2Dull, ctr,
-                                                    ((unsigned long long)i_own << 20) | (unsigned long long)d);
-                    const float2 gz = box_muller(r.x, r.y);
-                    const float nxt = tanhf(acc) + 0.01f * gz.x;
-                    nxt_v[u] = nxt;
-                    st_v[u] = is_done ? box_muller(r.z, r.w).x : nxt;
-                    if (d == 0) rew = -q / (float)D + 0.1f * gz.y;
-                }
-            }
-            rew = __shfl_sync(0xffffffffu, rew, 0);
-            __syncwarp();                                   // every lane has finished reading s[] before it is replaced
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int d = lane + 32 * u;
-                if (d < D) {
-                    Nx[own * D + d] = nxt_v[u];
-                    s[d] = st_v[u];
-                    if (valid && final_step) p.obs_next[i_own * D + d] = nxt_v[u];
-                }
+                for (int k = 0; k < A; ++k) acc = fmaf(EWa[k * D + d], Ac[own * A + k], acc);
+                const float nxt = tanhf(acc) + 0.01f * Egx[own * D + d];
+                Nx[own * D + d] = nxt;
+                sown[d] = is_done ? Erz[own * D + d] : nxt;
+                if (valid && final_step) p.obs_next[i_own * D + d] = nxt;
             }
             if (lane == 0) {
                 s_ep[own] = is_done ? 0 : ep;
@@ -369,7 +384,7 @@ __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
                     p.reward[i_own] = rew;
                     p.done[i_own] = dn;
                 }
-                if (valid && s_pos[own] + 1 == p.n_step) {  // this step completes a window -> next outbox entry
+                if (valid && pos + 1 == p.n_step) {            // this step completes a window -> next outbox entry
                     const int w = s_cnt[own];
                     if (w < p.Wout) {
                         slot = (int)(i_own * p.Wout + w);
@@ -381,8 +396,8 @@ __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
                 }
             }
             slot = __shfl_sync(0xffffffffu, slot, 0);
+            __syncwarp();
         }
-        __syncthreads();
         // ---- window staging (block-wide barriers inside: every warp calls; only owners do work)
         commit_actor(valid, (int)i_own, lane, 32, Nx + (owner ? own : 0) * D, S + (owner ? own : 0) * D, rew, dn, p.n_step,
                      p.stride, D, A, s_pos + (owner ? own : 0), slot, p.stage_obs, p.stage_act, p.stage_pd, p.stage_rew,
@@ -520,11 +535,12 @@ bool rf_plan(const sb200_mlp* net, int D, int A, RfParams* p, size_t* smem_bytes
     const int oX0 = take(RF_ROWS * ldx0), oH1 = take(RF_ROWS * ldh1), oH2 = take(RF_OWN * ldh2);
     const int oPart = take(4LL * RF_ROWS * (Nc1 > Nc2 ? Nc1 : Nc2));
     const int oZf = take(2 * D), oEnv = take((long long)D * D + A * D);
-    const int oS = take(RF_OWN * D), oNext = take(RF_OWN * D), oAct = take(RF_OWN * A);
+    const int oS = take(RF_OWN * D), oNext = take(RF_OWN * D), oAct = take(4 * RF_OWN * A);
+    const int oPre = take(3 * RF_OWN * D + 2 * RF_OWN);
     if ((size_t)off * sizeof(float) > 224 * 1024) return false;
     if (p != nullptr) {
         p->oW1 = oW1; p->oW2 = oW2; p->oWh = oWh; p->oB = oB; p->oX0 = oX0; p->oH1 = oH1; p->oH2 = oH2; p->oPart = oPart;
-        p->oZf = oZf; p->oEnv = oEnv; p->oS = oS; p->oNext = oNext; p->oAct = oAct;
+        p->oZf = oZf; p->oEnv = oEnv; p->oS = oS; p->oNext = oNext; p->oAct = oAct; p->oPre = oPre;
         p->ldx0 = ldx0; p->ldh1 = ldh1; p->ldh2 = ldh2;
         p->D = D; p->H1 = H1; p->H2 = H2; p->A = A;
     }
