@@ -323,37 +323,61 @@ def count_launches(fn):
     return _lib.call_counter_kernels()
 
 
+class HostEnv:
+    """Batched HOST environment of the e2e measurement: numpy in, numpy out, like a vector of gym envs on the CPU.  The
+    dynamics are pre-generated (pinned) so that the host side costs what a real env's output buffer costs -- a
+    pointer -- and the number isolates OUR side of the boundary: every observation / reward / done crosses PCIe
+    host->device and every action crosses back, each env step."""
+
+    def __init__(self, N, D, A, T, seed=0):
+        import numpy as np
+        import torch
+        self.N, self.D, self.A, self.T = N, D, A, T
+        rng = np.random.default_rng(seed)
+        self._obs = torch.empty(T + 1, N, D, dtype=torch.float32, pin_memory=True)
+        self._obs.numpy()[...] = rng.standard_normal((T + 1, N, D)).astype(np.float32)
+        self._rew = torch.empty(T, N, dtype=torch.float32, pin_memory=True)
+        self._rew.numpy()[...] = rng.standard_normal((T, N)).astype(np.float32)
+        self._done = torch.zeros(T, N, dtype=torch.float32).pin_memory()
+        self._done[T - 1] = 1.0                                   # episodes of T steps
+        self._o = [self._obs[t].numpy() for t in range(T + 1)]
+        self._r = [self._rew[t].numpy() for t in range(T)]
+        self._d = [self._done[t].numpy() for t in range(T)]
+        self.t = 0
+
+    def reset(self):
+        self.t = 0
+        return {'low_dim': {'flat_inputs': self._o[0]}}, {}
+
+    def step(self, action):
+        assert action.shape == (self.N, self.A)
+        t = self.t
+        self.t = (t + 1) % self.T
+        nxt = self._o[t + 1]
+        # the successor is also what the actors observe next (the synthetic stream has no reset transient)
+        return {'low_dim': {'flat_inputs': nxt}}, self._r[t], self._d[t], {'obs_next': nxt}
+
+
 def run_e2e(agent, learner, lc, dev, steps):
-    """env-steps/s through PPOAgent.act(host obs) + PPOLearner.learn(host batch): every byte crosses PCIe inside the
-    timed region.  The per-step observations live in (pinned) host memory like the output of a host-side env; the
-    batch is assembled on the host in the learner's window layout as the steps arrive (the aggregator's job)."""
-    import numpy as np
+    """env-steps/s through the public actor loop with a HOST env: PPOAgent.act(numpy obs) -> env.step(numpy action)
+    -> ExpSender wrapper (H2D of obs / reward / done, window staging into the HBM FIFO) x T, then
+    learner.main_loop() (sample from the FIFO, learn, publish).  Every env step's inputs cross PCIe host->device
+    and its actions device->host inside the timed region; the learner's statistics are read back every step."""
     import torch
     N, T, D, A = N_ACTORS, HORIZON, OBS_DIM, ACT_DIM
-    rng = np.random.default_rng(0)
-    obs_steps = torch.empty(T + 1, N, D, dtype=torch.float32, pin_memory=True)
-    obs_steps.numpy()[...] = rng.standard_normal((T + 1, N, D)).astype(np.float32)
-    b_obs = torch.empty(N, T + 1, D, dtype=torch.float32, pin_memory=True)
-    b_act = torch.empty(N, T, A, dtype=torch.float32, pin_memory=True)
-    b_pd = torch.empty(N, T, 2 * A, dtype=torch.float32, pin_memory=True)
-    b_rew = torch.empty(N, T, dtype=torch.float32, pin_memory=True)
-    b_done = torch.zeros(N, T, dtype=torch.float32).pin_memory()
-    b_done[:, -1] = 1.0
-    b_rew.numpy()[...] = rng.standard_normal((N, T)).astype(np.float32)
-    o_np, a_np, p_np = b_obs.numpy(), b_act.numpy(), b_pd.numpy()
-    saved_env = agent.env
-    agent.env = None                                   # external-env mode: nothing is staged on the device
+    saved_env, saved_obs = agent.env, agent._obs
+    henv = HostEnv(N, D, A, T)
+    agent.env = w = agent.prepare_env_agent(henv)
+    replay = w.replay
+    while len(replay) > 0:                                        # start from an empty queue
+        replay.sample(min(len(replay), learner.batch_size))
 
     def step():
-        for t in range(T):
-            o = obs_steps[t].numpy()
-            a, info = agent.act(o)                     # H2D obs, kernels, D2H action + pd
-            o_np[:, t] = o
-            a_np[:, t] = a
-            p_np[:, t] = info[1][0]
-        o_np[:, T] = obs_steps[T].numpy()
-        return learner.learn({'obs_full': b_obs, 'obs': None, 'obs_next': None, 'actions': b_act, 'rewards': b_rew,
-                              'dones': b_done, 'persistent_infos': [b_pd], 'onetime_infos': None})
+        obs, _ = w.reset()
+        for _ in range(T):
+            a = agent.act(obs)                                    # H2D obs (first step), kernels, D2H action + pd
+            obs, _, _, _ = w.step(a)                              # host env; H2D next obs / reward / done; staging
+        learner.main_loop()                                       # FIFO -> learn -> publish; D2H statistics
 
     step()
     torch.cuda.synchronize()
@@ -362,13 +386,13 @@ def run_e2e(agent, learner, lc, dev, steps):
         step()
     torch.cuda.synchronize()
     dt = time.time() - t0
-    agent.env = saved_env
-    h2d = T * N * D * 4 + (N * (T + 1) * D + N * T * A + N * T * 2 * A + 2 * N * T) * 4
+    agent.env, agent._obs = saved_env, saved_obs
+    h2d = (T + 1) * N * D * 4 + T * 2 * N * 4
     d2h = T * N * (A + 2 * A) * 4 + 32 * 4 + (2 * D + 1) * 4
     return {'value': N * T * steps / dt, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
             'ms_per_step': dt / steps * 1e3, 'steps': steps,
-            'api': 'PPOAgent.act(host obs) x128 + PPOLearner.learn(host batch); pinned host memory, copies and the host-side '
-                   'batch assembly inside the timed region'}
+            'api': 'PPOAgent.act(numpy obs) -> HostEnv.step(numpy action) -> ExpSenderWrapper.step x128, then '
+                   'PPOLearner.main_loop(); pinned host memory; all copies inside the timed region'}
 
 
 # --------------------------------------------------------------------------------------------------

@@ -76,9 +76,8 @@ class DDPGAgent(Agent):
             self._obs_dev.copy_(self._obs_pin, non_blocking=True)
             x = self._obs_dev
         x = x.reshape(N, D)
-        if self._packed.supported and x.stride(1) == 1:
-            if not self._in_chunk:
-                self._packed.refresh()                             # inside a chunk: refreshed once, at its top
+        if self._in_chunk and self._packed.supported and x.stride(1) == 1:
+            # inside a multi-step chunk the weights are fixed: the chunk packed them once, at its top
             ops.mlp_forward_packed(self._packed, x, out=self._mean)
         else:
             ops.mlp_forward(self.model.actor, x, out=self._mean)

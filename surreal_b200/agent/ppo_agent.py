@@ -76,21 +76,24 @@ class PPOAgent(Agent):
                                             else np.concatenate(xs, -1))
         host = not isinstance(x, torch.Tensor)
         if host:
-            if self._obs_pin is None:
-                self._obs_pin = torch.empty(N, D, dtype=torch.float32, pin_memory=True)
-            xt = torch.from_numpy(x) if (isinstance(x, np.ndarray) and x.dtype == np.float32 and
-                                         x.flags['C_CONTIGUOUS'] and x.flags['WRITEABLE']) else None
-            if xt is not None and xt.is_pinned():                  # observation already in pinned memory: DMA directly
-                self._obs_dev.copy_(xt.view(N, D), non_blocking=True)
+            cached = self.env.cached_device_obs(x) if hasattr(self.env, 'cached_device_obs') else None
+            if cached is not None:
+                x = cached                                         # the wrapper already moved this observation
             else:
-                self._obs_pin.numpy()[...] = np.asarray(x, dtype=np.float32).reshape(N, D)
-                self._obs_dev.copy_(self._obs_pin, non_blocking=True)
-            x = self._obs_dev
+                if self._obs_pin is None:
+                    self._obs_pin = torch.empty(N, D, dtype=torch.float32, pin_memory=True)
+                xt = torch.from_numpy(x) if (isinstance(x, np.ndarray) and x.dtype == np.float32 and
+                                             x.flags['C_CONTIGUOUS'] and x.flags['WRITEABLE']) else None
+                if xt is not None and xt.is_pinned():              # observation already in pinned memory: DMA directly
+                    self._obs_dev.copy_(xt.view(N, D), non_blocking=True)
+                else:
+                    self._obs_pin.numpy()[...] = np.asarray(x, dtype=np.float32).reshape(N, D)
+                    self._obs_dev.copy_(self._obs_pin, non_blocking=True)
+                x = self._obs_dev
         x = x.reshape(N, D)
         m = self.model
-        if self._packed.supported and x.stride(1) == 1:
-            if not self._in_chunk:
-                self._packed.refresh()                             # inside a chunk: refreshed once, at its top
+        if self._in_chunk and self._packed.supported and x.stride(1) == 1:
+            # inside a multi-step chunk the weights are fixed: the chunk packed them once, at its top
             ops.mlp_forward_packed(self._packed, x, zf_stats=m.z_stats, zf_eps=m.z_eps, out=self._mean)
         else:
             ops.mlp_forward(m.actor, x, zf_stats=m.z_stats, zf_eps=m.z_eps, out=self._mean)

@@ -700,7 +700,9 @@ extern "C" int sb200_mlp_forward_f32(const sb200_mlp* net, const sb200_zfilter* 
     cudaStream_t st = (cudaStream_t)stream;
     // small batches: skinny kernel (8 rows per CTA, weights streamed once per CTA from L2)
     // default numerics: tensor-core 3xTF32 (fp32-level accuracy, ~1e-6 rel); SB200_MMA=0 selects the pure-FFMA kernels
-    if (g_forward_mode == 1) {
+    // measured (tools/bench_kernels.py, 64-256-256-8): at 1024 rows the FFMA skinny kernel (19 us) beats mma<1> (26 us),
+    // whose 64 CTAs leave most SMs idle; from ~4K rows the tensor-core tiles win
+    if (g_forward_mode == 1 && p.rows > 2048) {
         int rc = (p.rows <= 4096) ? launch_fwd_mma<1>(p, maxw, net, st) : launch_fwd_mma<4>(p, maxw, net, st);
         if (rc != SB200_ERR_UNSUPPORTED) return rc;
     }

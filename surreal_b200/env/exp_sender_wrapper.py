@@ -34,7 +34,38 @@ class _WrapperBase:
             raise RuntimeError('no replay registered for this session: construct the Replay before the agent '
                                'wraps its env (the ZeroMQ collector address of the reference is gone)')
         self.N, self.D, self.A = env.N, env.D, env.A
-        self.device = env.device
+        # a batched HOST env (numpy in / numpy out, attributes N, D, A) has no device: the staging lives with the replay
+        self.device = env.device if hasattr(env, 'device') else self.replay.device
+        self.host_env = not hasattr(env, 'device')
+        self._pins, self._devs = {}, {}
+        self._last_obs_host, self._last_obs_dev = None, None
+        if not hasattr(env, 'step_counter'):
+            self.step_counter = torch.zeros(1, dtype=torch.int64, device=self.device)   # Philox step counter
+
+    def _h2d(self, name, arr, shape):
+        """numpy -> device through a persistent pinned staging buffer (skipped when ``arr`` already is pinned)."""
+        import numpy as np
+        dev = self._devs.get(name)
+        if dev is None:
+            dev = self._devs[name] = torch.zeros(*shape, dtype=torch.float32, device=self.device)
+        src = None
+        if isinstance(arr, np.ndarray) and arr.dtype == np.float32 and arr.flags['C_CONTIGUOUS'] and arr.flags['WRITEABLE']:
+            t = torch.from_numpy(arr)
+            if t.is_pinned():
+                src = t.view(*shape)
+        if src is None:
+            pin = self._pins.get(name)
+            if pin is None:
+                pin = self._pins[name] = torch.empty(*shape, dtype=torch.float32, pin_memory=True)
+            pin.numpy()[...] = np.asarray(arr, dtype=np.float32).reshape(shape)
+            src = pin
+        dev.copy_(src, non_blocking=True)
+        return dev
+
+    def cached_device_obs(self, obs_arr):
+        """The device copy of the observation the last step() returned (the agent's next act() input), if
+        ``obs_arr`` is that very array: saves the second H2D of the same 256 KB."""
+        return self._last_obs_dev if (obs_arr is not None and obs_arr is self._last_obs_host) else None
 
     @property
     def unwrapped(self):
@@ -69,7 +100,13 @@ class ExpSenderWrapperMultiStepMovingWindowWithInfo(_WrapperBase):
     def reset(self):
         obs, info = self.env.reset()
         self.stage_pos.zero_()                                     # deque.clear() (exp_sender_wrapper.py:204-207)
-        self.stage_obs[:, 0].copy_(obs['low_dim']['flat_inputs'])
+        o = obs['low_dim']['flat_inputs'] if isinstance(obs, dict) else obs
+        if self.host_env:
+            d = self._h2d('obs', o, (self.N, self.D))
+            self.stage_obs[:, 0].copy_(d)
+            self._last_obs_host, self._last_obs_dev = o, d
+        else:
+            self.stage_obs[:, 0].copy_(o)
         return obs, info
 
     def rollout_outbox(self, T):
@@ -107,11 +144,23 @@ class ExpSenderWrapperMultiStepMovingWindowWithInfo(_WrapperBase):
         if ready and hasattr(self.env, 'step_and_commit_window'):
             return self.env.step_and_commit_window(a, self)        # env step + commit in ONE launch
         obs, reward, done, info = self.env.step(a)
+        o = obs['low_dim']['flat_inputs'] if isinstance(obs, dict) else obs
+        on = info['obs_next'] if (isinstance(info, dict) and 'obs_next' in info) else o
+        if self.host_env:
+            # host env: this step's successor observation / reward / done cross PCIe here (8 KB + 256 KB); the
+            # device copy of the next observation is handed to the agent's next act() (cached_device_obs)
+            d_o = self._h2d('obs', o, (self.N, self.D))
+            d_on = d_o if on is o else self._h2d('obs_next', on, (self.N, self.D))
+            d_r = self._h2d('rew', reward, (self.N,))
+            d_d = self._h2d('done', done, (self.N,))
+            self._last_obs_host, self._last_obs_dev = o, d_o
+        else:
+            d_o, d_on, d_r, d_d = o, on, reward, done
         check(_lib.lib().sb200_ppo_window_step_f32(
-            _p(info['obs_next']), _p(obs['low_dim']['flat_inputs']), _p(reward), _p(done), self.N, self.n_step,
+            _p(d_on), _p(d_o), _p(d_r), _p(d_d), self.N, self.n_step,
             self.stride, self.D, self.A, _p(self.stage_pos), _p(self.stage_obs), _p(self.stage_act),
             _p(self.stage_pd), _p(self.stage_rew), _p(self.stage_done), _p(self._dest), _p(r.state), _p(r.r_obs),
-            _p(r.r_act), _p(r.r_pd), _p(r.r_rew), _p(r.r_done), _p(self.env.step_counter), int(ready), _st()),
+            _p(r.r_act), _p(r.r_pd), _p(r.r_rew), _p(r.r_done), _p(self.step_counter), int(ready), _st()),
             'sb200_ppo_window_step_f32')
         return obs, reward, done, info
 

@@ -4,6 +4,7 @@ Nothing here computes on the CPU or through torch ops on the hot path; torch onl
 streams (``tensor.data_ptr()`` / ``torch.cuda.current_stream()``).
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -237,6 +238,8 @@ class MlpTrainer:
         self.d = [z(M, _ru(n, 4)) for n in net.dims[1:]]          # gradients w.r.t. pre-activations
         self.aux = None
         self._aux_pad = None
+        self.overlap_dw = os.environ.get('SB200_OVERLAP_DW', '1') != '0'
+        self._side = None
         if net.aux_layer >= 0 and net.aux_dim % 4 != 0:       # pre-allocated: nothing may allocate during graph capture
             self._aux_pad = z(M, _ru(net.aux_dim, 4))
 
@@ -258,11 +261,21 @@ class MlpTrainer:
         return self.out
 
     def backward(self, need_dx0=False):
-        """self.d[-1] must hold dL/d(pre-activation of the last layer)."""
+        """self.d[-1] must hold dL/d(pre-activation of the last layer).
+
+        The dX chain (layer l needs dY_l and W_l) is the critical path; the weight-gradient GEMMs (dW_l needs dY_l and
+        the saved input of layer l) hang off it.  With ``overlap_dw`` they are launched on a side stream that forks
+        after each dY_l is ready and joins before step(): inside a captured graph these become parallel branches."""
         L, net, M = _lib.lib(), self.net, self.M
-        st = _stream()
         base = self.slabs.data_ptr()
-        for l in reversed(range(net.n_layers)):
+        main = torch.cuda.current_stream()
+        side = None
+        if self.overlap_dw:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=net.device)
+            side = self._side
+
+        def dw_layer(l, st):
             lay = net.layout[l]
             K0, N, ldw = net.dims[l], lay['N'], lay['ldw']
             X = self.x_in if l == 0 else self.h[l - 1]
@@ -275,12 +288,26 @@ class MlpTrainer:
                 check(L.sb200_linear_bwd_dw_f32(_ptr(a), a.stride(0), _ptr(dY), dY.stride(0),
                                                 C.c_void_p(base + 4 * (lay['w'] + K0 * ldw)), None, net.size,
                                                 self.splits, ldw, M, net.aux_dim, N, st), 'sb200_linear_bwd_dw_f32(aux)')
-            if l > 0:
+
+        for l in reversed(range(net.n_layers)):
+            lay = net.layout[l]
+            K0, N, ldw = net.dims[l], lay['N'], lay['ldw']
+            dY = self.d[l]
+            if side is not None:
+                side.wait_stream(main)                  # dY_l is ready on the main stream
+            if l > 0:                                   # critical path first
                 Xa = self.h[l - 1]
                 dX = self.d[l - 1]
                 check(L.sb200_linear_bwd_dx_f32(_ptr(dY), dY.stride(0), C.c_void_p(net.params.data_ptr() + 4 * lay['w']),
-                                                ldw, _ptr(Xa), Xa.stride(0), _ptr(dX), dX.stride(0), M, N, K0, st),
+                                                ldw, _ptr(Xa), Xa.stride(0), _ptr(dX), dX.stride(0), M, N, K0, _stream()),
                       'sb200_linear_bwd_dx_f32')
+            if side is not None:
+                with torch.cuda.stream(side):
+                    dw_layer(l, _stream())
+            else:
+                dw_layer(l, _stream())
+        if side is not None:
+            main.wait_stream(side)
 
     def backward_inputs(self, stop_layer=1):
         """Only the dX chain from the last layer down to ``stop_layer`` (fills self.d[stop_layer-1 ...]); no weight

@@ -426,3 +426,71 @@ def test_persistent_rollout_policy_forward_close():
     assert float(p['r_pd'][:, 0, :A].abs().max()) > 0.05                       # ... and a non-trivial policy output
     for k in ['r_obs', 'r_act', 'r_pd', 'r_rew', 'env_state']:
         assert float((p[k] - s[k]).abs().max()) <= 2e-3, (k, float((p[k] - s[k]).abs().max()))
+
+
+class NumpyScriptEnv:
+    """Batched HOST env (numpy in / numpy out): deterministic observations, rewards and episode ends."""
+
+    def __init__(self, N, D, A, ep_len):
+        self.N, self.D, self.A, self.ep_len = N, D, A, ep_len
+        self.t = 0
+        self.seen_actions = []
+
+    def _obs(self, t):
+        i = np.arange(self.N, dtype=np.float32)[:, None]
+        d = np.arange(self.D, dtype=np.float32)[None, :]
+        return np.sin(0.1 * t + i + 0.01 * d).astype(np.float32)
+
+    def reset(self):
+        self.t = 0
+        return {'low_dim': {'flat_inputs': self._obs(0)}}, {}
+
+    def step(self, action):
+        assert isinstance(action, np.ndarray) and action.shape == (self.N, self.A)
+        self.seen_actions.append(action.astype(np.float32))
+        self.t += 1
+        done = np.full(self.N, float(self.t % self.ep_len == 0), dtype=np.float32)
+        rew = (self.t + np.arange(self.N) / 1000.0).astype(np.float32)
+        nxt = self._obs(self.t)
+        return {'low_dim': {'flat_inputs': nxt}}, rew, done, {'obs_next': nxt}
+
+
+def test_host_env_actor_loop_stages_windows_in_hbm():
+    """agent.act(numpy) -> host env.step(numpy) -> wrapper.step: observations / rewards / dones cross PCIe per step and
+    the windows land in the HBM FIFO in (step, actor) order with exactly the host's values; the exploration noise
+    advances every step (shared Philox counter owned by the wrapper)."""
+    from surreal_b200.agent import PPOAgent
+    from surreal_b200.replay import FIFOReplay
+    N, D, A, n, T = 6, 8, 3, 4, 16
+    lc, ec, sc = ppo_configs(D=D, A=A, actor_h=(32, 16), critic_h=(32, 16), n_step=n, stride=n, B=4, memory_size=64)
+    ec.num_envs = N
+    R = FIFOReplay(lc, ec, sc)
+    ag = PPOAgent(lc, ec, sc, 0, 'training')
+    env = NumpyScriptEnv(N, D, A, ep_len=8)
+    ag.env = w = ag.prepare_env_agent(env)
+    assert w.host_env
+    obs, _ = w.reset()
+    pds = []
+    for _ in range(T):
+        a = ag.act(obs)
+        assert isinstance(a[0], np.ndarray) and a[0].dtype == np.float64
+        pds.append(a[1][1][0].copy())
+        obs, _, _, _ = w.step(a)
+    torch.cuda.synchronize()
+    st = R._read_state()
+    assert st['count'] == N * (T // n) and int(w.step_counter.item()) == T
+    acts = np.stack(env.seen_actions)                              # [T, N, A]
+    assert np.abs(acts[1] - acts[0]).max() > 1e-3                  # fresh noise every step
+    for k in range(T // n):                                        # completion step n*(k+1)-1, actors in order
+        for i in range(N):
+            b = R.sample(1)
+            t0 = k * n
+            exp_obs = np.stack([env._obs(t0 + j)[i] for j in range(n)])
+            np.testing.assert_array_equal(b['obs']['low_dim']['flat_inputs'][0].cpu().numpy(), exp_obs)
+            np.testing.assert_array_equal(b['obs_next']['low_dim']['flat_inputs'][0, 0].cpu().numpy(), env._obs(t0 + n)[i])
+            np.testing.assert_array_equal(b['actions'][0].cpu().numpy(), acts[t0:t0 + n, i])
+            np.testing.assert_array_equal(b['persistent_infos'][0][0].cpu().numpy(), np.stack([pds[t0 + j][i] for j in range(n)]))
+            np.testing.assert_array_equal(b['rewards'][0].cpu().numpy(),
+                                          np.array([t0 + j + 1 + i / 1000.0 for j in range(n)], dtype=np.float32))
+            np.testing.assert_array_equal(b['dones'][0].cpu().numpy(),
+                                          np.array([float((t0 + j + 1) % 8 == 0) for j in range(n)], dtype=np.float32))

@@ -1,13 +1,13 @@
 #!/bin/bash
-# Run on the GPU box (gpurun): launch list of one bench step + one full ncu capture of the dominant kernel.
-# Outputs land in gpurun_out/ ; summaries are copied into profiles/ by tools/summarize_profiles.py here.
+# Run on the GPU box (gpurun): launch list of a few bench steps + full ncu captures of the two dominant kernels.
+# Outputs land in gpurun_out/ ; summaries are written into profiles/ by tools/summarize_profiles.py (run here).
 set -x
 mkdir -p gpurun_out
-export SB200_CUDA_GRAPH=${SB200_CUDA_GRAPH:-0}      # eager launches: every kernel is a separate ncu record
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 2450 -c 850 --csv \
-    --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --lite > gpurun_out/launches_bench.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:mlp_fwd_kernelILi8E -s 3 -c 1 \
-    -o gpurun_out/prof_critic -f python bench.py --steps 1 --warmup 3 --lite > gpurun_out/prof_critic.log 2>&1
-timeout 300 ncu --set full --clock-control none -k regex:gae_full -c 1 -o gpurun_out/prof_gae -f \
-    python bench.py --steps 1 --warmup 3 --lite > gpurun_out/prof_gae.log 2>&1
+# eager launches so that every kernel is a separate ncu record (graphs replay the same sequence)
+SB200_CUDA_GRAPH=0 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv \
+    --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --lite --sequential > gpurun_out/launches_bench.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:ppo_rollout_kernel -s 2 -c 1 \
+    -o gpurun_out/prof_rollout -f python tools/prof_rollout.py 128 1 > gpurun_out/prof_rollout.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:mlp_fwd_mma_kernelILi4E -s 2 -c 1 \
+    -o gpurun_out/prof_critic -f python bench.py --steps 1 --warmup 3 --lite --sequential > gpurun_out/prof_critic.log 2>&1
 ls -la gpurun_out
