@@ -212,7 +212,8 @@ def run_ours(args):
     os.environ['SB200_CUDA_GRAPH'] = '1'
     learner.profile_events = False
     calls = _lib.profile_calls(False)
-    learner.pop_profile('critic_pass'), learner.pop_profile('gae')
+    crit_ms = learner.pop_profile('critic_pass')
+    learner.pop_profile('gae')
     per_step = {k: (c / n_prof, ms / n_prof, ms / c) for k, (c, ms) in calls.items()}
     total_kernel_ms = sum(v[1] for v in per_step.values())
     breakdown = [{'call': k, 'launches_per_step': round(v[0], 1), 'ms_per_step': round(v[1], 4), 'avg_us': round(v[2] * 1e3, 2),
@@ -242,6 +243,13 @@ def run_ours(args):
                        'mlp_fwd_mma_kernel<1> (learner minibatch forward on %d rows)' % N)
     roof_critic = mlp_roof('sb200_mlp_forward_f32[rows=%d]' % rows, rows, 1,
                            'mlp_fwd_mma_kernel<4> (fused critic pass over %d rows)' % rows)
+    if roof_critic is None and crit_ms:
+        # dual-pipe critic pass: two concurrent kernels (tensor-core tiles + FFMA tiles); timed as a pair by the
+        # learner's own CUDA events on the main stream, which joins the side stream
+        per_step['critic_pass(dual)'] = (1.0, sum(crit_ms) / len(crit_ms), sum(crit_ms) / len(crit_ms))
+        roof_critic = mlp_roof('critic_pass(dual)', rows, 1,
+                               'mlp_fwd_mma_kernel<2> || mlp_fwd_kernel<4,16> (critic pass over %d rows, tensor pipe and '
+                               'FMA pipe concurrently)' % rows)
     roof_roll = None
     rk = 'sb200_ppo_rollout_f32'
     if rk in per_step:

@@ -90,6 +90,12 @@ typedef struct {
  * ddpg_net.py:63-91. */
 int sb200_mlp_forward_f32(const sb200_mlp* net, const sb200_zfilter* zf, const sb200_rows* in,
                           float* const* save, const int64_t* ld_save, void* stream);
+/* Same, with the kernel family chosen by the caller: variant 0 = default dispatch, 1 = tensor-core 3xTF32 tiles of
+ * 32 rows, 2 = fp32 FFMA tiles of 32 rows.  Variants 1 and 2 are sized to be co-resident on one SM (<= 128 registers
+ * per thread, 67 KB + 99 KB shared memory): launched on two streams over the two halves of a large batch they keep
+ * the tensor pipe and the FMA pipe busy at once (the critic pass of PPOLearner._gae_and_return). */
+int sb200_mlp_forward_variant_f32(const sb200_mlp* net, const sb200_zfilter* zf, const sb200_rows* in,
+                                  float* const* save, const int64_t* ld_save, int variant, void* stream);
 /* Small-batch inference on PRE-PACKED weights (the actors' per-step policy forward, ppo_agent.py:138-141 /
  * ddpg_agent.py:170-176): pack once per parameter version, then every step's forward reads the weights in
  * mma-fragment order, already split for 3xTF32, and a 2-CTA cluster shares each 16-row tile.
@@ -282,6 +288,23 @@ int sb200_synth_env_window_step_f32(float* state, const float* action, const flo
                                     float* stage_pd, float* stage_rew, float* stage_done, const int* dest,
                                     float* r_obs, float* r_act, float* r_pd, float* r_rew, float* r_done,
                                     void* stream);
+
+/* Host-env fast path (one C call per agent.act() / ExpSender-wrapper step when the environment lives on the host):
+ *   ppo_act_host: [H2D obs_host -> obs_dev unless obs_host is NULL] -> policy forward -> ppo_sample (ppo_sample_assign
+ *     when fifo_state != NULL) -> D2H action / pd -> ONE stream synchronisation.  Host pointers must be pinned.
+ *   ppo_window_step_host: H2D of the step's successor / next observation, reward and done, then ppo_window_step. */
+int sb200_ppo_act_host_f32(const sb200_mlp* net, const sb200_zfilter* zf, const float* obs_host, float* obs_dev, int N,
+                           float* mean_dev, const float* log_var, const float* log_noise, int deterministic,
+                           uint64_t seed, uint64_t* step_counter, float* action_dev, float* pd_dev,
+                           const int* stage_pos, float* stage_act, float* stage_pd, int n_step, void* fifo_state,
+                           int* dest, float* action_host, float* pd_host, void* stream);
+int sb200_ppo_window_step_host_f32(const float* obs_next_host, const float* obs_reset_host, const float* reward_host,
+                                   const float* done_host, float* obs_next_dev, float* obs_reset_dev,
+                                   float* reward_dev, float* done_dev, int N, int n_step, int stride, int D, int A,
+                                   int* stage_pos, float* stage_obs, float* stage_act, float* stage_pd,
+                                   float* stage_rew, float* stage_done, int* dest_scratch, void* fifo_state,
+                                   float* r_obs, float* r_act, float* r_pd, float* r_rew, float* r_done,
+                                   uint64_t* step_counter, int slots_assigned, void* stream);
 
 /* Persistent rollout: T steps of policy forward -> sample -> synthetic env step -> window staging for ALL N
  * actors in ONE launch (a 4-CTA cluster owns 32 actors for the whole chunk; the policy weights stay resident in

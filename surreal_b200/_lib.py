@@ -68,9 +68,15 @@ def _declare(lib):
         'sb200_launch_counter_add': (None, [C.c_uint64]),
         'sb200_mlp_forward_f32': (I, [C.POINTER(Mlp), C.POINTER(ZFilter), C.POINTER(Rows),
                                       C.POINTER(P), C.POINTER(L), P]),
+        'sb200_mlp_forward_variant_f32': (I, [C.POINTER(Mlp), C.POINTER(ZFilter), C.POINTER(Rows),
+                                              C.POINTER(P), C.POINTER(L), I, P]),
         'sb200_mlp_pack_floats': (S, [C.POINTER(Mlp)]),
         'sb200_mlp_pack_tf32': (I, [C.POINTER(Mlp), P, P]),
         'sb200_mlp_forward_packed_f32': (I, [C.POINTER(Mlp), P, C.POINTER(ZFilter), C.POINTER(Rows), P, L, P]),
+        'sb200_ppo_act_host_f32': (I, [C.POINTER(Mlp), C.POINTER(ZFilter), P, P, I, P, P, P, I, C.c_uint64, P, P, P, P, P, P,
+                                       I, P, P, P, P, P]),
+        'sb200_ppo_window_step_host_f32': (I, [P, P, P, P, P, P, P, P, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, P,
+                                               P, I, P]),
         'sb200_ppo_rollout_supported': (I, [C.POINTER(Mlp), I, I]),
         'sb200_ppo_rollout_scratch_ints': (S, [I, I, I]),
         'sb200_ppo_rollout_f32': (I, [C.POINTER(PPORollout), P]),
@@ -153,7 +159,7 @@ class _ProfilingProxy:
 
         def wrapped(*args):
             key = name
-            if name == 'sb200_mlp_forward_f32':
+            if name in ('sb200_mlp_forward_f32', 'sb200_mlp_forward_variant_f32'):
                 key = '%s[rows=%d]' % (name, int(args[2]._obj.rows))
             elif name == 'sb200_mlp_forward_packed_f32':
                 key = '%s[rows=%d]' % (name, int(args[3]._obj.rows))

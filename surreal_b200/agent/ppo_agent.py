@@ -75,6 +75,8 @@ class PPOAgent(Agent):
             x = xs[0] if len(xs) == 1 else (torch.cat(xs, -1) if isinstance(xs[0], torch.Tensor)
                                             else np.concatenate(xs, -1))
         host = not isinstance(x, torch.Tensor)
+        if host and eps is None and isinstance(x, np.ndarray):
+            return self._act_host(obs, x)                          # one C call: copies, kernels, one sync
         if host:
             cached = self.env.cached_device_obs(x) if hasattr(self.env, 'cached_device_obs') else None
             if cached is not None:
@@ -132,6 +134,53 @@ class PPOAgent(Agent):
                 action, pd = action.reshape(-1), pd.reshape(-1)
         else:
             action, pd = self._action, self._pd
+        if self.agent_mode != 'training':
+            return action
+        if self.env_config.sleep_time:
+            time.sleep(self.env_config.sleep_time)
+        return action, [[], [pd]]
+
+    def _act_host(self, obs, x):
+        """act() for a HOST observation batch through sb200_ppo_act_host_f32 (H2D -> forward -> sample -> D2H -> sync
+        issued back to back from C): numpy in, numpy out, same results as the generic path."""
+        N, A, D = self.num_envs, self.action_dim, self.model.low_dim
+        m, env = self.model, self.env
+        if self._out_pin is None:
+            self._out_pin = (torch.empty(N, A, dtype=torch.float32, pin_memory=True),
+                             torch.empty(N, 2 * A, dtype=torch.float32, pin_memory=True))
+        cached = env.cached_device_obs(x) if hasattr(env, 'cached_device_obs') else None
+        if cached is not None:
+            obs_host, obs_dev = None, cached                       # the wrapper already moved this observation
+        else:
+            src = x if (x.dtype == np.float32 and x.flags['C_CONTIGUOUS'] and x.flags['WRITEABLE'] and
+                        torch.from_numpy(x).is_pinned()) else None
+            if src is None:
+                if self._obs_pin is None:
+                    self._obs_pin = torch.empty(N, D, dtype=torch.float32, pin_memory=True)
+                self._obs_pin.numpy()[...] = np.asarray(x, dtype=np.float32).reshape(N, D)
+                src = self._obs_pin.numpy()
+            obs_host, obs_dev = C.c_void_p(src.ctypes.data), self._obs_dev
+        det = self.agent_mode in ['eval_deterministic', 'eval_deterministic_local']
+        staged = self.agent_mode == 'training' and isinstance(env, ExpSenderWrapperMultiStepMovingWindowWithInfo)
+        counter = env.step_counter if (env is not None and hasattr(env, 'step_counter')) else self._counter
+        fifo_state = dest = None
+        if staged and counter is not self._counter and env.fuse_launches:
+            fifo_state, dest = env.slot_assignment_args()
+        d = m.actor.desc()
+        zf = ops.zfilter_desc(m.z_stats, m.z_eps)
+        check(_lib.lib().sb200_ppo_act_host_f32(
+            C.byref(d), C.byref(zf), obs_host, _p(obs_dev), N, _p(self._mean), _p(m.log_var), _p(self._log_noise),
+            int(det), self.seed, _p(counter), _p(self._action), _p(self._pd), _p(env.stage_pos) if staged else None,
+            _p(env.stage_act) if staged else None, _p(env.stage_pd) if staged else None, env.n_step if staged else 1,
+            _p(fifo_state), _p(dest), C.c_void_p(self._out_pin[0].data_ptr()), C.c_void_p(self._out_pin[1].data_ptr()),
+            ops._stream()), 'sb200_ppo_act_host_f32')
+        if not staged and counter is self._counter:
+            self._counter += 1
+        action = self._out_pin[0].numpy().astype(np.float64)       # the reference hands the env float64 (ppo_net.py:83)
+        pd = self._out_pin[1].numpy().copy()
+        o0 = obs['low_dim'][next(iter(obs['low_dim']))] if isinstance(obs, dict) else obs
+        if N == 1 and np.asarray(o0).ndim == 1:
+            action, pd = action.reshape(-1), pd.reshape(-1)
         if self.agent_mode != 'training':
             return action
         if self.env_config.sleep_time:

@@ -520,6 +520,7 @@ extern "C" int sb200_set_forward_mode(int mode) {
 int sb200_mlp_fwd_init() {
     SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
     SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
+    SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
     SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_pk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
     SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     SB200_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET));
@@ -683,8 +684,22 @@ extern "C" int sb200_mlp_forward_packed_f32(const sb200_mlp* net, const float* p
     return sb200_launch_status();
 }
 
+static int mlp_forward_impl(const sb200_mlp* net, const sb200_zfilter* zf, const sb200_rows* in, float* const* save,
+                            const int64_t* ld_save, int variant, void* stream);
+
 extern "C" int sb200_mlp_forward_f32(const sb200_mlp* net, const sb200_zfilter* zf, const sb200_rows* in,
                                      float* const* save, const int64_t* ld_save, void* stream) {
+    return mlp_forward_impl(net, zf, in, save, ld_save, 0, stream);
+}
+
+extern "C" int sb200_mlp_forward_variant_f32(const sb200_mlp* net, const sb200_zfilter* zf, const sb200_rows* in,
+                                             float* const* save, const int64_t* ld_save, int variant, void* stream) {
+    SB200_REQUIRE(variant >= 0 && variant <= 2);
+    return mlp_forward_impl(net, zf, in, save, ld_save, variant, stream);
+}
+
+static int mlp_forward_impl(const sb200_mlp* net, const sb200_zfilter* zf, const sb200_rows* in, float* const* save,
+                            const int64_t* ld_save, int variant, void* stream) {
     FwdParams p;
     int maxw = 0;
     {
@@ -700,6 +715,14 @@ extern "C" int sb200_mlp_forward_f32(const sb200_mlp* net, const sb200_zfilter* 
     cudaStream_t st = (cudaStream_t)stream;
     // small batches: skinny kernel (8 rows per CTA, weights streamed once per CTA from L2)
     // default numerics: tensor-core 3xTF32 (fp32-level accuracy, ~1e-6 rel); SB200_MMA=0 selects the pure-FFMA kernels
+    // explicit variants for the dual-pipe critic pass (ops.mlp_forward_dual): a tensor-core kernel and an FFMA kernel
+    // that fit one SM TOGETHER (<= 128 registers per thread each, 67 KB + 99 KB of shared memory), so that the two
+    // halves of a large batch keep the tensor pipe and the FMA pipe busy at the same time
+    if (variant == 1) {
+        const int rc = launch_fwd_mma<2>(p, maxw, net, st);
+        if (rc != SB200_ERR_UNSUPPORTED) return rc;
+    }
+    if (variant == 2 && fits(32, 16)) return launch_fwd<4, 16>(p, maxw, st);
     // measured (tools/bench_kernels.py, 64-256-256-8): at 1024 rows the FFMA skinny kernel (19 us) beats mma<1> (26 us),
     // whose 64 CTAs leave most SMs idle; from ~4K rows the tensor-core tiles win
     if (g_forward_mode == 1 && p.rows > 2048) {

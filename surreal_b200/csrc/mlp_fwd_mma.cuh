@@ -33,7 +33,7 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], 
 }
 
 template <int MT>
-__global__ void __launch_bounds__(SB200_THREADS, (MT == 1) ? 2 : 1) mlp_fwd_mma_kernel(const __grid_constant__ FwdParams p) {
+__global__ void __launch_bounds__(SB200_THREADS, (MT <= 2) ? 2 : 1) mlp_fwd_mma_kernel(const __grid_constant__ FwdParams p) {
     constexpr int BM = 16 * MT;
     extern __shared__ __align__(16) float smem[];
     const int ldh = p.ldh;

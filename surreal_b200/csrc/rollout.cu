@@ -360,3 +360,72 @@ extern "C" int sb200_ppo_window_step_f32(const float* obs_next, const float* obs
                                                 r_obs, r_act, r_pd, r_rew, r_done);
     return sb200_launch_status(slots_assigned ? 1 : 2);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Host-env fast path: one C call per agent.act() / wrapper.step() with a HOST environment.  The per-step work is
+// tens of microseconds of GPU time, so the ~10 separate Python-level copy / launch calls of the generic path cost
+// more than the kernels; here the PCIe copies, launches and the single stream synchronisation are issued back to
+// back from C.  Host pointers must be pinned (cudaHostAlloc / torch pin_memory) for the copies to be asynchronous.
+extern "C" int sb200_ppo_act_host_f32(const sb200_mlp* net, const sb200_zfilter* zf, const float* obs_host,
+                                      float* obs_dev, int N, float* mean_dev, const float* log_var,
+                                      const float* log_noise, int deterministic, uint64_t seed,
+                                      uint64_t* step_counter, float* action_dev, float* pd_dev, const int* stage_pos,
+                                      float* stage_act, float* stage_pd, int n_step, void* fifo_state, int* dest,
+                                      float* action_host, float* pd_host, void* stream) {
+    SB200_REQUIRE(net != nullptr && obs_dev != nullptr && mean_dev != nullptr && N >= 1);
+    SB200_REQUIRE(action_dev && pd_dev && action_host && pd_host && step_counter);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = net->dims[0], A = net->dims[net->n_layers];
+    if (obs_host != nullptr)
+        SB200_CUDA(cudaMemcpyAsync(obs_dev, obs_host, (size_t)N * D * sizeof(float), cudaMemcpyHostToDevice, st));
+    sb200_rows in;
+    in.x = obs_dev;
+    in.x_next = nullptr;
+    in.ldx = D;
+    in.rows = N;
+    in.win_n = 0;
+    in.aux = nullptr;
+    in.aux_ld = 0;
+    in.save_x = nullptr;
+    in.ld_save_x = 0;
+    float* save[SB200_MAX_LAYERS] = {nullptr, nullptr, nullptr, nullptr};
+    int64_t lds[SB200_MAX_LAYERS] = {0, 0, 0, 0};
+    save[net->n_layers - 1] = mean_dev;
+    lds[net->n_layers - 1] = A;
+    int rc = sb200_mlp_forward_f32(net, zf, &in, save, lds, stream);
+    if (rc != SB200_OK) return rc;
+    if (fifo_state != nullptr)
+        rc = sb200_ppo_sample_assign_f32(mean_dev, A, log_var, log_noise, nullptr, N, A, deterministic, seed, step_counter,
+                                         action_dev, pd_dev, stage_pos, stage_act, stage_pd, n_step, fifo_state, dest,
+                                         stream);
+    else
+        rc = sb200_ppo_sample_f32(mean_dev, A, log_var, log_noise, nullptr, N, A, deterministic, seed, step_counter,
+                                  action_dev, pd_dev, stage_pos, stage_act, stage_pd, n_step, stream);
+    if (rc != SB200_OK) return rc;
+    SB200_CUDA(cudaMemcpyAsync(action_host, action_dev, (size_t)N * A * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SB200_CUDA(cudaMemcpyAsync(pd_host, pd_dev, (size_t)N * 2 * A * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SB200_CUDA(cudaStreamSynchronize(st));
+    return SB200_OK;
+}
+
+extern "C" int sb200_ppo_window_step_host_f32(const float* obs_next_host, const float* obs_reset_host,
+                                              const float* reward_host, const float* done_host, float* obs_next_dev,
+                                              float* obs_reset_dev, float* reward_dev, float* done_dev, int N,
+                                              int n_step, int stride, int D, int A, int* stage_pos, float* stage_obs,
+                                              float* stage_act, float* stage_pd, float* stage_rew, float* stage_done,
+                                              int* dest_scratch, void* fifo_state, float* r_obs, float* r_act,
+                                              float* r_pd, float* r_rew, float* r_done, uint64_t* step_counter,
+                                              int slots_assigned, void* stream) {
+    SB200_REQUIRE(obs_next_host && obs_reset_host && reward_host && done_host);
+    SB200_REQUIRE(obs_next_dev && obs_reset_dev && reward_dev && done_dev && N >= 1 && D >= 1);
+    cudaStream_t st = (cudaStream_t)stream;
+    SB200_CUDA(cudaMemcpyAsync(obs_reset_dev, obs_reset_host, (size_t)N * D * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (obs_next_host != obs_reset_host)
+        SB200_CUDA(cudaMemcpyAsync(obs_next_dev, obs_next_host, (size_t)N * D * sizeof(float), cudaMemcpyHostToDevice, st));
+    SB200_CUDA(cudaMemcpyAsync(reward_dev, reward_host, (size_t)N * sizeof(float), cudaMemcpyHostToDevice, st));
+    SB200_CUDA(cudaMemcpyAsync(done_dev, done_host, (size_t)N * sizeof(float), cudaMemcpyHostToDevice, st));
+    return sb200_ppo_window_step_f32((obs_next_host != obs_reset_host) ? obs_next_dev : obs_reset_dev, obs_reset_dev,
+                                     reward_dev, done_dev, N, n_step, stride, D, A, stage_pos, stage_obs, stage_act,
+                                     stage_pd, stage_rew, stage_done, dest_scratch, fifo_state, r_obs, r_act, r_pd, r_rew,
+                                     r_done, step_counter, slots_assigned, stream);
+}

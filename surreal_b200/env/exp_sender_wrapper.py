@@ -62,6 +62,24 @@ class _WrapperBase:
         dev.copy_(src, non_blocking=True)
         return dev
 
+    def _dev(self, name, shape):
+        dev = self._devs.get(name)
+        if dev is None:
+            dev = self._devs[name] = torch.zeros(*shape, dtype=torch.float32, device=self.device)
+        return dev
+
+    def _pinned(self, name, arr, shape):
+        """Address (c_void_p) of ``arr`` if it already lives in pinned memory, else of a pinned staging copy."""
+        import numpy as np
+        if isinstance(arr, np.ndarray) and arr.dtype == np.float32 and arr.flags['C_CONTIGUOUS'] and arr.flags['WRITEABLE'] \
+                and torch.from_numpy(arr).is_pinned():
+            return C.c_void_p(arr.ctypes.data)
+        pin = self._pins.get(name)
+        if pin is None:
+            pin = self._pins[name] = torch.empty(*shape, dtype=torch.float32, pin_memory=True)
+        pin.numpy()[...] = np.asarray(arr, dtype=np.float32).reshape(shape)
+        return C.c_void_p(pin.data_ptr())
+
     def cached_device_obs(self, obs_arr):
         """The device copy of the observation the last step() returned (the agent's next act() input), if
         ``obs_arr`` is that very array: saves the second H2D of the same 256 KB."""
@@ -147,17 +165,24 @@ class ExpSenderWrapperMultiStepMovingWindowWithInfo(_WrapperBase):
         o = obs['low_dim']['flat_inputs'] if isinstance(obs, dict) else obs
         on = info['obs_next'] if (isinstance(info, dict) and 'obs_next' in info) else o
         if self.host_env:
-            # host env: this step's successor observation / reward / done cross PCIe here (8 KB + 256 KB); the
-            # device copy of the next observation is handed to the agent's next act() (cached_device_obs)
-            d_o = self._h2d('obs', o, (self.N, self.D))
-            d_on = d_o if on is o else self._h2d('obs_next', on, (self.N, self.D))
-            d_r = self._h2d('rew', reward, (self.N,))
-            d_d = self._h2d('done', done, (self.N,))
+            # host env: this step's successor observation / reward / done cross PCIe here (256 KB + 8 KB), issued with
+            # the staging kernels from ONE C call; the device copy of the next observation is handed to the agent's
+            # next act() (cached_device_obs)
+            h_o, h_on = self._pinned('obs', o, (self.N, self.D)), None
+            h_on = h_o if on is o else self._pinned('obs_next', on, (self.N, self.D))
+            h_r, h_d = self._pinned('rew', reward, (self.N,)), self._pinned('done', done, (self.N,))
+            d_o, d_on = self._dev('obs', (self.N, self.D)), self._dev('obs_next', (self.N, self.D))
+            d_r, d_d = self._dev('rew', (self.N,)), self._dev('done', (self.N,))
+            check(_lib.lib().sb200_ppo_window_step_host_f32(
+                h_on, h_o, h_r, h_d, _p(d_on), _p(d_o), _p(d_r), _p(d_d), self.N, self.n_step, self.stride, self.D,
+                self.A, _p(self.stage_pos), _p(self.stage_obs), _p(self.stage_act), _p(self.stage_pd),
+                _p(self.stage_rew), _p(self.stage_done), _p(self._dest), _p(r.state), _p(r.r_obs), _p(r.r_act),
+                _p(r.r_pd), _p(r.r_rew), _p(r.r_done), _p(self.step_counter), int(ready), _st()),
+                'sb200_ppo_window_step_host_f32')
             self._last_obs_host, self._last_obs_dev = o, d_o
-        else:
-            d_o, d_on, d_r, d_d = o, on, reward, done
+            return obs, reward, done, info
         check(_lib.lib().sb200_ppo_window_step_f32(
-            _p(d_on), _p(d_o), _p(d_r), _p(d_d), self.N, self.n_step,
+            _p(on), _p(o), _p(reward), _p(done), self.N, self.n_step,
             self.stride, self.D, self.A, _p(self.stage_pos), _p(self.stage_obs), _p(self.stage_act),
             _p(self.stage_pd), _p(self.stage_rew), _p(self.stage_done), _p(self._dest), _p(r.state), _p(r.r_obs),
             _p(r.r_act), _p(r.r_pd), _p(r.r_rew), _p(r.r_done), _p(self.step_counter), int(ready), _st()),

@@ -148,6 +148,7 @@ class PPOLearner(Learner):
         self._gae_ws = torch.zeros(64, dtype=torch.uint8, device=dev)
         self.use_cuda_graph = ops.graphs_enabled()
         self.parallel_branches = os.environ.get("SB200_PPO_FORK", "1") != "0"   # policy || value epochs
+        self.dual_critic = os.environ.get("SB200_DUAL_CRITIC", "1") != "0"     # tensor pipe || FMA pipe critic pass
         self._graph = ops.GraphRunner()
         self.dp = None
         self.epoch_history = []
@@ -249,8 +250,13 @@ class PPOLearner(Learner):
         B, n = self.batch_size, self.n_step
         m = self.model
         ev = self._prof_begin()
-        ops.mlp_forward(m.critic, self._obs_full.view(B * (n + 1), -1), zf_stats=m.z_stats, zf_eps=m.z_eps,
-                        out=self._values)
+        rows = B * (n + 1)
+        if self.dual_critic and rows >= 32768:
+            ops.mlp_forward_dual(m.critic, self._obs_full.view(rows, -1), zf_stats=m.z_stats, zf_eps=m.z_eps,
+                                 out=self._values.view(rows, 1))
+        else:
+            ops.mlp_forward(m.critic, self._obs_full.view(rows, -1), zf_stats=m.z_stats, zf_eps=m.z_eps,
+                            out=self._values)
         self._prof_end('critic_pass', ev)
         rewards, scale = self._rewards, self.reward_scale
         if self.use_r_filter:
@@ -353,9 +359,17 @@ class PPOLearner(Learner):
         self._moments = torch.zeros(3, dtype=torch.float64, device=self.device)
         self._z_delta = torch.zeros_like(self.model.z_stats) if self.model.z_stats is not None else None
         self._graph = ops.GraphRunner()
-        # NCCL collectives inside a captured graph are supported by torch, but stay opt-in until proven on the box
-        import os
+        # One CUDA graph for the whole data-parallel learn(), NCCL collectives included (SB200_DP_GRAPH=0: the same
+        # launches eagerly).  Capture stays on ONE stream (no dW side stream) and every collective shape is issued
+        # once eagerly first: NCCL sets up its channels lazily, which must not happen under capture.
         self.dp_graph = os.environ.get('SB200_DP_GRAPH', '0') == '1'
+        if self.dp_graph:
+            self.actor_optim.overlap_dw = self.critic_optim.overlap_dw = False
+        for t in (self.actor_optim.grad, self.critic_optim.grad, self._kl_scalar, self._moments, self._z_delta,
+                  self._stats):
+            if t is not None:
+                self.dp.sum_(torch.zeros_like(t))
+        torch.cuda.synchronize()
         return self
 
     def _value_epoch(self):

@@ -161,8 +161,36 @@ def mlp_forward_packed(packed, x, zf_stats=None, zf_eps=1e-5, aux=None, out=None
     return out
 
 
+_dual_side = {}
+
+
+def mlp_forward_dual(net, x, zf_stats=None, zf_eps=1e-5, out=None, frac=None):
+    """Large-batch forward with BOTH math pipes busy: the first part of the rows runs on tensor cores (3xTF32
+    mma.sync tiles), the rest on the fp32 FMA pipe, as two kernels that fit one SM together, launched on two
+    streams (a fork / join inside a captured graph).  Each alone is bound by its own pipe's issue rate
+    (mma.sync TF32: ~48 TFLOP/s effective after the 3x split; FFMA: 72 TFLOP/s peak)."""
+    import os
+    rows = x.shape[0]
+    frac = float(os.environ.get('SB200_DUAL_FRAC', '0.5')) if frac is None else frac
+    r1 = int(rows * frac) // 64 * 64
+    if r1 <= 0 or r1 >= rows:
+        return mlp_forward(net, x, zf_stats=zf_stats, zf_eps=zf_eps, out=out)
+    if out is None:
+        out = torch.empty(rows, net.dims[-1], dtype=torch.float32, device=x.device)
+    main = torch.cuda.current_stream()
+    side = _dual_side.get(x.device)
+    if side is None:
+        side = _dual_side[x.device] = torch.cuda.Stream(device=x.device)
+    side.wait_stream(main)
+    mlp_forward(net, x[:r1], zf_stats=zf_stats, zf_eps=zf_eps, out=out[:r1], variant=1)
+    with torch.cuda.stream(side):
+        mlp_forward(net, x[r1:], zf_stats=zf_stats, zf_eps=zf_eps, out=out[r1:], variant=2)
+    main.wait_stream(side)
+    return out
+
+
 def mlp_forward(net, x, zf_stats=None, zf_eps=1e-5, x_next=None, win_n=0, aux=None, save_all=False,
-                params=None, out=None, rows=None, ldx=None, saves=None, save_x=None):
+                params=None, out=None, rows=None, ldx=None, saves=None, save_x=None, variant=0):
     """Run the fused forward.
 
     ``x``: [rows, D] (any row stride via ``ldx``), or [B, n, D] with ``x_next`` [B, 1, D] and win_n=n for
@@ -212,7 +240,11 @@ def mlp_forward(net, x, zf_stats=None, zf_eps=1e-5, x_next=None, win_n=0, aux=No
     ld = (C.c_int64 * MAX_LAYERS)(*[(t.stride(0) if t is not None else 0) for t in saves])
     zf = zfilter_desc(zf_stats, zf_eps)
     d = net.desc(params)
-    check(L.sb200_mlp_forward_f32(C.byref(d), C.byref(zf), C.byref(r), sv, ld, _stream()), 'sb200_mlp_forward_f32')
+    if variant:
+        check(L.sb200_mlp_forward_variant_f32(C.byref(d), C.byref(zf), C.byref(r), sv, ld, int(variant), _stream()),
+              'sb200_mlp_forward_variant_f32')
+    else:
+        check(L.sb200_mlp_forward_f32(C.byref(d), C.byref(zf), C.byref(r), sv, ld, _stream()), 'sb200_mlp_forward_f32')
     if not outs:
         return None
     return outs if save_all else outs[-1]

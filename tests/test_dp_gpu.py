@@ -19,6 +19,6 @@ def test_data_parallel_learner_matches_global_batch_oracle(env):
     port = 29600 + (os.getpid() % 300)
     r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
                         '--master-addr', '127.0.0.1', '--master-port', str(port), os.path.join(ROOT, 'tests', 'dp_check.py')],
-                       env=e, capture_output=True, text=True, timeout=600)
+                       env=e, capture_output=True, text=True, timeout=240)
     out = r.stdout + r.stderr
     assert r.returncode == 0 and out.count('DP_OK') == 2, out[-3000:]

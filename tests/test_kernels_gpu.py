@@ -123,6 +123,28 @@ def test_mlp_forward_packed_matches_oracle(dims, rows, zf, aux):
     assert not ops.PackedWeights(ops.FlatNet([64, 1024, 1024, 8], [ops.ACT_RELU] * 3, _dev())).supported
 
 
+def test_mlp_forward_dual_pipe_matches_single():
+    """Large-batch forward split over the tensor pipe (3xTF32 mma tiles) and the FMA pipe (FFMA tiles) on two
+    streams: same values as the default dispatch to fp32 rounding, every row written exactly once."""
+    from surreal_b200 import ops
+    gen = torch.Generator().manual_seed(11)
+    dims, rows = [64, 256, 256, 1], 40000 + 37
+    net = ops.FlatNet(dims, [ops.ACT_RELU, ops.ACT_RELU, ops.ACT_NONE], _dev()).load_layers(_rand_layers(dims, gen))
+    x = (torch.randn(rows, 64, generator=gen) * 1.5).to(_dev())
+    ozf = OZFilter(64)
+    ozf.update(torch.randn(300, 64, generator=gen) * 1.7 + 0.4)
+    stats = torch.cat([ozf.running_sum, ozf.running_sumsq, ozf.count]).to(_dev())
+    ref = ops.mlp_forward(net, x, zf_stats=stats)
+    for frac in (0.5, 0.3):
+        out = torch.full((rows, 1), float('nan'), device=_dev())
+        ops.mlp_forward_dual(net, x, zf_stats=stats, out=out, frac=frac)
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(out).all())
+        assert_close_scale(out, ref, 1e-5, 'dual-pipe forward, frac %.1f' % frac)
+    for v in (1, 2):
+        assert_close_scale(ops.mlp_forward(net, x, zf_stats=stats, variant=v), ref, 1e-5, 'variant %d' % v)
+
+
 def test_mlp_forward_window_rows_and_aux():
     """virtual cat([obs, obs_next]) row mapping (ppo.py:376-383) and the DDPG critic's cat(h, action)."""
     from surreal_b200 import ops

@@ -51,6 +51,12 @@ def main():
         med, mn = timeit(lambda: ops.mlp_forward(c, x, zf_stats=zs, out=out), flush=flush)
         flop = 2.0 * rows * (D * H + H * H + H)
         print(json.dumps(dict(kernel='critic_pass', rows=rows, median_us=med, min_us=mn, tflops=flop / med / 1e6, **tag)))
+        for v, name in ((1, 'mma<2>'), (2, 'ffma<4,16>')):
+            med, mn = timeit(lambda: ops.mlp_forward(c, x, zf_stats=zs, out=out, variant=v), flush=flush)
+            print(json.dumps(dict(kernel='critic_pass_variant', variant=name, median_us=med, min_us=mn, tflops=flop / med / 1e6)))
+        for frac in (0.35, 0.45, 0.5, 0.55, 0.65):
+            med, mn = timeit(lambda: ops.mlp_forward_dual(c, x, zf_stats=zs, out=out, frac=frac), flush=flush)
+            print(json.dumps(dict(kernel='critic_pass_dual', frac_tensor=frac, median_us=med, min_us=mn, tflops=flop / med / 1e6)))
     if what in ('small', 'all'):
         for rows in (1024, 4096):
             x = torch.randn(rows, D, device=dev)
