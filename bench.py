@@ -242,7 +242,7 @@ def run_ours(args):
     roof_mb = mlp_roof('sb200_mlp_forward_f32[rows=%d]' % N, N, A,
                        'mlp_fwd_mma_kernel<1> (learner minibatch forward on %d rows)' % N)
     roof_critic = mlp_roof('sb200_mlp_forward_f32[rows=%d]' % rows, rows, 1,
-                           'mlp_fwd_mma_kernel<4> (fused critic pass over %d rows)' % rows)
+                           'mlp_fwd_mma_kernel<2> (fused critic pass over %d rows, 3xTF32 mma.sync, 2 CTAs/SM)' % rows)
     if roof_critic is None and crit_ms:
         # dual-pipe critic pass: two concurrent kernels (tensor-core tiles + FFMA tiles); timed as a pair by the
         # learner's own CUDA events on the main stream, which joins the side stream

@@ -726,7 +726,10 @@ static int mlp_forward_impl(const sb200_mlp* net, const sb200_zfilter* zf, const
     // measured (tools/bench_kernels.py, 64-256-256-8): at 1024 rows the FFMA skinny kernel (19 us) beats mma<1> (26 us),
     // whose 64 CTAs leave most SMs idle; from ~4K rows the tensor-core tiles win
     if (g_forward_mode == 1 && p.rows > 2048) {
-        int rc = (p.rows <= 4096) ? launch_fwd_mma<1>(p, maxw, net, st) : launch_fwd_mma<4>(p, maxw, net, st);
+        // large M: 32-row tiles at 2 CTAs/SM (631 us on the 132 096-row critic pass) beat 64-row tiles at 1 CTA/SM
+        // (774 us): the second resident CTA hides the first one's fragment-load and barrier latencies
+        int rc = (p.rows <= 4096) ? launch_fwd_mma<1>(p, maxw, net, st) : launch_fwd_mma<2>(p, maxw, net, st);
+        if (rc == SB200_ERR_UNSUPPORTED && p.rows > 4096) rc = launch_fwd_mma<4>(p, maxw, net, st);
         if (rc != SB200_ERR_UNSUPPORTED) return rc;
     }
     static const int no_skinny = [] { const char* e = getenv("SB200_NO_SKINNY"); return e ? atoi(e) : 0; }();

@@ -148,7 +148,9 @@ class PPOLearner(Learner):
         self._gae_ws = torch.zeros(64, dtype=torch.uint8, device=dev)
         self.use_cuda_graph = ops.graphs_enabled()
         self.parallel_branches = os.environ.get("SB200_PPO_FORK", "1") != "0"   # policy || value epochs
-        self.dual_critic = os.environ.get("SB200_DUAL_CRITIC", "1") != "0"     # tensor pipe || FMA pipe critic pass
+        # tensor pipe || FMA pipe critic pass: measured SLOWER (701-757 us) than the 2-CTA/SM tensor-core tiles alone
+        # (631 us) -- both kernels are issue-bound, they do not add up -- so it stays an experiment
+        self.dual_critic = os.environ.get("SB200_DUAL_CRITIC", "0") == "1"
         self._graph = ops.GraphRunner()
         self.dp = None
         self.epoch_history = []

@@ -8,6 +8,6 @@ SB200_CUDA_GRAPH=0 timeout 900 ncu --metrics gpu__time_duration.sum --clock-cont
     --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --lite --sequential > gpurun_out/launches_bench.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:ppo_rollout_kernel -s 2 -c 1 \
     -o gpurun_out/prof_rollout -f python tools/prof_rollout.py 128 1 > gpurun_out/prof_rollout.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:mlp_fwd_mma_kernelILi4E -s 2 -c 1 \
+timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:mlp_fwd_mma_kernelILi2E -s 2 -c 1 \
     -o gpurun_out/prof_critic -f python bench.py --steps 1 --warmup 3 --lite --sequential > gpurun_out/prof_critic.log 2>&1
 ls -la gpurun_out
