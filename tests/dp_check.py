@@ -88,7 +88,10 @@ def main():
     chk('replica drift', float((p - L.model.actor.params).abs().max()), 0.0, 0.0)
     print('rank %d %s %s' % (rank, 'DP_OK' if ok else 'DP_FAIL', '; '.join(msgs)), flush=True)
     dist.barrier()
-    dist.destroy_process_group()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(0 if ok else 1)        # NCCL-in-graph teardown hangs: skip the destructors
     sys.exit(0 if ok else 1)
 
 

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize('env', [{'DP_MODE': 'clip'}, {'DP_MODE': 'adapt', 'DP_BIGLR': '1'}, {'DP_MODE': 'clip', 'SB200_DP_GRAPH': '1'}])
+@pytest.mark.parametrize('env', [{'DP_MODE': 'clip'}, {'DP_MODE': 'adapt', 'DP_BIGLR': '1'}, {'DP_MODE': 'clip', 'SB200_DP_GRAPH': '0'}])
 def test_data_parallel_learner_matches_global_batch_oracle(env):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
