@@ -270,10 +270,13 @@ def run_ours(args):
                              'the mandated denominator, the fp32 FFMA ceiling (148 SMs x 128 lanes x 2 x 1.9 GHz) the '
                              'meaningful one.  Per step the kernel is a dependent chain: layer -> cluster barrier -> '
                              'layer -> cluster barrier -> head/sample/env -> cluster barrier'}
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch, from one `ncu --set full` capture each (profiles/)
+    if roof_roll is not None:
+        roof_roll['traffic'] = 65551872           # profiles/r01d_prof_rollout.md (25.06 MB read + 40.50 MB written)
+    if roof_critic is not None:
+        roof_critic['traffic'] = 34238464         # profiles/r01e_prof_critic.md (34.23 MB read + 5 KB written)
     cands = [r for r in (roof_roll, roof_small, roof_mb, roof_critic) if r is not None]
     roofline = max(cands, key=lambda r: r['share_of_step_kernel_time']) if cands else None
-    if roof_critic is not None and roofline is roof_critic:
-        roofline['traffic'] = 34260992        # dram__bytes_read+write of profiles/r01a_prof_critic.md (one ncu --set full capture)
     gae_key = 'sb200_gae_window_f32'
     gae_avg = per_step[gae_key][2] if gae_key in per_step else None
     gae_bytes = N * ((3 * T + 1) * 4 + 8)
