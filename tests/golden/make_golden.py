@@ -305,6 +305,74 @@ def gen_ppo_learn():
         save('ppo_learn_' + tag, cfg=cfg, stats=stats_all, hyper=hyper, **out)
 
 
+def gen_ppo_learn_rnn():
+    """RNN mode (the reference's DEFAULT PPO config: LSTM stem + horizon GAE, ppo.py:389-406,507-525): learn() +
+    publish for a few iterations, LSTM trained by BOTH optimisers (ppo_net.py:202-224)."""
+    variants = [
+        ('rnn_clip', dict(mode='clip', B=8, n_step=7, rnn=True, horizon=3, rnn_hidden=10, exp_interval=16), 3),
+        ('rnn_adapt', dict(mode='adapt', B=8, n_step=7, rnn=True, horizon=3, rnn_hidden=10, exp_interval=16), 3),
+        ('rnn_adapt_biglr', dict(mode='adapt', B=8, n_step=6, rnn=True, horizon=2, rnn_hidden=6, lr=3e-3,
+                                 exp_interval=8), 2),
+    ]
+    for tag, kw, iters in variants:
+        torch.manual_seed(13)
+        lc, ec, sc = cfg_ppo(**kw)
+        L = H.construct_without_initialize(PPOLearner, lc, ec, sc)
+        L._ps_publisher = H._Any()
+        L.tensorplex = H._Any()
+        rng = np.random.default_rng(13)
+        B, n, D, A = L.batch_size, L.n_step, 11, 3
+        L.model.z_filter.z_update(torch.tensor((rng.standard_normal((40, D)) * 1.5 + 0.3).astype(np.float32)))
+        L.ref_target_model.update_target_params(L.model)
+        out = dict(**sd_np(L.model, 'init/'))
+        n_pol = []
+        orig_update = L._clip_update if L.ppo_mode == 'clip' else L._adapt_update
+
+        def counting(*a, **k):
+            n_pol[-1] += 1
+            return orig_update(*a, **k)
+        if L.ppo_mode == 'clip':
+            L._clip_update = counting
+        else:
+            L._adapt_update = counting
+        stats_all, hyper = [], []
+        captured = {}
+        orig_opt = L._optimize
+        orig_gae = L._gae_and_return
+
+        def opt_hook(*a, **k):
+            st = orig_opt(*a, **k)
+            captured['stats'] = {kk: float(vv) for kk, vv in st.items()}
+            return st
+
+        def gae_hook(*a, **k):
+            adv, ret = orig_gae(*a, **k)
+            captured['adv'], captured['ret'] = adv.detach().clone().numpy(), ret.detach().clone().numpy()
+            return adv, ret
+        L._optimize = opt_hook
+        L._gae_and_return = gae_hook
+        for it in range(iters):
+            batch, raw = make_ppo_batch(L, rng, B, n, D, A)
+            for k, v in raw.items():
+                out['it%d/%s' % (it, k)] = v
+            n_pol.append(0)
+            L.learn(batch)
+            stats_all.append(captured['stats'])
+            out['it%d/adv' % it], out['it%d/ret' % it] = captured['adv'], captured['ret']
+            L.publish_parameter(it, message='')
+            out.update(sd_np(L.model, 'it%d/after/' % it))
+            out.update(sd_np(L.ref_target_model, 'it%d/ref/' % it))
+            hyper.append(dict(clip_epsilon=getattr(L, 'clip_epsilon', None), beta=getattr(L, 'beta', None),
+                              exp_counter=L.exp_counter, n_policy_epochs=n_pol[-1],
+                              kl_record=list(map(float, L.kl_record))))
+        cfg = dict(mode=L.ppo_mode, B=B, n_step=n, D=D, A=A, actor_h=lc.model.actor_fc_hidden_sizes,
+                   critic_h=lc.model.critic_fc_hidden_sizes, lr=lc.algo.network.lr_actor, gamma=L.gamma,
+                   lam=L.lam, exp_interval=lc.parameter_publish.exp_interval, iters=iters, horizon=L.horizon,
+                   rnn_hidden=lc.algo.rnn.rnn_hidden, rnn_layer=lc.algo.rnn.rnn_layer,
+                   kl_target=L.kl_target, epoch_policy=L.epoch_policy, epoch_baseline=L.epoch_baseline)
+        save('ppo_learn_' + tag, cfg=cfg, stats=stats_all, hyper=hyper, **out)
+
+
 def cfg_ddpg(D=9, A=3, actor_h=(20, 12), critic_h=(24, 16), B=16, n_step=3, target='hard', interval=2,
              tau=0.05, clip_critic=False, double=False):
     lc = Config(copy.deepcopy(DDPG_DEFAULT_LEARNER_CONFIG.to_dict()))

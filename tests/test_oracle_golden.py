@@ -13,6 +13,7 @@ from oracle.filters import ZFilter, RewardFilter
 from oracle import nets
 from oracle.gae import gae_from_values, gae_reference_fp64
 from oracle.ppo import OraclePPOLearner
+from oracle.ppo_rnn import OraclePPOLearnerRNN
 from oracle.ddpg import OracleDDPGLearner
 from oracle.replay import FIFO, Uniform, MT19937
 from oracle.windowing import multistep_windows, ssar_nstep
@@ -147,6 +148,44 @@ def test_ppo_learn(golden, tag):
         np.testing.assert_allclose(L.ref_log_var.numpy(), b['ref/actor/log_var'], atol=1e-7)
         np.testing.assert_allclose(L.ref_zf.count.numpy(), b['ref/z_filter/count'], atol=0)
     assert any(h['n_policy_epochs'] < cfg['epoch_policy'] for h in hyper) == (tag == 'clip_biglr')
+
+
+@pytest.mark.parametrize('tag', ['rnn_clip', 'rnn_adapt', 'rnn_adapt_biglr'])
+def test_ppo_learn_rnn_mode(golden, tag):
+    """RNN mode (the reference's default PPO config): LSTM stem trained by both optimisers, horizon GAE over
+    eff_len positions, initial cells from onetime_infos -- learn() + publish against goldens produced by running the
+    real reference (tests/golden/make_golden.py::gen_ppo_learn_rnn).  Pins the oracle for SURVEY §8(f) rank 2; the
+    CUDA path for this mode is not built yet."""
+    g = golden('ppo_learn_' + tag)
+    cfg, hyper, stats = g.js('cfg'), g.js('hyper'), g.js('stats')
+    init = g.sub('init/')
+    actor, log_var, critic, zf = _ppo_model(init)
+    lstm = {k.split('/', 1)[1]: init[k] for k in init.keys() if k.startswith('rnn_stem/')}
+    L = OraclePPOLearnerRNN(actor, log_var, critic, zf, lstm, cfg['A'], cfg['n_step'], cfg['B'], cfg['horizon'],
+                            cfg['rnn_hidden'], cfg['rnn_layer'], ppo_mode=cfg['mode'], lr_actor=cfg['lr'],
+                            lr_critic=cfg['lr'], exp_interval=cfg['exp_interval'])
+    for it in range(cfg['iters']):
+        b = g.sub('it%d/' % it)
+        st = L.learn(dict(obs=b['obs'], obs_next=b['obs_next'], actions=b['actions'], rewards=b['rewards'],
+                          dones=b['dones'], pd=b['pd'], h0=b['h0'], c0=b['c0']))
+        np.testing.assert_allclose(L.last_adv.numpy(), b['adv'], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(L.last_ret.numpy(), b['ret'], rtol=0, atol=1e-6)
+        assert L.last_adv.shape == (cfg['B'], cfg['n_step'] - cfg['horizon'] + 1)
+        L.publish_parameter()
+        assert L.n_policy_epochs[-1] == hyper[it]['n_policy_epochs']
+        for k, v in stats[it].items():
+            assert st[k] == pytest.approx(v, rel=1e-5, abs=1e-6), k
+        _state_matches(L, g.sub('it%d/after/' % it), atol=1e-6)
+        after = g.sub('it%d/after/' % it)
+        for name, p in L.rnn.named_parameters():
+            np.testing.assert_allclose(p.detach().numpy(), after['rnn_stem/' + name], rtol=0, atol=1e-6, err_msg=name)
+        for name, p in L.ref_rnn.named_parameters():
+            np.testing.assert_allclose(p.detach().numpy(), b['ref/rnn_stem/' + name], rtol=0, atol=1e-6, err_msg=name)
+        if cfg['mode'] == 'clip':
+            assert L.clip_epsilon == pytest.approx(hyper[it]['clip_epsilon'], rel=1e-12)
+        else:
+            assert L.beta == pytest.approx(hyper[it]['beta'], rel=1e-12)
+        assert L.exp_counter == hyper[it]['exp_counter']
 
 
 def _ddpg_nets(sd):
