@@ -115,6 +115,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        # small messages (600 KB gradients, scalars): a few channels are plenty, and a collective kernel must always
+        # find free SMs next to the persistent rollout kernel (128 of 148 SMs) and the other branch's collective
+        os.environ.setdefault('NCCL_MAX_NCHANNELS', '4')
         dist.init_process_group('nccl', device_id=dev)
     import __graft_entry__
     if rank == 0:

@@ -153,6 +153,7 @@ class PPOLearner(Learner):
         self.dual_critic = os.environ.get("SB200_DUAL_CRITIC", "0") == "1"
         self._graph = ops.GraphRunner()
         self.dp = None
+        self.dp_v = None
         self.epoch_history = []
         self._sync_hyper()
         self.last_n_policy_epochs = 0
@@ -349,8 +350,12 @@ class PPOLearner(Learner):
         if self.use_r_filter:
             raise NotImplementedError('reward filter + data parallel')
         self.dp = LearnerDP(group)
+        # the value branch gets its OWN communicator: with the policy || value fork both branches issue collectives
+        # concurrently, and two streams must never interleave on one communicator
+        import torch.distributed as dist
+        self.dp_v = LearnerDP(dist.new_group(ranks=list(range(self.dp.world)))) if self.parallel_branches else self.dp
         self.actor_optim.dp = self.dp
-        self.critic_optim.dp = self.dp
+        self.critic_optim.dp = self.dp_v
         for mdl in (self.model, self.ref_target_model):
             self.dp.broadcast_(mdl.actor.params)
             self.dp.broadcast_(mdl.critic.params)
@@ -366,13 +371,15 @@ class PPOLearner(Learner):
         # once eagerly first: NCCL sets up its channels lazily, which must not happen under capture.
         # (validated on 2 GPUs: same parameters / statistics as the oracle on the global batch; learn() 5.2 -> 3.7 ms.)
         # NOTE: a process that captured NCCL work must leave with os._exit() -- ProcessGroupNCCL's teardown hangs
-        # (bench.py, tests/dp_check.py).  The policy || value fork stays off: two branches would issue collectives
-        # on one communicator in an undefined order.  The dW side stream carries no collective and stays on.
+        # (bench.py, tests/dp_check.py).  The policy || value fork is kept: the value branch reduces on its own
+        # communicator (dp_v).  The dW side stream carries no collective.
         self.dp_graph = os.environ.get('SB200_DP_GRAPH', '1') != '0'
         for t in (self.actor_optim.grad, self.critic_optim.grad, self._kl_scalar, self._moments, self._z_delta,
                   self._stats):
             if t is not None:
                 self.dp.sum_(torch.zeros_like(t))
+        if self.dp_v is not self.dp:
+            self.dp_v.sum_(torch.zeros_like(self.critic_optim.grad))
         torch.cuda.synchronize()
         return self
 
@@ -429,7 +436,8 @@ class PPOLearner(Learner):
         # inputs: they run as two concurrent branches (a fork / join inside the captured graph), so the step costs
         # max(policy chain, value chain) instead of their sum.  With a data-parallel learner both branches would
         # issue collectives on one communicator, so that case stays sequential.
-        fork = self.dp is None and self.parallel_branches and not self.profile_events
+        fork = self.parallel_branches and not self.profile_events and \
+            (self.dp is None or (self.dp_graph and self.dp_v is not self.dp))
         if fork:
             if self._side_stream is None:
                 self._side_stream = torch.cuda.Stream(device=self.device)

@@ -20,6 +20,7 @@ def main():
     from surreal_b200.learner import PPOLearner
     rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
     torch.cuda.set_device(int(os.environ['LOCAL_RANK']))
+    os.environ.setdefault('NCCL_MAX_NCHANNELS', '4')
     dist.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ['LOCAL_RANK'])))
     B, n, D, A = 256, 16, 24, 4
     mode = os.environ.get('DP_MODE', 'clip')
