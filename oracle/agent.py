@@ -25,6 +25,28 @@ def ppo_act(obs_row, actor_layers, log_var, zfilter, log_noise, eps=None, determ
     return act.reshape(-1), pdv.reshape(-1)
 
 
+def ppo_act_rnn(obs_row, actor_layers, log_var, zfilter, lstm, cells, log_noise, eps=None, deterministic=False):
+    """One env step of one PPO actor in RNN mode (ppo_agent.py:133-149, ppo_net.py:317-351): ``lstm`` is a
+    torch.nn.LSTM(batch_first=True), ``cells`` = (h, c) of shape [layers, 1, hidden] carried between steps.
+    Returns (action, pd, (h_before, c_before) as shipped in onetime_infos, new cells)."""
+    A = log_var.numel()
+    onetime = (cells[0].squeeze(1).numpy().copy(), cells[1].squeeze(1).numpy().copy())
+    with torch.no_grad():
+        x = torch.tensor(obs_row, dtype=torch.float32).unsqueeze(0).unsqueeze(0)     # [1, 1, D]
+        if zfilter is not None:
+            x = zfilter.forward(x)
+        feat, new_cells = lstm(x, cells)
+        feat = feat.contiguous()
+        pdv = nets.ppo_actor(feat.view(-1, feat.shape[2]), actor_layers, log_var).numpy()
+    pdv[:, A:] *= np.exp(log_noise)
+    if deterministic:
+        act = PD.maxprob(pdv, A).copy()
+    else:
+        act = PD.sample(pdv, A, np.asarray(eps).reshape(1, A))
+    act = np.clip(act, -1, 1)
+    return act.reshape(-1), pdv.reshape(-1), onetime, (new_cells[0].detach(), new_cells[1].detach())
+
+
 def ddpg_act(obs_row, actor_layers, sigma, unit_noise=None, deterministic=False):
     """ddpg_agent.py:155-184 with NormalActionNoise(0, sigma) (action_noise.py:9-16):
     clip -> + noise -> clip.  ``unit_noise`` ~ N(0,1) so that noise = sigma * unit_noise."""

@@ -657,6 +657,35 @@ def gen_act():
     save('ddpg_act', obs=obs, unit_noise=eps, sigma=Ag.sigma, actions=acts, **sd_np(Ag.model, 'model/'))
 
 
+def gen_act_rnn():
+    """PPOAgent.act in RNN mode (ppo_agent.py:84-93,133-137,169-183): the LSTM cells travel with the agent, the
+    cells BEFORE each step are what the exp-sender ships as onetime_infos, reset() zeroes them."""
+    torch.manual_seed(43)
+    lc, ec, sc = cfg_ppo(D=11, A=3, rnn=True, horizon=3, rnn_hidden=10)
+    sc.agent.num_gpus = 0
+    np.random.seed(43)
+    Ag = H.construct_without_initialize(PPOAgent, lc, ec, sc, 2, 'training')
+    noise = Ag.noise
+    rng = np.random.default_rng(43)
+    Ag.model.z_filter.z_update(torch.tensor((rng.standard_normal((40, 11)) * 1.5 + 0.3).astype(np.float32)))
+    obs = rng.standard_normal((7, 11)).astype(np.float32)
+    np.random.seed(4343)
+    eps = np.random.randn(7, 1, 3)
+    np.random.seed(4343)
+    acts, pds, h_before, c_before = [], [], [], []
+    for i in range(7):
+        if i == 4:
+            Ag.reset()                                            # new episode: zero cells
+        a, info = Ag.act({'low_dim': {'flat_inputs': obs[i]}})
+        acts.append(a)
+        pds.append(info[1][0])
+        h_before.append(info[0][0])
+        c_before.append(info[0][1])
+    save('ppo_act_rnn', obs=obs, eps=eps[:, 0, :], noise=noise, actions=np.stack(acts), pds=np.stack(pds),
+         h_before=np.stack(h_before), c_before=np.stack(c_before), reset_at=4, rnn_hidden=10,
+         **sd_np(Ag.model, 'model/'))
+
+
 def gen_configs():
     """Default config trees exactly as the reference builds them (main/ppo_configs.py:15-175,
     main/ddpg_configs.py:16-174, session/default_configs.py:4-259)."""

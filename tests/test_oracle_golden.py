@@ -18,7 +18,7 @@ from oracle.ddpg import OracleDDPGLearner
 from oracle.replay import FIFO, Uniform, MT19937
 from oracle.windowing import multistep_windows, ssar_nstep
 from oracle.aggregator import multistep_aggregate, ssar_aggregate
-from oracle.agent import ppo_act, ddpg_act
+from oracle.agent import ppo_act, ddpg_act, ppo_act_rnn
 
 torch.set_num_threads(1)
 T = torch.tensor
@@ -186,6 +186,29 @@ def test_ppo_learn_rnn_mode(golden, tag):
         else:
             assert L.beta == pytest.approx(hyper[it]['beta'], rel=1e-12)
         assert L.exp_counter == hyper[it]['exp_counter']
+
+
+def test_ppo_act_rnn_mode(golden):
+    """Actor side of RNN mode: cells carried between steps, the PRE-step cells are what travels as onetime_infos,
+    reset() zeroes them (ppo_agent.py:84-93,133-137,169-183)."""
+    g = golden('ppo_act_rnn')
+    sd = g.sub('model/')
+    actor, log_var, _, zf = _ppo_model(sd)
+    Hd = int(g['rnn_hidden'])
+    lstm = torch.nn.LSTM(11, Hd, 1, batch_first=True)
+    lstm.load_state_dict({k.split('/', 1)[1]: T(sd[k]) for k in sd.keys() if k.startswith('rnn_stem/')})
+    zero = lambda: (torch.zeros(1, 1, Hd), torch.zeros(1, 1, Hd))   # noqa: E731
+    cells = zero()
+    for i in range(len(g['obs'])):
+        if i == int(g['reset_at']):
+            cells = zero()
+        a, pdv, onetime, cells = ppo_act_rnn(g['obs'][i], actor, log_var, zf, lstm, cells, float(g['noise']), eps=g['eps'][i])
+        # torch's CPU LSTM differs by 1 ulp between thread counts (golden: default threads, here: 1)
+        np.testing.assert_allclose(onetime[0], g['h_before'][i], rtol=0, atol=1e-7)
+        np.testing.assert_allclose(onetime[1], g['c_before'][i], rtol=0, atol=1e-7)
+        np.testing.assert_allclose(pdv, g['pds'][i], rtol=0, atol=1e-7)
+        np.testing.assert_allclose(a, g['actions'][i], rtol=0, atol=1e-7)
+    assert np.abs(g['h_before'][1]).max() > 0 and np.abs(g['h_before'][int(g['reset_at'])]).max() == 0
 
 
 def _ddpg_nets(sd):
