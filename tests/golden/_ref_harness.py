@@ -239,6 +239,27 @@ class _AttrDict(dict):
     def __setattr__(self, k, v):
         self[k] = v
 
+    def __delattr__(self, k):
+        del self[k]
+
+    # BeneDict's YAML helpers (used by surreal/utils/checkpoint.py for the metadata file).  benedict is absent, so
+    # the exact dump STYLE is unpinned (block style assumed); any YAML loader reads either style, which is all the
+    # cross-implementation checkpoint test needs.
+    def to_dict(self):
+        return {k: (v.to_dict() if isinstance(v, _AttrDict) else v) for k, v in self.items()}
+
+    def dump_yaml_file(self, path):
+        import yaml
+        with open(os.path.expanduser(path), 'w') as fp:
+            yaml.safe_dump(self.to_dict(), fp, default_flow_style=False)
+
+    @classmethod
+    def load_yaml_file(cls, path):
+        import yaml
+        with open(os.path.expanduser(path)) as fp:
+            d = yaml.safe_load(fp)
+        return cls({k: (cls(v) if isinstance(v, dict) else v) for k, v in d.items()})
+
 
 def construct_without_initialize(cls, *args, **kwargs):
     """Run cls.__init__ but skip AutoInitializeMeta._initialize (surreal/utils/common.py:270-275),

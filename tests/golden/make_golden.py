@@ -686,6 +686,33 @@ def gen_act_rnn():
          **sd_np(Ag.model, 'model/'))
 
 
+def gen_checkpoint():
+    """Files written by the REFERENCE's PeriodicCheckpoint (utils/checkpoint.py:18-347) for a small tracked object:
+    the raw bytes of every file in the folder, so that the product's loader can be tested against them."""
+    from surreal.utils.checkpoint import PeriodicCheckpoint
+
+    class Obj:
+        pass
+    torch.manual_seed(5)
+    o = Obj()
+    o.model = torch.nn.Linear(3, 2)
+    o.optim = torch.optim.Adam(o.model.parameters(), lr=1e-3)
+    o.current_iteration = 0
+    folder = tempfile.mkdtemp()
+    ck = PeriodicCheckpoint(folder, 'learner', period=2, min_interval=0, tracked_obj=o,
+                            tracked_attrs=['model', 'optim', 'current_iteration'], keep_history=2, keep_best=1)
+    weights = {}
+    for step in range(1, 7):
+        o.model.weight.data += 0.5
+        o.current_iteration = step
+        if ck.save(score=float(step % 4), global_steps=step):
+            weights[str(step)] = o.model.weight.detach().numpy().copy()
+    files = {fn: np.frombuffer(open(os.path.join(folder, fn), 'rb').read(), dtype=np.uint8)
+             for fn in sorted(os.listdir(folder))}
+    save('checkpoint', file_names=sorted(files), **{'file/' + k: v for k, v in files.items()},
+         **{'weight/' + k: v for k, v in weights.items()})
+
+
 def gen_configs():
     """Default config trees exactly as the reference builds them (main/ppo_configs.py:15-175,
     main/ddpg_configs.py:16-174, session/default_configs.py:4-259)."""

@@ -136,3 +136,42 @@ def test_launcher_component_parsing(tmp_path):
     from surreal_b200.main.ppo_configs import ppo_argparser
     a = ppo_argparser().parse_args(['--env', 'synthetic:64:8', '--num-agents', '1024', '--experiment-folder', str(tmp_path)])
     assert a.num_agents == 1024 and a.unit_test is False
+
+
+def test_checkpoint_reads_and_extends_reference_written_folder(tmp_path, golden):
+    """tests/golden/checkpoint.npz holds the raw files the REFERENCE's PeriodicCheckpoint wrote (pickled state_dicts of
+    a torch module + optimiser + a plain attribute, metadata yml): our Checkpoint must restore from them (newest,
+    older, best) and keep saving into the same folder with the same metadata schema."""
+    import torch
+    from surreal_b200.checkpoint import PeriodicCheckpoint
+    g = golden('checkpoint')
+    for fn in g.js('file_names'):
+        (tmp_path / fn).write_bytes(bytes(g['file/' + fn]))
+    ref_meta = yaml.safe_load(open(tmp_path / 'metadata.learner.yml'))
+
+    class Obj:
+        pass
+    o = Obj()
+    o.model = torch.nn.Linear(3, 2)
+    o.optim = torch.optim.Adam(o.model.parameters(), lr=1e-3)
+    o.current_iteration = -1
+    ck = PeriodicCheckpoint(str(tmp_path), 'learner', period=1, tracked_obj=o, tracked_attrs=None)
+    assert ck.restore(target=0, mode='history').endswith('learner.6.ckpt')
+    assert o.current_iteration == 6 and np.array_equal(o.model.weight.detach().numpy(), g['weight/6'])
+    assert ck.restore(target=1, mode='history').endswith('learner.4.ckpt')
+    assert o.current_iteration == 4 and np.array_equal(o.model.weight.detach().numpy(), g['weight/4'])
+    assert ck.restore(target=0, mode='best').endswith('learner.best-6.ckpt')
+    assert o.current_iteration == 6
+    assert ck.restore(target='6', mode='history').endswith('learner.6.ckpt')
+    # keep writing where the reference stopped: counters continue, pruning follows keep_history / keep_best
+    o.current_iteration = 7
+    assert ck.save(score=3.0, global_steps=7) is True
+    meta = yaml.safe_load(open(tmp_path / 'metadata.learner.yml'))
+    assert set(meta.keys()) == set(ref_meta.keys())
+    assert meta['save_counter'] == ref_meta['save_counter'] + 1 and meta['tracked_attrs'] == ref_meta['tracked_attrs']
+    assert meta['history_ckpt_files'] == ['learner.7.ckpt', 'learner.6.ckpt']
+    assert meta['best_ckpt_files'] == ['learner.best-7.ckpt'] and not os.path.exists(tmp_path / 'learner.best-6.ckpt')
+    assert not os.path.exists(tmp_path / 'learner.4.ckpt')
+    assert set(meta['ckpt']['learner.7.ckpt'].keys()) == set(ref_meta['ckpt']['learner.6.ckpt'].keys())
+    data = pickle.load(open(tmp_path / 'learner.7.ckpt', 'rb'))
+    assert list(data.keys()) == ['model', 'optim', 'current_iteration'] and set(data['optim'].keys()) == {'state', 'param_groups'}
