@@ -91,14 +91,16 @@ typedef struct {
 int sb200_mlp_forward_f32(const sb200_mlp* net, const sb200_zfilter* zf, const sb200_rows* in,
                           float* const* save, const int64_t* ld_save, void* stream);
 /* Same, with the kernel family chosen by the caller: variant 0 = default dispatch, 1 = tensor-core 3xTF32 tiles of
- * 32 rows, 2 = fp32 FFMA tiles of 32 rows.  Variants 1 and 2 are sized to be co-resident on one SM (<= 128 registers
- * per thread, 67 KB + 99 KB shared memory): launched on two streams over the two halves of a large batch they keep
- * the tensor pipe and the FMA pipe busy at once (the critic pass of PPOLearner._gae_and_return). */
+ * 32 rows, 2 = fp32 FFMA tiles of 32 rows (both <= 128 registers per thread, 2 CTAs/SM).  Variant 1 is what large
+ * batches get by default (631 us on the 132 096-row critic pass).  Launching 1 and 2 on two streams over the two
+ * halves of a batch -- tensor pipe and FMA pipe at once -- was measured SLOWER (700-760 us): both kernels are bound
+ * by instruction issue, not by their math pipes; it stays available as an experiment (SB200_DUAL_CRITIC=1). */
 int sb200_mlp_forward_variant_f32(const sb200_mlp* net, const sb200_zfilter* zf, const sb200_rows* in,
                                   float* const* save, const int64_t* ld_save, int variant, void* stream);
 /* Small-batch inference on PRE-PACKED weights (the actors' per-step policy forward, ppo_agent.py:138-141 /
  * ddpg_agent.py:170-176): pack once per parameter version, then every step's forward reads the weights in
- * mma-fragment order, already split for 3xTF32, and a 2-CTA cluster shares each 16-row tile.
+ * mma-fragment order and a 4-CTA cluster shares each 32-row tile (each CTA keeps a quarter of the weights resident in
+ * shared memory and exchanges layer outputs through distributed shared memory).
  *   pack_floats: size of `packed` in floats (0: this architecture is not supported -- use sb200_mlp_forward_f32;
  *     supported = every layer but the last wider than 32 outputs).
  *   pack_tf32: (re)builds `packed` from net->W.  Must be re-run after ANY change of the parameters.
@@ -107,8 +109,9 @@ size_t sb200_mlp_pack_floats(const sb200_mlp* net);
 int sb200_mlp_pack_tf32(const sb200_mlp* net, float* packed, void* stream);
 int sb200_mlp_forward_packed_f32(const sb200_mlp* net, const float* packed, const sb200_zfilter* zf,
                                  const sb200_rows* in, float* out, int64_t ld_out, void* stream);
-/* Numerics of the wide layers of sb200_mlp_forward_f32: 1 (default) = tensor-core mma.sync TF32 with the 3xTF32
- * error-compensated split (fp32-level accuracy, ~1e-6 relative); 0 = fp32 FFMA kernels.  Env SB200_MMA overrides
+/* Kernel family of the wide layers of sb200_mlp_forward_f32: 1 (default) = tensor-core mma.sync TF32 with the 3xTF32
+ * error-compensated split (fp32-level accuracy, ~1e-6 relative) for batches above 2048 rows, fp32 FFMA below (where
+ * the FFMA kernel is faster: 19 us vs 26 us at 1024 rows); 0 = fp32 FFMA kernels everywhere.  Env SB200_MMA overrides
  * the initial value. */
 int sb200_set_forward_mode(int mode);
 
