@@ -686,6 +686,67 @@ def gen_act_rnn():
          **sd_np(Ag.model, 'model/'))
 
 
+def gen_ppo_learn_pixel():
+    """Pixel mode (BASELINE cfg 4 shape, scaled down): uint8 frames -> /255 -> CNN stem (16k8s4, 32k4s2, FC) shared by
+    actor and critic and trained by BOTH optimisers (ppo_net.py:136-140,202-224,268-273), no z-filter."""
+    C, HW, F = 2, 20, 12
+    for tag, mode in (('pixel_clip', 'clip'), ('pixel_adapt', 'adapt')):
+        torch.manual_seed(17)
+        lc, ec, sc = cfg_ppo(mode=mode, B=6, n_step=4, stride=4, use_z=False, exp_interval=12)
+        ec.obs_spec = {'pixel': {'camera0': (C, HW, HW)}}
+        ec.pixel_input = True
+        lc.model.cnn_feature_dim = F
+        L = H.construct_without_initialize(PPOLearner, lc, ec, sc)
+        L._ps_publisher = H._Any()
+        L.tensorplex = H._Any()
+        L.ref_target_model.update_target_params(L.model)
+        rng = np.random.default_rng(17)
+        B, n, A = L.batch_size, L.n_step, 3
+        out = dict(**sd_np(L.model, 'init/'))
+        stats_all, hyper, captured = [], [], {}
+        orig_opt, orig_gae = L._optimize, L._gae_and_return
+
+        def opt_hook(*a, **k):
+            st = orig_opt(*a, **k)
+            captured['stats'] = {kk: float(vv) for kk, vv in st.items()}
+            return st
+
+        def gae_hook(*a, **k):
+            adv, ret = orig_gae(*a, **k)
+            captured['adv'], captured['ret'] = adv.detach().clone().numpy(), ret.detach().clone().numpy()
+            return adv, ret
+        L._optimize, L._gae_and_return = opt_hook, gae_hook
+        for it in range(2):
+            obs = rng.integers(0, 256, size=(B, n, C, HW, HW), dtype=np.uint8)
+            obs_next = rng.integers(0, 256, size=(B, 1, C, HW, HW), dtype=np.uint8)
+            with torch.no_grad():
+                flat = {'pixel': {'camera0': torch.tensor(obs.reshape(B * n, C, HW, HW), dtype=torch.float32)}}
+                pd = L.model.forward_actor(flat).numpy().reshape(B, n, 2 * A)
+            pd = pd.copy()
+            pd[:, :, A:] *= np.exp(rng.uniform(-0.25, 0.25, size=(B, 1, 1))).astype(np.float32)
+            actions = np.clip(rng.standard_normal((B, n, A)) * pd[:, :, A:] + pd[:, :, :A], -1, 1)
+            rewards = rng.standard_normal((B, n)) * 0.5 + 0.1
+            dones = np.zeros((B, n), dtype=np.float32)
+            dones[rng.random(B) < 0.3, n - 1] = 1.0
+            batch = H._AttrDict(obs={'pixel': {'camera0': obs.copy()}}, obs_next={'pixel': {'camera0': obs_next.copy()}},
+                                actions=actions.copy(), rewards=rewards.copy(), dones=dones.copy(),
+                                persistent_infos=[pd.astype(np.float32).copy()], onetime_infos=None)
+            for k, v in dict(obs=obs, obs_next=obs_next, actions=actions, rewards=rewards, dones=dones,
+                             pd=pd.astype(np.float32)).items():
+                out['it%d/%s' % (it, k)] = v
+            L.learn(batch)
+            stats_all.append(captured['stats'])
+            out['it%d/adv' % it], out['it%d/ret' % it] = captured['adv'], captured['ret']
+            L.publish_parameter(it, message='')
+            out.update(sd_np(L.model, 'it%d/after/' % it))
+            hyper.append(dict(clip_epsilon=getattr(L, 'clip_epsilon', None), beta=getattr(L, 'beta', None),
+                              exp_counter=L.exp_counter, kl_record=list(map(float, L.kl_record))))
+        cfg = dict(mode=L.ppo_mode, B=B, n_step=n, A=A, C=C, HW=HW, cnn_feature_dim=F,
+                   actor_h=lc.model.actor_fc_hidden_sizes, critic_h=lc.model.critic_fc_hidden_sizes,
+                   lr=lc.algo.network.lr_actor, exp_interval=lc.parameter_publish.exp_interval, iters=2)
+        save('ppo_learn_' + tag, cfg=cfg, stats=stats_all, hyper=hyper, **out)
+
+
 def gen_checkpoint():
     """Files written by the REFERENCE's PeriodicCheckpoint (utils/checkpoint.py:18-347) for a small tracked object:
     the raw bytes of every file in the folder, so that the product's loader can be tested against them."""

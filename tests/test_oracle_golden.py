@@ -14,6 +14,7 @@ from oracle import nets
 from oracle.gae import gae_from_values, gae_reference_fp64
 from oracle.ppo import OraclePPOLearner
 from oracle.ppo_rnn import OraclePPOLearnerRNN
+from oracle.ppo_pixel import OraclePPOLearnerPixel
 from oracle.ddpg import OracleDDPGLearner
 from oracle.replay import FIFO, Uniform, MT19937
 from oracle.windowing import multistep_windows, ssar_nstep
@@ -186,6 +187,47 @@ def test_ppo_learn_rnn_mode(golden, tag):
         else:
             assert L.beta == pytest.approx(hyper[it]['beta'], rel=1e-12)
         assert L.exp_counter == hyper[it]['exp_counter']
+
+
+@pytest.mark.parametrize('tag', ['pixel_clip', 'pixel_adapt'])
+def test_ppo_learn_pixel_mode(golden, tag):
+    """Pixel mode (BASELINE cfg 4 shape, scaled down): uint8 frames, CNN stem shared by actor and critic and trained
+    by both optimisers, no z-filter -- against goldens produced by the real reference.  Pins the oracle for the CNN
+    branch of SURVEY §8 rows a2/a26; the CUDA conv kernels are not built yet."""
+    g = golden('ppo_learn_' + tag)
+    cfg, hyper, stats = g.js('cfg'), g.js('hyper'), g.js('stats')
+    init = g.sub('init/')
+    actor = nets.params_from_state(init, 'actor/model/')
+    critic = nets.params_from_state(init, 'critic/model/')
+    log_var = T(init['actor/log_var'])
+    conv = [(T(init['cnn_stem/model/seq/%d/weight' % i]), T(init['cnn_stem/model/seq/%d/bias' % i])) for i in (0, 2)]
+    fc = (T(init['cnn_stem/model/seq/5/weight']), T(init['cnn_stem/model/seq/5/bias']))
+    L = OraclePPOLearnerPixel(actor, log_var, critic, conv, [4, 2], fc, cfg['A'], cfg['n_step'], cfg['B'],
+                              ppo_mode=cfg['mode'], lr_actor=cfg['lr'], lr_critic=cfg['lr'],
+                              exp_interval=cfg['exp_interval'])
+    for it in range(cfg['iters']):
+        b = g.sub('it%d/' % it)
+        assert b['obs'].dtype == np.uint8
+        st = L.learn(dict(obs=b['obs'], obs_next=b['obs_next'], actions=b['actions'], rewards=b['rewards'],
+                          dones=b['dones'], pd=b['pd']))
+        np.testing.assert_allclose(L.last_adv.numpy(), b['adv'], rtol=0, atol=2e-6)
+        np.testing.assert_allclose(L.last_ret.numpy(), b['ret'], rtol=0, atol=2e-6)
+        L.publish_parameter()
+        for k, v in stats[it].items():
+            assert st[k] == pytest.approx(v, rel=1e-5, abs=1e-6), k
+        after = g.sub('it%d/after/' % it)
+        for i, (w, bb) in zip((0, 2), L.conv):
+            np.testing.assert_allclose(w.detach().numpy(), after['cnn_stem/model/seq/%d/weight' % i], rtol=0, atol=1e-6)
+            np.testing.assert_allclose(bb.detach().numpy(), after['cnn_stem/model/seq/%d/bias' % i], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(L.fc[0].detach().numpy(), after['cnn_stem/model/seq/5/weight'], rtol=0, atol=1e-6)
+        for i, (w, bb) in enumerate(L.actor):
+            np.testing.assert_allclose(w.detach().numpy(), after['actor/model/seq/%d/weight' % (2 * i)], rtol=0, atol=1e-6)
+        for i, (w, bb) in enumerate(L.critic):
+            np.testing.assert_allclose(w.detach().numpy(), after['critic/model/seq/%d/weight' % (2 * i)], rtol=0, atol=1e-6)
+        if cfg['mode'] == 'clip':
+            assert L.clip_epsilon == pytest.approx(hyper[it]['clip_epsilon'], rel=1e-12)
+        else:
+            assert L.beta == pytest.approx(hyper[it]['beta'], rel=1e-12)
 
 
 def test_ppo_act_rnn_mode(golden):
