@@ -274,6 +274,12 @@ int sb200_ppo_sample_assign_f32(const float* mean, int64_t ldm, const float* log
 int sb200_ddpg_noise_f32(const float* mean, int64_t ldm, const float* sigma, const float* unit_noise, int N,
                          int A, int deterministic, uint64_t seed, const uint64_t* step_counter,
                          float* action, void* stream);
+/*   ddpg_ou_noise: the same with Ornstein-Uhlenbeck exploration (surreal/agent/action_noise.py:22-39): ou_state [N][A]
+ *     float64 is advanced in place, x <- x + theta*(0 - x)*dt + sigma_i*sqrt(dt)*N(0,1); sigma [N] float64.  The caller
+ *     zeroes ou_state at episode start (DDPGAgent.pre_episode, ddpg_agent.py:205-208). */
+int sb200_ddpg_ou_noise_f32(const float* mean, int64_t ldm, const double* sigma, const float* unit_noise, int N, int A,
+                            int deterministic, uint64_t seed, const uint64_t* step_counter, double theta, double dt,
+                            double* ou_state, float* action, void* stream);
 /* Synthetic device-resident environment of the benchmark configs: s' = tanh(Ws s + Wa a) + 0.01 xi,
  * r = -|s|^2/D + 0.1 xi', done at max_steps (MaxStepWrapper, env/wrapper.py:142-163) with auto-reset.
  * state [N,D] is updated in place to what the agent observes next; obs_next is the true successor.

@@ -57,3 +57,19 @@ def ddpg_act(obs_row, actor_layers, sigma, unit_noise=None, deterministic=False)
     if not deterministic:
         a += sigma * np.asarray(unit_noise)        # in-place on the float32 array (ddpg_agent.py:181)
     return a.clip(-1, 1)
+
+
+def ddpg_act_ou(obs_row, actor_layers, x_prev, sigma, theta, dt, unit_noise=None, deterministic=False):
+    """ddpg_agent.py:155-184 with OrnsteinUhlenbeckActionNoise (action_noise.py:22-39): float64 state
+    x <- x + theta*(mu - x)*dt + sigma*sqrt(dt)*N(0,1), mu = 0; ``unit_noise`` are the N(0,1) draws.
+    Returns (action float32 [A], new state float64 [A])."""
+    with torch.no_grad():
+        x = torch.tensor(obs_row, dtype=torch.float32).unsqueeze(0)
+        a = nets.ddpg_actor(x, actor_layers).numpy()[0]
+    a = a.clip(-1, 1)
+    x_new = np.asarray(x_prev, dtype=np.float64)
+    if not deterministic:
+        mu = np.zeros_like(x_new)
+        x_new = x_new + theta * (mu - x_new) * dt + sigma * np.sqrt(dt) * np.asarray(unit_noise, dtype=np.float64)
+        a += x_new                                  # in-place on the float32 array (ddpg_agent.py:181)
+    return a.clip(-1, 1), x_new

@@ -3,7 +3,8 @@
 Exploration follows the reference: actor i of ``num_agents`` explores with sigma_i = max_sigma * i /
 num_agents (max_sigma / 3 for a single agent; agent 0 therefore explores with sigma = 0,
 ddpg_agent.py:78-83); ``act`` = clip(pi(s)) + N(0, sigma_i) then clip again (ddpg_agent.py:176-183).
-Ornstein-Uhlenbeck noise (action_noise.py:22-39) and parameter noise (off by default) are not built."""
+``noise_type: ou_noise`` selects Ornstein-Uhlenbeck exploration (action_noise.py:22-39; float64 state per actor, reset in
+pre_episode like ddpg_agent.py:205-208).  Parameter noise (off by default) is not built."""
 import ctypes as C
 import time
 
@@ -37,9 +38,7 @@ class DDPGAgent(Agent):
         if ex.param_noise_type is not None:
             raise NotImplementedError('parameter noise (param_noise.py) is off by default and not built')
         self.noise_type = ex.noise_type
-        if self.noise_type != 'normal':
-            if self.noise_type == 'ou_noise':
-                raise NotImplementedError('Ornstein-Uhlenbeck action noise is not built; use noise_type "normal"')
+        if self.noise_type not in ('normal', 'ou_noise'):
             raise ConfigError('Noise type {} undefined.'.format(self.noise_type))
         N = self.num_envs
         total = int(env_config.num_agents)
@@ -55,6 +54,11 @@ class DDPGAgent(Agent):
                                device=self.device)
         A, D = self.action_dim, self.model.input_dim
         self._sigma = torch.tensor(self.sigma, dtype=torch.float32, device=self.device)
+        self._ou_state = None
+        if self.noise_type == 'ou_noise':
+            self.ou_theta, self.ou_dt = float(ex.theta), float(ex.dt)
+            self._sigma64 = torch.tensor(self.sigma, dtype=torch.float64, device=self.device)
+            self._ou_state = torch.zeros(N, A, dtype=torch.float64, device=self.device)
         self._mean = torch.zeros(N, A, device=self.device)
         self._packed = ops.PackedWeights(self.model.actor)          # per-step inference copy of the policy weights
         self._action = torch.zeros(N, A, device=self.device)
@@ -87,14 +91,25 @@ class DDPGAgent(Agent):
         un = None
         if unit_noise is not None:
             un = torch.as_tensor(np.asarray(unit_noise, dtype=np.float32).reshape(N, A)).to(self.device)
-        check(_lib.lib().sb200_ddpg_noise_f32(_p(self._mean), A, _p(self._sigma), _p(un), N, A, int(det), self.seed,
-                                              _p(counter), _p(self._action), ops._stream()), 'sb200_ddpg_noise_f32')
+        if self._ou_state is not None:
+            check(_lib.lib().sb200_ddpg_ou_noise_f32(_p(self._mean), A, _p(self._sigma64), _p(un), N, A, int(det),
+                                                     self.seed, _p(counter), self.ou_theta, self.ou_dt,
+                                                     _p(self._ou_state), _p(self._action), ops._stream()),
+                  'sb200_ddpg_ou_noise_f32')
+        else:
+            check(_lib.lib().sb200_ddpg_noise_f32(_p(self._mean), A, _p(self._sigma), _p(un), N, A, int(det), self.seed,
+                                                  _p(counter), _p(self._action), ops._stream()), 'sb200_ddpg_noise_f32')
         if counter is self._counter:
             self._counter += 1
         if host:
             a = self._action.cpu().numpy()
             return a.reshape(-1) if (N == 1 and np.asarray(x.shape).size and np.asarray(obs['low_dim']['flat_inputs'] if isinstance(obs, dict) else obs).ndim == 1) else a
         return self._action
+
+    def pre_episode(self):
+        super().pre_episode()
+        if self._ou_state is not None and self.agent_mode not in ['eval_deterministic', 'eval_deterministic_local']:
+            self._ou_state.zero_()                                  # noise.reset() (ddpg_agent.py:205-208)
 
     def module_dict(self, model=None):
         return {'ddpg': self.model if model is None else model}

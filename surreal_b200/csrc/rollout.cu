@@ -113,6 +113,41 @@ __global__ void __launch_bounds__(RT) ddpg_noise_kernel(const float* __restrict_
     }
 }
 
+// DDPGAgent.act with Ornstein-Uhlenbeck exploration (action_noise.py:22-39): per-actor float64 state
+//   x <- x + theta*(mu - x)*dt + sigma_i*sqrt(dt)*N(0,1)   (mu = 0; numpy evaluates it left to right in float64),
+// action = clip(clip(pi(s)) + x).  One thread per (actor, action dim); no FMA contraction, to match numpy.
+__global__ void __launch_bounds__(RT) ddpg_ou_noise_kernel(const float* __restrict__ mean, long long ldm,
+                                                           const double* __restrict__ sigma,
+                                                           const float* __restrict__ unit_noise, int N, int A,
+                                                           int deterministic, unsigned long long seed,
+                                                           const unsigned long long* __restrict__ step_ctr, double theta,
+                                                           double dt, double* __restrict__ ou_state,
+                                                           float* __restrict__ action) {
+    const int idx = blockIdx.x * RT + threadIdx.x;
+    if (idx >= N * A) return;
+    const int i = idx / A, j = idx - i * A;
+    float a = fminf(fmaxf(mean[(long long)i * ldm + j], -1.0f), 1.0f);
+    if (!deterministic) {
+        double e;
+        if (unit_noise != nullptr) {
+            e = (double)unit_noise[idx];
+        } else {
+            const unsigned long long ctr = (step_ctr != nullptr) ? *step_ctr : 0ull;
+            const Philox4 r = philox4x32_10(seed, ctr, ((unsigned long long)i << 16) | (unsigned long long)(j >> 2));
+            const float2 z01 = box_muller(r.x, r.y), z23 = box_muller(r.z, r.w);
+            const int c = j & 3;
+            e = (double)((c == 0) ? z01.x : (c == 1) ? z01.y : (c == 2) ? z23.x : z23.y);
+        }
+        const double xp = ou_state[idx];
+        const double drift = __dmul_rn(__dmul_rn(theta, 0.0 - xp), dt);
+        const double diff = __dmul_rn(__dmul_rn(sigma[i], sqrt(dt)), e);
+        const double x = __dadd_rn(__dadd_rn(xp, drift), diff);
+        ou_state[idx] = x;
+        a = (float)((double)a + x);                          // float32 array += float64 noise
+    }
+    action[(long long)i * A + j] = fminf(fmaxf(a, -1.0f), 1.0f);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Synthetic environment of SURVEY §8(d) cfg 2/3/5, batched and device-resident:
 //   s' = tanh(Ws s + Wa a) + 0.01*xi,   r = -|s|^2 / D + 0.1*xi',   done when the episode reaches
@@ -301,6 +336,16 @@ extern "C" int sb200_ddpg_noise_f32(const float* mean, int64_t ldm, const float*
     ddpg_noise_kernel<<<(N + RT - 1) / RT, RT, 0, (cudaStream_t)stream>>>(
         mean, ldm, sigma, unit_noise, N, A, deterministic, (unsigned long long)seed,
         (const unsigned long long*)step_counter, action);
+    return sb200_launch_status();
+}
+
+extern "C" int sb200_ddpg_ou_noise_f32(const float* mean, int64_t ldm, const double* sigma, const float* unit_noise,
+                                       int N, int A, int deterministic, uint64_t seed, const uint64_t* step_counter,
+                                       double theta, double dt, double* ou_state, float* action, void* stream) {
+    SB200_REQUIRE(mean && sigma && ou_state && action && N >= 1 && A >= 1 && ldm >= A);
+    ddpg_ou_noise_kernel<<<(N * A + RT - 1) / RT, RT, 0, (cudaStream_t)stream>>>(
+        mean, ldm, sigma, unit_noise, N, A, deterministic, (unsigned long long)seed,
+        (const unsigned long long*)step_counter, theta, dt, ou_state, action);
     return sb200_launch_status();
 }
 

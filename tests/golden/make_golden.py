@@ -747,6 +747,31 @@ def gen_ppo_learn_pixel():
         save('ppo_learn_' + tag, cfg=cfg, stats=stats_all, hyper=hyper, **out)
 
 
+def gen_act_ou():
+    """DDPGAgent.act with Ornstein-Uhlenbeck exploration (action_noise.py:22-39, ddpg_agent.py:128-134,176-183,205-208):
+    float64 state, reset in pre_episode()."""
+    torch.manual_seed(44)
+    lc, ec, sc = cfg_ddpg(D=9, A=3)
+    lc.algo.exploration.noise_type = 'ou_noise'
+    lc.algo.exploration.theta = 0.15
+    lc.algo.exploration.dt = 1e-3
+    ec.num_agents = 4
+    Ag = H.construct_without_initialize(DDPGAgent, lc, ec, sc, 3, 'training')
+    rng = np.random.default_rng(44)
+    obs = rng.standard_normal((8, 9)).astype(np.float32)
+    np.random.seed(778)
+    eps = np.stack([np.random.normal(size=3) for _ in range(8)])      # the unit draws __call__ will make, in order
+    np.random.seed(778)
+    acts, states = [], []
+    for i in range(8):
+        if i == 5:
+            Ag.pre_episode()                                            # noise.reset()
+        acts.append(Ag.act({'low_dim': {'flat_inputs': obs[i]}}))
+        states.append(np.array(Ag.noise.x_prev, dtype=np.float64))
+    save('ddpg_act_ou', obs=obs, unit_noise=eps, sigma=Ag.sigma, theta=0.15, dt=1e-3, reset_at=5,
+         actions=np.stack(acts), ou_states=np.stack(states), **sd_np(Ag.model, 'model/'))
+
+
 def gen_checkpoint():
     """Files written by the REFERENCE's PeriodicCheckpoint (utils/checkpoint.py:18-347) for a small tracked object:
     the raw bytes of every file in the folder, so that the product's loader can be tested against them."""

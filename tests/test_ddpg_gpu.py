@@ -50,6 +50,34 @@ def test_ddpg_agent_act_matches_reference(golden):
     assert ag.sigma.tolist() == [0.0, 0.25, 0.5, 0.75, 1.0][:N] or N != 5
 
 
+def test_ddpg_agent_ou_noise_matches_reference(golden):
+    """noise_type 'ou_noise': the float64 Ornstein-Uhlenbeck walk of the reference (one actor, 8 steps, reset by
+    pre_episode after 5) replayed with the same unit draws; several actors keep independent states."""
+    from surreal_b200.agent import DDPGAgent
+    g = golden('ddpg_act_ou')
+    lc, ec, sc = ddpg_configs(D=9, A=3)
+    lc.algo.exploration.noise_type = 'ou_noise'
+    lc.algo.exploration.theta, lc.algo.exploration.dt = float(g['theta']), float(g['dt'])
+    ec.num_envs, ec.num_agents = 2, 4
+    ag = DDPGAgent(lc, ec, sc, 0, 'training')
+    ag.model.load_state_dict(ref_state_dict(g.sub('model/')))
+    ag._sigma64.fill_(float(g['sigma']))                     # both rows replay agent 3 of 4 of the fixture
+    for i in range(len(g['obs'])):
+        if i == int(g['reset_at']):
+            ag.pre_episode()
+        obs2 = np.stack([g['obs'][i], g['obs'][i]])
+        un = np.stack([g['unit_noise'][i], -g['unit_noise'][i]])              # second actor: mirrored draws
+        a = ag.act({'low_dim': {'flat_inputs': obs2}}, unit_noise=un)
+        np.testing.assert_allclose(a[0], g['actions'][i], rtol=0, atol=2e-6)
+        st = ag._ou_state.cpu().numpy()
+        np.testing.assert_allclose(st[0], g['ou_states'][i], rtol=0, atol=1e-7)
+        np.testing.assert_allclose(st[1], -g['ou_states'][i], rtol=0, atol=1e-7)
+    ag.agent_mode = 'eval_deterministic'
+    before = ag._ou_state.clone()
+    ag.act({'low_dim': {'flat_inputs': obs2}})
+    assert torch.equal(before, ag._ou_state)                 # deterministic evaluation does not advance the walk
+
+
 def test_ddpg_engine_end_to_end():
     """actors -> n-step SSAR staging -> UniformReplay ring -> CPython-exact sampling -> DDPGLearner."""
     import random

@@ -19,7 +19,7 @@ from oracle.ddpg import OracleDDPGLearner
 from oracle.replay import FIFO, Uniform, MT19937
 from oracle.windowing import multistep_windows, ssar_nstep
 from oracle.aggregator import multistep_aggregate, ssar_aggregate
-from oracle.agent import ppo_act, ddpg_act, ppo_act_rnn
+from oracle.agent import ppo_act, ddpg_act, ppo_act_rnn, ddpg_act_ou
 
 torch.set_num_threads(1)
 T = torch.tensor
@@ -228,6 +228,22 @@ def test_ppo_learn_pixel_mode(golden, tag):
             assert L.clip_epsilon == pytest.approx(hyper[it]['clip_epsilon'], rel=1e-12)
         else:
             assert L.beta == pytest.approx(hyper[it]['beta'], rel=1e-12)
+
+
+def test_ddpg_act_ou_noise(golden):
+    """Ornstein-Uhlenbeck exploration (action_noise.py:22-39): float64 state carried between steps, reset in
+    pre_episode()."""
+    g = golden('ddpg_act_ou')
+    actor = nets.params_from_state(g.sub('model/'), 'actor/model/')
+    x = np.zeros(3)
+    for i in range(len(g['obs'])):
+        if i == int(g['reset_at']):
+            x = np.zeros(3)
+        a, x = ddpg_act_ou(g['obs'][i], actor, x, float(g['sigma']), float(g['theta']), float(g['dt']),
+                           unit_noise=g['unit_noise'][i])
+        np.testing.assert_array_equal(x, g['ou_states'][i])
+        np.testing.assert_array_equal(a, g['actions'][i])
+    assert np.abs(g['ou_states'][4]).max() > np.abs(g['ou_states'][5]).max() * 0.5   # the walk restarted at reset_at
 
 
 def test_ppo_act_rnn_mode(golden):
