@@ -437,6 +437,54 @@ def gen_ddpg():
         save('ddpg_optimize_' + tag, cfg=cfg, stats=stats_all, **out)
 
 
+def gen_ddpg_td3():
+    """TD3 options of DDPGLearner._optimize (ddpg.py:267-283,298-321): second critic + target, y = min(y, y2) where
+    only Q'_2 sees the (noised, clipped) target action -- Q'_1 was computed BEFORE the noise is added."""
+    for tag, reg in (('td3_double', False), ('td3_double_reg', True)):
+        torch.manual_seed(23)
+        lc, ec, sc = cfg_ddpg(double=True, interval=2)
+        lc.algo.network.use_action_regularization = reg
+        L = H.construct_without_initialize(DDPGLearner, lc, ec, sc)
+        L.tensorplex = H._Any()
+        with torch.no_grad():
+            for mdl in (L.model_target, L.model_target2):
+                for p in mdl.parameters():
+                    p.add_(0.05 * torch.randn_like(p))
+        rng = np.random.default_rng(23)
+        B, D, A = L.batch_size, 9, 3
+        out = dict(**sd_np(L.model, 'init/model/'), **sd_np(L.model_target, 'init/target/'),
+                   **sd_np(L.model2, 'init/model2/'), **sd_np(L.model_target2, 'init/target2/'))
+        stats_all = []
+        for it in range(3):
+            raw = dict(obs=rng.standard_normal((B, D)).astype(np.float32),
+                       obs_next=rng.standard_normal((B, D)).astype(np.float32),
+                       actions=rng.uniform(-1, 1, (B, A)).astype(np.float32),
+                       rewards=rng.standard_normal((B, 1)),
+                       dones=(rng.random((B, 1)) < 0.2).astype(np.float64))
+            batch = H._AttrDict(obs={'low_dim': {'flat_inputs': raw['obs'].copy()}},
+                                obs_next={'low_dim': {'flat_inputs': raw['obs_next'].copy()}},
+                                actions=raw['actions'].copy(), rewards=raw['rewards'].copy(),
+                                dones=raw['dones'].copy())
+            batch = L.preprocess(batch)
+            np.random.seed(900 + it)
+            raw['policy_noise_unclipped'] = np.random.normal(0, 0.2, size=(B, A))      # the draw _optimize will make
+            np.random.seed(900 + it)
+            st = L._optimize(batch.obs, batch.actions, batch.rewards, batch.obs_next, batch.dones)
+            stats_all.append({k: float(v) for k, v in st.items() if not k.startswith('performance')})
+            for k, v in raw.items():
+                out['it%d/%s' % (it, k)] = v
+            for name, mdl in (('model', L.model), ('target', L.model_target), ('model2', L.model2),
+                              ('target2', L.model_target2)):
+                out.update(sd_np(mdl, 'it%d/%s/' % (it, name)))
+        cfg = dict(B=B, D=D, A=A, actor_h=lc.model.actor_fc_hidden_sizes, critic_h=lc.model.critic_fc_hidden_sizes,
+                   gamma=L.discount_factor, n_step=L.n_step, lr_actor=lc.algo.network.lr_actor,
+                   lr_critic=lc.algo.network.lr_critic, target=lc.algo.network.target_update.to_dict(),
+                   clip_actor=L.clip_actor_gradient, actor_clip=lc.algo.network.actor_gradient_value_clip,
+                   clip_critic=L.clip_critic_gradient, critic_clip=lc.algo.network.critic_gradient_value_clip,
+                   action_regularization=reg)
+        save('ddpg_optimize_' + tag, cfg=cfg, stats=stats_all, **out)
+
+
 def gen_replay():
     # FIFO: ids in, ids out; capacity memory_size + 3 silently drops oldest (fifo_replay.py:27)
     lc, ec, sc = cfg_ppo()

@@ -301,6 +301,38 @@ def test_ddpg_optimize(golden, tag):
                 np.testing.assert_allclose(bb.detach().numpy(), be.numpy(), rtol=0, atol=1e-7)
 
 
+@pytest.mark.parametrize('tag', ['td3_double', 'td3_double_reg'])
+def test_ddpg_optimize_td3_options(golden, tag):
+    """TD3 options (ddpg.py:267-283,298-321): second critic + its target, y = min(y, y2); the smoothing noise is added
+    to the target action only AFTER Q'_1 was evaluated (a reference quirk the oracle keeps)."""
+    g = golden('ddpg_optimize_' + tag)
+    cfg = g.js('cfg')
+    a, c = _ddpg_nets(g.sub('init/model/'))
+    at, ct = _ddpg_nets(g.sub('init/target/'))
+    crit = lambda sd: (nets.params_from_state(sd, 'critic/model_obs/', 1) +          # noqa: E731  (model2 holds no actor)
+                       nets.params_from_state(sd, 'critic/model_concat/', 2))
+    c2, c2t = crit(g.sub('init/model2/')), crit(g.sub('init/target2/'))
+    L = OracleDDPGLearner(a, c, at, ct, gamma=cfg['gamma'], n_step=cfg['n_step'], lr_actor=cfg['lr_actor'],
+                          lr_critic=cfg['lr_critic'], clip_actor=cfg['clip_actor'], actor_clip=cfg['actor_clip'],
+                          clip_critic=cfg['clip_critic'], critic_clip=cfg['critic_clip'],
+                          target_type=cfg['target']['type'], target_interval=cfg['target'].get('interval', 0),
+                          tau=cfg['target'].get('tau', 0.0), critic2=c2, critic2_t=c2t)
+    stats = g.js('stats')
+    for it in range(3):
+        b = g.sub('it%d/' % it)
+        noise = b['policy_noise_unclipped'] if cfg['action_regularization'] else None
+        st = L.optimize(b['obs'], b['actions'], b['rewards'], b['obs_next'], b['dones'], policy_noise=noise)
+        for k, v in stats[it].items():
+            assert st[k] == pytest.approx(v, rel=1e-6, abs=1e-7), k
+        assert 'Q_policy2' in st
+        ea, ec = _ddpg_nets(g.sub('it%d/model/' % it))
+        ec2, ec2t = crit(g.sub('it%d/model2/' % it)), crit(g.sub('it%d/target2/' % it))
+        for got, exp in [(L.actor, ea), (L.critic, ec), (L.critic2, ec2), (L.critic2_t, ec2t)]:
+            for (w, bb), (we, be) in zip(got, exp):
+                np.testing.assert_allclose(w.detach().numpy(), we.numpy(), rtol=0, atol=1e-7)
+                np.testing.assert_allclose(bb.detach().numpy(), be.numpy(), rtol=0, atol=1e-7)
+
+
 def test_fifo_replay_trace(golden):
     f = golden('replay').js('fifo')
     R = FIFO(f['memory_size'], f['batch_size'])
