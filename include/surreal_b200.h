@@ -243,6 +243,15 @@ int sb200_ddpg_target_f32(const float* rewards, const float* q_next, int64_t ldq
 /* MSE(q, y): dq = 2 (q - y) / B. */
 int sb200_ddpg_critic_loss_f32(const float* q, int64_t ldq, const float* y, int B, float* dq, int64_t ldd,
                                float* stats, void* workspace, void* stream);
+/* TD3 options (ddpg.py:267-283): target2 = ddpg_target with y = min(y, y2) over two target critics; smooth_action =
+ * clamp(pi + clip(policy_noise * N(0,1), -noise_clip, noise_clip), -1, 1) (unit_noise [B][A] injected draws, or NULL
+ * for Philox keyed by (seed, *step_counter, row)). */
+int sb200_ddpg_target2_f32(const float* rewards, const float* q_next, int64_t ldq, const float* q_next2, int64_t ldq2,
+                           const float* dones, const float* actions, int64_t lda, int B, int A, double discount,
+                           float* y, float* stats, void* workspace, void* stream);
+int sb200_ddpg_smooth_action_f32(const float* pi, int64_t ldp, const float* unit_noise, int B, int A,
+                                 double policy_noise, double noise_clip, uint64_t seed, const uint64_t* step_counter,
+                                 float* out, int64_t ldo, void* stream);
 /* actor loss -mean(q_pi): seeds dq = -1/B for the backward pass through the critic. */
 int sb200_ddpg_actor_seed_f32(const float* q_pi, int64_t ldq, int B, float* dq, int64_t ldd, float* stats,
                               void* workspace, void* stream);

@@ -20,14 +20,19 @@ __global__ void __launch_bounds__(DT) ddpg_target_kernel(const float* __restrict
                                                          const float* __restrict__ dones,
                                                          const float* __restrict__ actions, long long lda, int B, int A,
                                                          float discount, float* __restrict__ y,
-                                                         float* __restrict__ stats, DdpgWs* ws) {
+                                                         float* __restrict__ stats, DdpgWs* ws,
+                                                         const float* __restrict__ q_next2, long long ldq2) {
     __shared__ double sh[32];
     const int tid = threadIdx.x, b = blockIdx.x * DT + tid;
     double r = 0.0, an = 0.0, amax = 0.0, yy = 0.0;
     if (b < B) {
         const float rb = rewards[b];
         const float t = __fmul_rn(__fmul_rn(discount, q_next[(long long)b * ldq]), __fsub_rn(1.0f, dones[b]));
-        const float yb = __fadd_rn(rb, t);
+        float yb = __fadd_rn(rb, t);
+        if (q_next2 != nullptr) {                            // TD3 double critic: y = min(y, y2) (ddpg.py:280-283)
+            const float t2 = __fmul_rn(__fmul_rn(discount, q_next2[(long long)b * ldq2]), __fsub_rn(1.0f, dones[b]));
+            yb = fminf(yb, __fadd_rn(rb, t2));
+        }
         y[b] = yb;
         yy = (double)yb;
         r = (double)rb;
@@ -146,6 +151,32 @@ __global__ void tanh_bwd_kernel(const float* __restrict__ dout, long long ldo, c
 
 inline int nb(int B) { return (B + DT - 1) / DT; }
 
+
+// TD3 target-policy smoothing (ddpg.py:267-278): out = clamp(pi + clip(N(0, policy_noise), -c, c), -1, 1).
+// unit_noise [B][A] holds injected N(0,1) draws (tests) or NULL for Philox keyed by (seed, *step_counter, row).
+__global__ void __launch_bounds__(256) ddpg_smooth_action_kernel(const float* __restrict__ pi, long long ldp,
+                                                                 const float* __restrict__ unit_noise, int B, int A,
+                                                                 float policy_noise, float noise_clip,
+                                                                 unsigned long long seed,
+                                                                 const unsigned long long* __restrict__ step_ctr,
+                                                                 float* __restrict__ out, long long ldo) {
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= (long long)B * A) return;
+    const int b = (int)(idx / A), j = (int)(idx - (long long)b * A);
+    float e;
+    if (unit_noise != nullptr) {
+        e = unit_noise[idx];
+    } else {
+        const unsigned long long ctr = (step_ctr != nullptr) ? *step_ctr : 0ull;
+        const Philox4 r = philox4x32_10(seed, ctr, ((unsigned long long)b << 16) | (unsigned long long)(j >> 2));
+        const float2 z01 = box_muller(r.x, r.y), z23 = box_muller(r.z, r.w);
+        const int c = j & 3;
+        e = (c == 0) ? z01.x : (c == 1) ? z01.y : (c == 2) ? z23.x : z23.y;
+    }
+    const float nz = fminf(fmaxf(__fmul_rn(e, policy_noise), -noise_clip), noise_clip);
+    out[(long long)b * ldo + j] = fminf(fmaxf(__fadd_rn(pi[(long long)b * ldp + j], nz), -1.0f), 1.0f);
+}
+
 }  // namespace
 
 extern "C" size_t sb200_ddpg_workspace_bytes(int B) { return sizeof(DdpgWs) + (size_t)nb(B) * 4 * sizeof(double); }
@@ -155,7 +186,28 @@ extern "C" int sb200_ddpg_target_f32(const float* rewards, const float* q_next, 
                                      float* stats, void* workspace, void* stream) {
     SB200_REQUIRE(rewards && q_next && dones && actions && y && stats && workspace && B >= 1 && A >= 1);
     ddpg_target_kernel<<<nb(B), DT, 0, (cudaStream_t)stream>>>(rewards, q_next, ldq, dones, actions, lda, B, A,
-                                                              (float)discount, y, stats, (DdpgWs*)workspace);
+                                                              (float)discount, y, stats, (DdpgWs*)workspace, nullptr, 0);
+    return sb200_launch_status();
+}
+
+extern "C" int sb200_ddpg_target2_f32(const float* rewards, const float* q_next, int64_t ldq, const float* q_next2,
+                                      int64_t ldq2, const float* dones, const float* actions, int64_t lda, int B, int A,
+                                      double discount, float* y, float* stats, void* workspace, void* stream) {
+    SB200_REQUIRE(rewards && q_next && q_next2 && dones && actions && y && stats && workspace && B >= 1 && A >= 1);
+    ddpg_target_kernel<<<nb(B), DT, 0, (cudaStream_t)stream>>>(rewards, q_next, ldq, dones, actions, lda, B, A,
+                                                              (float)discount, y, stats, (DdpgWs*)workspace, q_next2,
+                                                              ldq2);
+    return sb200_launch_status();
+}
+
+extern "C" int sb200_ddpg_smooth_action_f32(const float* pi, int64_t ldp, const float* unit_noise, int B, int A,
+                                            double policy_noise, double noise_clip, uint64_t seed,
+                                            const uint64_t* step_counter, float* out, int64_t ldo, void* stream) {
+    SB200_REQUIRE(pi && out && B >= 1 && A >= 1 && ldp >= A && ldo >= A);
+    const long long n = (long long)B * A;
+    ddpg_smooth_action_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        pi, ldp, unit_noise, B, A, (float)policy_noise, (float)noise_clip, (unsigned long long)seed,
+        (const unsigned long long*)step_counter, out, ldo);
     return sb200_launch_status();
 }
 

@@ -1,6 +1,8 @@
-"""DDPGLearner: drop-in for surreal/learner/ddpg.py:12-440 (low-dim observations, single critic) running on
-hand-written kernels: target nets -> Bellman target -> critic MSE step -> actor step THROUGH the updated
-critic -> target update.  Statistics names and the order of operations follow ddpg.py:244-352."""
+"""DDPGLearner: drop-in for surreal/learner/ddpg.py:12-440 (low-dim observations) running on hand-written kernels:
+target nets -> Bellman target -> critic MSE step -> actor step THROUGH the updated critic -> target update.
+Statistics names and the order of operations follow ddpg.py:244-352, including the TD3 options
+(``use_double_critic``: second critic + target, y = min(y, y2); ``use_action_regularization``: clipped noise on the
+target action -- added, as in the reference, only AFTER Q'_1 was evaluated, so it reaches critic 2 alone)."""
 import ctypes as C
 
 import numpy as np
@@ -36,8 +38,6 @@ class DDPGLearner(Learner):
         self.use_layernorm = lc.model.use_layernorm
         self.use_double_critic = lc.algo.network.use_double_critic
         self.use_action_regularization = lc.algo.network.use_action_regularization
-        if self.use_double_critic or self.use_action_regularization:
-            raise NotImplementedError('TD3 options (ddpg.py:267-283) are "beta" and off by default; not built')
         self._num_gpus = 1
         self._target_update_init()
         net = lc.algo.network
@@ -62,6 +62,15 @@ class DDPGLearner(Learner):
                                           clip_mode=2 if self.clip_actor_gradient else 0,
                                           clip_value=self.actor_gradient_clip_value,
                                           weight_decay=net.actor_regularization)
+        self.model2 = self.model_target2 = self.critic_optim2 = None
+        if self.use_double_critic:                                           # ddpg.py:118-143,157-162
+            self.model2 = DDPGModel(critic_only=True, **mk)
+            self.model_target2 = DDPGModel(critic_only=True, **mk)
+            self.critic_optim2 = ops.MlpTrainer(self.model2.critic, B, net.lr_critic,
+                                                clip_mode=2 if self.clip_critic_gradient else 0,
+                                                clip_value=self.critic_gradient_clip_value,
+                                                weight_decay=net.critic_regularization)
+            self.model_target2.critic.params.copy_(self.model2.critic.params)
         self.aggregator = SSARAggregator(self.env_config.obs_spec, self.env_config.action_spec)
         self.model_target.actor.params.copy_(self.model.actor.params)        # hard_update (ddpg.py:174-175)
         self.model_target.critic.params.copy_(self.model.critic.params)
@@ -74,6 +83,12 @@ class DDPGLearner(Learner):
         self._pi_t, self._q_t, self._y = f(B, A), f(B, 1), f(B)
         self._dA = f(B, ops._ru(A, 4))
         self._stats = f(16)
+        self._stats2 = f(16)                                   # critic 2's loss / Q (critic_loss is overwritten by it)
+        self._pi_t2, self._q_t2 = f(B, A), f(B, 1)
+        self.policy_noise, self.noise_clip = 0.2, 0.5           # hard-coded in the reference (ddpg.py:269-270)
+        self._noise_draws = None                                # tests: injected N(0,1) draws [B, A], see setter below
+        self._td3_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._td3_seed = 77
         self._ws = torch.zeros(_lib.lib().sb200_ddpg_workspace_bytes(B), dtype=torch.uint8, device=self.device)
         self._pin = {}
         self.check_action_range = True
@@ -108,6 +123,19 @@ class DDPGLearner(Learner):
     def replay_out_buffers(self):
         return self._own
 
+    @property
+    def policy_noise_draws(self):
+        return self._noise_draws
+
+    @policy_noise_draws.setter
+    def policy_noise_draws(self, draws):
+        """Inject the N(0,1) draws of the TD3 target-action noise (parity tests).  They live in ONE persistent buffer,
+        so a captured graph keeps reading the right address; must be set before the first learn() (a graph captured
+        with Philox noise keeps using Philox)."""
+        if self._noise_draws is None:
+            self._noise_draws = torch.zeros(self.batch_size, self.action_dim, dtype=torch.float32, device=self.device)
+        self._noise_draws.copy_(torch.as_tensor(draws, dtype=torch.float32).reshape(self.batch_size, self.action_dim))
+
     def _optimize_device(self):
         """ddpg.py:244-333 as one fixed launch sequence (CUDA-graph body; no host round trip inside)."""
         L = _lib.lib()
@@ -117,9 +145,24 @@ class DDPGLearner(Learner):
         obs, obs_next, actions, rewards, dones = b['obs'], b['obs_next'], b['actions'], b['rewards'], b['dones']
         ops.mlp_forward(mt.actor, obs_next, out=self._pi_t)                              # ddpg.py:266
         ops.mlp_forward(mt.critic, obs_next, aux=self._pi_t, out=self._q_t)
-        check(L.sb200_ddpg_target_f32(_ptr(rewards), _ptr(self._q_t), 1, _ptr(dones), _ptr(actions), A, B, A,
-                                      float(pow(self.discount_factor, self.n_step)), _ptr(self._y),
-                                      _ptr(self._stats), _ptr(self._ws), st), 'sb200_ddpg_target_f32')
+        pi2 = self._pi_t
+        if self.use_action_regularization:                                               # ddpg.py:267-278
+            check(L.sb200_ddpg_smooth_action_f32(_ptr(self._pi_t), A, _ptr(self._noise_draws), B, A,
+                                                 self.policy_noise, self.noise_clip, self._td3_seed,
+                                                 _ptr(self._td3_counter), _ptr(self._pi_t2), A, st),
+                  'sb200_ddpg_smooth_action_f32')
+            self._td3_counter += 1
+            pi2 = self._pi_t2
+        disc = float(pow(self.discount_factor, self.n_step))
+        if self.use_double_critic:                                                       # ddpg.py:280-283
+            ops.mlp_forward(self.model_target2.critic, obs_next, aux=pi2, out=self._q_t2)
+            check(L.sb200_ddpg_target2_f32(_ptr(rewards), _ptr(self._q_t), 1, _ptr(self._q_t2), 1, _ptr(dones),
+                                           _ptr(actions), A, B, A, disc, _ptr(self._y), _ptr(self._stats),
+                                           _ptr(self._ws), st), 'sb200_ddpg_target2_f32')
+        else:
+            check(L.sb200_ddpg_target_f32(_ptr(rewards), _ptr(self._q_t), 1, _ptr(dones), _ptr(actions), A, B, A,
+                                          disc, _ptr(self._y), _ptr(self._stats), _ptr(self._ws), st),
+                  'sb200_ddpg_target_f32')
         ct = self.critic_optim
         q = ct.forward(obs, aux=actions)                                                # Q(s_t, a_t)
         check(L.sb200_ddpg_critic_loss_f32(_ptr(q), q.stride(0), _ptr(self._y), B, _ptr(ct.d[-1]),
@@ -127,6 +170,14 @@ class DDPGLearner(Learner):
               'sb200_ddpg_critic_loss_f32')
         ct.backward()
         ct.step()
+        if self.use_double_critic:                                                       # ddpg.py:298-303,311-321
+            c2 = self.critic_optim2
+            q2 = c2.forward(obs, aux=actions)
+            check(L.sb200_ddpg_critic_loss_f32(_ptr(q2), q2.stride(0), _ptr(self._y), B, _ptr(c2.d[-1]),
+                                               c2.d[-1].stride(0), _ptr(self._stats2), _ptr(self._ws), st),
+                  'sb200_ddpg_critic_loss_f32')
+            c2.backward()
+            c2.step()
         at = self.actor_optim
         a_pi = at.forward(obs)
         q_pi = ct.forward(obs, aux=at.h[-1])                  # through the UPDATED critic (ddpg.py:324-327)
@@ -139,7 +190,10 @@ class DDPGLearner(Learner):
         at.backward()
         at.step()
         if self.target_update_type == 'soft':                                           # ddpg.py:410-418
-            for t, s_ in ((mt.actor, m.actor), (mt.critic, m.critic)):
+            pairs = [(mt.actor, m.actor), (mt.critic, m.critic)]
+            if self.use_double_critic:
+                pairs.append((self.model_target2.critic, self.model2.critic))
+            for t, s_ in pairs:
                 check(L.sb200_soft_update_f32(_ptr(t.params), _ptr(s_.params), t.size, float(self.target_update_tau),
                                               st), 'sb200_soft_update_f32')
 
@@ -151,6 +205,7 @@ class DDPGLearner(Learner):
                 self._optimize_device()
         s = self._stats.cpu().numpy()
         self.last_d2h_bytes = s.nbytes
+        s2 = self._stats2.cpu().numpy() if self.use_double_critic else None
         if self.check_action_range and s[DS['ABSMAX']] > 1.0:
             raise AssertionError('actions outside [-1, 1] (ddpg.py:261-262)')
         stats = {'actor_loss': float(s[DS['ACTOR_LOSS']]), 'critic_loss': float(s[DS['CRITIC_LOSS']]),
@@ -159,11 +214,16 @@ class DDPGLearner(Learner):
                  'performance/forward_time': self.forward_time.avg,
                  'performance/critic_update_time': self.critic_update_time.avg,
                  'performance/actor_update_time': self.actor_update_time.avg}
+        if s2 is not None:                                       # ddpg.py:316,345-346: critic_loss is critic 2's
+            stats['critic_loss'] = float(s2[DS['CRITIC_LOSS']])
+            stats['Q_policy2'] = float(s2[DS['Q_POLICY']])
         if self.target_update_type == 'hard':                     # host-side counter (ddpg.py:419-428)
             self.target_update_counter += 1
             if self.target_update_counter % self.target_update_interval == 0:
                 self.model_target.actor.params.copy_(self.model.actor.params)
                 self.model_target.critic.params.copy_(self.model.critic.params)
+                if self.use_double_critic:
+                    self.model_target2.critic.params.copy_(self.model2.critic.params)
         return stats
 
     def learn(self, batch):
@@ -181,7 +241,10 @@ class DDPGLearner(Learner):
         return {'ddpg': self.model}
 
     def checkpoint_attributes(self):
-        return ['current_iteration', 'model', 'model_target']
+        attrs = ['current_iteration', 'model', 'model_target']
+        if self.use_double_critic:
+            attrs += ['model2', 'model_target2']
+        return attrs
 
     def _target_update_init(self):
         cfg = self.learner_config.algo.network.target_update
@@ -199,7 +262,10 @@ class DDPGLearner(Learner):
         m, mt = self.model, self.model_target
         if self.target_update_type == 'soft':
             L, st = _lib.lib(), ops._stream()
-            for t, s in ((mt.actor, m.actor), (mt.critic, m.critic)):
+            pairs = [(mt.actor, m.actor), (mt.critic, m.critic)]
+            if self.use_double_critic:
+                pairs.append((self.model_target2.critic, self.model2.critic))
+            for t, s in pairs:
                 check(L.sb200_soft_update_f32(_ptr(t.params), _ptr(s.params), t.size, float(self.target_update_tau), st),
                       'sb200_soft_update_f32')
         else:
@@ -207,6 +273,8 @@ class DDPGLearner(Learner):
             if self.target_update_counter % self.target_update_interval == 0:
                 mt.actor.params.copy_(m.actor.params)
                 mt.critic.params.copy_(m.critic.params)
+                if self.use_double_critic:
+                    self.model_target2.critic.params.copy_(self.model2.critic.params)
 
     def _prefetcher_preprocess(self, batch):
         if isinstance(batch, dict):

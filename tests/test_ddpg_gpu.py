@@ -34,6 +34,42 @@ def test_ddpg_optimize_matches_reference(golden, tag):
                 assert d <= 2e-5, '%s %s it%d drift %.3e' % (name, k, it, d)      # lr_critic = 1e-3: 2% of one step
 
 
+@pytest.mark.parametrize('tag', ['td3_double', 'td3_double_reg'])
+def test_ddpg_td3_options_match_reference(golden, tag):
+    """use_double_critic / use_action_regularization (ddpg.py:267-283,298-321) against goldens produced by the
+    reference: y = min over two target critics, the smoothing noise reaches only critic 2, critic_loss reports
+    critic 2's loss, both critics and target2 follow the reference's parameters."""
+    from surreal_b200.learner import DDPGLearner
+    g = golden('ddpg_optimize_' + tag)
+    cfg, stats = g.js('cfg'), g.js('stats')
+    lc, ec, sc = ddpg_configs(D=cfg['D'], A=cfg['A'], actor_h=cfg['actor_h'], critic_h=cfg['critic_h'], B=cfg['B'],
+                              n_step=cfg['n_step'], target=cfg['target'], clip_critic=cfg['clip_critic'],
+                              lr_actor=cfg['lr_actor'], lr_critic=cfg['lr_critic'])
+    lc.algo.network.use_double_critic = True
+    lc.algo.network.use_action_regularization = bool(cfg['action_regularization'])
+    L = DDPGLearner(lc, ec, sc)
+    L.model.load_state_dict(ref_state_dict(g.sub('init/model/')))
+    L.model_target.load_state_dict(ref_state_dict(g.sub('init/target/')))
+    L.model2.load_state_dict(ref_state_dict(g.sub('init/model2/')))
+    L.model_target2.load_state_dict(ref_state_dict(g.sub('init/target2/')))
+    for it in range(3):
+        b = g.sub('it%d/' % it)
+        if cfg['action_regularization']:                       # N(0, 0.2) draws of the fixture -> unit draws
+            L.policy_noise_draws = torch.tensor(b['policy_noise_unclipped'] / 0.2, dtype=torch.float32, device='cuda')
+        st = L.learn({'obs': {'low_dim': {'flat_inputs': b['obs']}}, 'obs_next': {'low_dim': {'flat_inputs': b['obs_next']}},
+                      'actions': b['actions'], 'rewards': b['rewards'], 'dones': b['dones']})
+        torch.cuda.synchronize()
+        for k, v in stats[it].items():
+            assert abs(st[k] - v) <= 1e-5 * max(1.0, abs(v)), '%s it%d: got %.9g expected %.9g' % (k, it, st[k], v)
+        for name, model in (('model', L.model), ('model2', L.model2), ('target', L.model_target),
+                            ('target2', L.model_target2)):
+            exp = ref_state_dict(g.sub('it%d/%s/' % (it, name)))
+            got = model.state_dict()
+            for k, e in exp.items():
+                d = float((got[k].cpu().reshape(e.shape) - e).abs().max())
+                assert d <= 2e-5, '%s %s it%d drift %.3e' % (name, k, it, d)
+
+
 def test_ddpg_agent_act_matches_reference(golden):
     from surreal_b200.agent import DDPGAgent
     g = golden('ddpg_act')
