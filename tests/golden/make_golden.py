@@ -15,12 +15,18 @@ every number stored here is produced by the reference's own functions:
   rfilter.npz           surreal/model/reward_filter.py:34-57
   gae_*.npz             surreal/learner/ppo.py:355-418   PPOLearner._gae_and_return (MLP + RNN mode)
   ppo_learn_*.npz       surreal/learner/ppo.py:420-666   PPOLearner.learn / publish_parameter / _post_publish
+  ppo_learn_rnn_*.npz   the same in RNN mode (LSTM stem, horizon GAE: ppo.py:389-406,507-525, ppo_net.py:143-152)
+  ppo_learn_pixel_*.npz the same in pixel mode (shared CNN stem: ppo_net.py:136-140,268-273, builders.py:8-33)
   ddpg_optimize_*.npz   surreal/learner/ddpg.py:186-428  DDPGLearner.preprocess/_optimize/_target_update
+  ddpg_optimize_td3_*   the same with use_double_critic / use_action_regularization (ddpg.py:267-283,298-321)
   replay.npz            surreal/replay/{fifo,uniform}_replay.py  insert / sample / start_sample_condition
   window_*.npz          surreal/env/exp_sender_wrapper.py:72-112,153-264
   aggregate.npz         surreal/learner/aggregator.py:33-103,106-262
   ppo_act.npz           surreal/agent/ppo_agent.py:106-154
+  ppo_act_rnn.npz       surreal/agent/ppo_agent.py:84-93,133-137,169-183  (LSTM cells hand-off, reset)
   ddpg_act.npz          surreal/agent/ddpg_agent.py:155-184 + action_noise.py:9-39
+  ddpg_act_ou.npz       the same with OrnsteinUhlenbeckActionNoise (action_noise.py:22-39) and pre_episode reset
+  checkpoint.npz        surreal/utils/checkpoint.py:18-347  files written by PeriodicCheckpoint
   configs.npz           the default config trees of main/{ppo,ddpg}_configs.py + session/default_configs.py
 
 All inputs are seeded here and stored next to the outputs, so the fixtures are self-contained.
@@ -862,7 +868,7 @@ def gen_configs():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['pd', 'filters', 'gae', 'ppo_learn', 'ddpg', 'replay', 'window', 'aggregate', 'act',
-                             'configs']
+    which = sys.argv[1:] or ['pd', 'filters', 'gae', 'ppo_learn', 'ppo_learn_rnn', 'ppo_learn_pixel', 'ddpg', 'ddpg_td3',
+                             'replay', 'window', 'aggregate', 'act', 'act_rnn', 'act_ou', 'checkpoint', 'configs']
     for w in which:
         globals()['gen_' + w]()
