@@ -17,6 +17,7 @@
 // same noise; the policy forward is fp32 FFMA (the per-step path uses 3xTF32 tensor-core products; both are
 // fp32-accurate, they differ by rounding order only).
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "rollout_dev.cuh"
@@ -99,7 +100,7 @@ __device__ __forceinline__ void rf_st_cluster_v4(unsigned addr, const float4& v)
 //   tiles are summed in a fixed order (deterministic) through `Part` [4][32][Nc].
 //   ALL_ROWS: the result is stored in every CTA's copy of Hout [32][ldout] (input of the next hidden layer);
 //   otherwise each row goes only to the CTA that owns the actor, into its Hout [8][ldout] (input of the head).
-template <bool ALL_ROWS>
+template <bool ALL_ROWS, bool F2>
 __device__ __forceinline__ void rf_layer(const float* __restrict__ Xin, int ldin, int K, const float* __restrict__ Ws,
                                          int Nc, const float* __restrict__ bias_s, int act, float* __restrict__ Hout,
                                          int ldout, int col0, float* __restrict__ Part, unsigned smem_base,
@@ -110,13 +111,49 @@ __device__ __forceinline__ void rf_layer(const float* __restrict__ Xin, int ldin
     const int k_lo = q * kq, k_hi = min(K, k_lo + kq);
     const int nq = Nc >> 2;
     for (int c4 = tx; c4 < nq; c4 += 16) {
+        const float* xr = Xin + (ty * 4) * ldin;
+        const float* wp = Ws + c4 * 4;
+        if constexpr (F2) {
+            // packed fma.rn.f32x2 (sm_100): two columns per instruction; each half is an IEEE fma, so the result is
+            // bit-identical to the scalar path -- it only halves the FFMA issue slots
+            float2 acc[4][2];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r][0] = acc[r][1] = make_float2(0.0f, 0.0f);
+#pragma unroll 2
+            for (int k = k_lo; k < k_hi; k += 4) {
+                float4 a[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) a[r] = *reinterpret_cast<const float4*>(xr + r * ldin + k);
+                const float4 w0 = *reinterpret_cast<const float4*>(wp + (k + 0) * Nc);
+                const float4 w1 = *reinterpret_cast<const float4*>(wp + (k + 1) * Nc);
+                const float4 w2 = *reinterpret_cast<const float4*>(wp + (k + 2) * Nc);
+                const float4 w3 = *reinterpret_cast<const float4*>(wp + (k + 3) * Nc);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    float2 aa = make_float2(a[r].x, a[r].x);
+                    acc[r][0] = __ffma2_rn(aa, make_float2(w0.x, w0.y), acc[r][0]);
+                    acc[r][1] = __ffma2_rn(aa, make_float2(w0.z, w0.w), acc[r][1]);
+                    aa = make_float2(a[r].y, a[r].y);
+                    acc[r][0] = __ffma2_rn(aa, make_float2(w1.x, w1.y), acc[r][0]);
+                    acc[r][1] = __ffma2_rn(aa, make_float2(w1.z, w1.w), acc[r][1]);
+                    aa = make_float2(a[r].z, a[r].z);
+                    acc[r][0] = __ffma2_rn(aa, make_float2(w2.x, w2.y), acc[r][0]);
+                    acc[r][1] = __ffma2_rn(aa, make_float2(w2.z, w2.w), acc[r][1]);
+                    aa = make_float2(a[r].w, a[r].w);
+                    acc[r][0] = __ffma2_rn(aa, make_float2(w3.x, w3.y), acc[r][0]);
+                    acc[r][1] = __ffma2_rn(aa, make_float2(w3.z, w3.w), acc[r][1]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                *reinterpret_cast<float4*>(Part + ((q * RF_ROWS + ty * 4 + r) * Nc + c4 * 4)) =
+                    make_float4(acc[r][0].x, acc[r][0].y, acc[r][1].x, acc[r][1].y);
+        } else {
         float acc[4][4];
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
-        const float* xr = Xin + (ty * 4) * ldin;
-        const float* wp = Ws + c4 * 4;
 #pragma unroll 2
         for (int k = k_lo; k < k_hi; k += 4) {
             float4 a[4];
@@ -142,6 +179,7 @@ __device__ __forceinline__ void rf_layer(const float* __restrict__ Xin, int ldin
         for (int r = 0; r < 4; ++r)
             *reinterpret_cast<float4*>(Part + ((q * RF_ROWS + ty * 4 + r) * Nc + c4 * 4)) =
                 make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+        }
     }
     __syncthreads();
     for (int idx = tid; idx < RF_ROWS * nq; idx += RF_THREADS) {
@@ -172,6 +210,7 @@ __device__ __forceinline__ void rf_layer(const float* __restrict__ Xin, int ldin
     }
 }
 
+template <bool F2>
 __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
     ppo_rollout_kernel(const __grid_constant__ RfParams p) {
     cg::cluster_group cluster = cg::this_cluster();
@@ -270,9 +309,9 @@ __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
     for (int t = 0; t < p.T; ++t) {
         const unsigned long long ctr = ctr0 + (unsigned long long)t;
         const bool final_step = (t == p.T - 1);
-        rf_layer<true>(X0, p.ldx0, D, W1s, Nc1, B1s, p.act[0], Hb1, p.ldh1, (int)crank * Nc1, Part, smem_base, crank);
+        rf_layer<true, F2>(X0, p.ldx0, D, W1s, Nc1, B1s, p.act[0], Hb1, p.ldh1, (int)crank * Nc1, Part, smem_base, crank);
         cluster.sync();
-        rf_layer<false>(Hb1, p.ldh1, H1, W2s, Nc2, B2s, p.act[1], Hb2, p.ldh2, (int)crank * Nc2, Part, smem_base, crank);
+        rf_layer<false, F2>(Hb1, p.ldh1, H1, W2s, Nc2, B2s, p.act[1], Hb2, p.ldh2, (int)crank * Nc2, Part, smem_base, crank);
         cluster.sync();
 
         float rew = 0.0f, dn = 0.0f;
@@ -551,7 +590,8 @@ bool rf_plan(const sb200_mlp* net, int D, int A, RfParams* p, size_t* smem_bytes
 }  // namespace
 
 int sb200_rollout_fused_init() {
-    SB200_CUDA(cudaFuncSetAttribute(ppo_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    SB200_CUDA(cudaFuncSetAttribute(ppo_rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    SB200_CUDA(cudaFuncSetAttribute(ppo_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     return SB200_OK;
 }
 
@@ -618,7 +658,10 @@ extern "C" int sb200_ppo_rollout_f32(const sb200_ppo_rollout* a, void* stream) {
     p.T = a->T;
     p.step_ctr = (const unsigned long long*)a->step_counter;
     const long long clusters = ((long long)a->N + RF_ROWS - 1) / RF_ROWS;
-    ppo_rollout_kernel<<<(unsigned)(clusters * RF_CS), RF_THREADS, smem, (cudaStream_t)stream>>>(p);
+    // SB200_RF_FFMA2=1: packed fma.rn.f32x2 in the hidden layers (bit-identical results, fewer issue slots)
+    static const int f2 = [] { const char* e = getenv("SB200_RF_FFMA2"); return e ? atoi(e) : 0; }();
+    if (f2) ppo_rollout_kernel<true><<<(unsigned)(clusters * RF_CS), RF_THREADS, smem, (cudaStream_t)stream>>>(p);
+    else ppo_rollout_kernel<false><<<(unsigned)(clusters * RF_CS), RF_THREADS, smem, (cudaStream_t)stream>>>(p);
     return sb200_launch_status();
 }
 
