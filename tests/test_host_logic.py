@@ -175,3 +175,49 @@ def test_checkpoint_reads_and_extends_reference_written_folder(tmp_path, golden)
     assert set(meta['ckpt']['learner.7.ckpt'].keys()) == set(ref_meta['ckpt']['learner.6.ckpt'].keys())
     data = pickle.load(open(tmp_path / 'learner.7.ckpt', 'rb'))
     assert list(data.keys()) == ['model', 'optim', 'current_iteration'] and set(data['optim'].keys()) == {'state', 'param_groups'}
+
+
+def test_parameter_wire_semantics_on_cpu_tensors():
+    """The collapsed parameter wire (surreal/distributed/parameter_server.py:20-303): a fetch with the version the
+    client already holds returns nothing (the hash-cached REQ), a publish bumps the version and snapshots the weights
+    -- later learner updates do NOT leak to actors before the next publish (lagged actors) -- and the snapshot keeps
+    its buffers across publishes (stable addresses for graph replays)."""
+    import torch
+    from surreal_b200.distributed import ModuleDict, ParameterPublisher, ParameterClient, LocalHub
+
+    class FlatModel:
+        def __init__(self):
+            self.w = torch.zeros(5)
+
+        def flat_state(self):
+            return {'w': self.w}
+
+        def load_flat_state(self, st):
+            self.w.copy_(st['w'])
+
+    learner_m, actor_m = FlatModel(), FlatModel()
+    pub = ParameterPublisher({'ppo': learner_m})
+    cli = ParameterClient(pub)
+    assert cli.fetch_parameter_with_info() == (None, None)          # nothing published yet
+    learner_m.w += 1.0
+    pub.publish(3, message='batch 3')
+    state, info = cli.fetch_parameter_with_info()
+    assert info['iteration'] == 3 and info['message'] == 'batch 3' and info['hash'] == pub.version == 1
+    ModuleDict({'ppo': actor_m}).load(state)
+    assert torch.equal(actor_m.w, torch.ones(5))
+    snap_ptr = state['ppo']['__flat__']['w'].data_ptr()
+    assert cli.fetch_parameter_with_info()[0] is None               # same version: cached
+    learner_m.w += 1.0                                              # learner moves on; actors must not see it yet
+    assert torch.equal(pub.fetch(None)[0]['ppo']['__flat__']['w'], torch.ones(5))
+    pub.publish(4)
+    state, info = cli.fetch_parameter_with_info()
+    assert info['hash'] == 2 and torch.equal(state['ppo']['__flat__']['w'], torch.full((5,), 2.0))
+    assert state['ppo']['__flat__']['w'].data_ptr() == snap_ptr      # persistent snapshot buffer
+    with pytest.raises(AssertionError):
+        ModuleDict({1: actor_m})
+    LocalHub.reset()
+
+    from surreal_b200.session import Config
+    a, b = LocalHub.get(Config({'folder': '/tmp/x'})), LocalHub.get(Config({'folder': '/tmp/x'}))
+    assert a is b and LocalHub.get(Config({'folder': '/tmp/y'})) is not a
+    LocalHub.reset()
