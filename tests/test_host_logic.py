@@ -221,3 +221,29 @@ def test_parameter_wire_semantics_on_cpu_tensors():
     a, b = LocalHub.get(Config({'folder': '/tmp/x'})), LocalHub.get(Config({'folder': '/tmp/x'}))
     assert a is b and LocalHub.get(Config({'folder': '/tmp/y'})) is not a
     LocalHub.reset()
+
+
+def test_lr_scheduler_linear_with_floor():
+    """algo.network.anneal (ppo.py:121-125,171-178): linear decay refreshed every update_freq steps, floored at min_lr;
+    the value lands in the optimiser's lr slot.  (torchx's exact formula is unpinned -- the source is absent.)"""
+    from surreal_b200.learner.scheduler import make_lr_scheduler
+
+    class Opt:
+        lr = None
+
+        def set_lr(self, v):
+            self.lr = v
+    o = Opt()
+    s = make_lr_scheduler('LinearWithMinLR', o, 1e-3, num_updates=10, update_freq=2, min_lr=2e-4)
+    seen = []
+    for _ in range(12):
+        s.step()
+        seen.append(s.get_lr()[0])
+    assert seen[0] == 1e-3 and seen[1] == pytest.approx(8e-4) and seen[2] == seen[1]          # refreshed every 2nd step
+    assert seen[7] == pytest.approx(2e-4) and seen[-1] == 2e-4 and o.lr == 2e-4                # floor
+    assert all(a >= b for a, b in zip(seen, seen[1:]))
+    s2 = make_lr_scheduler('LinearWithMinLR', Opt(), 1e-3, 10, 2, 2e-4)
+    s2.load_state_dict(s.state_dict())
+    assert s2.get_lr() == s.get_lr() and s2.n_step == 12
+    with pytest.raises(ValueError):
+        make_lr_scheduler('Cosine', o, 1e-3, 10, 1, 0.0)
