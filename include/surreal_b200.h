@@ -177,6 +177,7 @@ int sb200_reward_filter_f32(const float* rewards, int64_t n, double reward_scale
 #define SB200_STAT_IS_WEIGHT 12      /* _avg_is_weight */
 #define SB200_STAT_REF_BEHAVE_KL 13  /* _ref_behave_diff */
 #define SB200_STAT_EPOCHS 14         /* number of policy epochs executed this learn() */
+#define SB200_STAT_VAL_MOMENTS 16    /* 8 slots: mean(ret-v), mean((ret-v)^2), mean(ret), mean(ret^2) as (hi, lo) float pairs */
 #define SB200_STAT_COUNT 32
 
 size_t sb200_ppo_loss_workspace_bytes(int B, int A);   /* zero-initialise once */
@@ -222,8 +223,8 @@ int sb200_clip_adam_f32(float* params, const float* grad, float* exp_avg, float*
                         const double* lr, double beta1, double beta2, double eps, double weight_decay,
                         int clip_mode, double clip_value, void* workspace, float* norm_out,
                         const int* stop_flag, void* stream);
-/* target = target*(1-tau) + tau*src (soft target update, ddpg.py:410-418). */
-int sb200_soft_update_f32(float* target, const float* src, int64_t n, double tau, void* stream);
+/* target = target*(1-tau) + tau*src (soft target update, ddpg.py:410-418); a no-op when *stop_flag != 0. */
+int sb200_soft_update_f32(float* target, const float* src, int64_t n, double tau, const int* stop_flag, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * DDPG element-wise pieces (surreal/learner/ddpg.py:261-262,279,305,324-331,335-341); the networks run through
@@ -235,6 +236,10 @@ int sb200_soft_update_f32(float* target, const float* src, int64_t n, double tau
 #define SB200_DSTAT_Q_TARGET 4
 #define SB200_DSTAT_Q_POLICY 5
 #define SB200_DSTAT_ACTION_ABSMAX 6   /* for the deferred `assert |a| <= 1` of ddpg.py:261-262 */
+/* byte offset inside the DDPG workspace of the int32 "bad action" flag: sb200_ddpg_target*_f32 set it to 1 when
+ * max|a| > 1 (the reference asserts this BEFORE any update, ddpg.py:261-262); pass its address as stop_flag to the
+ * optimiser / soft-update calls of the same learn() so an out-of-range batch leaves every parameter untouched. */
+size_t sb200_ddpg_bad_action_offset(void);
 size_t sb200_ddpg_workspace_bytes(int B);
 /* y = rewards + discount * q_next * (1 - dones), discount = gamma ** n_step. */
 int sb200_ddpg_target_f32(const float* rewards, const float* q_next, int64_t ldq, const float* dones,

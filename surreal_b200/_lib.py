@@ -126,7 +126,8 @@ def _declare(lib):
         'sb200_optim_workspace_bytes': (S, []),
         'sb200_grad_reduce_norm_f32': (I, [P, L, I, P, L, D, I, P, P, P]),
         'sb200_clip_adam_f32': (I, [P, P, P, P, L, P, D, D, D, D, I, D, P, P, P, P]),
-        'sb200_soft_update_f32': (I, [P, P, L, D, P]),
+        'sb200_soft_update_f32': (I, [P, P, L, D, P, P]),
+        'sb200_ddpg_bad_action_offset': (S, []),
         'sb200_gae_window_f32': (I, [P, P, P, I, I, I, D, D, D, I, P, P, P, P]),
     }
     sig.update(_EXTRA_SIGS)

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libsurreal_b200.so')
-STAMP = os.path.join(HERE, 'csrc', '.build_stamp')
+STAMP = LIB + '.stamp'      # source digest the .so was built from: git-ignored, travels with the .so to the GPU box
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
          '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-Xptxas', '-v']

@@ -2,6 +2,7 @@
 // Bellman target, the actor-loss seed gradient and tanh backward.
 // Replaces surreal/learner/ddpg.py:261-262,279,324-331,335-341 (and torch autograd through them).
 #include "common.cuh"
+#include <stddef.h>
 
 namespace {
 
@@ -9,7 +10,7 @@ constexpr int DT = 256;
 
 struct DdpgWs {
     unsigned int counter;
-    unsigned int pad;
+    int bad_action;          // 1 when max|a| > 1 (ddpg.py:261-262): optimiser / target kernels of this learn() no-op
     double partial[1];       // [blocks][4]
 };
 
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(DT) ddpg_target_kernel(const float* __restrict
             stats[SB200_DSTAT_ACTION_NORM] = (float)(s1 / B);
             stats[SB200_DSTAT_Q_TARGET] = (float)(s2 / B);
             stats[SB200_DSTAT_ACTION_ABSMAX] = (float)mx;
+            ws->bad_action = (mx > 1.0) ? 1 : 0;
         }
     }
 }
@@ -178,6 +180,8 @@ __global__ void __launch_bounds__(256) ddpg_smooth_action_kernel(const float* __
 }
 
 }  // namespace
+
+extern "C" size_t sb200_ddpg_bad_action_offset(void) { return offsetof(DdpgWs, bad_action); }
 
 extern "C" size_t sb200_ddpg_workspace_bytes(int B) { return sizeof(DdpgWs) + (size_t)nb(B) * 4 * sizeof(double); }
 

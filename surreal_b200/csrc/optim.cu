@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(OT) clip_adam_kernel(float* __restrict__ p, co
 }
 
 __global__ void __launch_bounds__(OT) soft_update_kernel(float* __restrict__ target, const float* __restrict__ src,
-                                                         long long n, float tau) {
+                                                         long long n, float tau, const int* __restrict__ stop) {
+    if (stop != nullptr && *stop) return;
     const float keep = 1.0f - tau;
     for (long long i = (long long)blockIdx.x * OT + threadIdx.x; i < n; i += (long long)gridDim.x * OT)
         target[i] = __fadd_rn(__fmul_rn(target[i], keep), __fmul_rn(tau, src[i]));
@@ -124,8 +125,9 @@ extern "C" int sb200_clip_adam_f32(float* params, const float* grad, float* exp_
     return sb200_launch_status();
 }
 
-extern "C" int sb200_soft_update_f32(float* target, const float* src, int64_t n, double tau, void* stream) {
+extern "C" int sb200_soft_update_f32(float* target, const float* src, int64_t n, double tau, const int* stop_flag,
+                                     void* stream) {
     SB200_REQUIRE(target && src && n >= 1);
-    soft_update_kernel<<<grid_for(n), OT, 0, (cudaStream_t)stream>>>(target, src, n, (float)tau);
+    soft_update_kernel<<<grid_for(n), OT, 0, (cudaStream_t)stream>>>(target, src, n, (float)tau, stop_flag);
     return sb200_launch_status();
 }

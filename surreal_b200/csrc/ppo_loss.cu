@@ -242,6 +242,14 @@ __global__ void __launch_bounds__(LT) value_loss_kernel(const float* __restrict_
             stats[SB200_STAT_VAL_LOSS] = (float)(s[1] / n);
             stats[SB200_STAT_EXPLAINED_VAR] = (float)(1.0 - var_d / var_r);
             stats[SB200_STAT_RETURN_MEAN] = (float)(s[2] / n);
+            // raw moments as (hi, lo) float pairs: a data-parallel learner averages them over ranks and recomputes the
+            // explained variance of the GLOBAL batch (a mean of per-rank ratios is not the ratio of the global moments)
+            for (int q = 0; q < 4; ++q) {
+                const double m = s[q] / n;
+                const float hi = (float)m;
+                stats[SB200_STAT_VAL_MOMENTS + 2 * q] = hi;
+                stats[SB200_STAT_VAL_MOMENTS + 2 * q + 1] = (float)(m - (double)hi);
+            }
         }
     }
 }

@@ -76,8 +76,6 @@ class DDPGLearner(Learner):
         self.model_target.critic.params.copy_(self.model.critic.params)
         self.total_learn_time = U.TimeRecorder()
         self.forward_time = U.TimeRecorder()
-        self.critic_update_time = U.TimeRecorder()
-        self.actor_update_time = U.TimeRecorder()
         f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.device)  # noqa: E731
         self._own = dict(obs=f(B, D), obs_next=f(B, D), actions=f(B, A), rewards=f(B, 1), dones=f(B, 1))
         self._pi_t, self._q_t, self._y = f(B, A), f(B, 1), f(B)
@@ -90,6 +88,10 @@ class DDPGLearner(Learner):
         self._td3_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._td3_seed = 77
         self._ws = torch.zeros(_lib.lib().sb200_ddpg_workspace_bytes(B), dtype=torch.uint8, device=self.device)
+        # device flag raised by the target kernel when max|a| > 1: every optimiser / soft-update kernel of that learn()
+        # then no-ops, so the AssertionError below leaves the learner exactly as the reference's pre-update assert does
+        off = int(_lib.lib().sb200_ddpg_bad_action_offset())
+        self._bad = self._ws[off:off + 4].view(torch.int32)
         self._pin = {}
         self.check_action_range = True
         self.use_cuda_graph = ops.graphs_enabled()
@@ -169,7 +171,7 @@ class DDPGLearner(Learner):
                                            ct.d[-1].stride(0), _ptr(self._stats), _ptr(self._ws), st),
               'sb200_ddpg_critic_loss_f32')
         ct.backward()
-        ct.step()
+        ct.step(stop_flag=self._bad)
         if self.use_double_critic:                                                       # ddpg.py:298-303,311-321
             c2 = self.critic_optim2
             q2 = c2.forward(obs, aux=actions)
@@ -177,7 +179,7 @@ class DDPGLearner(Learner):
                                                c2.d[-1].stride(0), _ptr(self._stats2), _ptr(self._ws), st),
                   'sb200_ddpg_critic_loss_f32')
             c2.backward()
-            c2.step()
+            c2.step(stop_flag=self._bad)
         at = self.actor_optim
         a_pi = at.forward(obs)
         q_pi = ct.forward(obs, aux=at.h[-1])                  # through the UPDATED critic (ddpg.py:324-327)
@@ -188,14 +190,14 @@ class DDPGLearner(Learner):
         check(L.sb200_tanh_bwd_f32(_ptr(self._dA), self._dA.stride(0), _ptr(a_pi), a_pi.stride(0), B, A,
                                    _ptr(at.d[-1]), at.d[-1].stride(0), st), 'sb200_tanh_bwd_f32')
         at.backward()
-        at.step()
+        at.step(stop_flag=self._bad)
         if self.target_update_type == 'soft':                                           # ddpg.py:410-418
             pairs = [(mt.actor, m.actor), (mt.critic, m.critic)]
             if self.use_double_critic:
                 pairs.append((self.model_target2.critic, self.model2.critic))
             for t, s_ in pairs:
                 check(L.sb200_soft_update_f32(_ptr(t.params), _ptr(s_.params), t.size, float(self.target_update_tau),
-                                              st), 'sb200_soft_update_f32')
+                                              _ptr(self._bad), st), 'sb200_soft_update_f32')
 
     def _optimize(self):
         with self.forward_time.time():
@@ -211,9 +213,9 @@ class DDPGLearner(Learner):
         stats = {'actor_loss': float(s[DS['ACTOR_LOSS']]), 'critic_loss': float(s[DS['CRITIC_LOSS']]),
                  'action_norm': float(s[DS['ACTION_NORM']]), 'rewards': float(s[DS['REWARDS']]),
                  'Q_target': float(s[DS['Q_TARGET']]), 'Q_policy': float(s[DS['Q_POLICY']]),
-                 'performance/forward_time': self.forward_time.avg,
-                 'performance/critic_update_time': self.critic_update_time.avg,
-                 'performance/actor_update_time': self.actor_update_time.avg}
+                 'performance/forward_time': self.forward_time.avg}
+        # (the reference's critic_update_time / actor_update_time split does not exist here: the whole update is one
+        #  CUDA graph; performance/forward_time covers it)
         if s2 is not None:                                       # ddpg.py:316,345-346: critic_loss is critic 2's
             stats['critic_loss'] = float(s2[DS['CRITIC_LOSS']])
             stats['Q_policy2'] = float(s2[DS['Q_POLICY']])
@@ -266,7 +268,7 @@ class DDPGLearner(Learner):
             if self.use_double_critic:
                 pairs.append((self.model_target2.critic, self.model2.critic))
             for t, s in pairs:
-                check(L.sb200_soft_update_f32(_ptr(t.params), _ptr(s.params), t.size, float(self.target_update_tau), st),
+                check(L.sb200_soft_update_f32(_ptr(t.params), _ptr(s.params), t.size, float(self.target_update_tau), None, st),
                       'sb200_soft_update_f32')
         else:
             self.target_update_counter += 1

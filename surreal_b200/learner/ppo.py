@@ -21,7 +21,7 @@ from .base import Learner
 from .scheduler import make_lr_scheduler
 
 S = dict(SURR=0, LOSS=1, ENTROPY=2, KL_PRE=3, KL_POST=4, GN_ACTOR=5, VAL_LOSS=6, EXPL_VAR=7, GN_CRITIC=8,
-         RET_MEAN=9, LOG_SIG=10, BEHAVE_LIK=11, IS_WEIGHT=12, REF_BEHAVE=13, EPOCHS=14, COUNT=32)
+         RET_MEAN=9, LOG_SIG=10, BEHAVE_LIK=11, IS_WEIGHT=12, REF_BEHAVE=13, EPOCHS=14, VAL_MOMENTS=16, COUNT=32)
 
 
 def _ptr(t):
@@ -178,10 +178,12 @@ class PPOLearner(Learner):
         dst.copy_(self._pin[name], non_blocking=True)
         return dst.numel() * 4
 
-    @staticmethod
-    def _low_dim(obs):
+    def _low_dim(self, obs):
         if isinstance(obs, dict):
-            xs = [obs['low_dim'][k] for k in obs['low_dim']]
+            # the reference concatenates in obs_spec order (ppo_net.py:168-178), not in the batch dict's order
+            keys = [k for k in self.obs_spec['low_dim'] if k in obs['low_dim']] if 'low_dim' in self.obs_spec \
+                else list(obs['low_dim'])
+            xs = [obs['low_dim'][k] for k in keys]
             if len(xs) == 1:
                 return xs[0]
             return torch.cat(xs, -1) if isinstance(xs[0], torch.Tensor) else np.concatenate(xs, -1)
@@ -487,6 +489,13 @@ class PPOLearner(Learner):
         stats['_pol_kl'] = float(s[S['KL_POST']])
         stats['_val_loss'] = float(s[S['VAL_LOSS']])
         stats['_val_explained_var'] = float(s[S['EXPL_VAR']])
+        if self.dp is not None:
+            # global-batch explained variance (ppo.py:323-331) from the rank-averaged raw moments
+            mo = s[S['VAL_MOMENTS']:S['VAL_MOMENTS'] + 8].astype(np.float64)
+            md, md2, mr, mr2 = (mo[0] + mo[1], mo[2] + mo[3], mo[4] + mo[5], mo[6] + mo[7])
+            ng = float(self.batch_size * self.dp.world)
+            var_d, var_r = (md2 - md * md) * ng / (ng - 1.0), (mr2 - mr * mr) * ng / (ng - 1.0)
+            stats['_val_explained_var'] = float(1.0 - var_d / var_r)
         if self.clip_critic_gradient:
             stats['grad_norm_critic'] = float(s[S['GN_CRITIC']])
         stats['_avg_return_targ'] = float(s[S['RET_MEAN']])

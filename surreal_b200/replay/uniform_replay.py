@@ -74,6 +74,7 @@ class UniformReplay(Replay):
         self._dirty = False
         self.stream = PyRandomStream()
         self._idx_pin = None
+        self._idx_event = None
         self._idx_dev = None
         self._pin = None
 
@@ -128,6 +129,8 @@ class UniformReplay(Replay):
         if self._idx_pin is None or self._idx_pin.numel() < batch_size:
             self._idx_pin = torch.empty(batch_size, dtype=torch.int64, pin_memory=True)
             self._idx_dev = torch.empty(batch_size, dtype=torch.int64, device=self.device)
+        if self._idx_event is not None:
+            self._idx_event.synchronize()                         # the previous batch's H2D copy has consumed the buffer
         out = self._idx_pin.numpy()[:batch_size]
         self.stream.randint_fill(n, batch_size, out)
         return out
@@ -138,6 +141,10 @@ class UniformReplay(Replay):
         self.sample_indices(batch_size)
         idx = self._idx_dev[:batch_size]
         idx.copy_(self._idx_pin[:batch_size], non_blocking=True)
+        if self._idx_event is None:
+            self._idx_event = torch.cuda.Event()
+        self._idx_event.record()                                  # refilling the pinned buffer waits for this copy
+        indices = self._idx_pin[:batch_size].clone()              # the caller's copy: later samples do not alias it
         if out is None:
             f = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)  # noqa: E731
             out = dict(obs=f(batch_size, D), obs_next=f(batch_size, D), actions=f(batch_size, A),
@@ -149,4 +156,4 @@ class UniformReplay(Replay):
                   'sb200_replay_gather_f32')
         return {'obs': {'low_dim': {'flat_inputs': out['obs']}}, 'obs_next': {'low_dim': {'flat_inputs': out['obs_next']}},
                 'actions': out['actions'], 'rewards': out['rewards'], 'dones': out['dones'],
-                'indices': self._idx_pin[:batch_size]}
+                'indices': indices}

@@ -145,3 +145,29 @@ def test_ddpg_engine_end_to_end():
     for k in ['actor_loss', 'critic_loss', 'Q_target', 'Q_policy', 'action_norm', 'rewards']:
         assert np.isfinite(st[k])
     assert float(replay.r_act.abs().max()) <= 1.0
+
+
+def test_ddpg_out_of_range_actions_leave_state_untouched():
+    """The reference asserts |a| <= 1 BEFORE any update (ddpg.py:261-262).  Here the whole update is one graph, so the
+    target kernel raises a device flag that turns every optimiser / soft-update kernel of that learn() into a no-op:
+    the AssertionError must leave actor, critic, targets and Adam moments bit-identical."""
+    from surreal_b200.learner import DDPGLearner
+    lc, ec, sc = ddpg_configs(D=9, A=3, B=16, target={'type': 'soft', 'tau': 0.01, 'interval': 1})
+    L = DDPGLearner(lc, ec, sc)
+    rng = np.random.default_rng(0)
+    mk = lambda amax: {'obs': {'low_dim': {'flat_inputs': rng.standard_normal((16, 9)).astype(np.float32)}},   # noqa: E731
+                       'obs_next': {'low_dim': {'flat_inputs': rng.standard_normal((16, 9)).astype(np.float32)}},
+                       'actions': (rng.uniform(-1, 1, (16, 3)) * amax).astype(np.float32),
+                       'rewards': rng.standard_normal((16, 1)), 'dones': np.zeros((16, 1))}
+    L.learn(mk(1.0))                                            # a good batch first (captures the graph, moves Adam)
+    snap = [t.clone() for t in (L.model.actor.params, L.model.critic.params, L.model_target.actor.params,
+                                L.model_target.critic.params, L.actor_optim.exp_avg, L.critic_optim.exp_avg_sq)]
+    with pytest.raises(AssertionError):
+        L.learn(mk(3.0))
+    torch.cuda.synchronize()
+    for a, b in zip(snap, (L.model.actor.params, L.model.critic.params, L.model_target.actor.params,
+                           L.model_target.critic.params, L.actor_optim.exp_avg, L.critic_optim.exp_avg_sq)):
+        assert torch.equal(a, b)
+    before = L.model.critic.params.clone()
+    L.learn(mk(1.0))                                            # and the learner keeps working afterwards
+    assert not torch.equal(before, L.model.critic.params)

@@ -247,3 +247,33 @@ def test_lr_scheduler_linear_with_floor():
     assert s2.get_lr() == s.get_lr() and s2.n_step == 12
     with pytest.raises(ValueError):
         make_lr_scheduler('Cosine', o, 1e-3, 10, 1, 0.0)
+
+
+def test_lr_scheduler_restores_foreign_state_dicts():
+    """A reference-written PPO learner checkpoint carries torchx's scheduler dict, not ours: torch-style keys
+    are mapped onto the step count, unknown dicts leave the schedule untouched instead of raising KeyError."""
+    import warnings
+    from surreal_b200.learner.scheduler import LinearWithMinLR
+
+    class Opt:
+        lr = None
+
+        def set_lr(self, v):
+            self.lr = v
+
+    o = Opt()
+    s = LinearWithMinLR(o, 1e-3, num_updates=100, update_freq=1, min_lr=1e-5)
+    for _ in range(7):
+        s.step()
+    own = s.state_dict()
+    s2 = LinearWithMinLR(Opt(), 1e-3, 100, 1, 1e-5)
+    s2.load_state_dict(own)
+    assert s2.n_step == 7 and abs(s2.lr - s.lr) < 1e-15
+    s3 = LinearWithMinLR(Opt(), 1e-3, 100, 1, 1e-5)
+    s3.load_state_dict({'last_epoch': 7, 'base_lrs': [1e-3], '_step_count': 8})
+    assert s3.n_step == 7 and abs(s3.lr - s.lr) < 1e-15 and abs(s3.optim.lr - s.lr) < 1e-15
+    s4 = LinearWithMinLR(Opt(), 1e-3, 100, 1, 1e-5)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter('always')
+        s4.load_state_dict({'something_else': 3})
+    assert s4.n_step == 0 and s4.lr == 1e-3 and len(w) == 1
