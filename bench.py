@@ -312,7 +312,9 @@ def run_ours(args):
             e2e['d2h_bytes_per_step'] *= world
         if world == 1 and rank == 0:
             cpu_baseline = cpu_reference(steps=3, warmup=1)
+    dp_parity = None
     if world > 1:
+        dp_parity = dp_parity_check(learner, dev, rank, world)
         dist.barrier()
     if rank == 0:
         out = {
@@ -327,7 +329,7 @@ def run_ours(args):
             'gpu_launches': per_step_launches * args.steps, 'gpu_launches_per_step': per_step_launches,
             'clocks': clk, 'roofline': roofline, 'roofline_critic_pass': roof_critic, 'roofline_gae': roofline_gae,
             'phase_ms_sequential': phase_ms, 'roofline_rollout': roof_roll, 'kernel_breakdown': breakdown[:12], 'e2e': e2e,
-            'cpu_baseline': cpu_baseline, 'wall_s': t_wall, 'wall_env_steps_per_s': env_steps / t_wall / world * world,
+            'cpu_baseline': cpu_baseline, 'dp_parity': dp_parity, 'wall_s': t_wall, 'wall_env_steps_per_s': env_steps / t_wall / world * world,
         }
         print(json.dumps(out))
     if world > 1:
@@ -339,6 +341,35 @@ def run_ours(args):
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
+
+
+def dp_parity_check(learner, dev, rank, world):
+    """Correctness evidence a multi-GPU bench line carries with it (the 1-GPU test box cannot run tests/test_dp_gpu.py):
+    (1) replica drift of the benchmarked learner after all its steps -- every rank's actor / critic / z-filter state
+    must be BIT-identical to rank 0's; (2) one small data-parallel learn() (each rank feeds 1/world of a 256-window
+    global batch) against the CPU oracle on the full batch (tests/dp_check.py; the oracle is the checker here)."""
+    import torch
+    import torch.distributed as dist
+    drift = 0.0
+    for t in (learner.model.actor.params, learner.model.critic.params, learner.model.z_stats,
+              learner.actor_optim.exp_avg, learner.critic_optim.exp_avg_sq):
+        if t is None:
+            continue
+        ref = t.clone()
+        dist.broadcast(ref, 0)
+        drift = max(drift, float((ref - t).abs().max().item()))
+    d = torch.tensor([drift], device=dev, dtype=torch.float64)
+    dist.all_reduce(d, op=dist.ReduceOp.MAX)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from dp_check import run_check
+    ok, msgs = run_check('clip', False)
+    flag = torch.tensor([0.0 if ok else 1.0], device=dev, dtype=torch.float64)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    return {'replica_drift_max_abs': float(d.item()), 'learn_vs_oracle_ok': bool(flag.item() == 0.0),
+            'ok': bool(flag.item() == 0.0 and d.item() == 0.0), 'messages_rank0': msgs,
+            'check': 'bitwise replica agreement of the benchmarked learner (params, z-filter, Adam moments) + one DP learn() on '
+                     'a 256 x 16 global batch vs the CPU oracle on the full batch (advantages, losses, KL <= 1e-5; parameters '
+                     'within 2 % of an Adam step; z-filter sums)'}
 
 
 def count_launches(fn):

@@ -12,18 +12,16 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 
-def main():
+def run_check(mode='clip', big_lr=False):
+    """One data-parallel learn() (every rank feeds 1/world of a global batch) against the single-process oracle on
+    the FULL batch, plus replica drift.  Needs an initialised NCCL process group; returns (ok, [messages])."""
     from helpers import ppo_configs
     from oracle import nets as onets
     from oracle.filters import ZFilter as OZ
     from oracle.ppo import OraclePPOLearner
     from surreal_b200.learner import PPOLearner
-    rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
-    torch.cuda.set_device(int(os.environ['LOCAL_RANK']))
-    os.environ.setdefault('NCCL_MAX_NCHANNELS', '4')
-    dist.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ['LOCAL_RANK'])))
+    rank, world = dist.get_rank(), dist.get_world_size()
     B, n, D, A = 256, 16, 24, 4
-    mode = os.environ.get('DP_MODE', 'clip')
     gen = torch.Generator().manual_seed(3)
 
     def layers(dims):
@@ -47,7 +45,7 @@ def main():
     rewards = rng.standard_normal((B, n)) * 0.3
     dones = np.zeros((B, n), dtype=np.float32)
     dones[rng.random(B) < 0.3, n - 1] = 1
-    lr = 3e-3 if os.environ.get('DP_BIGLR') else 1e-4
+    lr = 3e-3 if big_lr else 1e-4
     O = OraclePPOLearner(al, log_var, cl, zf, A, n, B, ppo_mode=mode, lr_actor=lr, lr_critic=lr)
     st_o = O.learn(dict(obs=obs, obs_next=obs_next, actions=actions, rewards=rewards, dones=dones, pd=pd))
     Bl = B // world
@@ -71,7 +69,7 @@ def main():
         if abs(a - b) > tol:
             ok = False
             msgs.append('%s: %g vs %g' % (name, a, b))
-    assert L.last_n_policy_epochs == O.n_policy_epochs[-1], (L.last_n_policy_epochs, O.n_policy_epochs[-1])
+    chk('policy epochs', float(L.last_n_policy_epochs), float(O.n_policy_epochs[-1]), 0.0)
     adv = L._adv.cpu().view(-1)
     chk('adv', float((adv - O.last_adv.view(-1)[sl]).abs().max()), 0.0, 1e-5)
     for k in ['_surr_loss', '_clip_surr_loss', '_kl_loss_adapt', '_pol_kl', '_val_loss', '_entropy', '_avg_return_targ']:
@@ -87,6 +85,15 @@ def main():
     p = L.model.actor.params.clone()
     dist.broadcast(p, 0)
     chk('replica drift', float((p - L.model.actor.params).abs().max()), 0.0, 0.0)
+    return ok, msgs
+
+
+def main():
+    rank = int(os.environ['RANK'])
+    torch.cuda.set_device(int(os.environ['LOCAL_RANK']))
+    os.environ.setdefault('NCCL_MAX_NCHANNELS', '4')
+    dist.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ['LOCAL_RANK'])))
+    ok, msgs = run_check(os.environ.get('DP_MODE', 'clip'), bool(os.environ.get('DP_BIGLR')))
     print('rank %d %s %s' % (rank, 'DP_OK' if ok else 'DP_FAIL', '; '.join(msgs)), flush=True)
     dist.barrier()
     dist.barrier()
