@@ -109,6 +109,20 @@ size_t sb200_mlp_pack_floats(const sb200_mlp* net);
 int sb200_mlp_pack_tf32(const sb200_mlp* net, float* packed, void* stream);
 int sb200_mlp_forward_packed_f32(const sb200_mlp* net, const float* packed, const sb200_zfilter* zf,
                                  const sb200_rows* in, float* out, int64_t ld_out, void* stream);
+/* Blackwell-native large-batch forward (csrc/mlp_fwd_tc5.cu): tcgen05.mma kind::tf32 tiles of 128 rows with the
+ * accumulators in tensor memory, weights streamed by the TMA engine (cp.async.bulk), 3xTF32 split for fp32-level
+ * accuracy, both hidden layers and the narrow head fused in one persistent kernel (one CTA per SM).  The critic pass of
+ * PPOLearner._gae_and_return (ppo.py:376-387: B*(n+1) rows through D-256-256-1) is its customer.
+ *   supported: 3 layers, ReLU-ReLU-any, dims[0] in {32,64,96,128}, dims[1] multiple of 32 and dims[2] multiple of 64 (both
+ *     <= 256), dims[3] <= 8, no aux input, rows >= 128.  Returns 1 / 0.
+ *   workspace_bytes: caller-owned scratch for the per-call weight images (hi / lo planes in operand layout); 0 when
+ *     unsupported.  One workspace must not be shared by calls that may run concurrently.
+ *   forward: out[rows][ld_out] = network output (only the last layer is written: no saved activations, no save_x).
+ *     SB200_ERR_UNSUPPORTED for other shapes -- callers then use sb200_mlp_forward_f32. */
+int sb200_mlp_tc5_supported(const sb200_mlp* net, int64_t rows);
+size_t sb200_mlp_tc5_workspace_bytes(const sb200_mlp* net);
+int sb200_mlp_forward_tc5_f32(const sb200_mlp* net, const sb200_zfilter* zf, const sb200_rows* in, float* out,
+                              int64_t ld_out, void* workspace, void* stream);
 /* Kernel family of the wide layers of sb200_mlp_forward_f32: 1 (default) = tensor-core mma.sync TF32 with the 3xTF32
  * error-compensated split (fp32-level accuracy, ~1e-6 relative) for batches above 2048 rows, fp32 FFMA below (where
  * the FFMA kernel is faster: 19 us vs 26 us at 1024 rows); 0 = fp32 FFMA kernels everywhere.  Env SB200_MMA overrides

@@ -70,6 +70,9 @@ def _declare(lib):
                                       C.POINTER(P), C.POINTER(L), P]),
         'sb200_mlp_forward_variant_f32': (I, [C.POINTER(Mlp), C.POINTER(ZFilter), C.POINTER(Rows),
                                               C.POINTER(P), C.POINTER(L), I, P]),
+        'sb200_mlp_tc5_supported': (I, [C.POINTER(Mlp), L]),
+        'sb200_mlp_tc5_workspace_bytes': (S, [C.POINTER(Mlp)]),
+        'sb200_mlp_forward_tc5_f32': (I, [C.POINTER(Mlp), C.POINTER(ZFilter), C.POINTER(Rows), P, L, P, P]),
         'sb200_mlp_pack_floats': (S, [C.POINTER(Mlp)]),
         'sb200_mlp_pack_tf32': (I, [C.POINTER(Mlp), P, P]),
         'sb200_mlp_forward_packed_f32': (I, [C.POINTER(Mlp), P, C.POINTER(ZFilter), C.POINTER(Rows), P, L, P]),
@@ -157,7 +160,7 @@ class _ProfilingProxy:
     def __getattr__(self, name):
         fn = getattr(self._real, name)
         if not name.endswith('_f32') and name not in ('sb200_fifo_pop', 'sb200_fifo_push', 'sb200_ppo_kl_apply',
-                                                      'sb200_mlp_pack_tf32'):
+                                                      'sb200_mlp_pack_tf32'):   # noqa: E501
             return fn
         import torch
 

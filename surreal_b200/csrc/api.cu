@@ -24,6 +24,7 @@ extern "C" const char* sb200_status_string(int status) {
 int sb200_mlp_fwd_init();
 int sb200_gae_init();
 int sb200_rollout_fused_init();
+int sb200_mlp_tc5_init();
 
 extern "C" void sb200_launch_counter_add(uint64_t kernels) { g_sb200_launches += kernels; }
 
@@ -39,6 +40,8 @@ extern "C" int sb200_init(void) {
     int rc = sb200_mlp_fwd_init();
     if (rc != SB200_OK) return rc;
     rc = sb200_gae_init();
+    if (rc != SB200_OK) return rc;
+    rc = sb200_mlp_tc5_init();
     if (rc != SB200_OK) return rc;
     return sb200_rollout_fused_init();
 }

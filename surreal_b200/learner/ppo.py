@@ -152,6 +152,8 @@ class PPOLearner(Learner):
         # (631 us) -- both kernels are issue-bound, they do not add up -- so it stays an experiment
         self.dual_critic = os.environ.get("SB200_DUAL_CRITIC", "0") == "1"
         self._graph = ops.GraphRunner()
+        self._tc5 = ops.Tc5Forward(self.model.critic)     # critic pass on tcgen05 / TMEM when the shape qualifies
+        self.tc5_min_rows = int(os.environ.get('SB200_TC5_MIN_ROWS', '4096'))
         self.dp = None
         self.dp_v = None
         self.epoch_history = []
@@ -256,7 +258,10 @@ class PPOLearner(Learner):
         m = self.model
         ev = self._prof_begin()
         rows = B * (n + 1)
-        if self.dual_critic and rows >= 32768:
+        if rows >= self.tc5_min_rows and self._tc5.supported(rows):
+            # Blackwell-native path: tcgen05.mma tiles, accumulators in TMEM, weights streamed by the TMA engine
+            self._tc5(self._obs_full.view(rows, -1), self._values.view(rows, 1), zf_stats=m.z_stats, zf_eps=m.z_eps)
+        elif self.dual_critic and rows >= 32768:
             ops.mlp_forward_dual(m.critic, self._obs_full.view(rows, -1), zf_stats=m.z_stats, zf_eps=m.z_eps,
                                  out=self._values.view(rows, 1))
         else:

@@ -161,6 +161,41 @@ def mlp_forward_packed(packed, x, zf_stats=None, zf_eps=1e-5, aux=None, out=None
     return out
 
 
+class Tc5Forward:
+    """Large-batch forward of a FlatNet on the tcgen05 / TMEM kernel (sb200_mlp_forward_tc5_f32).  Owns the workspace of
+    the per-call weight images; ``supported(rows)`` says whether the shape qualifies (else callers use mlp_forward)."""
+
+    def __init__(self, net):
+        self.net = net
+        d = net.desc()
+        n = int(_lib.lib().sb200_mlp_tc5_workspace_bytes(C.byref(d)))
+        self.ws = torch.zeros(n, dtype=torch.uint8, device=net.device) if n > 0 else None
+
+    def supported(self, rows):
+        if self.ws is None or os.environ.get('SB200_TC5', '1') == '0':
+            return False
+        d = self.net.desc()
+        return bool(_lib.lib().sb200_mlp_tc5_supported(C.byref(d), int(rows)))
+
+    def __call__(self, x, out, zf_stats=None, zf_eps=1e-5, x_next=None, win_n=0, params=None):
+        """x: [rows, D] (contiguous rows) or [B, n, D] + x_next [B, 1, D] with win_n = n; out: [rows, out_dim]."""
+        net = self.net
+        r = Rows()
+        if win_n > 0:
+            _f32c(x), _f32c(x_next)
+            r.x, r.x_next, r.ldx, r.rows, r.win_n = x.data_ptr(), x_next.data_ptr(), net.dims[0], x.shape[0] * (win_n + 1), win_n
+        else:
+            x2 = x.reshape(-1, x.shape[-1])
+            assert x2.stride(1) == 1
+            r.x, r.x_next, r.ldx, r.rows, r.win_n = x2.data_ptr(), None, x2.stride(0), x2.shape[0], 0
+        r.aux, r.aux_ld, r.save_x, r.ld_save_x = None, 0, None, 0
+        zf = zfilter_desc(zf_stats, zf_eps)
+        d = net.desc(params)
+        check(_lib.lib().sb200_mlp_forward_tc5_f32(C.byref(d), C.byref(zf), C.byref(r), _ptr(out), out.stride(0), _ptr(self.ws),
+                                                   _stream()), 'sb200_mlp_forward_tc5_f32')
+        return out
+
+
 _dual_side = {}
 
 

@@ -203,3 +203,52 @@ def test_gae_matches_oracle(B, n, H, norm):
     # a second call must reuse the (self-resetting) workspace correctly
     adv2, _ = ops.gae_window(r.to(_dev()), v.to(_dev()), d.to(_dev()), 0.995, 0.97, horizon=H, norm_adv=norm)
     assert torch.equal(adv, adv2)
+
+
+@pytest.mark.parametrize('dims,rows,zf,win', [
+    ([64, 256, 256, 1], 132096, True, 0),      # the cfg2 critic pass: 1032 tiles of 128 rows, 7 tiles per CTA
+    ([64, 256, 256, 1], 128 * 5 + 77, True, 0),   # ragged last tile
+    ([64, 256, 256, 8], 4096, True, 0),        # 8 output columns, tanh head
+    ([32, 128, 64, 3], 19205, False, 0),       # narrower layers (UMMA N = 128 / 64), single layer-1 chunk (odd chunk count)
+    ([128, 256, 256, 1], 1000, True, 0),       # four layer-1 chunks
+    ([64, 256, 256, 1], 0, True, 16),          # virtual cat([obs, obs_next]) rows of ppo.py:376-383 (B = 600 windows)
+])
+def test_tcgen05_forward_matches_oracle(dims, rows, zf, win):
+    """sb200_mlp_forward_tc5_f32 (tcgen05.mma kind::tf32, accumulators in TMEM, 3xTF32 split) against the fp32 oracle
+    network at 1e-5 * max(1, rms): same bar as the mma.sync / FFMA forward kernels."""
+    from surreal_b200 import ops
+    gen = torch.Generator().manual_seed(sum(dims) + rows + win)
+    layers = _rand_layers(dims, gen)
+    acts = [ops.ACT_RELU, ops.ACT_RELU, ops.ACT_TANH if dims[-1] > 1 else ops.ACT_NONE]
+    D = dims[0]
+    if win:
+        B = 600
+        xw = torch.randn(B, win, D, generator=gen) * 2 + 0.5
+        xn = torch.randn(B, 1, D, generator=gen) * 2 + 0.5
+        x = torch.cat([xw, xn], 1).reshape(-1, D)
+        rows = x.shape[0]
+    else:
+        x = torch.randn(rows, D, generator=gen) * 2 + 0.5
+    ozf, stats = None, None
+    if zf:
+        ozf = OZFilter(D)
+        ozf.update(torch.randn(200, D, generator=gen) * 1.7 + 0.4)
+        stats = torch.cat([ozf.running_sum, ozf.running_sumsq, ozf.count]).to(_dev())
+    net = ops.FlatNet(dims, acts, _dev()).load_layers(layers)
+    f = ops.Tc5Forward(net)
+    assert f.supported(rows)
+    out = torch.full((rows, dims[-1]), float('nan'), device=_dev())
+    if win:
+        f(xw.to(_dev()), out, zf_stats=stats, x_next=xn.to(_dev()), win_n=win)
+    else:
+        f(x.to(_dev()), out, zf_stats=stats)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        h = ozf.forward(x) if zf else x
+        for l, (w, b) in enumerate(layers):
+            h = torch.nn.functional.linear(h, w, b)
+            h = torch.relu(h) if acts[l] == ops.ACT_RELU else (torch.tanh(h) if acts[l] == ops.ACT_TANH else h)
+    assert_close_scale(out, h, 1e-5, 'tcgen05 forward')
+    # and the same rows through the default dispatcher (mma.sync / FFMA kernels) agree to the same bar
+    ref = ops.mlp_forward(net, x.to(_dev()), zf_stats=stats)
+    assert_close_scale(out, ref, 1e-5, 'tcgen05 vs default forward')
