@@ -4,9 +4,12 @@
   <folder>/metadata.<name>.yml          version, save_counter, history_ckpt_files (newest first), ckpt{...},
                                         tracked_attrs, keep_history, keep_best, best_ckpt_files, best_scores
 
-so checkpoints written by either implementation restore into the other.  Attributes exposing
-``state_dict()/load_state_dict()`` are stored through them (tensors moved to the CPU); everything else
-is pickled as is.  Saving happens every ``period`` calls AND at least ``min_interval`` seconds apart."""
+so model / target-model / counter attributes written by either implementation restore into the other.
+Attributes exposing ``state_dict()/load_state_dict()`` are stored through them (tensors moved to the CPU);
+everything else is pickled as is.  One asymmetry is unavoidable: the reference pickles its LR schedulers as
+OBJECTS of an un-vendored class (torchx); reading such a file works here (the object's step count is mapped onto
+our schedule, unknown classes load as placeholders), while the reference would need torchx importable to read its
+own file and cannot rebuild its scheduler objects from the state dicts written here.  Saving happens every ``period`` calls AND at least ``min_interval`` seconds apart."""
 import datetime
 import os
 import pickle
@@ -18,6 +21,45 @@ import torch
 import yaml
 
 CHECKPOINT_VERSION = '0.0.1'
+
+
+class ForeignObject:
+    """Placeholder for an instance of a class that cannot be imported here.  The reference pickles non-Module tracked
+    attributes AS OBJECTS (utils/checkpoint.py:239-246) -- a PPO learner checkpoint holds two
+    ``torchx.nn.hyper_scheduler.LinearWithMinLR`` instances -- and torchx is not installable; the rest of such a file
+    must still load.  The instance keeps whatever state the pickle carried in ``__dict__``."""
+    _foreign_name = '?'
+
+    def __init__(self, *args, **kwargs):
+        self._foreign_args = args
+
+    def __setstate__(self, state):
+        if isinstance(state, dict):
+            self.__dict__.update(state)
+        else:
+            self._foreign_state = state
+
+
+class _TolerantUnpickler(pickle.Unpickler):
+    def find_class(self, module, name):
+        try:
+            return super().find_class(module, name)
+        except (ImportError, AttributeError):
+            return type(name, (ForeignObject,), {'_foreign_name': '%s.%s' % (module, name)})
+
+
+def _as_state_dict(value):
+    """What to hand to ``load_state_dict`` for a tracked attribute: dicts pass through; objects (the reference's pickled
+    schedulers, or their ForeignObject stand-ins) contribute their plain scalar fields."""
+    if isinstance(value, dict):
+        return value
+    if hasattr(value, 'state_dict') and not isinstance(value, ForeignObject):
+        try:
+            return value.state_dict()
+        except Exception:
+            pass
+    fields = getattr(value, '__dict__', {})
+    return {k: v for k, v in fields.items() if isinstance(v, (int, float, bool, list, tuple, str))}
 
 
 def _to_cpu(obj):
@@ -127,11 +169,14 @@ class Checkpoint:
                 raise FileNotFoundError(path + ' missing.')
             return None
         with open(path, 'rb') as fp:
-            data = pickle.load(fp)
+            data = _TolerantUnpickler(fp).load()
         for a in self.metadata['tracked_attrs']:
             cur = getattr(self.tracked_obj, a)
             if hasattr(cur, 'load_state_dict'):
-                cur.load_state_dict(data[a])
+                cur.load_state_dict(_as_state_dict(data[a]))
+            elif isinstance(data[a], ForeignObject):
+                raise TypeError('checkpoint attribute %r is an instance of %s, which cannot be imported here'
+                                % (a, data[a]._foreign_name))
             else:
                 setattr(self.tracked_obj, a, data[a])
         return path

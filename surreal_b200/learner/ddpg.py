@@ -246,6 +246,12 @@ class DDPGLearner(Learner):
         attrs = ['current_iteration', 'model', 'model_target']
         if self.use_double_critic:
             attrs += ['model2', 'model_target2']
+        ck = self.session_config.checkpoint.learner
+        if 'include_optimizer' in ck and ck.include_optimizer:     # extension (off by default): bit-identical continuation
+            attrs += ['actor_optim', 'critic_optim', 'target_update_counter'] if self.target_update_type == 'hard' \
+                else ['actor_optim', 'critic_optim']
+            if self.use_double_critic:
+                attrs += ['critic_optim2']
         return attrs
 
     def _target_update_init(self):

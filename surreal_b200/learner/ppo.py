@@ -567,7 +567,31 @@ class PPOLearner(Learner):
         self.critic_lr_scheduler.step()
 
     def checkpoint_attributes(self):
-        return ['model', 'ref_target_model', 'actor_lr_scheduler', 'critic_lr_scheduler', 'current_iteration']
+        """ppo.py:668-678.  With ``session_config.checkpoint.learner.include_optimizer`` (an extension, off by default
+        so that the files keep the reference's attribute list) the Adam state and the publish-time adaptation state are
+        tracked too, which makes a restored learner continue BIT-identically."""
+        attrs = ['model', 'ref_target_model', 'actor_lr_scheduler', 'critic_lr_scheduler', 'current_iteration']
+        ck = self.session_config.checkpoint.learner
+        if 'include_optimizer' in ck and ck.include_optimizer:
+            attrs += ['actor_optim', 'critic_optim', 'adapt_state']
+        return attrs
+
+    @property
+    def adapt_state(self):
+        return {'clip_epsilon': getattr(self, 'clip_epsilon', None), 'beta': getattr(self, 'beta', None),
+                'exp_counter': self.exp_counter, 'kl_record': list(self.kl_record), 'global_step': self.global_step,
+                'rfilter': self._rfilter_stats.cpu() if self._rfilter_stats is not None else None}
+
+    @adapt_state.setter
+    def adapt_state(self, st):
+        if st.get('clip_epsilon') is not None:
+            self.clip_epsilon = st['clip_epsilon']
+        if st.get('beta') is not None:
+            self.beta = st['beta']
+        self.exp_counter, self.kl_record, self.global_step = st['exp_counter'], list(st['kl_record']), st['global_step']
+        if st.get('rfilter') is not None and self._rfilter_stats is not None:
+            self._rfilter_stats.copy_(st['rfilter'].to(self.device))
+        self._sync_hyper()
 
     def _prefetcher_preprocess(self, batch):
         if isinstance(batch, dict):          # the HBM replay already returns an aggregated device batch

@@ -35,24 +35,23 @@ class LinearWithMinLR:
         (its source is not vendored; torch-style schedulers use `last_epoch` / `_step_count` / `base_lrs`): the step
         count is taken from whichever of those keys exists and the rate is recomputed with this class's formula;
         a dict with none of them leaves the schedule at its initial state (with a warning) instead of raising."""
-        if 'n_step' in sd:
-            self.n_step = int(sd['n_step'])
-            self.lr = float(sd.get('lr', self.lr))
-        else:
-            n = None
-            for k in ('last_epoch', '_step_count', 'step_count', 'num_steps'):
-                if k in sd:
-                    n = int(sd[k]) - (1 if k == '_step_count' else 0)
-                    break
-            if n is None:
-                import warnings
-                warnings.warn('LinearWithMinLR.load_state_dict: foreign scheduler state %s has no step count; the '
-                              'schedule restarts' % sorted(sd.keys()))
-                return
-            self.n_step = max(n, 0)
-            base = sd.get('base_lrs')
-            if base:
-                self.base_lr = float(base[0])
+        n = None
+        for k in ('n_step', 'last_epoch', '_step_count', 'step_count', 'num_steps'):
+            if k in sd:
+                n = int(sd[k]) - (1 if k == '_step_count' else 0)
+                break
+        if n is None:
+            import warnings
+            warnings.warn('LinearWithMinLR.load_state_dict: foreign scheduler state %s has no step count; the '
+                          'schedule restarts' % sorted(sd.keys()))
+            return
+        self.n_step = max(n, 0)
+        base = sd.get('base_lrs')
+        if base:
+            self.base_lr = float(base[0])
+        if 'lr' in sd:
+            self.lr = float(sd['lr'])
+        else:                                   # recompute with this class's formula
             steps = self.n_step // self.update_freq * self.update_freq
             self.lr = self.base_lr if steps == 0 else max(self.min_lr, self.base_lr * max(0.0, 1.0 - steps / self.num_updates))
         self.optim.set_lr(self.lr)

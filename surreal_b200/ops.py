@@ -421,6 +421,18 @@ class MlpTrainer:
     def set_lr(self, lr):
         self.lr.fill_(float(lr))
 
+    def state_dict(self):
+        """Adam moments (kernel layout), the optimiser workspace (holds the step count) and the learning rate."""
+        return {'exp_avg': self.exp_avg.detach().clone(), 'exp_avg_sq': self.exp_avg_sq.detach().clone(),
+                'workspace': self.ws.detach().clone(), 'lr': float(self.lr.item()), 'layout': list(self.net.dims)}
+
+    def load_state_dict(self, sd):
+        assert list(sd['layout']) == list(self.net.dims), 'optimizer state belongs to a different network'
+        self.exp_avg.copy_(torch.as_tensor(sd['exp_avg']).to(self.net.device))
+        self.exp_avg_sq.copy_(torch.as_tensor(sd['exp_avg_sq']).to(self.net.device))
+        self.ws.copy_(torch.as_tensor(sd['workspace']).to(self.net.device))
+        self.set_lr(sd['lr'])
+
 
 class GraphRunner:
     """Capture a fixed launch sequence once into a CUDA graph and replay it (B200: a launch-bound inner loop of

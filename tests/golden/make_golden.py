@@ -853,6 +853,62 @@ def gen_checkpoint():
          **{'weight/' + k: v for k, v in weights.items()})
 
 
+def gen_ppo_learner_ckpt():
+    """A checkpoint folder written by the REFERENCE for a real PPOLearner (ppo.py:668-678 attributes: model,
+    ref_target_model, both LR schedulers, current_iteration; utils/checkpoint.py:234-314 format) after two learn() +
+    publish iterations, plus the state the loader must end up with and one more batch with the reference's result of
+    learning on it from the restored state with FRESH optimisers (the reference does not checkpoint Adam moments)."""
+    from surreal.utils.checkpoint import PeriodicCheckpoint
+    torch.manual_seed(21)
+    lc, ec, sc = cfg_ppo(mode='clip', B=16, n_step=6, exp_interval=16)
+    L = H.construct_without_initialize(PPOLearner, lc, ec, sc)
+    L._ps_publisher = H._Any()
+    L.tensorplex = H._Any()
+    rng = np.random.default_rng(21)
+    B, n, D, A = L.batch_size, L.n_step, 11, 3
+    L.model.z_filter.z_update(torch.tensor((rng.standard_normal((40, D)) * 1.5 + 0.3).astype(np.float32)))
+    L.ref_target_model.update_target_params(L.model)
+    folder = tempfile.mkdtemp()
+    ck = PeriodicCheckpoint(folder, 'learner', period=1, min_interval=0, tracked_obj=L,
+                            tracked_attrs=L.checkpoint_attributes(), keep_history=2, keep_best=0)
+    L.periodic_checkpoint = lambda **kw: ck.save(score=None, global_steps=kw.get('global_steps'))
+    for it in range(2):
+        batch, raw = make_ppo_batch(L, rng, B, n, D, A)
+        L.learn(batch)
+        L.publish_parameter(it, message='')
+    ck.save(score=None, global_steps=L.current_iteration)          # state AFTER the second publish
+    out = dict(**sd_np(L.model, 'saved/model/'), **sd_np(L.ref_target_model, 'saved/ref/'))
+    files = {fn: np.frombuffer(open(os.path.join(folder, fn), 'rb').read(), dtype=np.uint8) for fn in sorted(os.listdir(folder))}
+    # what the reference itself computes when it restores that folder into a fresh learner and learns one more batch
+    torch.manual_seed(99)
+    lc2, ec2, sc2 = cfg_ppo(mode='clip', B=16, n_step=6, exp_interval=16)
+    L2 = H.construct_without_initialize(PPOLearner, lc2, ec2, sc2)
+    L2._ps_publisher = H._Any()
+    L2.tensorplex = H._Any()
+    ck2 = PeriodicCheckpoint(folder, 'learner', period=1, min_interval=0, tracked_obj=L2,
+                             tracked_attrs=L2.checkpoint_attributes(), keep_history=2, keep_best=0)
+    assert ck2.restore(target=0, mode='history', check_ckpt_exists=True)
+    L2.periodic_checkpoint = lambda **kw: None
+    captured = {}
+    orig_opt = L2._optimize
+
+    def opt_hook(*a, **k):
+        st = orig_opt(*a, **k)
+        captured['stats'] = {kk: float(vv) for kk, vv in st.items()}
+        return st
+    L2._optimize = opt_hook
+    batch, raw = make_ppo_batch(L2, rng, B, n, D, A)
+    for k, v in raw.items():
+        out['next/%s' % k] = v
+    L2.learn(batch)
+    out.update(sd_np(L2.model, 'next/after/'))
+    save('ppo_learner_ckpt', file_names=sorted(files), cfg=dict(B=B, n_step=n, D=D, A=A, exp_interval=16,
+         actor_h=lc.model.actor_fc_hidden_sizes, critic_h=lc.model.critic_fc_hidden_sizes, lr=lc.algo.network.lr_actor,
+         current_iteration=int(L.current_iteration), clip_epsilon=float(L.clip_epsilon),
+         restored_iteration=int(L2.current_iteration - 1), sched_n_step=int(L.actor_lr_scheduler.n_step)),
+         next_stats=captured['stats'], **{'file/' + k: v for k, v in files.items()}, **out)
+
+
 def gen_configs():
     """Default config trees exactly as the reference builds them (main/ppo_configs.py:15-175,
     main/ddpg_configs.py:16-174, session/default_configs.py:4-259)."""
@@ -869,6 +925,6 @@ def gen_configs():
 
 if __name__ == '__main__':
     which = sys.argv[1:] or ['pd', 'filters', 'gae', 'ppo_learn', 'ppo_learn_rnn', 'ppo_learn_pixel', 'ddpg', 'ddpg_td3',
-                             'replay', 'window', 'aggregate', 'act', 'act_rnn', 'act_ou', 'checkpoint', 'configs']
+                             'replay', 'window', 'aggregate', 'act', 'act_rnn', 'act_ou', 'checkpoint', 'ppo_learner_ckpt', 'configs']
     for w in which:
         globals()['gen_' + w]()

@@ -277,3 +277,44 @@ def test_lr_scheduler_restores_foreign_state_dicts():
         warnings.simplefilter('always')
         s4.load_state_dict({'something_else': 3})
     assert s4.n_step == 0 and s4.lr == 1e-3 and len(w) == 1
+
+
+def test_reference_written_ppo_learner_checkpoint_loads_without_its_classes(tmp_path, golden):
+    """tests/golden/ppo_learner_ckpt.npz: the folder the REFERENCE's PeriodicCheckpoint wrote for a real PPOLearner.  It
+    pickles the two LR schedulers as OBJECTS of a class that does not exist here (torchx in a real deployment,
+    _ref_harness in the fixture): the loader must still restore models, counters and the schedulers' step counts."""
+    import json
+    import torch
+    from surreal_b200.checkpoint import PeriodicCheckpoint
+    from surreal_b200.learner.scheduler import LinearWithMinLR
+    g = golden('ppo_learner_ckpt')
+    cfg = g.js('cfg')
+    for fn in g.js('file_names') if g['file_names'].ndim == 0 else [str(x) for x in g['file_names']]:
+        (tmp_path / fn).write_bytes(bytes(g['file/' + fn]))
+
+    class Mod:
+        def __init__(self):
+            self.sd = None
+
+        def load_state_dict(self, sd):
+            self.sd = sd
+
+    class Opt:
+        def set_lr(self, v):
+            self.lr = v
+
+    class Obj:
+        pass
+    o = Obj()
+    o.model, o.ref_target_model = Mod(), Mod()
+    o.actor_lr_scheduler = LinearWithMinLR(Opt(), 1e-4, 1000, 1, 1e-6)
+    o.critic_lr_scheduler = LinearWithMinLR(Opt(), 1e-4, 1000, 1, 1e-6)
+    o.current_iteration = 0
+    ck = PeriodicCheckpoint(str(tmp_path), 'learner', period=1, tracked_obj=o, tracked_attrs=None)
+    assert ck.restore(target=0, mode='history', check_ckpt_exists=True)
+    assert o.current_iteration == cfg['current_iteration']
+    assert o.actor_lr_scheduler.n_step == cfg['sched_n_step'] == o.critic_lr_scheduler.n_step
+    saved = g.sub('saved/model/')
+    assert set(k.replace('.', '/') for k in o.model.sd) == set(saved)
+    for k, v in o.model.sd.items():
+        np.testing.assert_array_equal(torch.as_tensor(v).numpy().reshape(-1), saved[k.replace('.', '/')].reshape(-1))
