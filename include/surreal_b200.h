@@ -419,6 +419,10 @@ int sb200_fifo_pop(void* fifo_state, int batch, int* idx, int* status, void* str
 int sb200_fifo_push(void* fifo_state, int k, int* slots, void* stream);
 int sb200_replay_gather_f32(const float* src, int64_t record_floats, const int* idx32, const int64_t* idx64,
                             int batch, float* out, void* stream);
+/* Every field of the sampled records in ONE launch (srcs / outs / record_floats are HOST arrays of nfields <= 8 entries):
+ * outs[f][b] = srcs[f][idx[b]].  Replaces the per-key np.stack loops of aggregator.py:52-103,151-205. */
+int sb200_replay_gather_multi_f32(const float* const* srcs, float* const* outs, const int64_t* record_floats,
+                                  int nfields, const int* idx32, const int64_t* idx64, int batch, void* stream);
 /*   ssar_step: ExpSenderWrapperSSARNStepBootstrap._step (exp_sender_wrapper.py:96-112) for N actors +
  *     UniformReplay.insert (uniform_replay.py:36-41): k-th insert -> slot k % capacity, actor order.
  *     uniform_state: sb200_uniform_state_bytes() bytes {int64 next_idx,size,capacity,total_in}. */

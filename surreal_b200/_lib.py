@@ -114,6 +114,7 @@ def _declare(lib):
         'sb200_fifo_pop': (I, [P, I, P, P, P]),
         'sb200_fifo_push': (I, [P, I, P, P]),
         'sb200_replay_gather_f32': (I, [P, L, P, P, I, P, P]),
+        'sb200_replay_gather_multi_f32': (I, [P, P, P, I, P, P, I, P]),
         'sb200_uniform_state_bytes': (S, []),
         'sb200_ssar_step_f32': (I, [P, P, P, P, P, I, I, D, I, I, P, P, P, P, P, P, P, P, P, P, P, P, P, P]),
         'sb200_mt19937_state_bytes': (S, []),

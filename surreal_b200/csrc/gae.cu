@@ -13,10 +13,14 @@
 namespace {
 
 constexpr int GAE_WARPS = 8;
+constexpr int GAE_MAX_GRID = 1184;          // persistent grid: 148 SMs x 8 resident CTAs
+constexpr int GAE_FUSED_NORM_MAX = 16384;   // up to here the last CTA normalises alone (one launch); above: a parallel pass
 
 struct GaeWs {
     unsigned int counter;
-    unsigned int pad[3];
+    unsigned int pad;
+    float mean, denom;                      // batch statistics of the large-batch path (read by gae_normalize_kernel)
+    double partial[2 * GAE_MAX_GRID];       // per-CTA (sum, sum of squares) of the advantages
 };
 
 __device__ __forceinline__ float pow_table(float base_f32, int k) {
@@ -56,8 +60,8 @@ __global__ void __launch_bounds__(GAE_WARPS * 32) gae_full_kernel(const float* _
         tab[n + k] = pow_table(lam_f, k);
     }
     __syncthreads();
-    const int b = blockIdx.x * GAE_WARPS + warp;
-    if (b < B) {
+    double blk_s = 0.0, blk_q = 0.0;               // this warp's share of sum(adv), sum(adv^2) (large-batch path)
+    for (int b = blockIdx.x * GAE_WARPS + warp; b < B; b += gridDim.x * GAE_WARPS) {
         const float* r = rewards + (long long)b * n;
         const float* v = values + (long long)b * (n + 1);
         const float* d = dones + (long long)b * n;
@@ -76,13 +80,42 @@ __global__ void __launch_bounds__(GAE_WARPS * 32) gae_full_kernel(const float* _
         r_sum = warp_sum(r_sum);
         if (lane == 0) {
             const float vn = __fmul_rn(v[n], __fsub_rn(1.0f, d[n - 1]));
-            adv[b] = (float)a_sum;
+            const float af = (float)a_sum;
+            adv[b] = af;
             ret[b] = __fadd_rn((float)r_sum, __fmul_rn(vn, gamma_pow_n));
+            blk_s += (double)af;
+            blk_q += (double)af * (double)af;
         }
     }
-    if (norm_adv) {
+    if (norm_adv == 1) {
         if (last_block_ticket(&ws->counter, gridDim.x)) normalize_all(adv, (long long)B, sh);
+    } else if (norm_adv == 2) {
+        // large batch: per-CTA fp64 partials in a fixed order; the last CTA turns them into (mean, max(std, 1e-4)) and
+        // gae_normalize_kernel applies them with the whole grid
+        const double ts = block_sum((lane == 0) ? blk_s : 0.0, sh);
+        const double tq = block_sum((lane == 0) ? blk_q : 0.0, sh);
+        if (threadIdx.x == 0) {
+            ws->partial[2 * blockIdx.x] = ts;
+            ws->partial[2 * blockIdx.x + 1] = tq;
+        }
+        if (last_block_ticket(&ws->counter, gridDim.x)) {
+            if (threadIdx.x == 0) {
+                double S = 0.0, Q = 0.0;
+                for (unsigned int k = 0; k < gridDim.x; ++k) { S += ws->partial[2 * k]; Q += ws->partial[2 * k + 1]; }
+                const double mean = S / (double)B;
+                const double var = (Q - S * S / (double)B) / (double)(B - 1);
+                const float std_f = (float)sqrt(var > 0.0 ? var : 0.0);
+                ws->mean = (float)mean;
+                ws->denom = (std_f > 1e-4f) ? std_f : 1e-4f;
+            }
+        }
     }
+}
+
+__global__ void __launch_bounds__(256) gae_normalize_kernel(float* __restrict__ adv, long long total, const GaeWs* __restrict__ ws) {
+    const float mean = ws->mean, denom = ws->denom;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+        adv[i] = (adv[i] - mean) / denom;
 }
 
 // RNN branch: E = n - H + 1 outputs per window, each an H-term sum (ppo.py:389-406).
@@ -148,6 +181,7 @@ extern "C" size_t sb200_gae_workspace_bytes(int B, int n, int horizon) {
     return sizeof(GaeWs);
 }
 
+
 extern "C" int sb200_gae_window_f32(const float* rewards, const float* values, const float* dones, int B, int n,
                                     int horizon, double gamma, double lam, double reward_scale, int norm_adv, float* adv,
                                     float* ret, void* workspace, void* stream) {
@@ -159,8 +193,17 @@ extern "C" int sb200_gae_window_f32(const float* rewards, const float* values, c
     if (horizon == n) {
         const float gpn = (float)pow(gamma, (double)n);          // Python `gamma ** n_step` (double) -> fp32 scalar
         SB200_REQUIRE((size_t)2 * n * sizeof(float) <= 48 * 1024);
-        gae_full_kernel<<<grid, GAE_WARPS * 32, (size_t)2 * n * sizeof(float), st>>>(rewards, values, dones, B, n, gamma_f, lam_f, gpn, (float)reward_scale, norm_adv,
+        // persistent grid: the gamma^k / lam^k tables (2n double-precision pow) are built once per CTA, not once per 8
+        // windows; windows are walked grid-stride
+        const int pgrid = grid < GAE_MAX_GRID ? grid : GAE_MAX_GRID;
+        const int mode = !norm_adv ? 0 : (B <= GAE_FUSED_NORM_MAX ? 1 : 2);
+        gae_full_kernel<<<pgrid, GAE_WARPS * 32, (size_t)2 * n * sizeof(float), st>>>(rewards, values, dones, B, n, gamma_f, lam_f, gpn, (float)reward_scale, mode,
                                                          adv, ret, (GaeWs*)workspace);
+        if (mode == 2) {
+            const long long nb = ((long long)B + 256 * 4 - 1) / (256 * 4);
+            gae_normalize_kernel<<<(unsigned)(nb < 2048 ? nb : 2048), 256, 0, st>>>(adv, (long long)B, (const GaeWs*)workspace);
+            return sb200_launch_status(2);
+        }
     } else {
         const float gph = (float)pow(gamma, (double)horizon);
         const size_t smem = (size_t)(2 * horizon + GAE_WARPS * (3 * n + 1)) * sizeof(float);

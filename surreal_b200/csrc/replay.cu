@@ -254,6 +254,41 @@ inline uint32_t mt_next(MT* g) {
     return y;
 }
 
+// All fields of a record in ONE launch: out_f[b] = src_f[idx[b]] for f < nf.  A warp owns a record; its lanes walk the
+// record's chunks across fields (16-byte chunks for fields whose record size / alignment allow, 4-byte otherwise), so a
+// 552-byte SSAR record (obs 64, obs_next 64, action 8, reward 1, done 1 floats) is two loads + two stores per lane.
+constexpr int GATHER_MAX_FIELDS = 8;
+struct GatherFields {
+    const float* src[GATHER_MAX_FIELDS];
+    float* out[GATHER_MAX_FIELDS];
+    long long rec[GATHER_MAX_FIELDS];     // floats per record
+    int unit[GATHER_MAX_FIELDS];          // 4 (float4 chunks) or 1
+    int chunk_end[GATHER_MAX_FIELDS];     // prefix sums of chunks per record
+    int nf;
+};
+
+__global__ void __launch_bounds__(256) gather_multi_kernel(const __grid_constant__ GatherFields f, const int* __restrict__ idx,
+                                                           const long long* __restrict__ idx64, int batch) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int total = f.chunk_end[f.nf - 1];
+    for (int b = warp; b < batch; b += nwarps) {
+        const long long s = (idx64 != nullptr) ? idx64[b] : (long long)idx[b];
+        for (int c = lane; c < total; c += 32) {
+            int q = 0;
+#pragma unroll
+            for (int k = 0; k < GATHER_MAX_FIELDS - 1; ++k) q += (k < f.nf - 1 && c >= f.chunk_end[k]) ? 1 : 0;
+            const int local = c - (q > 0 ? f.chunk_end[q - 1] : 0);
+            if (f.unit[q] == 4) {
+                reinterpret_cast<float4*>(f.out[q] + (long long)b * f.rec[q])[local] =
+                    ld_stream4(f.src[q] + s * f.rec[q] + 4 * local);
+            } else {
+                f.out[q][(long long)b * f.rec[q] + local] = __ldg(f.src[q] + s * f.rec[q] + local);
+            }
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int sb200_fifo_pop(void* fifo_state, int batch, int* idx, int* status, void* stream) {
@@ -276,6 +311,30 @@ extern "C" int sb200_replay_gather_f32(const float* src, int64_t record_floats, 
     if (blocks > 148 * 8) blocks = 148 * 8;
     gather_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, record_floats, idx32, (const long long*)idx64, batch, out,
                                                             vec);
+    return sb200_launch_status();
+}
+
+extern "C" int sb200_replay_gather_multi_f32(const float* const* srcs, float* const* outs, const int64_t* record_floats,
+                                             int nfields, const int* idx32, const int64_t* idx64, int batch, void* stream) {
+    SB200_REQUIRE(srcs && outs && record_floats && (idx32 || idx64) && batch >= 1);
+    SB200_REQUIRE(nfields >= 1 && nfields <= GATHER_MAX_FIELDS);
+    GatherFields f;
+    int end = 0;
+    for (int k = 0; k < nfields; ++k) {
+        SB200_REQUIRE(srcs[k] && outs[k] && record_floats[k] >= 1 && record_floats[k] < (1ll << 28));
+        f.src[k] = srcs[k];
+        f.out[k] = outs[k];
+        f.rec[k] = record_floats[k];
+        const bool vec = (record_floats[k] % 4 == 0) && ((((uintptr_t)srcs[k]) | ((uintptr_t)outs[k])) & 15) == 0;
+        f.unit[k] = vec ? 4 : 1;
+        end += (int)(record_floats[k] / f.unit[k]);
+        f.chunk_end[k] = end;
+    }
+    for (int k = nfields; k < GATHER_MAX_FIELDS; ++k) { f.src[k] = nullptr; f.out[k] = nullptr; f.rec[k] = 0; f.unit[k] = 1; f.chunk_end[k] = end; }
+    f.nf = nfields;
+    int blocks = (batch + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    gather_multi_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(f, idx32, (const long long*)idx64, batch);
     return sb200_launch_status();
 }
 

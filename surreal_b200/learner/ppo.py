@@ -145,7 +145,7 @@ class PPOLearner(Learner):
         self._rfilter_stats = torch.tensor([1e-5, 0.0, 0.0], dtype=torch.float32, device=dev) \
             if self.use_r_filter else None
         self._pin = {}
-        self._gae_ws = torch.zeros(64, dtype=torch.uint8, device=dev)
+        self._gae_ws = torch.zeros(int(L.sb200_gae_workspace_bytes(B, n, n)), dtype=torch.uint8, device=dev)
         self.use_cuda_graph = ops.graphs_enabled()
         self.parallel_branches = os.environ.get("SB200_PPO_FORK", "1") != "0"   # policy || value epochs
         # tensor pipe || FMA pipe critic pass: measured SLOWER (701-757 us) than the 2-CTA/SM tensor-core tiles alone

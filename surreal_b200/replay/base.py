@@ -7,6 +7,20 @@ from .. import utils as U
 from ..distributed import LocalHub
 
 
+def gather_fields(pairs, idx32, idx64, batch):
+    """ONE launch for every field of the sampled records: ``pairs`` = [(src ring, out buffer, floats per record)]."""
+    import ctypes as C
+    from .. import _lib
+    from ..ops import _stream
+    n = len(pairs)
+    srcs = (C.c_void_p * n)(*[p[0].data_ptr() for p in pairs])
+    outs = (C.c_void_p * n)(*[p[1].data_ptr() for p in pairs])
+    recs = (C.c_int64 * n)(*[int(p[2]) for p in pairs])
+    _lib.check(_lib.lib().sb200_replay_gather_multi_f32(
+        srcs, outs, recs, n, C.c_void_p(idx32.data_ptr()) if idx32 is not None else None,
+        C.c_void_p(idx64.data_ptr()) if idx64 is not None else None, int(batch), _stream()), 'sb200_replay_gather_multi_f32')
+
+
 class Replay:
     def __init__(self, learner_config, env_config, session_config, index=0):
         self.learner_config = learner_config

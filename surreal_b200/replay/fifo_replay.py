@@ -15,7 +15,7 @@ import torch
 
 from .. import _lib
 from .._lib import check
-from .base import Replay
+from .base import Replay, gather_fields
 
 
 def _p(t):
@@ -118,11 +118,9 @@ class FIFOReplay(Replay):
             f = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)  # noqa: E731
             out = dict(obs_full=f(batch_size, n + 1, D), actions=f(batch_size, n, A), pd=f(batch_size, n, 2 * A),
                        rewards=f(batch_size, n), dones=f(batch_size, n))
-        for src, dst, rec in ((self.r_obs, out['obs_full'], (n + 1) * D), (self.r_act, out['actions'], n * A),
-                              (self.r_pd, out['pd'], n * 2 * A), (self.r_rew, out['rewards'], n),
-                              (self.r_done, out['dones'], n)):
-            check(L.sb200_replay_gather_f32(_p(src), rec, _p(self._idx), None, batch_size, _p(dst), _st()),
-                  'sb200_replay_gather_f32')
+        gather_fields([(self.r_obs, out['obs_full'], (n + 1) * D), (self.r_act, out['actions'], n * A),
+                       (self.r_pd, out['pd'], n * 2 * A), (self.r_rew, out['rewards'], n), (self.r_done, out['dones'], n)],
+                      self._idx, None, batch_size)                      # all five fields: one launch
         if self.check_underflow and int(self._status.item()) != 0:      # host sync; the engine polls
             raise IndexError('pop from a FIFO replay holding fewer than %d windows' % batch_size)   # len() instead
         obs_full = out['obs_full']

@@ -16,7 +16,7 @@ import torch
 
 from .. import _lib
 from .._lib import check
-from .base import Replay
+from .base import Replay, gather_fields
 
 
 def _p(t):
@@ -149,11 +149,8 @@ class UniformReplay(Replay):
             f = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)  # noqa: E731
             out = dict(obs=f(batch_size, D), obs_next=f(batch_size, D), actions=f(batch_size, A),
                        rewards=f(batch_size, 1), dones=f(batch_size, 1))
-        for src, dst, rec in ((self.r_obs, out['obs'], D), (self.r_obs_next, out['obs_next'], D),
-                              (self.r_act, out['actions'], A), (self.r_rew, out['rewards'], 1),
-                              (self.r_done, out['dones'], 1)):
-            check(L.sb200_replay_gather_f32(_p(src), rec, None, _p(idx), batch_size, _p(dst), _st()),
-                  'sb200_replay_gather_f32')
+        gather_fields([(self.r_obs, out['obs'], D), (self.r_obs_next, out['obs_next'], D), (self.r_act, out['actions'], A),
+                       (self.r_rew, out['rewards'], 1), (self.r_done, out['dones'], 1)], None, idx, batch_size)
         return {'obs': {'low_dim': {'flat_inputs': out['obs']}}, 'obs_next': {'low_dim': {'flat_inputs': out['obs_next']}},
                 'actions': out['actions'], 'rewards': out['rewards'], 'dones': out['dones'],
                 'indices': indices}

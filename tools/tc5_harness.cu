@@ -281,6 +281,7 @@ int main(int argc, char** argv) {
     fails += run_unit(32, 1) ? 1 : 0;
     if (argc > 1 && !strcmp(argv[1], "unit")) return fails;
     CK(sb200_mlp_tc5_init() == 0 ? cudaSuccess : cudaErrorUnknown);
+    if (argc > 1 && !strcmp(argv[1], "prof")) return run_full(132096, 64, 256, 256, 1, true, 3);
     fails += run_full(128, 64, 256, 256, 1, false, 0);
     fails += run_full(128 * 3 + 37, 64, 256, 256, 1, true, 0);
     fails += run_full(128 * 150 + 5, 32, 128, 64, 3, true, 0);
