@@ -70,6 +70,16 @@ def build_configs(n_actors=N_ACTORS, horizon=HORIZON):
     return lc, ec, sc
 
 
+def load_profile_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, as recorded in profiles/traffic.json from the
+    committed `ncu --set full` captures (tools/summarize_profiles.py writes it); None when no capture is on file."""
+    p = os.path.join(ROOT, 'profiles', 'traffic.json')
+    try:
+        return json.load(open(p)).get(kernel, {}).get('dram_bytes')
+    except Exception:                                             # noqa: BLE001
+        return None
+
+
 def bench_config(world):
     """The `config` object of BOTH arms' JSON lines (identical: same workload, same keys, same values)."""
     return {'workload': 'PPO synthetic 64-dim obs, 1024 actors x horizon 128, 2x256 MLP (BASELINE configs[1])',
@@ -80,37 +90,56 @@ def bench_config(world):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region.  The timed region is tens of milliseconds, far shorter
+    than nvidia-smi's start-up, so the samples come from NVML directly (pynvml, 2 ms polling thread)."""
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.rows, self._run, self._thr, self.h, self.err = index, [], False, None, None, None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES; NVML enumerates physical devices
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(vis.split(',')[index]) if vis and all(v.strip().isdigit() for v in vis.split(',')) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:                                    # noqa: BLE001
+            self.err = repr(e)
+
+    def _poll(self):
+        nv = self.nv
+        while self._run:
+            try:
+                self.rows.append((int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                                  int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))))
+            except Exception as e:                                # noqa: BLE001
+                self.err = repr(e)
+                return
+            time.sleep(0.002)
 
     def start(self):
-        q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
-            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
-        try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+        if self.h is None:
+            return
+        self._run = True
+        self._thr = threading.Thread(target=self._poll, daemon=True)
+        self._thr.start()
 
     def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == 'Active' for r in self.rows)]
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
-                'samples': len(sm)}
+        if self.h is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['NVML unavailable: %s' % self.err]}
+        self._run = False
+        self._thr.join(timeout=1.0)
+        nv = self.nv
+        sm = sorted(r[0] for r in self.rows)
+        bits = 0
+        for r in self.rows:
+            bits |= r[1]
+        names = [('hw_slowdown', nv.nvmlClocksEventReasonHwSlowdown), ('hw_thermal_slowdown', nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ('sw_thermal_slowdown', nv.nvmlClocksEventReasonSwThermalSlowdown), ('sw_power_cap', nv.nvmlClocksEventReasonSwPowerCap)]
+        reasons = [n for n, b in names if bits & b]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': self.max_mhz, 'reasons': reasons, 'samples': len(sm),
+                'source': 'NVML polled every 2 ms during the timed region'}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -253,15 +282,18 @@ def run_ours(args):
                           'mlp_fwd_pk_kernel (per-env-step policy forward of %d actors, 2-CTA clusters)' % N)
     roof_mb = mlp_roof('sb200_mlp_forward_f32[rows=%d]' % N, N, A,
                        'mlp_fwd_mma_kernel<1> (learner minibatch forward on %d rows)' % N)
-    roof_critic = mlp_roof('sb200_mlp_forward_f32[rows=%d]' % rows, rows, 1,
-                           'mlp_fwd_mma_kernel<2> (fused critic pass over %d rows, 3xTF32 mma.sync, 2 CTAs/SM)' % rows)
-    if roof_critic is None and crit_ms:
-        # dual-pipe critic pass: two concurrent kernels (tensor-core tiles + FFMA tiles); timed as a pair by the
-        # learner's own CUDA events on the main stream, which joins the side stream
-        per_step['critic_pass(dual)'] = (1.0, sum(crit_ms) / len(crit_ms), sum(crit_ms) / len(crit_ms))
-        roof_critic = mlp_roof('critic_pass(dual)', rows, 1,
-                               'mlp_fwd_mma_kernel<2> || mlp_fwd_kernel<4,16> (critic pass over %d rows, tensor pipe and '
-                               'FMA pipe concurrently)' % rows)
+    roof_critic = None
+    if 'sb200_mlp_forward_tc5_f32' in per_step:
+        roof_critic = mlp_roof('sb200_mlp_forward_tc5_f32', rows, 1,
+                               'tc5_prep_kernel + mlp3_tc5_kernel (fused critic pass over %d rows: tcgen05.mma kind::tf32 tiles of '
+                               '128 rows, accumulators in TMEM, weight images streamed by the TMA engine, 3xTF32)' % rows)
+        roof_critic['note'] = ('fp32-accurate 3xTF32: every algorithmic product is 3 tensor-core MMAs, so the tensor pipe executes 3x '
+                               'the algorithmic FLOP counted here; denominator = measured dense bf16 peak (the mandated one), the '
+                               'tf32 pipe peaks at half of it')
+        roof_critic['tensor_pipe_tflops_executed'] = 3.0 * roof_critic['achieved']
+    else:
+        roof_critic = mlp_roof('sb200_mlp_forward_f32[rows=%d]' % rows, rows, 1,
+                               'mlp_fwd_mma_kernel<2> (fused critic pass over %d rows, 3xTF32 mma.sync, 2 CTAs/SM)' % rows)
     roof_roll = None
     rk = 'sb200_ppo_rollout_f32'
     if rk in per_step:
@@ -284,9 +316,9 @@ def run_ours(args):
                              'layer -> cluster barrier -> head/sample/env -> cluster barrier'}
     # dram__bytes_read.sum + dram__bytes_write.sum per launch, from one `ncu --set full` capture each (profiles/)
     if roof_roll is not None:
-        roof_roll['traffic'] = 65551872           # profiles/r01d_prof_rollout.md (25.06 MB read + 40.50 MB written)
+        roof_roll['traffic'] = load_profile_traffic('rollout')
     if roof_critic is not None:
-        roof_critic['traffic'] = 34238464         # profiles/r01e_prof_critic.md (34.23 MB read + 5 KB written)
+        roof_critic['traffic'] = load_profile_traffic('critic')   # dram__bytes of one `ncu --set full` capture (profiles/)
     cands = [r for r in (roof_roll, roof_small, roof_mb, roof_critic) if r is not None]
     roofline = max(cands, key=lambda r: r['share_of_step_kernel_time']) if cands else None
     gae_key = 'sb200_gae_window_f32'
@@ -299,6 +331,7 @@ def run_ours(args):
 
     e2e = None
     cpu_baseline = None
+    extras = None
     if not args.lite:
         # every rank drives its own actors / learner shard through the host API (the learner's collectives need all
         # ranks); the job-level number is all ranks' env-steps over the slowest rank's time
@@ -311,6 +344,7 @@ def run_ours(args):
             e2e['h2d_bytes_per_step'] *= world
             e2e['d2h_bytes_per_step'] *= world
         if world == 1 and rank == 0:
+            extras = run_extras(dev, peaks, flush)
             cpu_baseline = cpu_reference(steps=3, warmup=1)
     dp_parity = None
     if world > 1:
@@ -329,7 +363,7 @@ def run_ours(args):
             'gpu_launches': per_step_launches * args.steps, 'gpu_launches_per_step': per_step_launches,
             'clocks': clk, 'roofline': roofline, 'roofline_critic_pass': roof_critic, 'roofline_gae': roofline_gae,
             'phase_ms_sequential': phase_ms, 'roofline_rollout': roof_roll, 'kernel_breakdown': breakdown[:12], 'e2e': e2e,
-            'cpu_baseline': cpu_baseline, 'dp_parity': dp_parity, 'wall_s': t_wall, 'wall_env_steps_per_s': env_steps / t_wall / world * world,
+            'cpu_baseline': cpu_baseline, 'dp_parity': dp_parity, 'extras': extras, 'wall_s': t_wall, 'wall_env_steps_per_s': env_steps / t_wall / world * world,
         }
         print(json.dumps(out))
     if world > 1:
@@ -341,6 +375,99 @@ def run_ours(args):
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
+
+
+def run_extras(dev, peaks, flush):
+    """Measurements the metric names beside the headline number (bounded: a few seconds):
+      gae_sweep : the windowed-GAE kernel at cfg2 (1024 x 128), cfg5 (4096 x 256) and 262 144 windows x 128 -- achieved
+                  HBM GB/s on the ALGORITHMIC bytes ((3n+1)*4 read + 8 written per window) vs the measured copy peak;
+      ddpg_cfg3 : BASELINE configs[2] -- 1 M-slot UniformReplay in HBM, batch 4096, nets 300-200 / 400-300: replay.sample
+                  (CPython-exact host index stream + one fused gather launch), learn() (one CUDA graph), the loop, and
+                  the gather kernel alone on a 1 M-sample batch (HBM-bound regime)."""
+    import random
+    import torch
+    from surreal_b200 import ops
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from helpers import ddpg_configs
+    from surreal_b200.replay import UniformReplay
+    from surreal_b200.replay.base import gather_fields
+    from surreal_b200.learner import DDPGLearner
+    out = {}
+
+    def dev_time(fn, iters, do_flush=True):
+        ms = []
+        for _ in range(iters + 2):
+            if do_flush:
+                flush.fill_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        ms = sorted(ms[2:])
+        return ms[len(ms) // 2]
+    sweep = []
+    for (B, n, tag) in ((1024, 128, 'cfg2'), (4096, 256, 'cfg5'), (262144, 128, '2^18 windows')):
+        g = torch.Generator(device=dev).manual_seed(B)
+        r = torch.randn(B, n, device=dev, generator=g)
+        v = torch.randn(B, n + 1, device=dev, generator=g)
+        d = (torch.rand(B, n, device=dev, generator=g) < 0.01).float()
+        adv, ret = torch.empty(B, 1, device=dev), torch.empty(B, 1, device=dev)
+        ms = dev_time(lambda: ops.gae_window(r, v, d, 0.995, 0.97, adv=adv, ret=ret), 10)
+        byts = B * ((3 * n + 1) * 4 + 8)
+        sweep.append({'case': tag, 'windows': B, 'n_step': n, 'ms': ms, 'algorithmic_bytes': byts, 'achieved_gbs': byts / (ms / 1e3) / 1e9,
+                      'frac_of_hbm_peak': byts / (ms / 1e3) / 1e9 / peaks['hbm_gbs'], 'launches': 1 if B <= 16384 else 2})
+        del r, v, d
+    out['gae_sweep'] = {'kernel': 'gae_full_kernel (+ gae_normalize_kernel above 16 384 windows)', 'bound': 'hbm', 'peak': peaks['hbm_gbs'],
+                        'unit': 'GB/s', 'cases': sweep, 'l2': 'flushed before every timed launch'}
+    D, A, B, CAP = 64, 8, 4096, 1 << 20
+    lc, ec, sc = ddpg_configs(D=D, A=A, actor_h=(300, 200), critic_h=(400, 300), B=B, n_step=3, memory_size=CAP, start=3000)
+    R = UniformReplay(lc, ec, sc)
+    g = torch.Generator(device=dev).manual_seed(4)
+    R.r_obs.copy_(torch.randn(CAP, D, device=dev, generator=g))
+    R.r_obs_next.copy_(torch.randn(CAP, D, device=dev, generator=g))
+    R.r_act.copy_(torch.rand(CAP, A, device=dev, generator=g) * 2 - 1)
+    R.r_rew.copy_(torch.randn(CAP, device=dev, generator=g))
+    R.r_done.copy_((torch.rand(CAP, device=dev, generator=g) < 0.005).float())
+    R.state[0], R.state[1] = 0, CAP
+    R.mark_device_inserts()
+    L = DDPGLearner(lc, ec, sc)
+    random.seed(5)
+    for _ in range(5):
+        L.learn(R.sample(B))
+    torch.cuda.synchronize()
+    batch = R.sample(B)
+    learn_ms = dev_time(lambda: L.learn(batch), 20, do_flush=False)
+
+    def wall(fn, n):
+        torch.cuda.synchronize()
+        t0 = time.time()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        return (time.time() - t0) * 1e3 / n
+    sample_ms = wall(lambda: R.sample(B), 50)
+    loop_ms = wall(lambda: L.learn(R.sample(B)), 50)
+    rec = (2 * D + A + 2) * 4
+    big = 1 << 20
+    idx = torch.randint(0, CAP, (big,), device=dev, dtype=torch.int64)
+    o = dict(obs=torch.empty(big, D, device=dev), obs_next=torch.empty(big, D, device=dev), act=torch.empty(big, A, device=dev),
+             rew=torch.empty(big, 1, device=dev), done=torch.empty(big, 1, device=dev))
+    pairs = [(R.r_obs, o['obs'], D), (R.r_obs_next, o['obs_next'], D), (R.r_act, o['act'], A), (R.r_rew, o['rew'], 1), (R.r_done, o['done'], 1)]
+    big_ms = dev_time(lambda: gather_fields(pairs, None, idx, big), 10)
+    small_ms = dev_time(lambda: gather_fields(pairs, None, idx[:B], B), 10)
+    out['ddpg_cfg3'] = {'workload': 'DDPG synthetic 64-dim obs, 1M-slot UniformReplay in HBM, batch 4096, nets 300-200 / 400-300, n_step 3 '
+                                    '(BASELINE configs[2])',
+                        'learn_ms_device': learn_ms, 'sample_ms_wall': sample_ms, 'loop_ms_wall': loop_ms,
+                        'learner_updates_per_sec': 1e3 / loop_ms,
+                        'gather': {'kernel': 'gather_multi_kernel (all five record fields, one launch)', 'bound': 'hbm',
+                                   'bytes_per_sample': 2 * rec + 8, 'batch_4096_ms': small_ms,
+                                   'batch_4096_gbs': B * (2 * rec + 8) / (small_ms / 1e3) / 1e9,
+                                   'batch_1M_ms': big_ms, 'batch_1M_gbs': big * (2 * rec + 8) / (big_ms / 1e3) / 1e9,
+                                   'batch_1M_frac_of_hbm_peak': big * (2 * rec + 8) / (big_ms / 1e3) / 1e9 / peaks['hbm_gbs'],
+                                   'peak': peaks['hbm_gbs'], 'unit': 'GB/s'}}
+    return out
 
 
 def dp_parity_check(learner, dev, rank, world):
