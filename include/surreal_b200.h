@@ -123,6 +123,25 @@ int sb200_mlp_tc5_supported(const sb200_mlp* net, int64_t rows);
 size_t sb200_mlp_tc5_workspace_bytes(const sb200_mlp* net);
 int sb200_mlp_forward_tc5_f32(const sb200_mlp* net, const sb200_zfilter* zf, const sb200_rows* in, float* out,
                               int64_t ld_out, void* workspace, void* stream);
+/* ---------------------------------------------------------------------------------------------
+ * CNN stem of the pixel path (CNNStemNetwork, builders.py:8-33; used by PPOModel / DDPGModel with pixel input,
+ * ppo_net.py:136-140,268-273,368-375): Conv2d(16, k8, s4)+ReLU -> Conv2d(32, k4, s2)+ReLU -> Flatten -> Linear+ReLU.
+ * The two convolutions (csrc/stem.cu); the Linear layer is an ordinary sb200_mlp layer.
+ *   frames [rows][C][H][W] (uint8 scaled by in_scale = 1/255, or float); outputs [rows][COUT][HO][WO] (torch order);
+ *   Wk: kernel layout [(c*KS + ky)*KS + kx][COUT] = transpose of torch's [COUT][C][KS][KS]; bias [COUT].
+ *   layer 1 = Conv2d(16, k8, s4), layer 2 = Conv2d(32, k4, s2) (the reference's fixed stem).
+ *   forward: y = relu(conv(x * in_scale) + bias).
+ *   backward_dw: partial gradients of `frames` frames w.r.t. Wk / bias, written into `splits` slabs at
+ *     slab_w + s*slab_stride / slab_b + s*slab_stride (reduce with sb200_grad_reduce_norm_f32); dy = gradient w.r.t. the
+ *     PRE-activation output.
+ *   backward_dx (layer 2 only): dx = relu'(act) * conv_transpose(dy), act = layer 1's output (may be NULL: no mask). */
+int sb200_conv_forward_f32(int layer, const void* x, int in_u8, int64_t frames, int CIN, int H, int W, const float* Wk,
+                           const float* bias, double in_scale, float* y, void* stream);
+int sb200_conv_backward_dw_f32(int layer, const void* x, int in_u8, const float* dy, int64_t frames, int CIN, int H, int W,
+                               double in_scale, float* slab_w, float* slab_b, int64_t slab_stride, int splits, void* stream);
+int sb200_conv_backward_dx_f32(int layer, const float* dy, const float* Wk, const float* act, int64_t frames, int CIN, int H,
+                               int W, float* dx, void* stream);
+
 /* Kernel family of the wide layers of sb200_mlp_forward_f32: 1 (default) = tensor-core mma.sync TF32 with the 3xTF32
  * error-compensated split (fp32-level accuracy, ~1e-6 relative) for batches above 2048 rows, fp32 FFMA below (where
  * the FFMA kernel is faster: 19 us vs 26 us at 1024 rows); 0 = fp32 FFMA kernels everywhere.  Env SB200_MMA overrides

@@ -58,6 +58,15 @@ struct Tc5Params {
     long long n_tiles;
 };
 
+// Optional timeline trace (harness builds with -DTC5_TRACE): CTA 0 stamps clock64() at pipeline events of its first tiles.
+#ifdef TC5_TRACE
+__device__ long long g_tc5_trace[4096];
+#define TC5_STAMP(slot) do { if (blockIdx.x == 0 && (slot) < 4096) g_tc5_trace[(slot)] = clock64(); } while (0)
+#else
+#define TC5_STAMP(slot) do { } while (0)
+#endif
+// trace slots: role*1024 + (tile_iter*NC + chunk)*4 + event;  role 0 = loader, 1 = mma, 2 = producer group 0, 3 = group 1
+
 struct SmemSmall {
     uint64_t full_a[2], full_b[2], empty[2];
     uint64_t acc1_full, acc2_full, acc1_empty, acc2_empty;
@@ -165,7 +174,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp3_tc5_kernel(const __grid_cons
                 for (int c = 0; c < NC; ++c, ++q) {
                     const int s = (int)(q & 1);
                     const uint32_t u = (uint32_t)(q >> 1);
+                    TC5_STAMP(0 * 1024 + (int)q * 4 + 0);
                     mbar_wait(&sm->empty[s], (u & 1u) ^ 1u);
+                    TC5_STAMP(0 * 1024 + (int)q * 4 + 1);
                     const uint32_t bytes = (c < NC1) ? bytes1 : bytes2;
                     unsigned char* st = stage_base + (size_t)s * STAGE_BYTES + 2 * A_PLANE;
                     const unsigned char* src = p.wimg + (size_t)c * 2 * B_PLANE;
@@ -188,8 +199,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp3_tc5_kernel(const __grid_cons
                     const uint32_t u = (uint32_t)(q >> 1);
                     if (it > 0 && c == 0) mbar_wait(&sm->acc1_empty, tph ^ 1u);      // previous tile's accumulator 1 was read
                     if (it > 0 && c == NC1) mbar_wait(&sm->acc2_empty, tph ^ 1u);    // previous tile's accumulator 2 was read
+                    TC5_STAMP(1 * 1024 + (int)q * 4 + 0);
                     mbar_wait(&sm->full_a[s], u & 1u);
+                    TC5_STAMP(1 * 1024 + (int)q * 4 + 1);
                     mbar_wait(&sm->full_b[s], u & 1u);
+                    TC5_STAMP(1 * 1024 + (int)q * 4 + 2);
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(stage_base + (size_t)s * STAGE_BYTES);
                     const uint32_t a_lo = a_hi + A_PLANE, b_hi = a_hi + 2 * A_PLANE, b_lo = b_hi + B_PLANE;
@@ -206,6 +220,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp3_tc5_kernel(const __grid_cons
                         mma_tf32_ss(acc, dah, dbh, idesc, 1u);
                     }
                     mma_commit(&sm->empty[s]);                                        // stage s may be refilled
+                    TC5_STAMP(1 * 1024 + (int)q * 4 + 3);
                     if (c == NC1 - 1) mma_commit(&sm->acc1_full);
                     if (c == NC - 1) mma_commit(&sm->acc2_full);
                 }
@@ -236,7 +251,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp3_tc5_kernel(const __grid_cons
                     tc_fence_after();
                     acc1_ready = true;
                 }
+                if (qd == 0 && lane == 0) TC5_STAMP((2 + g) * 1024 + (int)q * 4 + 0);
                 mbar_wait(&sm->empty[g], (u & 1u) ^ 1u);          // the MMAs that read this stage's previous content are done
+                if (qd == 0 && lane == 0) TC5_STAMP((2 + g) * 1024 + (int)q * 4 + 1);
                 if (c < NC1) {
                     // ---- layer-1 operand: 128 rows x 32 input columns, z-filtered, split into hi / lo planes
                     const int kbase = c * KC;
@@ -284,6 +301,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp3_tc5_kernel(const __grid_cons
                 fence_async_smem();                       // generic-proxy stores -> visible to tcgen05.mma
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm->full_a[g]);
+                if (qd == 0 && lane == 0) TC5_STAMP((2 + g) * 1024 + (int)q * 4 + 2);
             }
             // every layer-2 operand of this group has been read out of accumulator 1
             tc_fence_before();

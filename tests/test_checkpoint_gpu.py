@@ -38,8 +38,10 @@ def test_ppo_learner_checkpoint_roundtrip_continues_bit_identically(tmp_path, mo
     torch.manual_seed(3)
     A_ = make(tmp_path / 'a')
     for it in range(3):
-        A_.learn(_ppo_batch(rng, B, n, D, A))
-        A_.publish_parameter(it)                               # clip_epsilon / beta adaptation, ref-model refresh, LR schedule
+        A_.learn(_ppo_batch(rng, B, n, D, A))                   # learn() writes the checkpoint (ppo.py:607) ...
+        if it < 2:
+            A_.publish_parameter(it)                           # ... BEFORE the publish-time adaptation (clip_epsilon / beta,
+                                                               # ref-model refresh, LR schedule) of the same iteration
     torch.manual_seed(999)                                      # the fresh learner starts from DIFFERENT weights
     B_ = make(tmp_path / 'b', restore_from=tmp_path / 'a')
     assert B_.current_iteration == A_.current_iteration == 3
@@ -129,4 +131,8 @@ def test_reference_written_ppo_learner_checkpoint_restores_into_gpu_learner(tmp_
     exp = ref_state_dict(g.sub('next/after/'))
     got = L.model.state_dict()
     for k, e in exp.items():
-        assert float((got[k].cpu().reshape(e.shape) - e).abs().max()) <= 2e-6, k        # lr 1e-4: 2 % of one Adam step
+        d = float((got[k].cpu().reshape(e.shape) - e).abs().max())
+        if k.startswith('z_filter'):
+            assert d <= 2e-7 * float(e.abs().max()), k          # running sums ~2e2: one fp32 ulp of summation order
+        else:
+            assert d <= 2e-6, k                                   # lr 1e-4: 2 % of one Adam step

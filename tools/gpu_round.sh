@@ -26,3 +26,12 @@ if has ref; then
   timeout 600 python bench.py --impl reference --steps 5 --warmup 2 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
   echo "ref rc=$?"; tail -c 600 gpurun_out/bench_ref.json
 fi
+if has trace; then
+  timeout 120 tools/tc5_trace trace > gpurun_out/tc5_trace.log 2>&1
+  echo "trace rc=$?"; tail -34 gpurun_out/tc5_trace.log
+fi
+if has newtests; then
+  timeout 900 python -m pytest tests/test_stem_gpu.py tests/test_checkpoint_gpu.py -m gpu -q --timeout=600 -p no:cacheprovider > gpurun_out/pytest_new.log 2>&1
+  echo "pytest-new rc=$?" >> gpurun_out/pytest_new.log
+  tail -30 gpurun_out/pytest_new.log
+fi

@@ -282,6 +282,29 @@ int main(int argc, char** argv) {
     if (argc > 1 && !strcmp(argv[1], "unit")) return fails;
     CK(sb200_mlp_tc5_init() == 0 ? cudaSuccess : cudaErrorUnknown);
     if (argc > 1 && !strcmp(argv[1], "prof")) return run_full(132096, 64, 256, 256, 1, true, 3);
+#ifdef TC5_TRACE
+    if (argc > 1 && !strcmp(argv[1], "trace")) {
+        run_full(132096, 64, 256, 256, 1, true, 0);
+        static long long tr[4096];
+        CK(cudaMemcpyFromSymbol(tr, g_tc5_trace, sizeof(tr)));
+        long long t0 = tr[1 * 1024 + 0];
+        const char* roles[4] = {"loader", "mma", "prod0", "prod1"};
+        printf("timeline of CTA 0 (cycles since the MMA thread first waited); chunks q = tile*10 + c\n");
+        for (int q = 0; q < 30; ++q) {
+            printf("q=%2d |", q);
+            for (int r = 0; r < 4; ++r) {
+                printf(" %s:", roles[r]);
+                for (int e = 0; e < 4; ++e) {
+                    long long v = tr[r * 1024 + q * 4 + e];
+                    if (v) printf(" %7lld", v - t0); else printf("       -");
+                }
+                printf(" |");
+            }
+            printf("\n");
+        }
+        return 0;
+    }
+#endif
     fails += run_full(128, 64, 256, 256, 1, false, 0);
     fails += run_full(128 * 3 + 37, 64, 256, 256, 1, true, 0);
     fails += run_full(128 * 150 + 5, 32, 128, 64, 3, true, 0);
