@@ -113,7 +113,7 @@ int sb200_mlp_forward_packed_f32(const sb200_mlp* net, const float* packed, cons
  * accumulators in tensor memory, weights streamed by the TMA engine (cp.async.bulk), 3xTF32 split for fp32-level
  * accuracy, both hidden layers and the narrow head fused in one persistent kernel (one CTA per SM).  The critic pass of
  * PPOLearner._gae_and_return (ppo.py:376-387: B*(n+1) rows through D-256-256-1) is its customer.
- *   supported: 3 layers, ReLU-ReLU-any, dims[0] in {32,64,96,128}, dims[1] multiple of 32 and dims[2] multiple of 64 (both
+ *   supported: 3 layers, ReLU-ReLU-any, dims[0] a multiple of 32 up to 256, dims[1] multiple of 32 and dims[2] multiple of 64 (both
  *     <= 256), dims[3] <= 8, no aux input, rows >= 128.  Returns 1 / 0.
  *   workspace_bytes: caller-owned scratch for the per-call weight images (hi / lo planes in operand layout); 0 when
  *     unsupported.  One workspace must not be shared by calls that may run concurrently.

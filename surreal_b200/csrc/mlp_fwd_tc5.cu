@@ -13,10 +13,11 @@
 //
 // B_c comes from a per-call "image" of the weights (hi / lo planes, already in the SWIZZLE_128B operand layout, built by
 // tc5_prep_kernel from the flat parameter buffer) with one 32 KB bulk copy per plane.  Two 96 KB stages
-// {A_hi, A_lo, B_hi, B_lo} form the ring; chunk q uses stage q & 1, and producer group g (4 warps) always fills stage g.
+// {A_hi, A_lo, B_hi, B_lo} form the ring; chunk q uses stage q & 1.
 //
 // Warp roles (12 warps): 0 = weight loader (one lane), 1 = MMA issuer (one lane), 2 = TMEM allocator, 3 = idle,
-// 4..11 = two producer/epilogue groups of 4 warps (warp % 4 selects the TMEM lane quarter a warp may read).
+// 4..11 = producer / epilogue warps (warp % 4 selects the TMEM lane quarter a warp may read; every warp converts a slice of
+// every operand chunk).
 //
 // Algorithmic HBM bytes per row: 4*D read + 4*n_out written; weights (640 KB of images per call) stay in L2.
 #include "common.cuh"
@@ -35,7 +36,7 @@ constexpr int B_PLANE = MAXN * 128;        // 32 KB
 constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;     // 96 KB
 constexpr int NTHREADS = 384;
 constexpr int EPI_WARP0 = 4;
-constexpr int MAX_K0 = 128;
+constexpr int MAX_K0 = 256;
 
 struct Tc5Params {
     const float* x;
@@ -65,16 +66,18 @@ __device__ long long g_tc5_trace[4096];
 #else
 #define TC5_STAMP(slot) do { } while (0)
 #endif
-// trace slots: role*1024 + (tile_iter*NC + chunk)*4 + event;  role 0 = loader, 1 = mma, 2 = producer group 0, 3 = group 1
+// trace slots: role*1024 + (tile_iter*NC + chunk)*4 + event;  role 0 = loader, 1 = mma, 2 = producer warp 0, 3 = head (per tile)
 
 struct SmemSmall {
     uint64_t full_a[2], full_b[2], empty[2];
     uint64_t acc1_full, acc2_full, acc1_empty, acc2_empty;
     uint32_t tmem_base;
     uint32_t pad_;
-    float zmean[MAX_K0], zstd[MAX_K0];
-    float b1[MAXN], b2[MAXN];
-    float w3[MAXN * MAX_OUT];
+    alignas(16) float zmean[MAX_K0];
+    alignas(16) float zstd[MAX_K0];
+    alignas(16) float b1[MAXN];
+    alignas(16) float b2[MAXN];
+    alignas(16) float w3[MAXN * MAX_OUT];
     float b3[MAX_OUT];
     float part[2][TM * MAX_OUT];
 };
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp3_tc5_kernel(const __grid_cons
     // ---- one-time setup ---------------------------------------------------------------------------------------------
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&sm->full_a[s], 4);          // the 4 warps of producer group s
+            mbar_init(&sm->full_a[s], 8);          // all 8 producer warps (each converts a slice of every chunk)
             mbar_init(&sm->full_b[s], 1);          // loader's arrive.expect_tx (+ the copies' bytes)
             mbar_init(&sm->empty[s], 1);           // tcgen05.commit
         }
@@ -144,9 +147,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp3_tc5_kernel(const __grid_cons
     if (warp == 2) tmem_alloc(&sm->tmem_base, 512);
     for (int i = tid; i < p.N1; i += NTHREADS) sm->b1[i] = p.b1[i];
     for (int i = tid; i < p.N2; i += NTHREADS) sm->b2[i] = p.b2[i];
-    for (int i = tid; i < p.N2 * p.n_out; i += NTHREADS) {
-        const int k = i / p.n_out, o = i - k * p.n_out;
-        sm->w3[k * MAX_OUT + o] = p.W3[(long long)k * p.ldw3 + o];
+    if (p.n_out == 1) {
+        for (int i = tid; i < p.N2; i += NTHREADS) sm->w3[i] = p.W3[(long long)i * p.ldw3];            // w3[col]
+    } else {
+        for (int i = tid; i < p.N2 * MAX_OUT; i += NTHREADS) {                                          // w3[col][8], zero-padded
+            const int k = i / MAX_OUT, o = i - k * MAX_OUT;
+            sm->w3[i] = (o < p.n_out) ? p.W3[(long long)k * p.ldw3 + o] : 0.0f;
+        }
     }
     if (tid < p.n_out) sm->b3[tid] = p.b3[tid];
     if (p.zf != nullptr) {
@@ -155,7 +162,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp3_tc5_kernel(const __grid_cons
             const float mean = p.zf[k] / cnt;
             const float var = p.zf[p.K0 + k] / cnt - mean * mean;
             sm->zmean[k] = mean;
-            sm->zstd[k] = fmaxf(sqrtf(var), p.zf_eps);
+            sm->zstd[k] = 1.0f / fmaxf(sqrtf(var), p.zf_eps);       // reciprocal: the filter multiplies (1 ulp vs the division)
         }
     }
     tc_fence_before();
@@ -228,14 +235,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp3_tc5_kernel(const __grid_cons
         }
         __syncwarp();
     } else if (warp >= EPI_WARP0) {
-        // ================= producer / epilogue groups =================
-        const int g = (warp - EPI_WARP0) >> 2;          // group 0 / 1 <-> stage 0 / 1
+        // ================= producer / epilogue warps =================
+        // All 8 warps work on EVERY chunk (halves the empty -> full latency of a stage): warp = (lane quarter qd, column
+        // half hf).  Layer-1 chunks are staged by the 256 threads together; of a layer-2 chunk a warp converts its 32 rows x
+        // 16 columns of accumulator 1.
+        const int w8 = warp - EPI_WARP0;
+        const int hf = w8 >> 2;                         // column half of a chunk / of the head
         const int qd = warp & 3;                        // TMEM lane quarter of this warp
-        const int gt = (warp - EPI_WARP0 - 4 * g) * 32 + lane;      // thread index inside the group, 0..127
+        const int t256 = w8 * 32 + lane;
         const int row = qd * 32 + lane;                 // tile row this thread owns in TMEM
         const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
-        unsigned char* a_hi = stage_base + (size_t)g * STAGE_BYTES;
-        unsigned char* a_lo = a_hi + A_PLANE;
         long long q = 0;
         for (long long it = 0; it < my_tiles; ++it) {
             const long long tile = (long long)blockIdx.x + it * gridDim.x;
@@ -243,34 +252,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp3_tc5_kernel(const __grid_cons
             const uint32_t tph = (uint32_t)(it & 1);
             bool acc1_ready = false;
             for (int c = 0; c < NC; ++c, ++q) {
-                if ((int)(q & 1) != g) continue;
+                const int s = (int)(q & 1);
                 const uint32_t u = (uint32_t)(q >> 1);
+                unsigned char* a_hi = stage_base + (size_t)s * STAGE_BYTES;
+                unsigned char* a_lo = a_hi + A_PLANE;
                 if (c >= NC1 && !acc1_ready) {
-                    // first layer-2 chunk of this group in this tile: accumulator 1 must be complete
-                    mbar_wait(&sm->acc1_full, tph);
+                    mbar_wait(&sm->acc1_full, tph);       // first layer-2 chunk of the tile: accumulator 1 must be complete
                     tc_fence_after();
                     acc1_ready = true;
                 }
-                if (qd == 0 && lane == 0) TC5_STAMP((2 + g) * 1024 + (int)q * 4 + 0);
-                mbar_wait(&sm->empty[g], (u & 1u) ^ 1u);          // the MMAs that read this stage's previous content are done
-                if (qd == 0 && lane == 0) TC5_STAMP((2 + g) * 1024 + (int)q * 4 + 1);
+                if (w8 == 0 && lane == 0) TC5_STAMP(2 * 1024 + (int)q * 4 + 0);
+                mbar_wait(&sm->empty[s], (u & 1u) ^ 1u);  // the MMAs that read this stage's previous content are done
+                if (w8 == 0 && lane == 0) TC5_STAMP(2 * 1024 + (int)q * 4 + 1);
                 if (c < NC1) {
                     // ---- layer-1 operand: 128 rows x 32 input columns, z-filtered, split into hi / lo planes
                     const int kbase = c * KC;
 #pragma unroll
-                    for (int pss = 0; pss < 8; ++pss) {
-                        const int idx = pss * 128 + gt;
+                    for (int pss = 0; pss < 4; ++pss) {
+                        const int idx = pss * 256 + t256;
                         const int r = idx >> 3, c16 = idx & 7;
                         const long long gr = row0 + r;
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (gr < p.rows) {
-                            v = *reinterpret_cast<const float4*>(row_ptr(p, gr) + kbase + c16 * 4);
+                            v = ld_stream4(row_ptr(p, gr) + kbase + c16 * 4);
                             if (p.zf != nullptr) {
                                 const int k = kbase + c16 * 4;
-                                v.x = fminf(fmaxf((v.x - sm->zmean[k + 0]) / sm->zstd[k + 0], -5.0f), 5.0f);
-                                v.y = fminf(fmaxf((v.y - sm->zmean[k + 1]) / sm->zstd[k + 1], -5.0f), 5.0f);
-                                v.z = fminf(fmaxf((v.z - sm->zmean[k + 2]) / sm->zstd[k + 2], -5.0f), 5.0f);
-                                v.w = fminf(fmaxf((v.w - sm->zmean[k + 3]) / sm->zstd[k + 3], -5.0f), 5.0f);
+                                v.x = fminf(fmaxf((v.x - sm->zmean[k + 0]) * sm->zstd[k + 0], -5.0f), 5.0f);
+                                v.y = fminf(fmaxf((v.y - sm->zmean[k + 1]) * sm->zstd[k + 1], -5.0f), 5.0f);
+                                v.z = fminf(fmaxf((v.z - sm->zmean[k + 2]) * sm->zstd[k + 2], -5.0f), 5.0f);
+                                v.w = fminf(fmaxf((v.w - sm->zmean[k + 3]) * sm->zstd[k + 3], -5.0f), 5.0f);
                             }
                         }
                         float4 hi, lo;
@@ -281,62 +291,80 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp3_tc5_kernel(const __grid_cons
                         *reinterpret_cast<float4*>(a_lo + off) = lo;
                     }
                 } else {
-                    // ---- layer-2 operand: relu(acc1[:, 32j .. 32j+32) + b1), this thread's row
+                    // ---- layer-2 operand: relu(acc1[:, 32j + 16hf .. +16) + b1), this thread's row
                     const int j = c - NC1;
-                    float v[32];
-                    tmem_ld32(acc1 + lane_base + (uint32_t)(j * KC), v);
-                    const float* bb = sm->b1 + j * KC;
+                    float v[16];
+                    tmem_ld16(acc1 + lane_base + (uint32_t)(j * KC + hf * 16), v);
+                    const float* bb = sm->b1 + j * KC + hf * 16;
 #pragma unroll
-                    for (int c16 = 0; c16 < 8; ++c16) {
+                    for (int i4 = 0; i4 < 4; ++i4) {
                         float4 hi, lo;
-                        split_tf32(fmaxf(v[c16 * 4 + 0] + bb[c16 * 4 + 0], 0.0f), hi.x, lo.x);
-                        split_tf32(fmaxf(v[c16 * 4 + 1] + bb[c16 * 4 + 1], 0.0f), hi.y, lo.y);
-                        split_tf32(fmaxf(v[c16 * 4 + 2] + bb[c16 * 4 + 2], 0.0f), hi.z, lo.z);
-                        split_tf32(fmaxf(v[c16 * 4 + 3] + bb[c16 * 4 + 3], 0.0f), hi.w, lo.w);
-                        const uint32_t off = sw128_off((uint32_t)row, (uint32_t)(c16 * 4));
+                        split_tf32(fmaxf(v[i4 * 4 + 0] + bb[i4 * 4 + 0], 0.0f), hi.x, lo.x);
+                        split_tf32(fmaxf(v[i4 * 4 + 1] + bb[i4 * 4 + 1], 0.0f), hi.y, lo.y);
+                        split_tf32(fmaxf(v[i4 * 4 + 2] + bb[i4 * 4 + 2], 0.0f), hi.z, lo.z);
+                        split_tf32(fmaxf(v[i4 * 4 + 3] + bb[i4 * 4 + 3], 0.0f), hi.w, lo.w);
+                        const uint32_t off = sw128_off((uint32_t)row, (uint32_t)(hf * 16 + i4 * 4));
                         *reinterpret_cast<float4*>(a_hi + off) = hi;
                         *reinterpret_cast<float4*>(a_lo + off) = lo;
                     }
                 }
                 fence_async_smem();                       // generic-proxy stores -> visible to tcgen05.mma
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&sm->full_a[g]);
-                if (qd == 0 && lane == 0) TC5_STAMP((2 + g) * 1024 + (int)q * 4 + 2);
+                if (lane == 0) mbar_arrive(&sm->full_a[s]);
+                if (w8 == 0 && lane == 0) TC5_STAMP(2 * 1024 + (int)q * 4 + 2);
             }
-            // every layer-2 operand of this group has been read out of accumulator 1
+            // every layer-2 operand has been read out of accumulator 1
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm->acc1_empty);
-            // ---- head: relu(acc2 + b2) . W3 + b3; group g covers columns [g*N2/2, (g+1)*N2/2)
+            // ---- head: relu(acc2 + b2) . W3 + b3; column half hf covers [hf*N2/2, (hf+1)*N2/2)
             mbar_wait(&sm->acc2_full, tph);
             tc_fence_after();
+            if (w8 == 0 && lane == 0) TC5_STAMP(3 * 1024 + (int)it * 4 + 0);
             float o[MAX_OUT];
 #pragma unroll
             for (int k = 0; k < MAX_OUT; ++k) o[k] = 0.0f;
             const int half = p.N2 >> 1;
-            for (int cc = g * half; cc < (g + 1) * half; cc += 32) {
-                float v[32];
-                tmem_ld32(acc2 + lane_base + (uint32_t)cc, v);
+            if (p.n_out == 1) {
+                for (int cc = hf * half; cc < (hf + 1) * half; cc += 32) {
+                    float v[32];
+                    tmem_ld32(acc2 + lane_base + (uint32_t)cc, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float h = fmaxf(v[i] + sm->b2[cc + i], 0.0f);
-                    const float* wr = sm->w3 + (cc + i) * MAX_OUT;
+                    for (int i4 = 0; i4 < 8; ++i4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(sm->b2 + cc + i4 * 4);
+                        const float4 w4 = *reinterpret_cast<const float4*>(sm->w3 + cc + i4 * 4);     // n_out == 1: w3[col]
+                        o[0] = fmaf(fmaxf(v[i4 * 4 + 0] + b4.x, 0.0f), w4.x, o[0]);
+                        o[0] = fmaf(fmaxf(v[i4 * 4 + 1] + b4.y, 0.0f), w4.y, o[0]);
+                        o[0] = fmaf(fmaxf(v[i4 * 4 + 2] + b4.z, 0.0f), w4.z, o[0]);
+                        o[0] = fmaf(fmaxf(v[i4 * 4 + 3] + b4.w, 0.0f), w4.w, o[0]);
+                    }
+                }
+            } else {
+                for (int cc = hf * half; cc < (hf + 1) * half; cc += 32) {
+                    float v[32];
+                    tmem_ld32(acc2 + lane_base + (uint32_t)cc, v);
 #pragma unroll
-                    for (int k = 0; k < MAX_OUT; ++k)
-                        if (k < p.n_out) o[k] = fmaf(h, wr[k], o[k]);
+                    for (int i = 0; i < 32; ++i) {
+                        const float h = fmaxf(v[i] + sm->b2[cc + i], 0.0f);
+                        const float4 wa = *reinterpret_cast<const float4*>(sm->w3 + (cc + i) * MAX_OUT);       // zero-padded
+                        const float4 wb = *reinterpret_cast<const float4*>(sm->w3 + (cc + i) * MAX_OUT + 4);
+                        o[0] = fmaf(h, wa.x, o[0]); o[1] = fmaf(h, wa.y, o[1]); o[2] = fmaf(h, wa.z, o[2]); o[3] = fmaf(h, wa.w, o[3]);
+                        o[4] = fmaf(h, wb.x, o[4]); o[5] = fmaf(h, wb.y, o[5]); o[6] = fmaf(h, wb.z, o[6]); o[7] = fmaf(h, wb.w, o[7]);
+                    }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm->acc2_empty);
+            if (w8 == 0 && lane == 0) TC5_STAMP(3 * 1024 + (int)it * 4 + 1);
             float* part = sm->part[it & 1];
-            if (g == 1) {
+            if (hf == 1) {
 #pragma unroll
                 for (int k = 0; k < MAX_OUT; ++k)
                     if (k < p.n_out) part[row * MAX_OUT + k] = o[k];
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");          // the 8 epilogue warps only
-            if (g == 0) {
+            if (hf == 0) {
                 const long long gr = row0 + row;
                 if (gr < p.rows) {
 #pragma unroll

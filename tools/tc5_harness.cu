@@ -151,7 +151,7 @@ static void cpu_forward(const Net& n, const float* x, const float* zf, float eps
             const float mean = zf[k] / cnt;
             const float var = zf[n.K0 + k] / cnt - mean * mean;
             const float sd = fmaxf(sqrtf(var), eps);
-            v = fminf(fmaxf((v - mean) / sd, -5.f), 5.f);
+            v = fminf(fmaxf((v - mean) / sd, -5.f), 5.f);            // the reference divides; the kernel multiplies by 1/sd
         }
         h0[k] = v;
     }
@@ -288,7 +288,7 @@ int main(int argc, char** argv) {
         static long long tr[4096];
         CK(cudaMemcpyFromSymbol(tr, g_tc5_trace, sizeof(tr)));
         long long t0 = tr[1 * 1024 + 0];
-        const char* roles[4] = {"loader", "mma", "prod0", "prod1"};
+        const char* roles[4] = {"loader", "mma", "prod", "head(tile q)"};
         printf("timeline of CTA 0 (cycles since the MMA thread first waited); chunks q = tile*10 + c\n");
         for (int q = 0; q < 30; ++q) {
             printf("q=%2d |", q);
