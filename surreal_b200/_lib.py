@@ -73,6 +73,7 @@ def _declare(lib):
         'sb200_mlp_tc5_supported': (I, [C.POINTER(Mlp), L]),
         'sb200_mlp_tc5_workspace_bytes': (S, [C.POINTER(Mlp)]),
         'sb200_mlp_forward_tc5_f32': (I, [C.POINTER(Mlp), C.POINTER(ZFilter), C.POINTER(Rows), P, L, P, P]),
+        'sb200_synth_pixel_env_step_u8': (I, [P, P, I, L, I, I, P, C.c_uint64, P, P, P, P, P]),
         'sb200_conv_forward_f32': (I, [I, P, I, L, I, I, I, P, P, D, P, P]),
         'sb200_conv_backward_dw_f32': (I, [I, P, I, P, L, I, I, I, D, P, P, L, I, P]),
         'sb200_conv_backward_dx_f32': (I, [I, P, P, P, L, I, I, I, P, P]),

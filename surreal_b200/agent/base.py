@@ -162,7 +162,8 @@ class Agent(metaclass=U.AutoInitializeMeta):
         if not getattr(self.env, 'graph_safe', False):
             return False
         import torch
-        x = obs['low_dim']['flat_inputs'] if isinstance(obs, dict) else obs
+        from ..utils import obs_flat
+        x = obs_flat(obs)
         return isinstance(x, torch.Tensor) and x.is_cuda
 
     def get_env(self):
@@ -173,6 +174,11 @@ class Agent(metaclass=U.AutoInitializeMeta):
             raise ValueError('only the device-resident synthetic env ships with surreal_b200 (env_name "synthetic"); '
                              'gym / dm_control / robosuite adapters are out of scope -- pass your own env to '
                              'main_setup(env)')
+        from ..utils import obs_is_pixel
+        if obs_is_pixel(ec.obs_spec):
+            from ..env import SyntheticPixelEnv
+            return SyntheticPixelEnv(self.num_envs, tuple(ec.obs_spec['pixel']['camera0']), ec.action_spec.dim[0],
+                                     ec.limit_episode_length, seed=int(ec.seed) if 'seed' in ec else 0)
         D = sum(v[0] for v in ec.obs_spec['low_dim'].values())
         return SyntheticEnv(self.num_envs, D, ec.action_spec.dim[0], ec.limit_episode_length,
                             seed=int(ec.seed) if 'seed' in ec else 0)

@@ -69,6 +69,8 @@ class PPOAgent(Agent):
         """-> action (eval) or (action, [onetime_infos, [pd]]) in training, like ppo_agent.py:151-154.
         Device observations give device results; numpy in, numpy out."""
         N, A, D = self.num_envs, self.action_dim, self.model.low_dim
+        if self.model.cnn_stem is not None:
+            return self._act_pixel(obs, eps)
         x = obs
         if isinstance(obs, dict):
             xs = [obs['low_dim'][k] for k in obs['low_dim']]
@@ -132,6 +134,62 @@ class PPOAgent(Agent):
             pd = self._out_pin[1].numpy().copy()
             if N == 1 and np.asarray(obs['low_dim'][next(iter(obs['low_dim']))] if isinstance(obs, dict) else obs).ndim == 1:
                 action, pd = action.reshape(-1), pd.reshape(-1)
+        else:
+            action, pd = self._action, self._pd
+        if self.agent_mode != 'training':
+            return action
+        if self.env_config.sleep_time:
+            time.sleep(self.env_config.sleep_time)
+        return action, [[], [pd]]
+
+    def _act_pixel(self, obs, eps=None):
+        """act() on uint8 frames [N, C, H, W] (device tensor or numpy): CNN stem -> actor head -> sampling kernel
+        (ppo_net.py:268-273,368-375; ppo_agent.py:138-149)."""
+        N, A = self.num_envs, self.action_dim
+        m, stem = self.model, self.model.cnn_stem
+        fr = obs['pixel']['camera0'] if isinstance(obs, dict) else obs
+        host = not isinstance(fr, torch.Tensor)
+        if host:
+            if self._obs_pin is None:
+                self._obs_pin = torch.empty(N, stem.C, stem.H, stem.W, dtype=torch.uint8, pin_memory=True)
+                self._frames_dev = torch.empty(N, stem.C, stem.H, stem.W, dtype=torch.uint8, device=self.device)
+            self._obs_pin.numpy()[...] = np.asarray(fr, dtype=np.uint8).reshape(N, stem.C, stem.H, stem.W)
+            self._frames_dev.copy_(self._obs_pin, non_blocking=True)
+            fr = self._frames_dev
+        fr = fr.reshape(N, stem.C, stem.H, stem.W)
+        if getattr(self, '_stem_bufs', None) is None:
+            self._stem_bufs = stem.buffers(N)
+        feat = stem.forward(fr, self._stem_bufs)
+        ops.mlp_forward(m.actor, feat, out=self._mean)
+        det = self.agent_mode in ['eval_deterministic', 'eval_deterministic_local']
+        env = self.env
+        staged = self.agent_mode == 'training' and isinstance(env, ExpSenderWrapperMultiStepMovingWindowWithInfo)
+        counter = env.step_counter if (env is not None and hasattr(env, 'step_counter')) else self._counter
+        eps_dev = None
+        if eps is not None:
+            eps_dev = torch.as_tensor(np.asarray(eps, dtype=np.float32).reshape(N, A)).to(self.device)
+        if staged and counter is not self._counter and env.fuse_launches:
+            fifo_state, dest = env.slot_assignment_args()
+            check(_lib.lib().sb200_ppo_sample_assign_f32(
+                _p(self._mean), A, _p(m.log_var), _p(self._log_noise), _p(eps_dev), N, A, int(det), self.seed,
+                _p(counter), _p(self._action), _p(self._pd), _p(env.stage_pos), _p(env.stage_act), _p(env.stage_pd),
+                env.n_step, _p(fifo_state), _p(dest), ops._stream()), 'sb200_ppo_sample_assign_f32')
+        else:
+            check(_lib.lib().sb200_ppo_sample_f32(
+                _p(self._mean), A, _p(m.log_var), _p(self._log_noise), _p(eps_dev), N, A, int(det), self.seed,
+                _p(counter), _p(self._action), _p(self._pd), _p(env.stage_pos) if staged else None,
+                _p(env.stage_act) if staged else None, _p(env.stage_pd) if staged else None,
+                env.n_step if staged else 1, ops._stream()), 'sb200_ppo_sample_f32')
+        if not staged and counter is self._counter:
+            self._counter += 1
+        if host:
+            if self._out_pin is None:
+                self._out_pin = (torch.empty(N, A, dtype=torch.float32, pin_memory=True),
+                                 torch.empty(N, 2 * A, dtype=torch.float32, pin_memory=True))
+            self._out_pin[0].copy_(self._action, non_blocking=True)
+            self._out_pin[1].copy_(self._pd, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            action, pd = self._out_pin[0].numpy().astype(np.float64), self._out_pin[1].numpy().copy()
         else:
             action, pd = self._action, self._pd
         if self.agent_mode != 'training':

@@ -69,7 +69,7 @@ __device__ long long g_tc5_trace[4096];
 // trace slots: role*1024 + (tile_iter*NC + chunk)*4 + event;  role 0 = loader, 1 = mma, 2 = producer warp 0, 3 = head (per tile)
 
 struct SmemSmall {
-    uint64_t full_a[2], full_b[2], empty[2];
+    uint64_t full[2], empty[2];
     uint64_t acc1_full, acc2_full, acc1_empty, acc2_empty;
     uint32_t tmem_base;
     uint32_t pad_;
@@ -134,8 +134,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp3_tc5_kernel(const __grid_cons
     // ---- one-time setup ---------------------------------------------------------------------------------------------
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&sm->full_a[s], 8);          // all 8 producer warps (each converts a slice of every chunk)
-            mbar_init(&sm->full_b[s], 1);          // loader's arrive.expect_tx (+ the copies' bytes)
+            mbar_init(&sm->full[s], 9);            // 8 producer warps (operand A slices) + the loader's arrive.expect_tx (B bytes)
             mbar_init(&sm->empty[s], 1);           // tcgen05.commit
         }
         mbar_init(&sm->acc1_full, 1);
@@ -187,9 +186,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp3_tc5_kernel(const __grid_cons
                     const uint32_t bytes = (c < NC1) ? bytes1 : bytes2;
                     unsigned char* st = stage_base + (size_t)s * STAGE_BYTES + 2 * A_PLANE;
                     const unsigned char* src = p.wimg + (size_t)c * 2 * B_PLANE;
-                    mbar_arrive_expect_tx(&sm->full_b[s], 2 * bytes);
-                    bulk_g2s(st, src, bytes, &sm->full_b[s]);
-                    bulk_g2s(st + B_PLANE, src + B_PLANE, bytes, &sm->full_b[s]);
+                    mbar_arrive_expect_tx(&sm->full[s], 2 * bytes);
+                    bulk_g2s(st, src, bytes, &sm->full[s]);
+                    bulk_g2s(st + B_PLANE, src + B_PLANE, bytes, &sm->full[s]);
                 }
             }
         }
@@ -207,9 +206,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp3_tc5_kernel(const __grid_cons
                     if (it > 0 && c == 0) mbar_wait(&sm->acc1_empty, tph ^ 1u);      // previous tile's accumulator 1 was read
                     if (it > 0 && c == NC1) mbar_wait(&sm->acc2_empty, tph ^ 1u);    // previous tile's accumulator 2 was read
                     TC5_STAMP(1 * 1024 + (int)q * 4 + 0);
-                    mbar_wait(&sm->full_a[s], u & 1u);
-                    TC5_STAMP(1 * 1024 + (int)q * 4 + 1);
-                    mbar_wait(&sm->full_b[s], u & 1u);
+                    mbar_wait(&sm->full[s], u & 1u);                                  // operand A written AND operand B landed
                     TC5_STAMP(1 * 1024 + (int)q * 4 + 2);
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(stage_base + (size_t)s * STAGE_BYTES);
@@ -245,6 +242,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp3_tc5_kernel(const __grid_cons
         const int t256 = w8 * 32 + lane;
         const int row = qd * 32 + lane;                 // tile row this thread owns in TMEM
         const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+        // the first XPF layer-1 chunks of the NEXT tile are loaded into registers before the head of the current one, so
+        // that their global-memory latency hides behind the head instead of sitting on the tile boundary
+        constexpr int XPF = 2;
+        float4 xpf[XPF][4];
+        auto prefetch_x = [&](long long r0) {
+#pragma unroll
+            for (int c = 0; c < XPF; ++c)
+#pragma unroll
+                for (int pss = 0; pss < 4; ++pss) {
+                    const int idx = pss * 256 + t256;
+                    const long long gr = r0 + (idx >> 3);
+                    xpf[c][pss] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (c < NC1 && gr < p.rows) xpf[c][pss] = ld_stream4(row_ptr(p, gr) + c * KC + (idx & 7) * 4);
+                }
+        };
+        if (my_tiles > 0) prefetch_x((long long)blockIdx.x * TM);
         long long q = 0;
         for (long long it = 0; it < my_tiles; ++it) {
             const long long tile = (long long)blockIdx.x + it * gridDim.x;
@@ -274,7 +287,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp3_tc5_kernel(const __grid_cons
                         const long long gr = row0 + r;
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (gr < p.rows) {
-                            v = ld_stream4(row_ptr(p, gr) + kbase + c16 * 4);
+                            if (c < XPF) v = (c == 0) ? xpf[0][pss] : xpf[1][pss];
+                            else v = ld_stream4(row_ptr(p, gr) + kbase + c16 * 4);
                             if (p.zf != nullptr) {
                                 const int k = kbase + c16 * 4;
                                 v.x = fminf(fmaxf((v.x - sm->zmean[k + 0]) * sm->zstd[k + 0], -5.0f), 5.0f);
@@ -310,13 +324,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp3_tc5_kernel(const __grid_cons
                 }
                 fence_async_smem();                       // generic-proxy stores -> visible to tcgen05.mma
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&sm->full_a[s]);
+                if (lane == 0) mbar_arrive(&sm->full[s]);
                 if (w8 == 0 && lane == 0) TC5_STAMP(2 * 1024 + (int)q * 4 + 2);
             }
             // every layer-2 operand has been read out of accumulator 1
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm->acc1_empty);
+            if (it + 1 < my_tiles) prefetch_x((tile + gridDim.x) * TM);
             // ---- head: relu(acc2 + b2) . W3 + b3; column half hf covers [hf*N2/2, (hf+1)*N2/2)
             mbar_wait(&sm->acc2_full, tph);
             tc_fence_after();

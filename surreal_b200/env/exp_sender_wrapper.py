@@ -13,6 +13,7 @@ from .. import _lib
 from .._lib import check
 from ..distributed import LocalHub
 from ..session import ConfigError
+from ..utils import obs_flat
 
 
 def _p(t):
@@ -118,7 +119,7 @@ class ExpSenderWrapperMultiStepMovingWindowWithInfo(_WrapperBase):
     def reset(self):
         obs, info = self.env.reset()
         self.stage_pos.zero_()                                     # deque.clear() (exp_sender_wrapper.py:204-207)
-        o = obs['low_dim']['flat_inputs'] if isinstance(obs, dict) else obs
+        o = obs_flat(obs)
         if self.host_env:
             d = self._h2d('obs', o, (self.N, self.D))
             self.stage_obs[:, 0].copy_(d)
@@ -162,8 +163,8 @@ class ExpSenderWrapperMultiStepMovingWindowWithInfo(_WrapperBase):
         if ready and hasattr(self.env, 'step_and_commit_window'):
             return self.env.step_and_commit_window(a, self)        # env step + commit in ONE launch
         obs, reward, done, info = self.env.step(a)
-        o = obs['low_dim']['flat_inputs'] if isinstance(obs, dict) else obs
-        on = info['obs_next'] if (isinstance(info, dict) and 'obs_next' in info) else o
+        o = obs_flat(obs)
+        on = obs_flat(info['obs_next']) if (isinstance(info, dict) and 'obs_next' in info) else o
         if self.host_env:
             # host env: this step's successor observation / reward / done cross PCIe here (256 KB + 8 KB), issued with
             # the staging kernels from ONE C call; the device copy of the next observation is handed to the agent's

@@ -80,3 +80,57 @@ class SyntheticEnv:
 
     def close(self):
         pass
+
+
+class SyntheticPixelEnv:
+    """Batched device-resident PIXEL env of BASELINE configs[3] (SURVEY §8d cfg 4): every step each actor observes a fresh
+    uint8 frame [C, H, W] of uniform random bytes; reward = -mean(a^2) + 0.1 xi; episodes end at ``limit_episode_length``.
+    The staging / replay kernels see a frame as C*H*W/4 opaque 32-bit words (``D``), so frames stay uint8 in HBM."""
+    metadata = {}
+    graph_safe = True
+
+    def __init__(self, num_envs, frame_shape=(4, 84, 84), action_dim=8, limit_episode_length=200, seed=0, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError('SyntheticPixelEnv is device-resident: a CUDA device is required')
+        self.device = torch.device(device if device is not None else ('cuda:%d' % torch.cuda.current_device()))
+        self.N, self.A = num_envs, action_dim
+        self.frame_shape = tuple(int(v) for v in frame_shape)
+        self.frame_bytes = 1
+        for v in self.frame_shape:
+            self.frame_bytes *= v
+        assert self.frame_bytes % 16 == 0, 'C*H*W must be a multiple of 16 bytes'
+        self.D = self.frame_bytes // 4
+        self.max_steps = int(limit_episode_length)
+        self.seed = int(seed)
+        self._g = torch.Generator().manual_seed(self.seed + 1)
+        self.state = torch.zeros(num_envs, self.frame_bytes, dtype=torch.uint8, device=self.device)
+        self.obs_next = torch.zeros_like(self.state)
+        self.ep_step = torch.zeros(num_envs, dtype=torch.int32, device=self.device)
+        self.reward = torch.zeros(num_envs, device=self.device)
+        self.done = torch.zeros(num_envs, device=self.device)
+        self.step_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+
+    def _obs(self, frames):
+        return {'pixel': {'camera0': frames.view(self.N, *self.frame_shape)}}
+
+    def observation_spec(self):
+        return {'pixel': {'camera0': self.frame_shape}}
+
+    def action_spec(self):
+        return {'dim': (self.A,), 'type': 'continuous'}
+
+    def reset(self):
+        self.state.copy_(torch.randint(0, 256, (self.N, self.frame_bytes), generator=self._g, dtype=torch.uint8).to(self.device))
+        self.ep_step.zero_()
+        return self._obs(self.state), {}
+
+    def step(self, action):
+        if isinstance(action, tuple):
+            action = action[0]
+        check(_lib.lib().sb200_synth_pixel_env_step_u8(
+            _p(self.state), _p(action), self.N, self.frame_bytes, self.A, self.max_steps, _p(self.ep_step), self.seed + 7,
+            _p(self.step_counter), _p(self.obs_next), _p(self.reward), _p(self.done), _stream()), 'sb200_synth_pixel_env_step_u8')
+        return self._obs(self.state), self.reward, self.done, {'obs_next': self._obs(self.obs_next)}
+
+    def close(self):
+        pass

@@ -13,6 +13,7 @@ import numpy as np
 import torch
 
 from .. import _lib, ops
+from .. import utils as U
 from .._lib import check
 from ..model.ppo_net import PPOModel, DiagGauss
 from ..session import ConfigError
@@ -26,6 +27,10 @@ S = dict(SURR=0, LOSS=1, ENTROPY=2, KL_PRE=3, KL_POST=4, GN_ACTOR=5, VAL_LOSS=6,
 
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def stem_shape(stem):
+    return (stem.C, stem.H, stem.W)
 
 
 class PPOLearner(Learner):
@@ -99,17 +104,32 @@ class PPOLearner(Learner):
         self.critic_gradient_clip_value = net.critic_gradient_norm_clip
 
         B, n, A = self.batch_size, self.n_step, self.action_dim
-        D = self.model.low_dim
+        self.pixel = self.model.cnn_stem is not None
+        # width of one observation in the batch buffers: the low-dim features, or the uint8 frame as 32-bit words
+        D = U.obs_packed_dim(self.obs_spec) if self.pixel else self.model.low_dim
         self.low_dim = D
         dev = self.device
         self.actor_optim = ops.MlpTrainer(self.model.actor, B, self.lr_actor,
                                           clip_mode=1 if self.clip_actor_gradient else 0,
                                           clip_value=self.actor_gradient_clip_value,
-                                          weight_decay=net.actor_regularization)
+                                          weight_decay=net.actor_regularization, input_grad=self.pixel)
         self.critic_optim = ops.MlpTrainer(self.model.critic, B, self.lr_critic,
                                            clip_mode=1 if self.clip_critic_gradient else 0,
                                            clip_value=self.critic_gradient_clip_value,
-                                           weight_decay=net.critic_regularization)
+                                           weight_decay=net.critic_regularization, input_grad=self.pixel)
+        if self.pixel:
+            # the CNN stem is shared by actor and critic and trained by BOTH optimisers, each with its own Adam state
+            # (ppo_net.py:202-224): one StemTrainer per optimiser, gradients of head + stem in one contiguous buffer
+            from ..model.cnn_stem import StemTrainer
+            stem = self.model.cnn_stem
+            self.actor_stem, self.critic_stem = StemTrainer(stem, B), StemTrainer(stem, B)
+            self._g_actor = torch.zeros(self.model.actor.size + stem.size, dtype=torch.float32, device=dev)
+            self._g_critic = torch.zeros(self.model.critic.size + stem.size, dtype=torch.float32, device=dev)
+            self.actor_optim.grad = self._g_actor[:self.model.actor.size]
+            self.critic_optim.grad = self._g_critic[:self.model.critic.size]
+            self._frames0 = torch.zeros(B, *stem_shape(stem), dtype=torch.uint8, device=dev)
+            self._stem_all = None                                 # activation buffers of the B*(n+1)-frame critic pass
+            self._ref_stem_bufs = self.ref_target_model.cnn_stem.buffers(B)
 
         # learning-rate schedule (ppo.py:121-125,171-178)
         an = net.anneal
@@ -147,7 +167,8 @@ class PPOLearner(Learner):
         self._pin = {}
         self._gae_ws = torch.zeros(int(L.sb200_gae_workspace_bytes(B, n, n)), dtype=torch.uint8, device=dev)
         self.use_cuda_graph = ops.graphs_enabled()
-        self.parallel_branches = os.environ.get("SB200_PPO_FORK", "1") != "0"   # policy || value epochs
+        # policy || value epochs as concurrent graph branches -- not in pixel mode, where both optimisers update the SHARED stem
+        self.parallel_branches = os.environ.get("SB200_PPO_FORK", "1") != "0" and not self.pixel
         # tensor pipe || FMA pipe critic pass: measured SLOWER (701-757 us) than the 2-CTA/SM tensor-core tiles alone
         # (631 us) -- both kernels are issue-bound, they do not add up -- so it stays an experiment
         self.dual_critic = os.environ.get("SB200_DUAL_CRITIC", "0") == "1"
@@ -229,6 +250,21 @@ class PPOLearner(Learner):
             own['obs_full'].copy_(full, non_blocking=True)
             nbytes += own['obs_full'].numel() * 4
             obs = None
+        elif self.pixel:
+            obs = None
+            fo, fn = get('obs')['pixel']['camera0'], get('obs_next')['pixel']['camera0']
+            u8 = own['obs_full'].view(torch.uint8).view(B, n + 1, -1)
+            if isinstance(fo, torch.Tensor):
+                u8[:, :n].copy_(fo.reshape(B, n, -1), non_blocking=True)
+                u8[:, n:].copy_(fn.reshape(B, 1, -1), non_blocking=True)
+            else:
+                if 'frames' not in self._pin:
+                    self._pin['frames'] = torch.empty(B, n + 1, u8.shape[-1], dtype=torch.uint8, pin_memory=True)
+                pf = self._pin['frames'].numpy()
+                pf[:, :n] = np.asarray(fo, dtype=np.uint8).reshape(B, n, -1)
+                pf[:, n:] = np.asarray(fn, dtype=np.uint8).reshape(B, 1, -1)
+                u8.copy_(self._pin['frames'], non_blocking=True)
+                nbytes += u8.numel()
         else:
             obs, obs_next = self._low_dim(get('obs')), self._low_dim(get('obs_next'))
         if obs is None:
@@ -258,7 +294,18 @@ class PPOLearner(Learner):
         m = self.model
         ev = self._prof_begin()
         rows = B * (n + 1)
-        if rows >= self.tc5_min_rows and self._tc5.supported(rows):
+        if self.pixel:
+            # all B*(n+1) frames through the shared stem, then the critic head on the features (ppo.py:376-387, 5-D obs)
+            stem = m.cnn_stem
+            if self._stem_all is None:
+                self._stem_all = stem.buffers(rows)
+            frames = self._obs_full.view(torch.uint8).view(rows, *stem_shape(stem))
+            feat = stem.forward(frames, self._stem_all)
+            if rows >= self.tc5_min_rows and self._tc5.supported(rows):
+                self._tc5(feat, self._values.view(rows, 1))
+            else:
+                ops.mlp_forward(m.critic, feat, out=self._values)
+        elif rows >= self.tc5_min_rows and self._tc5.supported(rows):
             # Blackwell-native path: tcgen05.mma tiles, accumulators in TMEM, weights streamed by the TMA engine
             self._tc5(self._obs_full.view(rows, -1), self._values.view(rows, 1), zf_stats=m.z_stats, zf_eps=m.z_eps)
         elif self.dual_critic and rows >= 32768:
@@ -318,8 +365,11 @@ class PPOLearner(Learner):
         L = _lib.lib()
         B, n, A, D = self.batch_size, self.n_step, self.action_dim, self.low_dim
         m, tr, st = self.model, self.actor_optim, ops._stream()
-        mean = tr.forward(self._obs_full, zf_stats=m.z_stats, zf_eps=m.z_eps, rows=B, ldx=(n + 1) * D) if fresh \
-            else tr.out
+        if self.pixel:
+            mean = tr.forward(self.actor_stem.forward(self._frames0)) if fresh else tr.out
+        else:
+            mean = tr.forward(self._obs_full, zf_stats=m.z_stats, zf_eps=m.z_eps, rows=B, ldx=(n + 1) * D) if fresh \
+                else tr.out
         mode = 0 if self.ppo_mode == 'clip' else 1
         if mode == 1:
             self._kl(mean, S['KL_PRE'], 0.0, stop)
@@ -330,9 +380,15 @@ class PPOLearner(Learner):
                                           tr.d[-1].stride(0), _ptr(dlog_var), _ptr(self._stats), _ptr(self._loss_ws),
                                           _ptr(stop), st), 'sb200_ppo_policy_loss_f32')
         tr.backward()
-        tr.step(norm_out=self._stats[S['GN_ACTOR']:S['GN_ACTOR'] + 1], stop_flag=stop)
-        # post-step KL(ref || current) (ppo.py:553-556)
-        self._cur_mean = tr.forward(self._obs_full, zf_stats=m.z_stats, zf_eps=m.z_eps, rows=B, ldx=(n + 1) * D)
+        if self.pixel:
+            from ..model.cnn_stem import joint_step
+            self.actor_stem.backward(tr.dx0)
+            joint_step(tr, self.actor_stem, self._g_actor, norm_out=self._stats[S['GN_ACTOR']:S['GN_ACTOR'] + 1], stop_flag=stop)
+            self._cur_mean = tr.forward(self.actor_stem.forward(self._frames0))
+        else:
+            tr.step(norm_out=self._stats[S['GN_ACTOR']:S['GN_ACTOR'] + 1], stop_flag=stop)
+            # post-step KL(ref || current) (ppo.py:553-556)
+            self._cur_mean = tr.forward(self._obs_full, zf_stats=m.z_stats, zf_eps=m.z_eps, rows=B, ldx=(n + 1) * D)
         self._kl(self._cur_mean, S['KL_POST'], 4.0 * self.kl_target, self._stop)
 
     def _kl(self, mean, slot, threshold, stop):
@@ -394,18 +450,32 @@ class PPOLearner(Learner):
         L = _lib.lib()
         B, n, D = self.batch_size, self.n_step, self.low_dim
         m, tr, st = self.model, self.critic_optim, ops._stream()
-        v = tr.forward(self._obs_full, zf_stats=m.z_stats, zf_eps=m.z_eps, rows=B, ldx=(n + 1) * D)
+        if self.pixel:
+            v = tr.forward(self.critic_stem.forward(self._frames0))
+        else:
+            v = tr.forward(self._obs_full, zf_stats=m.z_stats, zf_eps=m.z_eps, rows=B, ldx=(n + 1) * D)
         check(L.sb200_value_loss_f32(_ptr(v), v.stride(0), _ptr(self._ret), B, _ptr(tr.d[-1]), tr.d[-1].stride(0),
                                      _ptr(self._stats), _ptr(self._loss_ws_v), st), 'sb200_value_loss_f32')
         tr.backward()
-        tr.step(norm_out=self._stats[S['GN_CRITIC']:S['GN_CRITIC'] + 1])
+        if self.pixel:
+            from ..model.cnn_stem import joint_step
+            self.critic_stem.backward(tr.dx0)
+            joint_step(tr, self.critic_stem, self._g_critic, norm_out=self._stats[S['GN_CRITIC']:S['GN_CRITIC'] + 1])
+        else:
+            tr.step(norm_out=self._stats[S['GN_CRITIC']:S['GN_CRITIC'] + 1])
 
     def _optimize_head(self):
         B, n, A, D = self.batch_size, self.n_step, self.action_dim, self.low_dim
         ref = self.ref_target_model
         self._gae_and_return()
-        ops.mlp_forward(ref.actor, self._obs_full, zf_stats=ref.z_stats, zf_eps=ref.z_eps, rows=B, ldx=(n + 1) * D,
-                        out=self._ref_mean)
+        if self.pixel:
+            # step-0 frames of every window, contiguous (ppo.py:527-537), then the reference policy on them
+            fr = self._obs_full.view(torch.uint8).view(B, n + 1, -1)
+            self._frames0.view(B, -1).copy_(fr[:, 0])
+            ops.mlp_forward(ref.actor, ref.cnn_stem.forward(self._frames0, self._ref_stem_bufs), out=self._ref_mean)
+        else:
+            ops.mlp_forward(ref.actor, self._obs_full, zf_stats=ref.z_stats, zf_eps=ref.z_eps, rows=B, ldx=(n + 1) * D,
+                            out=self._ref_mean)
         ops.make_pd(self._ref_mean, ref.log_var, B, A, self._ref_pd)
         self._stats.zero_()
         self._stop.zero_()

@@ -25,8 +25,8 @@ def _default_linear_init(dims, seed_gen=None):
 
 
 class PPOModel:
-    """Same constructor keywords as the reference's PPOModel (ppo_net.py:110-118).  The LSTM / CNN stems are
-    'next' rows of SURVEY §8f and raise here."""
+    """Same constructor keywords as the reference's PPOModel (ppo_net.py:110-118).  The LSTM stem is a
+    'next' row of SURVEY §8f and raises here; the CNN stem (pixel input) is model/cnn_stem.py."""
 
     def __init__(self, obs_spec, action_dim, model_config, use_cuda=True, init_log_sig=0, use_z_filter=False,
                  if_pixel_input=False, rnn_config=None, device=None):
@@ -36,8 +36,7 @@ class PPOModel:
         self.obs_spec, self.action_dim, self.model_config = obs_spec, action_dim, model_config
         self.use_z_filter, self.init_log_sig = use_z_filter, init_log_sig
         self.if_pixel_input, self.rnn_config = if_pixel_input, rnn_config
-        if if_pixel_input:
-            raise NotImplementedError('CNN stem (builders.py:8-33) is not built yet (SURVEY §8 K16)')
+        self.cnn_stem = None
         if rnn_config is not None and rnn_config.if_rnn_policy:
             raise NotImplementedError('LSTM stem (ppo_net.py:143-152) is a "next" row (SURVEY §8f rank 2); '
                                       'set algo.rnn.if_rnn_policy=False')
@@ -45,7 +44,15 @@ class PPOModel:
         if 'low_dim' in obs_spec:
             for key in obs_spec['low_dim']:
                 self.low_dim += obs_spec['low_dim'][key][0]
-        D, A = self.low_dim, action_dim
+        if if_pixel_input:
+            # optional CNN stem feature extractor (ppo_net.py:136-140), shared by actor and critic
+            if self.low_dim > 0:
+                raise NotImplementedError('mixed low_dim + pixel observations (ppo_net.py:268-275 concatenates them) are not '
+                                          'supported: the HBM replay records carry one observation kind')
+            from .cnn_stem import CNNStem
+            self.cnn_stem = CNNStem(obs_spec['pixel']['camera0'], model_config.cnn_feature_dim, self.device)
+        in_dim = self.low_dim + (model_config.cnn_feature_dim if if_pixel_input else 0)
+        D, A = in_dim, action_dim
         ah, ch = list(model_config.actor_fc_hidden_sizes), list(model_config.critic_fc_hidden_sizes)
         R, T, N = ops.ACT_RELU, ops.ACT_TANH, ops.ACT_NONE
         self.actor = ops.FlatNet([D] + ah + [A], [R] * len(ah) + [T], self.device, extra=A)
@@ -55,8 +62,8 @@ class PPOModel:
         self.z_eps = 1e-5
         self.z_stats = None
         if use_z_filter:
-            assert D > 0, 'No low dimensional input, please turn off z-filter'
-            self.z_stats = torch.cat([torch.zeros(D), self.z_eps * torch.ones(D),
+            assert self.low_dim > 0, 'No low dimensional input, please turn off z-filter'
+            self.z_stats = torch.cat([torch.zeros(self.low_dim), self.z_eps * torch.ones(self.low_dim),
                                       torch.tensor([self.z_eps])]).to(self.device)
 
     # -- parameters --------------------------------------------------------------------------------
@@ -68,6 +75,8 @@ class PPOModel:
         """ppo_net.py:226-242: actor, critic and z-filter."""
         self.actor.params.copy_(net.actor.params)
         self.critic.params.copy_(net.critic.params)
+        if self.cnn_stem is not None:
+            self.cnn_stem.params.copy_(net.cnn_stem.params)
         if self.use_z_filter:
             self.z_stats.copy_(net.z_stats)
 
@@ -78,6 +87,8 @@ class PPOModel:
     def flat_state(self):
         """The raw device buffers (kernel layout) -- what the collapsed parameter wire ships."""
         st = {'actor': self.actor.params, 'critic': self.critic.params}
+        if self.cnn_stem is not None:
+            st['cnn_stem'] = self.cnn_stem.params
         if self.use_z_filter:
             st['z_stats'] = self.z_stats
         return st
@@ -85,6 +96,8 @@ class PPOModel:
     def load_flat_state(self, st):
         self.actor.params.copy_(st['actor'])
         self.critic.params.copy_(st['critic'])
+        if self.cnn_stem is not None and 'cnn_stem' in st:
+            self.cnn_stem.params.copy_(st['cnn_stem'])
         if self.use_z_filter and 'z_stats' in st:
             self.z_stats.copy_(st['z_stats'])
 
@@ -92,6 +105,9 @@ class PPOModel:
         """Keys follow the reference module tree (actor.log_var, actor.model.*, critic.model.*, z_filter.*);
         Linear weights are exported in torch's [out, in] convention."""
         sd = collections.OrderedDict()
+        if self.cnn_stem is not None:
+            for k, v in self.cnn_stem.state_items():
+                sd[k] = v
         sd['actor.log_var'] = self.log_var.detach().clone().view(1, -1)
         for name, net in (('actor', self.actor), ('critic', self.critic)):
             for l in range(net.n_layers):
@@ -107,6 +123,8 @@ class PPOModel:
 
     def load_state_dict(self, sd):
         g = lambda k: torch.as_tensor(sd[k], dtype=torch.float32)  # noqa: E731
+        if self.cnn_stem is not None:
+            self.cnn_stem.load_state(sd)
         self.log_var.copy_(g('actor.log_var').reshape(-1).to(self.device))
         for name, net in (('actor', self.actor), ('critic', self.critic)):
             for l in range(net.n_layers):
@@ -123,8 +141,24 @@ class PPOModel:
             return xs[0] if len(xs) == 1 else torch.cat(xs, -1)
         return obs
 
+    def _features(self, obs):
+        """Pixel mode: uint8 frames [rows, C, H, W] -> CNN features (ppo_net.py:268-273,368-375)."""
+        fr = obs['pixel']['camera0'] if isinstance(obs, dict) else obs
+        fr = fr.reshape(-1, *fr.shape[-3:]).contiguous()
+        rows = fr.shape[0]
+        if getattr(self, '_stem_bufs_rows', None) != rows:
+            self._stem_bufs, self._stem_bufs_rows = self.cnn_stem.buffers(rows), rows
+        return self.cnn_stem.forward(fr, self._stem_bufs)
+
     def forward_actor(self, obs, cells=None, out_pd=None):
         """-> [rows, 2A] = cat(mean, std) (builders.py:114-132)."""
+        if self.cnn_stem is not None:
+            x2 = self._features(obs)
+            mean = ops.mlp_forward(self.actor, x2)
+            B, A = mean.shape[0], self.action_dim
+            pd = out_pd if out_pd is not None else torch.empty(B, 2 * A, dtype=torch.float32, device=self.device)
+            ops.make_pd(mean, self.log_var, B, A, pd)
+            return pd
         x = self._flat(obs)
         x2 = x.reshape(-1, x.shape[-1])
         mean = ops.mlp_forward(self.actor, x2, zf_stats=self.z_stats, zf_eps=self.z_eps)
@@ -134,6 +168,8 @@ class PPOModel:
         return pd
 
     def forward_critic(self, obs, cells=None):
+        if self.cnn_stem is not None:
+            return ops.mlp_forward(self.critic, self._features(obs))
         x = self._flat(obs)
         x2 = x.reshape(-1, x.shape[-1])
         return ops.mlp_forward(self.critic, x2, zf_stats=self.z_stats, zf_eps=self.z_eps)

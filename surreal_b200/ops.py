@@ -289,7 +289,7 @@ class MlpTrainer:
     """Forward-with-saved-activations, hand-written backward and Adam for one FlatNet on a fixed
     batch size M.  All buffers are allocated once; every method only launches kernels (graph-safe)."""
 
-    def __init__(self, net, M, lr, clip_mode=0, clip_value=0.0, weight_decay=0.0, splits=None):
+    def __init__(self, net, M, lr, clip_mode=0, clip_value=0.0, weight_decay=0.0, splits=None, input_grad=False):
         L = _lib.lib()
         self.net, self.M = net, M
         dev = net.device
@@ -305,6 +305,9 @@ class MlpTrainer:
         self.d = [z(M, _ru(n, 4)) for n in net.dims[1:]]          # gradients w.r.t. pre-activations
         self.aux = None
         self._aux_pad = None
+        # gradient w.r.t. the pre-activation of whatever produced the network input (times relu'(input)): the CNN stem's
+        # Linear layer sits in front of the PPO heads in pixel mode
+        self.dx0 = z(M, _ru(net.dims[0], 4)) if input_grad else None
         self.overlap_dw = os.environ.get('SB200_OVERLAP_DW', '1') != '0'
         self._side = None
         if net.aux_layer >= 0 and net.aux_dim % 4 != 0:       # pre-allocated: nothing may allocate during graph capture
@@ -373,6 +376,11 @@ class MlpTrainer:
                     dw_layer(l, _stream())
             else:
                 dw_layer(l, _stream())
+        if self.dx0 is not None:
+            lay = net.layout[0]
+            check(L.sb200_linear_bwd_dx_f32(_ptr(self.d[0]), self.d[0].stride(0), C.c_void_p(net.params.data_ptr() + 4 * lay['w']),
+                                            lay['ldw'], _ptr(self.x_in), self.x_in.stride(0), _ptr(self.dx0), self.dx0.stride(0), M,
+                                            lay['N'], net.dims[0], _stream()), 'sb200_linear_bwd_dx_f32(input)')
         if side is not None:
             main.wait_stream(side)
 

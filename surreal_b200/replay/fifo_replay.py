@@ -40,7 +40,9 @@ class FIFOReplay(Replay):
             raise RuntimeError('surreal_b200.FIFOReplay lives in HBM: a CUDA device is required')
         self.device = torch.device('cuda', torch.cuda.current_device())
         self.n_step = self.learner_config.algo.n_step
-        self.D = sum(v[0] for v in self.env_config.obs_spec['low_dim'].values())
+        from ..utils import obs_packed_dim, obs_is_pixel
+        self.D = obs_packed_dim(self.env_config.obs_spec)       # pixel frames ride as opaque 32-bit words (uint8 in HBM)
+        self.pixel_shape = tuple(self.env_config.obs_spec['pixel']['camera0']) if obs_is_pixel(self.env_config.obs_spec) else None
         self.A = self.env_config.action_spec.dim[0]
         self.capacity = self.memory_size + 3                    # "+ 3 for a gentle buffering" (fifo_replay.py:27)
         C_, n, D, A = self.capacity, self.n_step, self.D, self.A
@@ -78,8 +80,11 @@ class FIFOReplay(Replay):
         """``exp``: the dict ExpSenderWrapperMultiStepMovingWindowWithInfo.send emits
         (exp_sender_wrapper.py:244-264): obs [n dicts], obs_next, actions, rewards, dones, persistent_infos."""
         n, D, A = self.n_step, self.D, self.A
-        flat = lambda o: np.concatenate([np.asarray(o['low_dim'][k], dtype=np.float32).reshape(-1)  # noqa: E731
-                                         for k in o['low_dim']])
+        if self.pixel_shape is not None:       # uint8 frame -> the same bytes viewed as float32 words
+            flat = lambda o: np.ascontiguousarray(np.asarray(o['pixel']['camera0'], dtype=np.uint8)).reshape(-1).view(np.float32)  # noqa: E731
+        else:
+            flat = lambda o: np.concatenate([np.asarray(o['low_dim'][k], dtype=np.float32).reshape(-1)  # noqa: E731
+                                             for k in o['low_dim']])
         assert len(exp['obs']) == n, 'window length %d != n_step %d' % (len(exp['obs']), n)
         rec = n * (D + A + 2 * A + 2) + D
         if self._pin is None:
@@ -124,6 +129,11 @@ class FIFOReplay(Replay):
         if self.check_underflow and int(self._status.item()) != 0:      # host sync; the engine polls
             raise IndexError('pop from a FIFO replay holding fewer than %d windows' % batch_size)   # len() instead
         obs_full = out['obs_full']
+        if self.pixel_shape is not None:
+            fr = obs_full.view(torch.uint8).view(batch_size, n + 1, *self.pixel_shape)
+            return {'obs': {'pixel': {'camera0': fr[:, :n]}}, 'obs_next': {'pixel': {'camera0': fr[:, n:]}},
+                    'obs_full': obs_full, 'actions': out['actions'], 'rewards': out['rewards'], 'dones': out['dones'],
+                    'persistent_infos': [out['pd']], 'onetime_infos': None}
         return {'obs': {'low_dim': {'flat_inputs': obs_full[:, :n, :]}},
                 'obs_next': {'low_dim': {'flat_inputs': obs_full[:, n:, :]}},
                 'obs_full': obs_full, 'actions': out['actions'], 'rewards': out['rewards'], 'dones': out['dones'],

@@ -133,3 +133,37 @@ def get_logger(name):
         log.addHandler(h)
         log.setLevel(logging.WARNING)
     return log
+
+
+def obs_is_pixel(obs_spec):
+    """True for a pixel-only observation spec ({'pixel': {'camera0': (C, H, W)}}, docs/env.md:79-108)."""
+    return 'pixel' in obs_spec and len(obs_spec['pixel']) > 0
+
+
+def obs_packed_dim(obs_spec):
+    """Floats per observation in the HBM staging / replay records.  Low-dim observations: the concatenated feature width.
+    Pixel observations: the uint8 frame is carried as an opaque run of C*H*W/4 32-bit words (only ever COPIED by the
+    windowing / replay kernels, never computed on), so frames stay uint8 in HBM: 28 224 B per 4x84x84 frame."""
+    if obs_is_pixel(obs_spec):
+        if 'low_dim' in obs_spec and len(obs_spec['low_dim']) > 0:
+            raise NotImplementedError('mixed low_dim + pixel observations are not supported by the HBM replay records')
+        shape = tuple(obs_spec['pixel']['camera0'])
+        n = 1
+        for v in shape:
+            n *= int(v)
+        if n % 16 != 0:
+            raise ValueError('pixel observations need C*H*W to be a multiple of 16 bytes, got %s' % (shape,))
+        return n // 4
+    return sum(v[0] for v in obs_spec['low_dim'].values())
+
+
+def obs_flat(obs):
+    """The per-actor rows [N, packed_dim] the staging kernels copy: the low-dim feature tensor, or the uint8 frames viewed
+    as 32-bit words."""
+    import torch
+    if isinstance(obs, dict):
+        if 'low_dim' in obs and len(obs['low_dim']) > 0:
+            return obs['low_dim']['flat_inputs'] if 'flat_inputs' in obs['low_dim'] else next(iter(obs['low_dim'].values()))
+        fr = obs['pixel']['camera0']
+        return fr.reshape(fr.shape[0], -1).view(torch.float32)
+    return obs
