@@ -148,6 +148,30 @@ int sb200_synth_pixel_env_step_u8(void* state, const float* action, int N, int64
                                   int* ep_step, uint64_t seed, const uint64_t* step_counter, void* obs_next, float* reward,
                                   float* done, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * One-shot all-reduce over NVLink peer memory (csrc/peer_allreduce.cu) for the small exchanges of the data-parallel
+ * learner (the reference has no collective at all): every rank maps every other rank's "symmetric" buffer
+ * (cudaMalloc + CUDA IPC), one kernel per all-reduce publishes its slice, waits for the peers' flags and sums the slots
+ * in rank order (bit-identical result on all ranks).
+ *   par_alloc / par_open / par_close: allocate + export (64-byte IPC handle) / map a peer's buffer / release.
+ *   par_allreduce_f32: out = scale * sum over ranks of x (n <= max_floats); with opt_workspace != NULL it also does
+ *     the gradient-norm / step bookkeeping of sb200_grad_reduce_norm_f32 on the result.  EVERY rank must issue the
+ *     same sequence of calls on one sb200_par (use separate ones for streams that run concurrently).
+ *   par_allreduce_f64: the same for a few float64 scalars. */
+typedef struct {
+    void* peers[8];                     /* device pointers of every rank's symmetric buffer, valid in THIS process */
+    int world;
+    int rank;
+    int64_t max_floats;                 /* capacity of one slot */
+} sb200_par;
+size_t sb200_par_buffer_bytes(int64_t max_floats);
+int sb200_par_alloc(int64_t max_floats, void** ptr_out, void* handle_out);
+int sb200_par_open(const void* handle, void** ptr_out);
+int sb200_par_close(void* ptr, int own);
+int sb200_par_allreduce_f32(const sb200_par* ctx, const float* x, float* out, int64_t n, double scale, int bump_step,
+                            void* opt_workspace, const int* stop_flag, void* stream);
+int sb200_par_allreduce_f64(const sb200_par* ctx, const double* x, double* out, int n, double scale, void* stream);
+
 /* Kernel family of the wide layers of sb200_mlp_forward_f32: 1 (default) = tensor-core mma.sync TF32 with the 3xTF32
  * error-compensated split (fp32-level accuracy, ~1e-6 relative) for batches above 2048 rows, fp32 FFMA below (where
  * the FFMA kernel is faster: 19 us vs 26 us at 1024 rows); 0 = fp32 FFMA kernels everywhere.  Env SB200_MMA overrides

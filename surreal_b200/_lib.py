@@ -43,6 +43,11 @@ class PPORollout(C.Structure):
                 ('n_step', C.c_int), ('stride', C.c_int), ('T', C.c_int), ('step_counter', C.c_void_p)]
 
 
+class Par(C.Structure):
+    """sb200_par (include/surreal_b200.h)."""
+    _fields_ = [('peers', C.c_void_p * 8), ('world', C.c_int), ('rank', C.c_int), ('max_floats', C.c_int64)]
+
+
 class ZFilter(C.Structure):
     _fields_ = [('stats', C.c_void_p), ('eps', C.c_float)]
 
@@ -74,6 +79,12 @@ def _declare(lib):
         'sb200_mlp_tc5_workspace_bytes': (S, [C.POINTER(Mlp)]),
         'sb200_mlp_forward_tc5_f32': (I, [C.POINTER(Mlp), C.POINTER(ZFilter), C.POINTER(Rows), P, L, P, P]),
         'sb200_synth_pixel_env_step_u8': (I, [P, P, I, L, I, I, P, C.c_uint64, P, P, P, P, P]),
+        'sb200_par_buffer_bytes': (S, [L]),
+        'sb200_par_alloc': (I, [L, C.POINTER(C.c_void_p), P]),
+        'sb200_par_open': (I, [P, C.POINTER(C.c_void_p)]),
+        'sb200_par_close': (I, [P, I]),
+        'sb200_par_allreduce_f32': (I, [C.POINTER(Par), P, P, L, D, I, P, P, P]),
+        'sb200_par_allreduce_f64': (I, [C.POINTER(Par), P, P, I, D, P]),
         'sb200_conv_forward_f32': (I, [I, P, I, L, I, I, I, P, P, D, P, P]),
         'sb200_conv_backward_dw_f32': (I, [I, P, I, P, L, I, I, I, D, P, P, L, I, P]),
         'sb200_conv_backward_dx_f32': (I, [I, P, P, P, L, I, I, I, P, P]),

@@ -412,11 +412,14 @@ class PPOLearner(Learner):
         from ..parallel import LearnerDP
         if self.use_r_filter:
             raise NotImplementedError('reward filter + data parallel')
-        self.dp = LearnerDP(group)
+        stem_n = self.model.cnn_stem.size if self.pixel else 0
+        peer_floats = max(self.model.actor.size, self.model.critic.size) + stem_n + 64
+        self.dp = LearnerDP(group, peer_floats=peer_floats)
         # the value branch gets its OWN communicator: with the policy || value fork both branches issue collectives
         # concurrently, and two streams must never interleave on one communicator
         import torch.distributed as dist
-        self.dp_v = LearnerDP(dist.new_group(ranks=list(range(self.dp.world)))) if self.parallel_branches else self.dp
+        self.dp_v = LearnerDP(dist.new_group(ranks=list(range(self.dp.world))), peer_floats=peer_floats) \
+            if self.parallel_branches else self.dp
         self.actor_optim.dp = self.dp
         self.critic_optim.dp = self.dp_v
         for mdl in (self.model, self.ref_target_model):

@@ -417,10 +417,11 @@ class MlpTrainer:
             # local slabs -> local grad; ONE flat all-reduce; average + global norm + step count
             check(L.sb200_grad_reduce_norm_f32(_ptr(self.slabs), net.size, self.splits, _ptr(self.grad), net.size,
                                                1.0, 0, _ptr(self.ws), None, st), 'sb200_grad_reduce_norm_f32')
-            dp.sum_(self.grad)
-            check(L.sb200_grad_reduce_norm_f32(_ptr(self.grad), net.size, 1, _ptr(self.grad), net.size,
-                                               1.0 / dp.world, 1, _ptr(self.ws), _ptr(stop_flag), st),
-                  'sb200_grad_reduce_norm_f32')
+            # one kernel over NVLink peer memory: all-reduce + average + global norm + step count; else NCCL + a second pass
+            if not (hasattr(dp, 'reduce_grad_') and dp.reduce_grad_(self.grad, self.ws, stop_flag)):
+                check(L.sb200_grad_reduce_norm_f32(_ptr(self.grad), net.size, 1, _ptr(self.grad), net.size,
+                                                   1.0 / dp.world, 1, _ptr(self.ws), _ptr(stop_flag), st),
+                      'sb200_grad_reduce_norm_f32')
         check(L.sb200_clip_adam_f32(_ptr(net.params), _ptr(self.grad), _ptr(self.exp_avg), _ptr(self.exp_avg_sq),
                                     net.size, _ptr(self.lr), 0.9, 0.999, 1e-8, self.weight_decay, self.clip_mode,
                                     self.clip_value, _ptr(self.ws), _ptr(norm_out), _ptr(stop_flag), st),
