@@ -257,81 +257,87 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp3_tc5_kernel(const __grid_cons
                     if (c < NC1 && gr < p.rows) xpf[c][pss] = ld_stream4(row_ptr(p, gr) + c * KC + (idx & 7) * 4);
                 }
         };
-        if (my_tiles > 0) prefetch_x((long long)blockIdx.x * TM);
-        long long q = 0;
+        // one operand chunk (tile iteration `it`, chunk c) into stage (q & 1)
+        auto produce = [&](long long it, int c) {
+            const long long q = it * NC + c;
+            const long long row0 = ((long long)blockIdx.x + it * gridDim.x) * TM;
+            const int s = (int)(q & 1);
+            const uint32_t u = (uint32_t)(q >> 1);
+            unsigned char* a_hi = stage_base + (size_t)s * STAGE_BYTES;
+            unsigned char* a_lo = a_hi + A_PLANE;
+            if (w8 == 0 && lane == 0) TC5_STAMP(2 * 1024 + (int)q * 4 + 0);
+            mbar_wait(&sm->empty[s], (u & 1u) ^ 1u);      // the MMAs that read this stage's previous content are done
+            if (w8 == 0 && lane == 0) TC5_STAMP(2 * 1024 + (int)q * 4 + 1);
+            if (c < NC1) {
+                // ---- layer-1 operand: 128 rows x 32 input columns, z-filtered, split into hi / lo planes
+                const int kbase = c * KC;
+#pragma unroll
+                for (int pss = 0; pss < 4; ++pss) {
+                    const int idx = pss * 256 + t256;
+                    const int r = idx >> 3, c16 = idx & 7;
+                    const long long gr = row0 + r;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (gr < p.rows) {
+                        if (c < XPF) v = (c == 0) ? xpf[0][pss] : xpf[1][pss];
+                        else v = ld_stream4(row_ptr(p, gr) + kbase + c16 * 4);
+                        if (p.zf != nullptr) {
+                            const int k = kbase + c16 * 4;
+                            v.x = fminf(fmaxf((v.x - sm->zmean[k + 0]) * sm->zstd[k + 0], -5.0f), 5.0f);
+                            v.y = fminf(fmaxf((v.y - sm->zmean[k + 1]) * sm->zstd[k + 1], -5.0f), 5.0f);
+                            v.z = fminf(fmaxf((v.z - sm->zmean[k + 2]) * sm->zstd[k + 2], -5.0f), 5.0f);
+                            v.w = fminf(fmaxf((v.w - sm->zmean[k + 3]) * sm->zstd[k + 3], -5.0f), 5.0f);
+                        }
+                    }
+                    float4 hi, lo;
+                    split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y);
+                    split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+                    const uint32_t off = sw128_off((uint32_t)r, (uint32_t)(c16 * 4));
+                    *reinterpret_cast<float4*>(a_hi + off) = hi;
+                    *reinterpret_cast<float4*>(a_lo + off) = lo;
+                }
+            } else {
+                // ---- layer-2 operand: relu(acc1[:, 32j + 16hf .. +16) + b1), this thread's row
+                const int j = c - NC1;
+                float v[16];
+                tmem_ld16(acc1 + lane_base + (uint32_t)(j * KC + hf * 16), v);
+                const float* bb = sm->b1 + j * KC + hf * 16;
+#pragma unroll
+                for (int i4 = 0; i4 < 4; ++i4) {
+                    float4 hi, lo;
+                    split_tf32(fmaxf(v[i4 * 4 + 0] + bb[i4 * 4 + 0], 0.0f), hi.x, lo.x);
+                    split_tf32(fmaxf(v[i4 * 4 + 1] + bb[i4 * 4 + 1], 0.0f), hi.y, lo.y);
+                    split_tf32(fmaxf(v[i4 * 4 + 2] + bb[i4 * 4 + 2], 0.0f), hi.z, lo.z);
+                    split_tf32(fmaxf(v[i4 * 4 + 3] + bb[i4 * 4 + 3], 0.0f), hi.w, lo.w);
+                    const uint32_t off = sw128_off((uint32_t)row, (uint32_t)(hf * 16 + i4 * 4));
+                    *reinterpret_cast<float4*>(a_hi + off) = hi;
+                    *reinterpret_cast<float4*>(a_lo + off) = lo;
+                }
+            }
+            fence_async_smem();                           // generic-proxy stores -> visible to tcgen05.mma
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm->full[s]);
+            if (w8 == 0 && lane == 0) TC5_STAMP(2 * 1024 + (int)q * 4 + 2);
+        };
+        // Order per tile: [layer-2 operands of tile it] -> [layer-1 operands of tile it+1] -> [head of tile it]: the next
+        // tile's first MMAs start while this tile's head is still being computed.
+        if (my_tiles > 0) {
+            prefetch_x((long long)blockIdx.x * TM);
+            for (int c = 0; c < NC1; ++c) produce(0, c);
+        }
         for (long long it = 0; it < my_tiles; ++it) {
             const long long tile = (long long)blockIdx.x + it * gridDim.x;
             const long long row0 = tile * TM;
             const uint32_t tph = (uint32_t)(it & 1);
-            bool acc1_ready = false;
-            for (int c = 0; c < NC; ++c, ++q) {
-                const int s = (int)(q & 1);
-                const uint32_t u = (uint32_t)(q >> 1);
-                unsigned char* a_hi = stage_base + (size_t)s * STAGE_BYTES;
-                unsigned char* a_lo = a_hi + A_PLANE;
-                if (c >= NC1 && !acc1_ready) {
-                    mbar_wait(&sm->acc1_full, tph);       // first layer-2 chunk of the tile: accumulator 1 must be complete
-                    tc_fence_after();
-                    acc1_ready = true;
-                }
-                if (w8 == 0 && lane == 0) TC5_STAMP(2 * 1024 + (int)q * 4 + 0);
-                mbar_wait(&sm->empty[s], (u & 1u) ^ 1u);  // the MMAs that read this stage's previous content are done
-                if (w8 == 0 && lane == 0) TC5_STAMP(2 * 1024 + (int)q * 4 + 1);
-                if (c < NC1) {
-                    // ---- layer-1 operand: 128 rows x 32 input columns, z-filtered, split into hi / lo planes
-                    const int kbase = c * KC;
-#pragma unroll
-                    for (int pss = 0; pss < 4; ++pss) {
-                        const int idx = pss * 256 + t256;
-                        const int r = idx >> 3, c16 = idx & 7;
-                        const long long gr = row0 + r;
-                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (gr < p.rows) {
-                            if (c < XPF) v = (c == 0) ? xpf[0][pss] : xpf[1][pss];
-                            else v = ld_stream4(row_ptr(p, gr) + kbase + c16 * 4);
-                            if (p.zf != nullptr) {
-                                const int k = kbase + c16 * 4;
-                                v.x = fminf(fmaxf((v.x - sm->zmean[k + 0]) * sm->zstd[k + 0], -5.0f), 5.0f);
-                                v.y = fminf(fmaxf((v.y - sm->zmean[k + 1]) * sm->zstd[k + 1], -5.0f), 5.0f);
-                                v.z = fminf(fmaxf((v.z - sm->zmean[k + 2]) * sm->zstd[k + 2], -5.0f), 5.0f);
-                                v.w = fminf(fmaxf((v.w - sm->zmean[k + 3]) * sm->zstd[k + 3], -5.0f), 5.0f);
-                            }
-                        }
-                        float4 hi, lo;
-                        split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y);
-                        split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
-                        const uint32_t off = sw128_off((uint32_t)r, (uint32_t)(c16 * 4));
-                        *reinterpret_cast<float4*>(a_hi + off) = hi;
-                        *reinterpret_cast<float4*>(a_lo + off) = lo;
-                    }
-                } else {
-                    // ---- layer-2 operand: relu(acc1[:, 32j + 16hf .. +16) + b1), this thread's row
-                    const int j = c - NC1;
-                    float v[16];
-                    tmem_ld16(acc1 + lane_base + (uint32_t)(j * KC + hf * 16), v);
-                    const float* bb = sm->b1 + j * KC + hf * 16;
-#pragma unroll
-                    for (int i4 = 0; i4 < 4; ++i4) {
-                        float4 hi, lo;
-                        split_tf32(fmaxf(v[i4 * 4 + 0] + bb[i4 * 4 + 0], 0.0f), hi.x, lo.x);
-                        split_tf32(fmaxf(v[i4 * 4 + 1] + bb[i4 * 4 + 1], 0.0f), hi.y, lo.y);
-                        split_tf32(fmaxf(v[i4 * 4 + 2] + bb[i4 * 4 + 2], 0.0f), hi.z, lo.z);
-                        split_tf32(fmaxf(v[i4 * 4 + 3] + bb[i4 * 4 + 3], 0.0f), hi.w, lo.w);
-                        const uint32_t off = sw128_off((uint32_t)row, (uint32_t)(hf * 16 + i4 * 4));
-                        *reinterpret_cast<float4*>(a_hi + off) = hi;
-                        *reinterpret_cast<float4*>(a_lo + off) = lo;
-                    }
-                }
-                fence_async_smem();                       // generic-proxy stores -> visible to tcgen05.mma
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm->full[s]);
-                if (w8 == 0 && lane == 0) TC5_STAMP(2 * 1024 + (int)q * 4 + 2);
-            }
+            if (it + 1 < my_tiles) prefetch_x((tile + gridDim.x) * TM);      // lands while layer 2 of this tile is converted
+            mbar_wait(&sm->acc1_full, tph);               // accumulator 1 of this tile is complete
+            tc_fence_after();
+            for (int c = NC1; c < NC; ++c) produce(it, c);
             // every layer-2 operand has been read out of accumulator 1
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm->acc1_empty);
-            if (it + 1 < my_tiles) prefetch_x((tile + gridDim.x) * TM);
+            if (it + 1 < my_tiles)
+                for (int c = 0; c < NC1; ++c) produce(it + 1, c);
             // ---- head: relu(acc2 + b2) . W3 + b3; column half hf covers [hf*N2/2, (hf+1)*N2/2)
             mbar_wait(&sm->acc2_full, tph);
             tc_fence_after();
