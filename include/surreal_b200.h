@@ -172,6 +172,23 @@ int sb200_par_allreduce_f32(const sb200_par* ctx, const float* x, float* out, in
                             void* opt_workspace, const int* stop_flag, void* stream);
 int sb200_par_allreduce_f64(const sb200_par* ctx, const double* x, double* out, int n, double scale, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * LSTM stem of RNN-mode PPO (csrc/lstm.cu; nn.LSTM(batch_first=True) of ppo_net.py:143-152,277-279,342-351; BPTT over
+ * eff_len = n_step - horizon + 1 steps, ppo.py:389-406,507-525).  Gate order i, f, g, o; WhhT = [H][4H].
+ *   rows_zfilter: out[b*L + t][0..D) = zfilter(x[b*batch_stride + t*row_stride + 0..D)) (plain gather if zf_stats NULL).
+ *   lstm_forward: pre_x [B*L][4H] = x W_ih^T + b_ih (an MLP-kernel call); h0 / c0 row b at element b*ld_cells (NULL: zeros);
+ *     h_out [B*L][ldh]; optional saves for the backward pass: h_prev (h_{t-1}, [B*L][ldh]), gates (post-activation), c_seq; optional
+ *     final cells h_last / c_last [B][H].
+ *   lstm_backward: dh_out [B*L][ldd] (gradient w.r.t. h_t) -> dpre [B*L][4H] (w.r.t. the gate pre-activations); the
+ *     weight gradients are then sb200_linear_bwd_dw_f32(x, dpre) and sb200_linear_bwd_dw_f32(h_prev, dpre). */
+int sb200_rows_zfilter_f32(const float* x, int64_t row_stride, int64_t batch_stride, int B, int L, int D,
+                           const float* zf_stats, double eps, float* out, int64_t ldo, void* stream);
+int sb200_lstm_forward_f32(const float* pre_x, const float* WhhT, const float* b_hh, const float* h0, const float* c0,
+                           int64_t ld_cells, int B, int L, int H, int ldh, float* h_out, float* h_prev, float* gates,
+                           float* c_seq, float* h_last, float* c_last, void* stream);
+int sb200_lstm_backward_f32(const float* dh_out, int64_t ldd, const float* gates, const float* c_seq, const float* c0,
+                            int64_t ld_cells, const float* WhhT, int B, int L, int H, float* dpre, void* stream);
+
 /* Kernel family of the wide layers of sb200_mlp_forward_f32: 1 (default) = tensor-core mma.sync TF32 with the 3xTF32
  * error-compensated split (fp32-level accuracy, ~1e-6 relative) for batches above 2048 rows, fp32 FFMA below (where
  * the FFMA kernel is faster: 19 us vs 26 us at 1024 rows); 0 = fp32 FFMA kernels everywhere.  Env SB200_MMA overrides

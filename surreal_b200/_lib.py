@@ -85,6 +85,9 @@ def _declare(lib):
         'sb200_par_close': (I, [P, I]),
         'sb200_par_allreduce_f32': (I, [C.POINTER(Par), P, P, L, D, I, P, P, P]),
         'sb200_par_allreduce_f64': (I, [C.POINTER(Par), P, P, I, D, P]),
+        'sb200_rows_zfilter_f32': (I, [P, L, L, I, I, I, P, D, P, L, P]),
+        'sb200_lstm_forward_f32': (I, [P, P, P, P, P, L, I, I, I, I, P, P, P, P, P, P, P]),
+        'sb200_lstm_backward_f32': (I, [P, L, P, P, P, L, P, I, I, I, P, P]),
         'sb200_conv_forward_f32': (I, [I, P, I, L, I, I, I, P, P, D, P, P]),
         'sb200_conv_backward_dw_f32': (I, [I, P, I, P, L, I, I, I, D, P, P, L, I, P]),
         'sb200_conv_backward_dx_f32': (I, [I, P, P, P, L, I, I, I, P, P]),

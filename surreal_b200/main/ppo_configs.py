@@ -85,6 +85,18 @@ def make_synthetic_env_config(env_config, num_envs, obs_dim=64, action_dim=8, se
     return env_config
 
 
+def make_synthetic_pixel_env_config(env_config, num_envs, frame_shape=(4, 84, 84), action_dim=8, seed=0):
+    """Pixel flavour (BASELINE configs[3]): obs_spec = {'pixel': {'camera0': (C, H, W)}}, pixel_input on -- what
+    surreal.env.make_env_config fills in for a pixel env (docs/env.md:79-108)."""
+    env_config.env_name = 'synthetic-pixel'
+    env_config.num_envs = int(num_envs)
+    env_config.seed = int(seed)
+    env_config.pixel_input = True
+    env_config.obs_spec = {'pixel': {'camera0': tuple(int(v) for v in frame_shape)}}
+    env_config.action_spec = {'dim': (action_dim,), 'type': 'continuous'}
+    return env_config
+
+
 class PPOLauncher:
     """PPOLauncher of ppo_configs.py:178-228 (constructed lazily so importing configs needs no GPU)."""
 

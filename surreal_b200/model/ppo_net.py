@@ -37,9 +37,8 @@ class PPOModel:
         self.use_z_filter, self.init_log_sig = use_z_filter, init_log_sig
         self.if_pixel_input, self.rnn_config = if_pixel_input, rnn_config
         self.cnn_stem = None
-        if rnn_config is not None and rnn_config.if_rnn_policy:
-            raise NotImplementedError('LSTM stem (ppo_net.py:143-152) is a "next" row (SURVEY §8f rank 2); '
-                                      'set algo.rnn.if_rnn_policy=False')
+        self.rnn_stem = None
+        self.if_rnn = bool(rnn_config is not None and rnn_config.if_rnn_policy)
         self.low_dim = 0
         if 'low_dim' in obs_spec:
             for key in obs_spec['low_dim']:
@@ -52,6 +51,13 @@ class PPOModel:
             from .cnn_stem import CNNStem
             self.cnn_stem = CNNStem(obs_spec['pixel']['camera0'], model_config.cnn_feature_dim, self.device)
         in_dim = self.low_dim + (model_config.cnn_feature_dim if if_pixel_input else 0)
+        if self.if_rnn:
+            # optional LSTM stem feature extractor (ppo_net.py:143-152), shared by actor and critic
+            if if_pixel_input:
+                raise NotImplementedError('CNN + LSTM stems together (pixel input with if_rnn_policy) are not built')
+            from .lstm_stem import LSTMStem
+            self.rnn_stem = LSTMStem(in_dim, rnn_config.rnn_hidden, self.device, layers=rnn_config.rnn_layer)
+            in_dim = rnn_config.rnn_hidden
         D, A = in_dim, action_dim
         ah, ch = list(model_config.actor_fc_hidden_sizes), list(model_config.critic_fc_hidden_sizes)
         R, T, N = ops.ACT_RELU, ops.ACT_TANH, ops.ACT_NONE
@@ -77,6 +83,8 @@ class PPOModel:
         self.critic.params.copy_(net.critic.params)
         if self.cnn_stem is not None:
             self.cnn_stem.params.copy_(net.cnn_stem.params)
+        if self.rnn_stem is not None:
+            self.rnn_stem.params.copy_(net.rnn_stem.params)
         if self.use_z_filter:
             self.z_stats.copy_(net.z_stats)
 
@@ -89,6 +97,8 @@ class PPOModel:
         st = {'actor': self.actor.params, 'critic': self.critic.params}
         if self.cnn_stem is not None:
             st['cnn_stem'] = self.cnn_stem.params
+        if self.rnn_stem is not None:
+            st['rnn_stem'] = self.rnn_stem.params
         if self.use_z_filter:
             st['z_stats'] = self.z_stats
         return st
@@ -98,6 +108,8 @@ class PPOModel:
         self.critic.params.copy_(st['critic'])
         if self.cnn_stem is not None and 'cnn_stem' in st:
             self.cnn_stem.params.copy_(st['cnn_stem'])
+        if self.rnn_stem is not None and 'rnn_stem' in st:
+            self.rnn_stem.params.copy_(st['rnn_stem'])
         if self.use_z_filter and 'z_stats' in st:
             self.z_stats.copy_(st['z_stats'])
 
@@ -107,6 +119,9 @@ class PPOModel:
         sd = collections.OrderedDict()
         if self.cnn_stem is not None:
             for k, v in self.cnn_stem.state_items():
+                sd[k] = v
+        if self.rnn_stem is not None:
+            for k, v in self.rnn_stem.state_items():
                 sd[k] = v
         sd['actor.log_var'] = self.log_var.detach().clone().view(1, -1)
         for name, net in (('actor', self.actor), ('critic', self.critic)):
@@ -125,6 +140,8 @@ class PPOModel:
         g = lambda k: torch.as_tensor(sd[k], dtype=torch.float32)  # noqa: E731
         if self.cnn_stem is not None:
             self.cnn_stem.load_state(sd)
+        if self.rnn_stem is not None:
+            self.rnn_stem.load_torch(sd, prefix='rnn_stem.')
         self.log_var.copy_(g('actor.log_var').reshape(-1).to(self.device))
         for name, net in (('actor', self.actor), ('critic', self.critic)):
             for l in range(net.n_layers):

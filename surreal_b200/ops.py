@@ -308,6 +308,7 @@ class MlpTrainer:
         # gradient w.r.t. the pre-activation of whatever produced the network input (times relu'(input)): the CNN stem's
         # Linear layer sits in front of the PPO heads in pixel mode
         self.dx0 = z(M, _ru(net.dims[0], 4)) if input_grad else None
+        self.input_grad = input_grad            # True / 'relu': times relu'(input) (CNN stem's Linear+ReLU); 'linear': as is (LSTM output)
         self.overlap_dw = os.environ.get('SB200_OVERLAP_DW', '1') != '0'
         self._side = None
         if net.aux_layer >= 0 and net.aux_dim % 4 != 0:       # pre-allocated: nothing may allocate during graph capture
@@ -379,7 +380,7 @@ class MlpTrainer:
         if self.dx0 is not None:
             lay = net.layout[0]
             check(L.sb200_linear_bwd_dx_f32(_ptr(self.d[0]), self.d[0].stride(0), C.c_void_p(net.params.data_ptr() + 4 * lay['w']),
-                                            lay['ldw'], _ptr(self.x_in), self.x_in.stride(0), _ptr(self.dx0), self.dx0.stride(0), M,
+                                            lay['ldw'], _ptr(None if self.input_grad == 'linear' else self.x_in), self.x_in.stride(0), _ptr(self.dx0), self.dx0.stride(0), M,
                                             lay['N'], net.dims[0], _stream()), 'sb200_linear_bwd_dx_f32(input)')
         if side is not None:
             main.wait_stream(side)
