@@ -71,6 +71,8 @@ class PPOAgent(Agent):
         N, A, D = self.num_envs, self.action_dim, self.model.low_dim
         if self.model.cnn_stem is not None:
             return self._act_pixel(obs, eps)
+        if self.model.rnn_stem is not None:
+            return self._act_rnn(obs, eps)
         x = obs
         if isinstance(obs, dict):
             xs = [obs['low_dim'][k] for k in obs['low_dim']]
@@ -141,6 +143,91 @@ class PPOAgent(Agent):
         if self.env_config.sleep_time:
             time.sleep(self.env_config.sleep_time)
         return action, [[], [pd]]
+
+    # -- RNN policy (the reference's default PPO config) ------------------------------------------------------------
+    def _rnn_state(self):
+        """LSTM cells of all N actors, zero-initialised (ppo_agent.py:84-93).  NOTE: like the reference -- whose
+        ``reset()`` no caller ever invokes -- the cells carry over from episode to episode."""
+        if getattr(self, '_h', None) is None:
+            N, H, D = self.num_envs, self.model.rnn_stem.H, self.model.low_dim
+            z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.device)  # noqa: E731
+            self._h, self._c, self._h_before, self._c_before = z(N, H), z(N, H), z(N, H), z(N, H)
+            self._xf = z(N, ops._ru(D, 4))[:, :D]
+            self._rnn_bufs = self.model.rnn_stem.buffers(N, 1, save=False)
+            self._aug_bufs = [z(N, D + 2 * H), z(N, D + 2 * H)]
+        return self._h, self._c
+
+    def _augment(self, o, which=0):
+        """Observation rows + the cells this agent holds right now (what it will act FROM on that observation): the rows the
+        HBM staging / replay carry in RNN mode (utils.record_obs_dim)."""
+        h, c = self._rnn_state()
+        D, H = self.model.low_dim, self.model.rnn_stem.H
+        buf = self._aug_bufs[which]
+        buf[:, :D].copy_(o.reshape(self.num_envs, D), non_blocking=True)
+        buf[:, D:D + H].copy_(h, non_blocking=True)
+        buf[:, D + H:].copy_(c, non_blocking=True)
+        return buf
+
+    def _act_rnn(self, obs, eps=None):
+        """act() with the LSTM stem: z-filter -> one LSTM step from each actor's cells -> actor head -> sampling
+        (ppo_net.py:317-351, ppo_agent.py:133-149).  The cells BEFORE the step are the step's onetime_info."""
+        from ..model.lstm_stem import rows_zfilter
+        N, A, D = self.num_envs, self.action_dim, self.model.low_dim
+        m, stem = self.model, self.model.rnn_stem
+        h, c = self._rnn_state()
+        x = obs
+        if isinstance(obs, dict):
+            xs = [obs['low_dim'][k] for k in obs['low_dim']]
+            x = xs[0] if len(xs) == 1 else (torch.cat(xs, -1) if isinstance(xs[0], torch.Tensor) else np.concatenate(xs, -1))
+        host = not isinstance(x, torch.Tensor)
+        if host:
+            if self._obs_pin is None:
+                self._obs_pin = torch.empty(N, D, dtype=torch.float32, pin_memory=True)
+            self._obs_pin.numpy()[...] = np.asarray(x, dtype=np.float32).reshape(N, D)
+            self._obs_dev.copy_(self._obs_pin, non_blocking=True)
+            x = self._obs_dev
+        x = x.reshape(N, D)
+        self._h_before.copy_(h, non_blocking=True)
+        self._c_before.copy_(c, non_blocking=True)
+        rows_zfilter(x, D, x.stride(0), N, 1, D, m.z_stats, m.z_eps, self._xf)
+        feat = stem.forward(self._xf, h, c, h.stride(0), N, 1, self._rnn_bufs, h_last=h, c_last=c)     # cells updated in place
+        ops.mlp_forward(m.actor, feat, out=self._mean)
+        det = self.agent_mode in ['eval_deterministic', 'eval_deterministic_local']
+        env = self.env
+        staged = self.agent_mode == 'training' and isinstance(env, ExpSenderWrapperMultiStepMovingWindowWithInfo)
+        counter = env.step_counter if (env is not None and hasattr(env, 'step_counter')) else self._counter
+        eps_dev = None
+        if eps is not None:
+            eps_dev = torch.as_tensor(np.asarray(eps, dtype=np.float32).reshape(N, A)).to(self.device)
+        if staged and counter is not self._counter and env.fuse_launches:
+            fifo_state, dest = env.slot_assignment_args()
+            check(_lib.lib().sb200_ppo_sample_assign_f32(
+                _p(self._mean), A, _p(m.log_var), _p(self._log_noise), _p(eps_dev), N, A, int(det), self.seed,
+                _p(counter), _p(self._action), _p(self._pd), _p(env.stage_pos), _p(env.stage_act), _p(env.stage_pd),
+                env.n_step, _p(fifo_state), _p(dest), ops._stream()), 'sb200_ppo_sample_assign_f32')
+        else:
+            check(_lib.lib().sb200_ppo_sample_f32(
+                _p(self._mean), A, _p(m.log_var), _p(self._log_noise), _p(eps_dev), N, A, int(det), self.seed,
+                _p(counter), _p(self._action), _p(self._pd), _p(env.stage_pos) if staged else None,
+                _p(env.stage_act) if staged else None, _p(env.stage_pd) if staged else None,
+                env.n_step if staged else 1, ops._stream()), 'sb200_ppo_sample_f32')
+        if not staged and counter is self._counter:
+            self._counter += 1
+        if host:
+            torch.cuda.current_stream().synchronize()
+            action = self._action.cpu().numpy().astype(np.float64)
+            pd = self._pd.cpu().numpy()
+            onetime = [self._h_before.cpu().numpy()[:, None, :], self._c_before.cpu().numpy()[:, None, :]]   # [N, layers, H]
+            if N == 1:
+                action, pd, onetime = action.reshape(-1), pd.reshape(-1), [onetime[0][0], onetime[1][0]]
+        else:
+            action, pd = self._action, self._pd
+            onetime = [self._h_before.unsqueeze(1), self._c_before.unsqueeze(1)]
+        if self.agent_mode != 'training':
+            return action
+        if self.env_config.sleep_time:
+            time.sleep(self.env_config.sleep_time)
+        return action, [onetime, [pd]]
 
     def _act_pixel(self, obs, eps=None):
         """act() on uint8 frames [N, C, H, W] (device tensor or numpy): CNN stem -> actor head -> sampling kernel
@@ -254,6 +341,8 @@ class PPOAgent(Agent):
         env = self.env
         if self.agent_mode != 'training' or os.environ.get('SB200_PERSISTENT_ROLLOUT', '1') == '0':
             return False
+        if self.model.rnn_stem is not None or self.model.cnn_stem is not None:
+            return False                       # the persistent kernel runs the plain MLP policy only
         if not isinstance(env, ExpSenderWrapperMultiStepMovingWindowWithInfo) or not env.persistent_rollout:
             return False
         if type(env.env) is not SyntheticEnv:
@@ -301,8 +390,18 @@ class PPOAgent(Agent):
         return {'model': {'convs': '_list_', 'fc_hidden_sizes': '_list_'}}
 
     def reset(self):
-        pass                                   # LSTM cells only (RNN stem is a "next" row)
+        """reset of LSTM hidden and cell states (ppo_agent.py:169-183; nothing in the reference calls it)."""
+        if self.model.rnn_stem is not None and getattr(self, '_h', None) is not None:
+            self._h.zero_()
+            self._c.zero_()
 
     def prepare_env_agent(self, env):
         env = super().prepare_env_agent(env)
+        if self.model.rnn_stem is not None:
+            self._rnn_state()
+            w = ExpSenderWrapperMultiStepMovingWindowWithInfo(env, self.learner_config, self.session_config,
+                                                              obs_extra=2 * self.model.rnn_stem.H)
+            w.obs_augment = self._augment
+            w.persistent_rollout = False
+            return w
         return ExpSenderWrapperMultiStepMovingWindowWithInfo(env, self.learner_config, self.session_config)

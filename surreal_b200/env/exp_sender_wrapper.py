@@ -26,7 +26,7 @@ def _st():
 
 
 class _WrapperBase:
-    def __init__(self, env, learner_config, session_config, replay=None):
+    def __init__(self, env, learner_config, session_config, replay=None, obs_extra=0):
         self.env = env
         self.learner_config = learner_config
         self.session_config = session_config
@@ -34,7 +34,10 @@ class _WrapperBase:
         if self.replay is None:
             raise RuntimeError('no replay registered for this session: construct the Replay before the agent '
                                'wraps its env (the ZeroMQ collector address of the reference is gone)')
-        self.N, self.D, self.A = env.N, env.D, env.A
+        self.N, self.D, self.A = env.N, env.D + int(obs_extra), env.A
+        # extra trailing floats per observation row, filled by ``obs_augment(rows [N, env.D]) -> [N, D]`` (an RNN agent appends
+        # its LSTM cells; utils.record_obs_dim)
+        self.obs_extra, self.obs_augment = int(obs_extra), None
         # a batched HOST env (numpy in / numpy out, attributes N, D, A) has no device: the staging lives with the replay
         self.device = env.device if hasattr(env, 'device') else self.replay.device
         self.host_env = not hasattr(env, 'device')
@@ -81,6 +84,12 @@ class _WrapperBase:
         pin.numpy()[...] = np.asarray(arr, dtype=np.float32).reshape(shape)
         return C.c_void_p(pin.data_ptr())
 
+    def _aug(self, o):
+        return self.obs_augment(o, 0) if (self.obs_extra and self.obs_augment is not None) else o
+
+    def _aug_next(self, o):
+        return self.obs_augment(o, 1) if (self.obs_extra and self.obs_augment is not None) else o
+
     def cached_device_obs(self, obs_arr):
         """The device copy of the observation the last step() returned (the agent's next act() input), if
         ``obs_arr`` is that very array: saves the second H2D of the same 256 KB."""
@@ -97,8 +106,8 @@ class _WrapperBase:
 class ExpSenderWrapperMultiStepMovingWindowWithInfo(_WrapperBase):
     """n_step windows with stride (exp_sender_wrapper.py:153-264) -> FIFOReplay ring."""
 
-    def __init__(self, env, learner_config, session_config, replay=None):
-        super().__init__(env, learner_config, session_config, replay)
+    def __init__(self, env, learner_config, session_config, replay=None, obs_extra=0):
+        super().__init__(env, learner_config, session_config, replay, obs_extra=obs_extra)
         self.n_step = self.learner_config.algo.n_step
         self.stride = self.learner_config.algo.stride
         if self.stride < 1:
@@ -125,7 +134,7 @@ class ExpSenderWrapperMultiStepMovingWindowWithInfo(_WrapperBase):
             self.stage_obs[:, 0].copy_(d)
             self._last_obs_host, self._last_obs_dev = o, d
         else:
-            self.stage_obs[:, 0].copy_(o)
+            self.stage_obs[:, 0].copy_(self._aug(o))
         return obs, info
 
     def rollout_outbox(self, T):
@@ -160,11 +169,13 @@ class ExpSenderWrapperMultiStepMovingWindowWithInfo(_WrapperBase):
         a = action[0] if isinstance(action, tuple) else action
         r = self.replay
         ready, self._slots_ready = self._slots_ready, False
-        if ready and hasattr(self.env, 'step_and_commit_window'):
+        if ready and hasattr(self.env, 'step_and_commit_window') and not self.obs_extra:
             return self.env.step_and_commit_window(a, self)        # env step + commit in ONE launch
         obs, reward, done, info = self.env.step(a)
         o = obs_flat(obs)
         on = obs_flat(info['obs_next']) if (isinstance(info, dict) and 'obs_next' in info) else o
+        if self.host_env and self.obs_extra:
+            raise NotImplementedError('RNN policy with a host env: stage the windows with replay.insert (onetime_infos) instead')
         if self.host_env:
             # host env: this step's successor observation / reward / done cross PCIe here (256 KB + 8 KB), issued with
             # the staging kernels from ONE C call; the device copy of the next observation is handed to the agent's
@@ -182,6 +193,12 @@ class ExpSenderWrapperMultiStepMovingWindowWithInfo(_WrapperBase):
                 'sb200_ppo_window_step_host_f32')
             self._last_obs_host, self._last_obs_dev = o, d_o
             return obs, reward, done, info
+        if self.obs_extra:
+            # both rows get the cells the agent holds NOW, i.e. before it acts on the next observation; `on` and `o` differ
+            # only where an episode ended
+            same = on is o
+            o = self._aug(o)
+            on = o if same else self._aug_next(on)
         check(_lib.lib().sb200_ppo_window_step_f32(
             _p(on), _p(o), _p(reward), _p(done), self.N, self.n_step,
             self.stride, self.D, self.A, _p(self.stage_pos), _p(self.stage_obs), _p(self.stage_act),

@@ -105,18 +105,40 @@ class PPOLearner(Learner):
 
         B, n, A = self.batch_size, self.n_step, self.action_dim
         self.pixel = self.model.cnn_stem is not None
-        # width of one observation in the batch buffers: the low-dim features, or the uint8 frame as 32-bit words
-        D = U.obs_packed_dim(self.obs_spec) if self.pixel else self.model.low_dim
+        self.rnn = self.model.rnn_stem is not None
+        self.obs_dim = self.model.low_dim                         # width of the low-dim features themselves
+        # width of one observation in the batch buffers: the low-dim features (+ the actor's LSTM cells h | c in RNN mode,
+        # which ride in the observation rows of the HBM records -- the reference ships them as onetime_infos), or the uint8
+        # frame as 32-bit words
+        D = U.record_obs_dim(lc, self.env_config)
         self.low_dim = D
+        self.eff_len = (n - self.horizon + 1) if self.rnn else 1
+        M = B * self.eff_len                                      # rows the heads train on (ppo.py:518-537)
+        self._rows = M
         dev = self.device
-        self.actor_optim = ops.MlpTrainer(self.model.actor, B, self.lr_actor,
+        ig = 'linear' if self.rnn else self.pixel
+        self.actor_optim = ops.MlpTrainer(self.model.actor, M, self.lr_actor,
                                           clip_mode=1 if self.clip_actor_gradient else 0,
                                           clip_value=self.actor_gradient_clip_value,
-                                          weight_decay=net.actor_regularization, input_grad=self.pixel)
-        self.critic_optim = ops.MlpTrainer(self.model.critic, B, self.lr_critic,
+                                          weight_decay=net.actor_regularization, input_grad=ig)
+        self.critic_optim = ops.MlpTrainer(self.model.critic, M, self.lr_critic,
                                            clip_mode=1 if self.clip_critic_gradient else 0,
                                            clip_value=self.critic_gradient_clip_value,
-                                           weight_decay=net.critic_regularization, input_grad=self.pixel)
+                                           weight_decay=net.critic_regularization, input_grad=ig)
+        if self.rnn:
+            # the LSTM stem is shared by actor and critic and trained by BOTH optimisers (ppo_net.py:202-224)
+            from ..model.lstm_stem import RnnTrainer
+            stem, E, Hh, od = self.model.rnn_stem, self.eff_len, self.model.rnn_stem.H, self.obs_dim
+            self.actor_rnn, self.critic_rnn = RnnTrainer(stem, B, E), RnnTrainer(stem, B, E)
+            self._g_actor = torch.zeros(self.model.actor.size + stem.size, dtype=torch.float32, device=dev)
+            self._g_critic = torch.zeros(self.model.critic.size + stem.size, dtype=torch.float32, device=dev)
+            self.actor_optim.grad = self._g_actor[:self.model.actor.size]
+            self.critic_optim.grad = self._g_critic[:self.model.critic.size]
+            zz = lambda r, w: torch.zeros(r, ops._ru(w, 4), dtype=torch.float32, device=dev)[:, :w]  # noqa: E731
+            self._xf_all, self._xf_eff, self._xf_ref, self._xraw_eff = zz(B * (n + 1), od), zz(M, od), zz(M, od), zz(M, od)
+            self._act_it, self._pd_it = torch.zeros(M, A, device=dev), torch.zeros(M, 2 * A, device=dev)
+            self._rnn_all = stem.buffers(B, n + 1, save=False)
+            self._rnn_ref = self.ref_target_model.rnn_stem.buffers(B, E, save=False)
         if self.pixel:
             # the CNN stem is shared by actor and critic and trained by BOTH optimisers, each with its own Adam state
             # (ppo_net.py:202-224): one StemTrainer per optimiser, gradients of head + stem in one contiguous buffer
@@ -152,14 +174,14 @@ class PPOLearner(Learner):
         self._rewards, self._dones = self._own['rewards'], self._own['dones']
         self._rewards_f = f(B, n) if self.use_r_filter else None
         self._values = f(B * (n + 1), 1)
-        self._adv, self._ret = f(B, 1), f(B, 1)
-        self._ref_mean, self._ref_pd = f(B, A), f(B, 2 * A)
-        self._cur_mean = f(B, A)
+        self._adv, self._ret = f(B, self.eff_len), f(B, self.eff_len)
+        self._ref_mean, self._ref_pd = f(M, A), f(M, 2 * A)
+        self._cur_mean = f(M, A)
         self._stats = f(S['COUNT'])
         self._hyper = torch.zeros(2, dtype=torch.float64, device=dev)
         self._stop = torch.zeros(1, dtype=torch.int32, device=dev)
         L = _lib.lib()
-        self._loss_ws = torch.zeros(L.sb200_ppo_loss_workspace_bytes(B, A), dtype=torch.uint8, device=dev)
+        self._loss_ws = torch.zeros(L.sb200_ppo_loss_workspace_bytes(M, A), dtype=torch.uint8, device=dev)
         self._loss_ws_v = torch.zeros_like(self._loss_ws)     # the value branch runs concurrently with the policy branch
         self._side_stream = None
         self._rfilter_stats = torch.tensor([1e-5, 0.0, 0.0], dtype=torch.float32, device=dev) \
@@ -168,7 +190,7 @@ class PPOLearner(Learner):
         self._gae_ws = torch.zeros(int(L.sb200_gae_workspace_bytes(B, n, n)), dtype=torch.uint8, device=dev)
         self.use_cuda_graph = ops.graphs_enabled()
         # policy || value epochs as concurrent graph branches -- not in pixel mode, where both optimisers update the SHARED stem
-        self.parallel_branches = os.environ.get("SB200_PPO_FORK", "1") != "0" and not self.pixel
+        self.parallel_branches = os.environ.get("SB200_PPO_FORK", "1") != "0" and not self.pixel and not self.rnn
         # tensor pipe || FMA pipe critic pass: measured SLOWER (701-757 us) than the 2-CTA/SM tensor-core tiles alone
         # (631 us) -- both kernels are issue-bound, they do not add up -- so it stays an experiment
         self.dual_critic = os.environ.get("SB200_DUAL_CRITIC", "0") == "1"
@@ -267,17 +289,28 @@ class PPOLearner(Learner):
                 nbytes += u8.numel()
         else:
             obs, obs_next = self._low_dim(get('obs')), self._low_dim(get('obs_next'))
+        od = self.obs_dim
         if obs is None:
             pass
         elif isinstance(obs, torch.Tensor):
-            own['obs_full'][:, :n].copy_(obs.reshape(B, n, D), non_blocking=True)
-            own['obs_full'][:, n:].copy_(obs_next.reshape(B, 1, D), non_blocking=True)
+            own['obs_full'][:, :n, :od].copy_(obs.reshape(B, n, od), non_blocking=True)
+            own['obs_full'][:, n:, :od].copy_(obs_next.reshape(B, 1, od), non_blocking=True)
+            if self.rnn:                                          # onetime_infos = [h0, c0] of the window's first step
+                hc = get('onetime_infos')
+                Hh = self.model.rnn_stem.H
+                own['obs_full'][:, 0, od:od + Hh].copy_(torch.as_tensor(hc[0]).reshape(B, Hh), non_blocking=True)
+                own['obs_full'][:, 0, od + Hh:od + 2 * Hh].copy_(torch.as_tensor(hc[1]).reshape(B, Hh), non_blocking=True)
         else:
             if 'obs_full' not in self._pin:
-                self._pin['obs_full'] = torch.empty(B, n + 1, D, dtype=torch.float32, pin_memory=True)
+                self._pin['obs_full'] = torch.zeros(B, n + 1, D, dtype=torch.float32).pin_memory()
             pf = self._pin['obs_full'].numpy()
-            pf[:, :n] = np.asarray(obs).reshape(B, n, D)
-            pf[:, n:] = np.asarray(obs_next).reshape(B, 1, D)
+            pf[:, :n, :od] = np.asarray(obs).reshape(B, n, od)
+            pf[:, n:, :od] = np.asarray(obs_next).reshape(B, 1, od)
+            if self.rnn:
+                hc = get('onetime_infos')
+                Hh = self.model.rnn_stem.H
+                pf[:, 0, od:od + Hh] = np.asarray(hc[0], dtype=np.float32).reshape(B, Hh)
+                pf[:, 0, od + Hh:od + 2 * Hh] = np.asarray(hc[1], dtype=np.float32).reshape(B, Hh)
             own['obs_full'].copy_(self._pin['obs_full'], non_blocking=True)
             nbytes += own['obs_full'].numel() * 4
         nbytes += self._h2d('actions', get('actions'), own['actions'])
@@ -294,7 +327,14 @@ class PPOLearner(Learner):
         m = self.model
         ev = self._prof_begin()
         rows = B * (n + 1)
-        if self.pixel:
+        if self.rnn:
+            # the critic over the whole [B, n+1] sequence through the LSTM from the window's initial cells (ppo.py:376-387),
+            # then the horizon-windowed GAE over eff_len positions (ppo.py:389-406)
+            self._rnn_prepare()
+            h0, c0, ld = self._cells()
+            h_all = m.rnn_stem.forward(self._xf_all, h0, c0, ld, B, n + 1, self._rnn_all)
+            ops.mlp_forward(m.critic, h_all, out=self._values)
+        elif self.pixel:
             # all B*(n+1) frames through the shared stem, then the critic head on the features (ppo.py:376-387, 5-D obs)
             stem = m.cnn_stem
             if self._stem_all is None:
@@ -324,7 +364,8 @@ class PPOLearner(Learner):
         ev = self._prof_begin()
         local_norm = self.norm_adv and self.dp is None
         ops.gae_window(rewards, self._values.view(B, n + 1), self._dones, self.gamma, self.lam, norm_adv=local_norm,
-                       reward_scale=scale, adv=self._adv, ret=self._ret, ws=self._gae_ws)
+                       horizon=self.horizon if self.rnn else None, reward_scale=scale, adv=self._adv, ret=self._ret,
+                       ws=self._gae_ws)
         if self.norm_adv and self.dp is not None:                 # statistics of the GLOBAL batch (ppo.py:413-416)
             L = _lib.lib()
             check(L.sb200_moments_f32(_ptr(self._adv), B, _ptr(self._moments), ops._stream()), 'sb200_moments_f32')
@@ -333,6 +374,28 @@ class PPOLearner(Learner):
                   'sb200_normalize_f32')
         self._prof_end('gae', ev)
         return self._adv, self._ret
+
+    # -- RNN mode helpers ---------------------------------------------------------------------------------
+    def _cells(self):
+        """(h0, c0, ld): the LSTM cells at the first step of every window; they ride in row 0 of the observation records
+        (the reference ships them as onetime_infos, ppo_agent.py:133-137, ppo.py:507-510)."""
+        od, Hh = self.obs_dim, self.model.rnn_stem.H
+        return self._obs_full[:, 0, od:od + Hh], self._obs_full[:, 0, od + Hh:od + 2 * Hh], self._obs_full.stride(0)
+
+    def _rnn_prepare(self):
+        """Once per learn(): contiguous, z-filtered sequence rows -- all n+1 steps for the critic pass, the first eff_len
+        for the updates (through the learner's AND the reference model's filter, ppo.py:507-539) -- and the step slices of
+        actions / behaviour policy the updates iterate on."""
+        from ..model.lstm_stem import rows_zfilter
+        B, n, A, E, od, Dp = self.batch_size, self.n_step, self.action_dim, self.eff_len, self.obs_dim, self.low_dim
+        m, ref = self.model, self.ref_target_model
+        o = self._obs_full
+        rows_zfilter(o, Dp, (n + 1) * Dp, B, n + 1, od, m.z_stats, m.z_eps, self._xf_all)
+        rows_zfilter(o, Dp, (n + 1) * Dp, B, E, od, m.z_stats, m.z_eps, self._xf_eff)
+        rows_zfilter(o, Dp, (n + 1) * Dp, B, E, od, ref.z_stats, ref.z_eps, self._xf_ref)
+        rows_zfilter(o, Dp, (n + 1) * Dp, B, E, od, None, 0.0, self._xraw_eff)
+        rows_zfilter(self._actions, A, n * A, B, E, A, None, 0.0, self._act_it)
+        rows_zfilter(self._pds, 2 * A, n * 2 * A, B, E, 2 * A, None, 0.0, self._pd_it)
 
     # -- live kernel timing for bench.py's roofline (CUDA events on the launching stream) ---------------
     def _prof_begin(self):
@@ -365,7 +428,11 @@ class PPOLearner(Learner):
         L = _lib.lib()
         B, n, A, D = self.batch_size, self.n_step, self.action_dim, self.low_dim
         m, tr, st = self.model, self.actor_optim, ops._stream()
-        if self.pixel:
+        M = self._rows
+        acts, lda, pds, ldp = (self._act_it, A, self._pd_it, 2 * A) if self.rnn else (self._actions, n * A, self._pds, n * 2 * A)
+        if self.rnn:
+            mean = tr.forward(self.actor_rnn.forward(self._xf_eff, *self._cells())) if fresh else tr.out
+        elif self.pixel:
             mean = tr.forward(self.actor_stem.forward(self._frames0)) if fresh else tr.out
         else:
             mean = tr.forward(self._obs_full, zf_stats=m.z_stats, zf_eps=m.z_eps, rows=B, ldx=(n + 1) * D) if fresh \
@@ -374,13 +441,18 @@ class PPOLearner(Learner):
         if mode == 1:
             self._kl(mean, S['KL_PRE'], 0.0, stop)
         dlog_var = tr.slabs[0, m.actor.extra_off:m.actor.extra_off + A]
-        check(L.sb200_ppo_policy_loss_f32(mode, _ptr(mean), mean.stride(0), _ptr(m.log_var), _ptr(self._actions), n * A,
-                                          _ptr(self._adv), _ptr(self._pds), n * 2 * A, _ptr(self._ref_pd), 2 * A, B, A,
+        check(L.sb200_ppo_policy_loss_f32(mode, _ptr(mean), mean.stride(0), _ptr(m.log_var), _ptr(acts), lda,
+                                          _ptr(self._adv), _ptr(pds), ldp, _ptr(self._ref_pd), 2 * A, M, A,
                                           _ptr(self._hyper), float(self.eta), float(self.kl_target), _ptr(tr.d[-1]),
                                           tr.d[-1].stride(0), _ptr(dlog_var), _ptr(self._stats), _ptr(self._loss_ws),
                                           _ptr(stop), st), 'sb200_ppo_policy_loss_f32')
         tr.backward()
-        if self.pixel:
+        if self.rnn:
+            from ..model.cnn_stem import joint_step
+            self.actor_rnn.backward(tr.dx0)
+            joint_step(tr, self.actor_rnn, self._g_actor, norm_out=self._stats[S['GN_ACTOR']:S['GN_ACTOR'] + 1], stop_flag=stop)
+            self._cur_mean = tr.forward(self.actor_rnn.forward(self._xf_eff, *self._cells()))
+        elif self.pixel:
             from ..model.cnn_stem import joint_step
             self.actor_stem.backward(tr.dx0)
             joint_step(tr, self.actor_stem, self._g_actor, norm_out=self._stats[S['GN_ACTOR']:S['GN_ACTOR'] + 1], stop_flag=stop)
@@ -395,7 +467,7 @@ class PPOLearner(Learner):
         """mean KL(ref || (mean, exp(log_var))) -> stats[slot]; raises the stop flag above `threshold`.  With a
         data-parallel learner the scalar is averaged over ranks between the two halves."""
         L = _lib.lib()
-        B, A, m, st = self.batch_size, self.action_dim, self.model, ops._stream()
+        B, A, m, st = self._rows, self.action_dim, self.model, ops._stream()
         dp = self.dp
         check(L.sb200_ppo_kl_f32(_ptr(self._ref_pd), 2 * A, _ptr(mean), mean.stride(0), _ptr(m.log_var), B, A,
                                  _ptr(self._stats), slot, float(threshold), _ptr(stop), 0 if dp is None else 1,
@@ -412,6 +484,8 @@ class PPOLearner(Learner):
         from ..parallel import LearnerDP
         if self.use_r_filter:
             raise NotImplementedError('reward filter + data parallel')
+        if self.rnn:
+            raise NotImplementedError('RNN mode + data parallel')
         stem_n = self.model.cnn_stem.size if self.pixel else 0
         peer_floats = max(self.model.actor.size, self.model.critic.size) + stem_n + 64
         self.dp = LearnerDP(group, peer_floats=peer_floats)
@@ -453,14 +527,20 @@ class PPOLearner(Learner):
         L = _lib.lib()
         B, n, D = self.batch_size, self.n_step, self.low_dim
         m, tr, st = self.model, self.critic_optim, ops._stream()
-        if self.pixel:
+        if self.rnn:
+            v = tr.forward(self.critic_rnn.forward(self._xf_eff, *self._cells()))
+        elif self.pixel:
             v = tr.forward(self.critic_stem.forward(self._frames0))
         else:
             v = tr.forward(self._obs_full, zf_stats=m.z_stats, zf_eps=m.z_eps, rows=B, ldx=(n + 1) * D)
-        check(L.sb200_value_loss_f32(_ptr(v), v.stride(0), _ptr(self._ret), B, _ptr(tr.d[-1]), tr.d[-1].stride(0),
+        check(L.sb200_value_loss_f32(_ptr(v), v.stride(0), _ptr(self._ret), self._rows, _ptr(tr.d[-1]), tr.d[-1].stride(0),
                                      _ptr(self._stats), _ptr(self._loss_ws_v), st), 'sb200_value_loss_f32')
         tr.backward()
-        if self.pixel:
+        if self.rnn:
+            from ..model.cnn_stem import joint_step
+            self.critic_rnn.backward(tr.dx0)
+            joint_step(tr, self.critic_rnn, self._g_critic, norm_out=self._stats[S['GN_CRITIC']:S['GN_CRITIC'] + 1])
+        elif self.pixel:
             from ..model.cnn_stem import joint_step
             self.critic_stem.backward(tr.dx0)
             joint_step(tr, self.critic_stem, self._g_critic, norm_out=self._stats[S['GN_CRITIC']:S['GN_CRITIC'] + 1])
@@ -471,7 +551,10 @@ class PPOLearner(Learner):
         B, n, A, D = self.batch_size, self.n_step, self.action_dim, self.low_dim
         ref = self.ref_target_model
         self._gae_and_return()
-        if self.pixel:
+        if self.rnn:
+            h_ref = ref.rnn_stem.forward(self._xf_ref, *self._cells(), B, self.eff_len, self._rnn_ref)
+            ops.mlp_forward(ref.actor, h_ref, out=self._ref_mean)
+        elif self.pixel:
             # step-0 frames of every window, contiguous (ppo.py:527-537), then the reference policy on them
             fr = self._obs_full.view(torch.uint8).view(B, n + 1, -1)
             self._frames0.view(B, -1).copy_(fr[:, 0])
@@ -479,7 +562,7 @@ class PPOLearner(Learner):
         else:
             ops.mlp_forward(ref.actor, self._obs_full, zf_stats=ref.z_stats, zf_eps=ref.z_eps, rows=B, ldx=(n + 1) * D,
                             out=self._ref_mean)
-        ops.make_pd(self._ref_mean, ref.log_var, B, A, self._ref_pd)
+        ops.make_pd(self._ref_mean, ref.log_var, self._rows, A, self._ref_pd)
         self._stats.zero_()
         self._stop.zero_()
 
@@ -490,13 +573,16 @@ class PPOLearner(Learner):
         if not value_done:
             for _ in range(self.epoch_baseline):
                 self._value_epoch()
+        acts, lda, pds, ldp = (self._act_it, A, self._pd_it, 2 * A) if self.rnn else (self._actions, n * A, self._pds, n * 2 * A)
         check(L.sb200_ppo_final_stats_f32(_ptr(self._cur_mean), self._cur_mean.stride(0), _ptr(m.log_var),
-                                          _ptr(self._actions), n * A,
-                                          _ptr(self._pds), n * 2 * A, _ptr(self._ref_pd), 2 * A, B, A,
+                                          _ptr(acts), lda, _ptr(pds), ldp, _ptr(self._ref_pd), 2 * A, self._rows, A,
                                           _ptr(self._stats), _ptr(self._loss_ws), st), 'sb200_ppo_final_stats_f32')
         if self.use_z_filter:
-            # step-0 rows only, AFTER the updates (ppo.py:578)
-            if self.dp is None:
+            # the rows the updates trained on (step 0 of every window; the first eff_len steps in RNN mode), AFTER the
+            # updates (ppo.py:578)
+            if self.rnn:
+                ops.zfilter_update(self._xraw_eff, self._rows, self.obs_dim, self._xraw_eff.stride(0), m.z_stats)
+            elif self.dp is None:
                 ops.zfilter_update(self._obs_full, B, D, (n + 1) * D, m.z_stats)
             else:
                 self._z_delta.zero_()
@@ -584,6 +670,7 @@ class PPOLearner(Learner):
         stats['_lr'] = self.actor_lr_scheduler.get_lr()[0]
         if self.use_z_filter:
             z = m.z_stats.cpu().double().numpy()
+            D = self.obs_dim
             zs, zq, zc = z[:D], z[D:2 * D], z[2 * D]
             stats['obs_running_mean'] = float(np.mean((zs / zc).astype(np.float32)))
             stats['obs_running_square'] = float(np.mean((zq / zc).astype(np.float32)))

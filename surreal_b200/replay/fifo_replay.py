@@ -40,8 +40,9 @@ class FIFOReplay(Replay):
             raise RuntimeError('surreal_b200.FIFOReplay lives in HBM: a CUDA device is required')
         self.device = torch.device('cuda', torch.cuda.current_device())
         self.n_step = self.learner_config.algo.n_step
-        from ..utils import obs_packed_dim, obs_is_pixel
-        self.D = obs_packed_dim(self.env_config.obs_spec)       # pixel frames ride as opaque 32-bit words (uint8 in HBM)
+        from ..utils import record_obs_dim, obs_packed_dim, obs_is_pixel
+        self.D = record_obs_dim(self.learner_config, self.env_config)   # pixel frames: opaque 32-bit words; RNN: + LSTM cells
+        self.obs_dim = obs_packed_dim(self.env_config.obs_spec)
         self.pixel_shape = tuple(self.env_config.obs_spec['pixel']['camera0']) if obs_is_pixel(self.env_config.obs_spec) else None
         self.A = self.env_config.action_spec.dim[0]
         self.capacity = self.memory_size + 3                    # "+ 3 for a gentle buffering" (fifo_replay.py:27)
@@ -92,8 +93,15 @@ class FIFOReplay(Replay):
             self._stage = torch.empty(rec, dtype=torch.float32, device=self.device)
         buf = self._pin.numpy()
         o = 0
-        buf[o:o + n * D] = np.stack([flat(x) for x in exp['obs']]).reshape(-1); o += n * D
-        buf[o:o + D] = flat(exp['obs_next']); o += D
+        rows = np.zeros((n + 1, D), dtype=np.float32)
+        od = self.obs_dim
+        rows[:n, :od] = np.stack([flat(x) for x in exp['obs']])
+        rows[n, :od] = flat(exp['obs_next'])
+        if D > od and exp.get('onetime_infos'):                 # [h, c] of the window's first step (ppo_agent.py:133-137)
+            Hh = (D - od) // 2
+            rows[0, od:od + Hh] = np.asarray(exp['onetime_infos'][0], dtype=np.float32).reshape(-1)[:Hh]
+            rows[0, od + Hh:] = np.asarray(exp['onetime_infos'][1], dtype=np.float32).reshape(-1)[:Hh]
+        buf[o:o + (n + 1) * D] = rows.reshape(-1); o += (n + 1) * D
         buf[o:o + n * A] = np.stack(exp['actions']).astype(np.float32).reshape(-1); o += n * A
         buf[o:o + n * 2 * A] = np.stack([p[-1] for p in exp['persistent_infos']]).astype(np.float32).reshape(-1)
         o += n * 2 * A
@@ -134,7 +142,12 @@ class FIFOReplay(Replay):
             return {'obs': {'pixel': {'camera0': fr[:, :n]}}, 'obs_next': {'pixel': {'camera0': fr[:, n:]}},
                     'obs_full': obs_full, 'actions': out['actions'], 'rewards': out['rewards'], 'dones': out['dones'],
                     'persistent_infos': [out['pd']], 'onetime_infos': None}
-        return {'obs': {'low_dim': {'flat_inputs': obs_full[:, :n, :]}},
-                'obs_next': {'low_dim': {'flat_inputs': obs_full[:, n:, :]}},
+        od = self.obs_dim
+        onetime = None
+        if D > od:                 # RNN policy: the LSTM cells of the window's first step ride behind the observation
+            Hh = (D - od) // 2
+            onetime = [obs_full[:, 0, od:od + Hh].unsqueeze(1), obs_full[:, 0, od + Hh:od + 2 * Hh].unsqueeze(1)]
+        return {'obs': {'low_dim': {'flat_inputs': obs_full[:, :n, :od]}},
+                'obs_next': {'low_dim': {'flat_inputs': obs_full[:, n:, :od]}},
                 'obs_full': obs_full, 'actions': out['actions'], 'rewards': out['rewards'], 'dones': out['dones'],
-                'persistent_infos': [out['pd']], 'onetime_infos': None}
+                'persistent_infos': [out['pd']], 'onetime_infos': onetime}

@@ -167,3 +167,15 @@ def obs_flat(obs):
         fr = obs['pixel']['camera0']
         return fr.reshape(fr.shape[0], -1).view(torch.float32)
     return obs
+
+
+def record_obs_dim(learner_config, env_config):
+    """Floats per observation row of the HBM staging / replay records and the learner's batch buffers: obs_packed_dim, plus
+    -- for an RNN policy -- 2 * rnn_hidden trailing floats that carry the actor's LSTM cells (h | c) BEFORE it acted on that
+    observation.  The reference ships the cells of a window's first step as ``onetime_infos``
+    (ppo_agent.py:133-137, exp_sender_wrapper.py:244-264); here they simply ride with every observation row."""
+    d = obs_packed_dim(env_config.obs_spec)
+    rnn = learner_config.algo.rnn if 'rnn' in learner_config.algo else None
+    if rnn is not None and rnn.if_rnn_policy:
+        d += 2 * int(rnn.rnn_hidden)
+    return d
