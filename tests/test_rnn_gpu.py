@@ -93,8 +93,8 @@ def test_ppo_learn_rnn_matches_reference(golden, tag):
         worst = 0.0
         for k, e in after.items():
             gk = got[k].cpu().reshape(e.shape)
-            if k.startswith('z_filter'):
-                assert float(((gk - e).abs() / e.abs().clamp_min(1.0)).max()) <= 1e-6, k
+            if k.startswith('z_filter'):     # running sums of +-O(1) values: fp32 summation order, relative to the vector's scale
+                assert float((gk - e).abs().max()) <= 1e-6 * max(1.0, float(e.abs().max())), k
                 continue
             worst = max(worst, float((gk - e).abs().max()))
         assert worst <= max(2e-6, 0.02 * lr), 'params drifted by %.3e' % worst
@@ -147,7 +147,7 @@ def test_default_ppo_config_runs_end_to_end():
     sc = Config(copy.deepcopy(PPO_DEFAULT_SESSION_CONFIG.to_dict()))
     sc.folder = tempfile.mkdtemp()
     assert lc.algo.rnn.if_rnn_policy and lc.algo.ppo_mode == 'adapt'          # the reference's defaults, untouched
-    N, D, A = 64, 17, 6
+    N, D, A = 32, 17, 6            # 2 windows x 32 actors = one default batch of 64 (the default FIFO holds 96 + 3)
     make_synthetic_env_config(ec, N, D, A, seed=3)
     ec.limit_episode_length = 200
     n, stride, Hh, B = lc.algo.n_step, lc.algo.stride, lc.algo.rnn.rnn_hidden, lc.replay.batch_size
@@ -163,15 +163,15 @@ def test_default_ppo_config_runs_end_to_end():
         assert torch.equal(a[1][0][0][:, 0], cells_at[t][0])      # onetime_info = cells BEFORE the step
         obs, _, _, _ = w.step(a)
     torch.cuda.synchronize()
-    assert len(R) == 2 * N
+    assert len(R) == 2 * N == B
     L = PPOLearner(lc, ec, sc)
     L.model.load_state_dict(ag.model.state_dict())
     L.ref_target_model.update_target_params(L.model)
-    b1 = R.sample(B)                                               # first windows of actors 0..63 (step 0 cells: zeros)
-    assert float(b1['onetime_infos'][0].abs().max()) == 0.0
-    b2 = R.sample(B)                                               # second windows start at step `stride`
-    assert torch.equal(b2['onetime_infos'][0][:, 0], cells_at[stride][0]) and torch.equal(b2['onetime_infos'][1][:, 0], cells_at[stride][1])
-    assert float(b2['onetime_infos'][0].abs().max()) > 0.0
+    b2 = R.sample(B)              # (step, actor) arrival order: rows 0..31 = first windows (cells: zeros), 32..63 = second ones
+    h0, c0 = b2['onetime_infos'][0][:, 0], b2['onetime_infos'][1][:, 0]
+    assert float(h0[:N].abs().max()) == 0.0 and float(c0[:N].abs().max()) == 0.0
+    assert torch.equal(h0[N:], cells_at[stride][0]) and torch.equal(c0[N:], cells_at[stride][1])    # windows start at step `stride`
+    assert float(h0[N:].abs().max()) > 0.0
     sd = {k: v.cpu() for k, v in L.model.state_dict().items()}
     al = [(sd['actor.model.seq.%d.weight' % (2 * i)], sd['actor.model.seq.%d.bias' % (2 * i)]) for i in range(3)]
     cl = [(sd['critic.model.seq.%d.weight' % (2 * i)], sd['critic.model.seq.%d.bias' % (2 * i)]) for i in range(3)]
