@@ -173,6 +173,61 @@ int sb200_par_allreduce_f32(const sb200_par* ctx, const float* x, float* out, in
 int sb200_par_allreduce_f64(const sb200_par* ctx, const double* x, double* out, int n, double scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Persistent learner kernel (csrc/epoch.cu): ALL minibatch epochs of one optimiser of PPOLearner._optimize
+ * (surreal/learner/ppo.py:194-353 losses + updates, 541-557 epoch loops + KL early stop) in ONE launch -- forward, loss,
+ * backward, slab reduction, gradient clip, Adam, post-step forward and KL of every epoch, phases separated by grid
+ * barriers instead of launches.  It writes the same buffers and statistics as the launch chain it replaces
+ * (sb200_mlp_forward_f32 + sb200_ppo_policy_loss_f32 / sb200_value_loss_f32 + sb200_linear_bwd_* +
+ * sb200_grad_reduce_norm_f32 + sb200_clip_adam_f32 + sb200_ppo_kl_f32).
+ *   supported: 3 layers ReLU-ReLU-any, no aux input, head <= 32 wide.
+ *   net->W / net->b must point INTO `params` (the flat buffer Adam updates); x_in/h1/h2/out/d1/d2/dpre are [M][ru4(width)]
+ *   with zero padding columns (x_in receives the z-filtered input rows).
+ *   mode 0 clip / 1 adapt (policy: out = tanh mean, log_var at params[extra_off..+A), early stop above stop_threshold),
+ *   mode 2 value (MSE on `returns`).  grid: CTAs to launch (all must be able to be co-resident: <= 2 per SM);
+ *   cta_shift rotates the tile -> CTA map so that two concurrent launches (policy || value) use different SMs.
+ *   par != NULL with world > 1: data-parallel -- the KL scalar and the flat gradient are averaged over the ranks inside
+ *   the kernel through the symmetric buffers of `par` (every rank must launch the same sequence). */
+typedef struct {
+    const sb200_mlp* net;
+    float* params;
+    int64_t n_params;
+    int extra_off;
+    const float* x;
+    int64_t ldx;
+    int M;
+    const float* zf_stats;              /* NULL: no z-filter */
+    double zf_eps;
+    float *x_in, *h1, *h2, *out, *d1, *d2, *dpre;
+    float* slabs;                       /* [splits][n_params] */
+    int splits;
+    float *grad, *exp_avg, *exp_avg_sq;
+    const double* lr;
+    double weight_decay;
+    int clip_mode;
+    double clip_value;
+    void* opt_workspace;                /* sb200_optim_workspace_bytes(): holds the Adam step count */
+    float* norm_out;                    /* optional: global gradient norm of the last step */
+    int mode;
+    const float* actions; int64_t lda;
+    const float* adv;
+    const float* behave_pd; int64_t ldb;
+    const float* ref_pd; int64_t ldr;
+    const float* returns;
+    const double* hyper;                /* device: [clip_epsilon, beta] */
+    double eta, kl_target, stop_threshold;
+    float* stats;
+    int* stop_flag;
+    int epochs;
+    void* workspace;                    /* sb200_ppo_epochs_workspace_bytes() */
+    int grid;
+    int cta_shift;
+    const sb200_par* par;
+} sb200_epochs;
+int sb200_ppo_epochs_supported(const sb200_mlp* net);
+size_t sb200_ppo_epochs_workspace_bytes(void);
+int sb200_ppo_epochs_f32(const sb200_epochs* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * LSTM stem of RNN-mode PPO (csrc/lstm.cu; nn.LSTM(batch_first=True) of ppo_net.py:143-152,277-279,342-351; BPTT over
  * eff_len = n_step - horizon + 1 steps, ppo.py:389-406,507-525).  Gate order i, f, g, o; WhhT = [H][4H].
  *   rows_zfilter: out[b*L + t][0..D) = zfilter(x[b*batch_stride + t*row_stride + 0..D)) (plain gather if zf_stats NULL).

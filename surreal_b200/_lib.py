@@ -48,6 +48,21 @@ class Par(C.Structure):
     _fields_ = [('peers', C.c_void_p * 8), ('world', C.c_int), ('rank', C.c_int), ('max_floats', C.c_int64)]
 
 
+class Epochs(C.Structure):
+    """sb200_epochs (include/surreal_b200.h): argument block of the persistent learner kernel."""
+    _fields_ = [('net', C.c_void_p), ('params', C.c_void_p), ('n_params', C.c_int64), ('extra_off', C.c_int),
+                ('x', C.c_void_p), ('ldx', C.c_int64), ('M', C.c_int), ('zf_stats', C.c_void_p), ('zf_eps', C.c_double),
+                ('x_in', C.c_void_p), ('h1', C.c_void_p), ('h2', C.c_void_p), ('out', C.c_void_p), ('d1', C.c_void_p), ('d2', C.c_void_p),
+                ('dpre', C.c_void_p), ('slabs', C.c_void_p), ('splits', C.c_int), ('grad', C.c_void_p),
+                ('exp_avg', C.c_void_p), ('exp_avg_sq', C.c_void_p), ('lr', C.c_void_p), ('weight_decay', C.c_double),
+                ('clip_mode', C.c_int), ('clip_value', C.c_double), ('opt_workspace', C.c_void_p), ('norm_out', C.c_void_p),
+                ('mode', C.c_int), ('actions', C.c_void_p), ('lda', C.c_int64), ('adv', C.c_void_p),
+                ('behave_pd', C.c_void_p), ('ldb', C.c_int64), ('ref_pd', C.c_void_p), ('ldr', C.c_int64),
+                ('returns', C.c_void_p), ('hyper', C.c_void_p), ('eta', C.c_double), ('kl_target', C.c_double),
+                ('stop_threshold', C.c_double), ('stats', C.c_void_p), ('stop_flag', C.c_void_p), ('epochs', C.c_int),
+                ('workspace', C.c_void_p), ('grid', C.c_int), ('cta_shift', C.c_int), ('par', C.c_void_p)]
+
+
 class ZFilter(C.Structure):
     _fields_ = [('stats', C.c_void_p), ('eps', C.c_float)]
 
@@ -85,6 +100,9 @@ def _declare(lib):
         'sb200_par_close': (I, [P, I]),
         'sb200_par_allreduce_f32': (I, [C.POINTER(Par), P, P, L, D, I, P, P, P]),
         'sb200_par_allreduce_f64': (I, [C.POINTER(Par), P, P, I, D, P]),
+        'sb200_ppo_epochs_supported': (I, [C.POINTER(Mlp)]),
+        'sb200_ppo_epochs_workspace_bytes': (S, []),
+        'sb200_ppo_epochs_f32': (I, [C.POINTER(Epochs), P]),
         'sb200_rows_zfilter_f32': (I, [P, L, L, I, I, I, P, D, P, L, P]),
         'sb200_lstm_forward_f32': (I, [P, P, P, P, P, L, I, I, I, I, P, P, P, P, P, P, P]),
         'sb200_lstm_backward_f32': (I, [P, L, P, P, P, L, P, I, I, I, P, P]),

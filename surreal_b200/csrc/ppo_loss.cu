@@ -7,13 +7,16 @@
 //
 // stats[] slots (fp32): see SB200_STAT_* in the header.
 #include "common.cuh"
+#include "ppo_loss_dev.cuh"
 #include <math.h>
 #include <stddef.h>
 
 namespace {
 
 constexpr int LT = 256;
-constexpr int MAX_A = 64;
+using ppo_dev::MAX_A;
+using ppo_dev::row_loglik;
+using ppo_dev::row_kl;
 
 struct LossWs {
     unsigned int counter;
@@ -21,30 +24,6 @@ struct LossWs {
     double kl_mean;          // written by the KL kernel, consumed by the adapt loss
     double partial[1];       // [blocks][slots]
 };
-
-__device__ __forceinline__ float row_loglik(const float* a, const float* mu, const float* sg, int A, float c0,
-                                            float* quad_out) {
-    // ppo_net.py:39-40:  -0.5*sum(((a-mu)/std)^2) - 0.5*log(2pi)*d - sum(log std)
-    float quad = 0.0f, slog = 0.0f;
-    for (int j = 0; j < A; ++j) {
-        const float z = (a[j] - mu[j]) / sg[j];
-        quad += z * z;
-        slog += logf(sg[j]);
-    }
-    if (quad_out) *quad_out = quad;
-    return -0.5f * quad - c0 - slog;
-}
-
-__device__ __forceinline__ float row_kl(const float* m0, const float* s0, const float* m1, const float* s1, int A) {
-    // ppo_net.py:61-62: KL(p0 || p1)
-    float t1 = 0.0f, t2 = 0.0f;
-    for (int j = 0; j < A; ++j) {
-        t1 += logf(s1[j] / s0[j]);
-        const float d = m0[j] - m1[j];
-        t2 += (s0[j] * s0[j] + d * d) / (2.0f * s1[j] * s1[j]);
-    }
-    return t1 + t2 - 0.5f * (float)A;
-}
 
 // ------------------------------------------------------------------------------------------------
 // mode 0: clip   mode 1: adapt (needs ws->kl_mean from kl_kernel(ref, learn))
@@ -70,55 +49,17 @@ __global__ void __launch_bounds__(LT) policy_loss_kernel(int mode, const float* 
     const double invB = 1.0 / (double)B;
 
     float mu[MAX_A], act[MAX_A];
-    float surr = 0.0f, rowloss = 0.0f, g_ll = 0.0f, klrow = 0.0f;
-    float c_kl = 0.0f;
+    ppo_dev::PolicyRow pr = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
     const bool live_row = b < B;
     if (live_row) {
         for (int j = 0; j < A; ++j) {
             mu[j] = mean[(long long)b * ldm + j];
             act[j] = actions[(long long)b * lda + j];
         }
-        const float ll = row_loglik(act, mu, s_sig, A, c0, nullptr);
-        const float Pl = expf(ll);
-        const float Ll = fmaxf(Pl, 1e-5f);
-        const bool live = Pl >= 1e-5f;                                    // clamp(min) passes grad where x >= min
-        const float* bp = behave + (long long)b * ldb;
-        const float llb = row_loglik(act, bp, bp + A, A, c0, nullptr);
-        const float Lb = fmaxf(expf(llb), 1e-5f);
-        const float ad = adv[b];
-        if (mode == 0) {
-            const float eps = (float)hyper[0];
-            const float lo = (float)(1.0 - hyper[0]), hi = (float)(1.0 + hyper[0]);
-            (void)eps;
-            const float ratio = Ll / Lb;
-            const float cr = fminf(fmaxf(ratio, lo), hi);
-            surr = -ratio * ad;
-            const float cs = -cr * ad;
-            rowloss = fmaxf(surr, cs);
-            const float g_ratio = (surr >= cs) ? -ad : 0.0f;              // max(1) routes grad to the first max
-            g_ll = live ? (float)((double)g_ratio * invB) * (Pl / Lb) : 0.0f;
-        } else {
-            const float* rp = ref + (long long)b * ldr;
-            klrow = row_kl(rp, rp + A, mu, s_sig, A);
-            const float den = fmaxf(Lb, 1e-2f);
-            surr = -ad * (Ll / den);
-            rowloss = surr;
-            g_ll = live ? (float)((double)(-ad / den) * invB) * Pl : 0.0f;
-            const double kl = ws->kl_mean;
-            double ck = hyper[1];
-            if (kl - 2.0 * kl_target > 0.0) ck += 2.0 * eta * (kl - 2.0 * kl_target);
-            c_kl = (float)(ck * invB);
-        }
-        // gradient w.r.t. the pre-tanh output (mean = tanh(pre))
-        const float* rp = ref + (long long)b * ldr;
-        for (int j = 0; j < A; ++j) {
-            const float z = (act[j] - mu[j]) / s_sig[j];
-            float dmu = g_ll * z / s_sig[j];
-            if (mode == 1) dmu += c_kl * (-(rp[j] - mu[j]) / (s_sig[j] * s_sig[j]));
-            dpre[(long long)b * ldd + j] = dmu * (1.0f - mu[j] * mu[j]);
-        }
-        for (int j = A; j < (int)ldd; ++j) dpre[(long long)b * ldd + j] = 0.0f;
+        pr = ppo_dev::policy_row(mode, mu, act, s_sig, behave + (long long)b * ldb, ref + (long long)b * ldr, adv[b], A, c0,
+                                 invB, hyper, eta, kl_target, ws->kl_mean, dpre + (long long)b * ldd, (int)ldd);
     }
+    const float surr = pr.surr, rowloss = pr.rowloss, klrow = pr.klrow;
     // ---- block partials: [surr, rowloss, kl] + dlog_var[A]
     double* part = ws->partial + (size_t)blockIdx.x * nslots;
     double t;
@@ -130,15 +71,7 @@ __global__ void __launch_bounds__(LT) policy_loss_kernel(int mode, const float* 
     if (tid == 0) part[2] = t;
     for (int j = 0; j < A; ++j) {
         float dl = 0.0f;
-        if (live_row) {
-            const float z = (act[j] - mu[j]) / s_sig[j];
-            dl = g_ll * (z * z - 1.0f);
-            if (mode == 1) {
-                const float* rp = ref + (long long)b * ldr;
-                const float d = rp[j] - mu[j];
-                dl += c_kl * (1.0f - (rp[A + j] * rp[A + j] + d * d) / (s_sig[j] * s_sig[j]));
-            }
-        }
+        if (live_row) dl = ppo_dev::policy_dlogvar(mode, j, mu, act, s_sig, ref + (long long)b * ldr, pr, A);
         t = block_sum((double)dl, sh);
         if (tid == 0) part[3 + j] = t;
     }

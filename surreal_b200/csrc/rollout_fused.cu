@@ -31,6 +31,20 @@ constexpr int RF_ROWS = 32;         // actors per cluster
 constexpr int RF_OWN = RF_ROWS / RF_CS;
 constexpr int RF_THREADS = 512;     // 16 warps: thread (ty = row 0..31, tx = column quad 0..15)
 
+// -DRF_TRACE (tools/rollout_trace.py builds that variant; never the shipped library): clock64 stamps of cluster 0's
+// first steps, one row per (CTA, step), read back through sb200_debug_rf_trace().
+#ifdef RF_TRACE
+constexpr int RF_TR_STEPS = 8, RF_TR_IDS = 32;
+__device__ long long g_rf_trace[RF_CS][RF_TR_STEPS][RF_TR_IDS];
+#define RF_STAMP(id, who)                                                                           \
+    do {                                                                                            \
+        if (blockIdx.x < RF_CS && threadIdx.x == (who) && rf_t >= 2 && rf_t < 2 + RF_TR_STEPS)      \
+            g_rf_trace[blockIdx.x][rf_t - 2][id] = clock64();                                       \
+    } while (0)
+#else
+#define RF_STAMP(id, who) do { } while (0)
+#endif
+
 struct RfParams {
     const float* W[3];
     const float* b[3];
@@ -104,7 +118,7 @@ template <bool ALL_ROWS, bool F2>
 __device__ __forceinline__ void rf_layer(const float* __restrict__ Xin, int ldin, int K, const float* __restrict__ Ws,
                                          int Nc, const float* __restrict__ bias_s, int act, float* __restrict__ Hout,
                                          int ldout, int col0, float* __restrict__ Part, unsigned smem_base,
-                                         unsigned crank) {
+                                         unsigned crank, int rf_t, int rf_id) {
     const int tid = threadIdx.x;
     const int q = tid >> 7, t128 = tid & 127, ty = t128 >> 4, tx = t128 & 15;
     const int kq = (((K >> 2) + 3) >> 2) << 2;               // k span of one group (multiple of 4)
@@ -181,7 +195,9 @@ __device__ __forceinline__ void rf_layer(const float* __restrict__ Xin, int ldin
                 make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
         }
     }
+    RF_STAMP(rf_id, 0);
     __syncthreads();
+    RF_STAMP(rf_id + 1, 0);
     for (int idx = tid; idx < RF_ROWS * nq; idx += RF_THREADS) {
         const int row = idx / nq, c4 = idx - row * nq;
         const float* pp = Part + row * Nc + c4 * 4;
@@ -309,10 +325,17 @@ __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
     for (int t = 0; t < p.T; ++t) {
         const unsigned long long ctr = ctr0 + (unsigned long long)t;
         const bool final_step = (t == p.T - 1);
-        rf_layer<true, F2>(X0, p.ldx0, D, W1s, Nc1, B1s, p.act[0], Hb1, p.ldh1, (int)crank * Nc1, Part, smem_base, crank);
+        const int rf_t = t;
+        RF_STAMP(0, 0);
+        rf_layer<true, F2>(X0, p.ldx0, D, W1s, Nc1, B1s, p.act[0], Hb1, p.ldh1, (int)crank * Nc1, Part, smem_base, crank, rf_t, 1);
+        RF_STAMP(3, 0);
         cluster.sync();
-        rf_layer<false, F2>(Hb1, p.ldh1, H1, W2s, Nc2, B2s, p.act[1], Hb2, p.ldh2, (int)crank * Nc2, Part, smem_base, crank);
+        RF_STAMP(4, 0);
+        rf_layer<false, F2>(Hb1, p.ldh1, H1, W2s, Nc2, B2s, p.act[1], Hb2, p.ldh2, (int)crank * Nc2, Part, smem_base, crank, rf_t, 5);
+        RF_STAMP(7, 0);
         cluster.sync();
+        RF_STAMP(8, 0);
+        RF_STAMP(16, 256);
 
         float rew = 0.0f, dn = 0.0f;
         int slot = SLOT_NONE;
@@ -378,7 +401,10 @@ __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
                 Zn[h * A + j] = (c == 0) ? z01.x : (c == 1) ? z01.y : (c == 2) ? z23.x : z23.y;
             }
         }
+        RF_STAMP(9, 0);
+        RF_STAMP(17, 256);
         __syncthreads();
+        RF_STAMP(10, 0);
         // ---- phase 2 (owner warps): action, env step, bookkeeping -- same arithmetic, operand order and Philox keys as
         // sample_one() / synth_env_block() of rollout.cu
         if (owner) {
@@ -437,10 +463,12 @@ __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
             slot = __shfl_sync(0xffffffffu, slot, 0);
             __syncwarp();
         }
+        RF_STAMP(11, 0);
         // ---- window staging (block-wide barriers inside: every warp calls; only owners do work)
         commit_actor(valid, (int)i_own, lane, 32, Nx + (owner ? own : 0) * D, S + (owner ? own : 0) * D, rew, dn, p.n_step,
                      p.stride, D, A, s_pos + (owner ? own : 0), slot, p.stage_obs, p.stage_act, p.stage_pd, p.stage_rew,
                      p.stage_done, p.o_obs, p.o_act, p.o_pd, p.o_rew, p.o_done);
+        RF_STAMP(12, 0);
         // ---- next observation -> z-filter -> every CTA's input tile
         if (owner) {
             const int q4 = lane;                            // D / 4 <= 32 float4 per row
@@ -463,7 +491,9 @@ __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
                 for (int c = 0; c < RF_CS - 1; ++c) rf_st_cluster_v4(peer_base[c] + off, v);
             }
         }
+        RF_STAMP(13, 0);
         cluster.sync();
+        RF_STAMP(14, 0);
     }
 
     // ---- write the per-actor control state back
@@ -594,6 +624,14 @@ int sb200_rollout_fused_init() {
     SB200_CUDA(cudaFuncSetAttribute(ppo_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     return SB200_OK;
 }
+
+#ifdef RF_TRACE
+extern "C" int sb200_debug_rf_trace(long long* host_out) {
+    SB200_CUDA(cudaDeviceSynchronize());
+    SB200_CUDA(cudaMemcpyFromSymbol(host_out, g_rf_trace, sizeof(g_rf_trace)));
+    return SB200_OK;
+}
+#endif
 
 extern "C" int sb200_ppo_rollout_supported(const sb200_mlp* net, int D, int A) {
     return rf_plan(net, D, A, nullptr, nullptr) ? 1 : 0;

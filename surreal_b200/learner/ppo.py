@@ -199,6 +199,10 @@ class PPOLearner(Learner):
         self.tc5_min_rows = int(os.environ.get('SB200_TC5_MIN_ROWS', '4096'))
         self.dp = None
         self.dp_v = None
+        # all epochs of one optimiser as ONE persistent kernel (csrc/epoch.cu) instead of ~13 launches per epoch
+        self.use_epoch_kernel = os.environ.get('SB200_EPOCH_KERNEL', '1') != '0' and not self.pixel and not self.rnn and \
+            ops.EpochKernel.supported(self.model.actor) and ops.EpochKernel.supported(self.model.critic)
+        self._ek = None
         self.epoch_history = []
         self._sync_hyper()
         self.last_n_policy_epochs = 0
@@ -592,6 +596,32 @@ class PPOLearner(Learner):
         if self.dp is not None:
             self.dp.mean_(self._stats)                            # every slot is a batch mean (or rank-invariant)
 
+    def _epoch_kernels(self):
+        """(policy, value) persistent-kernel bindings over the current batch buffers, or None when this configuration
+        takes the launch chain (pixel / RNN stems, unsupported layer shapes, NCCL-only data parallel)."""
+        if not self.use_epoch_kernel:
+            return None
+        if self.dp is not None and (self.dp.peer is None or self.dp_v.peer is None):
+            return None
+        B, n, A, D = self.batch_size, self.n_step, self.action_dim, self.low_dim
+        key = (self._obs_full.data_ptr(), self._actions.data_ptr(), self._pds.data_ptr(), id(self.dp))
+        if self._ek is None or self._ek[0] != key:
+            m = self.model
+            mode = 0 if self.ppo_mode == 'clip' else 1
+            pk = ops.EpochKernel(self.actor_optim, mode, self._obs_full, (n + 1) * D, B, m.z_stats, m.z_eps, self._stats,
+                                 self.epoch_policy, norm_out=self._stats[S['GN_ACTOR']:S['GN_ACTOR'] + 1], stop_flag=self._stop,
+                                 actions=self._actions, lda=n * A, adv=self._adv, behave_pd=self._pds, ldb=n * 2 * A,
+                                 ref_pd=self._ref_pd, ldr=2 * A, hyper=self._hyper, eta=self.eta, kl_target=self.kl_target,
+                                 stop_threshold=4.0 * self.kl_target, cta_shift=0)
+            vk = ops.EpochKernel(self.critic_optim, 2, self._obs_full, (n + 1) * D, B, m.z_stats, m.z_eps, self._stats,
+                                 self.epoch_baseline, norm_out=self._stats[S['GN_CRITIC']:S['GN_CRITIC'] + 1],
+                                 returns=self._ret, cta_shift=pk.args.grid // 2)
+            if self.dp is not None:
+                pk.set_peer(self.dp.peer)
+                vk.set_peer(self.dp_v.peer)
+            self._ek = (key, pk, vk)
+        return self._ek[1], self._ek[2]
+
     def _optimize_device(self):
         """The whole of ppo.py:487-586 as one fixed launch sequence (CUDA-graph body).  The KL early stop
         (ppo.py:556) is a DEVICE flag: the post-step KL kernel raises it, and the loss / reduce / Adam / KL
@@ -604,6 +634,24 @@ class PPOLearner(Learner):
         # issue collectives on one communicator, so that case stays sequential.
         fork = self.parallel_branches and not self.profile_events and \
             (self.dp is None or (self.dp_graph and self.dp_v is not self.dp))
+        ek = self._epoch_kernels()
+        if ek is not None:
+            # one persistent kernel per optimiser (all epochs, early stop and -- data-parallel -- the exchanges inside)
+            pk, vk = ek
+            if fork:
+                if self._side_stream is None:
+                    self._side_stream = torch.cuda.Stream(device=self.device)
+                main, side = torch.cuda.current_stream(), self._side_stream
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    vk.run()
+                self._cur_mean = pk.run()
+                main.wait_stream(side)
+            else:
+                self._cur_mean = pk.run()
+                vk.run()
+            self._optimize_tail(value_done=True)
+            return
         if fork:
             if self._side_stream is None:
                 self._side_stream = torch.cuda.Stream(device=self.device)

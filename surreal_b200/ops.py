@@ -444,6 +444,66 @@ class MlpTrainer:
         self.set_lr(sd['lr'])
 
 
+class EpochKernel:
+    """The persistent learner kernel (csrc/epoch.cu) bound to one MlpTrainer: all epochs of one optimiser in ONE launch.
+    ``mode`` 0 clip / 1 adapt (policy) or 2 (value).  The argument block is built once (fixed buffers: graph-safe)."""
+
+    def __init__(self, trainer, mode, x, ldx, M, zf_stats, zf_eps, stats, epochs, norm_out=None, stop_flag=None,
+                 actions=None, lda=0, adv=None, behave_pd=None, ldb=0, ref_pd=None, ldr=0, returns=None, hyper=None,
+                 eta=0.0, kl_target=0.0, stop_threshold=0.0, cta_shift=0, grid=None):
+        from ._lib import Epochs
+        L = _lib.lib()
+        net = trainer.net
+        assert EpochKernel.supported(net) and M == trainer.M
+        self.trainer = trainer
+        self._desc = net.desc()
+        self.ws = torch.zeros(L.sb200_ppo_epochs_workspace_bytes(), dtype=torch.uint8, device=net.device)
+        sm = C.c_int(0)
+        check(L.sb200_device_info(C.byref(sm), None, None), 'sb200_device_info')
+        self._keep = (x, zf_stats, stats, norm_out, stop_flag, actions, adv, behave_pd, ref_pd, returns, hyper)
+        a = Epochs()
+        a.net = C.addressof(self._desc)
+        a.params, a.n_params, a.extra_off = net.params.data_ptr(), net.size, net.extra_off
+        a.x, a.ldx, a.M = x.data_ptr(), int(ldx), int(M)
+        a.zf_stats = zf_stats.data_ptr() if zf_stats is not None else None
+        a.zf_eps = float(zf_eps)
+        h, d = trainer.h, trainer.d
+        a.x_in = trainer.x_in.data_ptr()
+        a.h1, a.h2, a.out, a.d1, a.d2, a.dpre = (h[0].data_ptr(), h[1].data_ptr(), h[2].data_ptr(), d[0].data_ptr(),
+                                                 d[1].data_ptr(), d[2].data_ptr())
+        a.slabs, a.splits, a.grad = trainer.slabs.data_ptr(), trainer.splits, trainer.grad.data_ptr()
+        a.exp_avg, a.exp_avg_sq = trainer.exp_avg.data_ptr(), trainer.exp_avg_sq.data_ptr()
+        a.lr, a.weight_decay = trainer.lr.data_ptr(), trainer.weight_decay
+        a.clip_mode, a.clip_value = trainer.clip_mode, trainer.clip_value
+        a.opt_workspace = trainer.ws.data_ptr()
+        a.norm_out = norm_out.data_ptr() if norm_out is not None else None
+        a.mode = int(mode)
+        g = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+        a.actions, a.lda, a.adv = g(actions), int(lda), g(adv)
+        a.behave_pd, a.ldb, a.ref_pd, a.ldr = g(behave_pd), int(ldb), g(ref_pd), int(ldr)
+        a.returns, a.hyper = g(returns), g(hyper)
+        a.eta, a.kl_target, a.stop_threshold = float(eta), float(kl_target), float(stop_threshold)
+        a.stats, a.stop_flag, a.epochs = stats.data_ptr(), g(stop_flag), int(epochs)
+        a.workspace = self.ws.data_ptr()
+        a.grid = int(grid) if grid is not None else int(sm.value)
+        a.cta_shift = int(cta_shift)
+        a.par = None
+        self.args = a
+
+    @staticmethod
+    def supported(net):
+        return bool(_lib.lib().sb200_ppo_epochs_supported(C.byref(net.desc())))
+
+    def set_peer(self, peer):
+        """Data-parallel: average the KL scalar and the flat gradient over the ranks of ``peer`` (a PeerChannel) in-kernel."""
+        self._peer = peer
+        self.args.par = C.addressof(peer.ctx) if peer is not None else None
+
+    def run(self):
+        check(_lib.lib().sb200_ppo_epochs_f32(C.byref(self.args), _stream()), 'sb200_ppo_epochs_f32')
+        return self.trainer.out
+
+
 class GraphRunner:
     """Capture a fixed launch sequence once into a CUDA graph and replay it (B200: a launch-bound inner loop of
     hundreds of small kernels becomes ONE submission).  Capture records without executing, so state is advanced
