@@ -507,6 +507,402 @@ __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
     }
 }
 
+
+// =====================================================================================================================
+// v2 of the persistent rollout kernel: same cluster / resident-weight / DSMEM structure, same arithmetic for sampling and
+// the environment, two changes of schedule that the clock64 trace of v1 asked for (tools/rollout_trace.py):
+//   * WARP SPECIALISATION.  In v1 the action-independent half of the env step (Philox + Box-Muller draws, Ws.s, |s|^2:
+//     ~6.8 K cycles on 8 helper warps) sat on the serial chain behind the layers.  Now warps 0..7 ("math warps") run
+//     the two hidden layers while warps 8..15 ("env warps") do that work for the SAME step concurrently -- it depends
+//     only on the state at the top of the step.  The env warps arrive at cluster barrier 1 before they start
+//     (barrier.cluster.arrive / .wait are split-phase), so they never hold the math warps up.
+//   * 8 x 4 REGISTER TILES in the layers (was 4 x 4): 12 LDS.128 per 128 FMA instead of 8 per 64 -- the layer loop was
+//     bound by shared-memory loads, not by FFMA issue.  A warp = 16 column quads x 2 k-halves over ONE 8-row group, so
+//     the activation loads are warp-wide broadcasts.
+//   * the head runs on all 16 warps (2 per owned actor, k halves) with a 9-shuffle transposing reduction.
+__device__ __forceinline__ void rf_bar_math() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void rf_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void rf_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+// sum over the 32 lanes of s[j], returned in the lanes with j == 4*bit4 + 2*bit3 + bit2 of the lane index (9 shuffles)
+__device__ __forceinline__ float rf_reduce8(const float (&s)[8], int lane) {
+    const bool u4 = (lane & 16) != 0, u3 = (lane & 8) != 0, u2 = (lane & 4) != 0;
+    float t[4], u[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float recv = __shfl_xor_sync(0xffffffffu, u4 ? s[i] : s[i + 4], 16);
+        t[i] = (u4 ? s[i + 4] : s[i]) + recv;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float recv = __shfl_xor_sync(0xffffffffu, u3 ? t[i] : t[i + 2], 8);
+        u[i] = (u3 ? t[i + 2] : t[i]) + recv;
+    }
+    float v = (u2 ? u[1] : u[0]) + __shfl_xor_sync(0xffffffffu, u2 ? u[0] : u[1], 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+// One hidden layer on the 8 math warps (tid 0..255): warp = (row group rg = warp & 3: rows 8rg..8rg+7, k quarter pair),
+// lane = (column quad, k half) -> 4-way k split, partial tiles summed in a fixed order through Part [4][32][Nc].
+template <bool ALL_ROWS>
+__device__ __forceinline__ void rf2_layer(const float* __restrict__ Xin, int ldin, int K, const float* __restrict__ Ws,
+                                          int Nc, const float* __restrict__ bias_s, int act, float* __restrict__ Hout,
+                                          int ldout, int col0, float* __restrict__ Part, unsigned smem_base,
+                                          unsigned crank, int rf_t, int rf_id) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rg = warp & 3, ks = ((warp >> 2) << 1) | (lane >> 4), cg0 = lane & 15;
+    const int kq = (((K >> 2) + 3) >> 2) << 2;               // k span of one split (multiple of 4)
+    const int k_lo = ks * kq, k_hi = min(K, k_lo + kq);
+    const int nq = Nc >> 2;
+    const float* xr = Xin + (rg * 8) * ldin;
+    for (int c4 = cg0; c4 < nq; c4 += 16) {
+        const float* wp = Ws + c4 * 4;
+        float2 acc[8][2];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[r][0] = acc[r][1] = make_float2(0.0f, 0.0f);
+#pragma unroll 2
+        for (int k = k_lo; k < k_hi; k += 4) {
+            const float4 w0 = *reinterpret_cast<const float4*>(wp + (k + 0) * Nc);
+            const float4 w1 = *reinterpret_cast<const float4*>(wp + (k + 1) * Nc);
+            const float4 w2 = *reinterpret_cast<const float4*>(wp + (k + 2) * Nc);
+            const float4 w3 = *reinterpret_cast<const float4*>(wp + (k + 3) * Nc);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const float4 a = *reinterpret_cast<const float4*>(xr + r * ldin + k);
+                float2 aa = make_float2(a.x, a.x);
+                acc[r][0] = __ffma2_rn(aa, make_float2(w0.x, w0.y), acc[r][0]);
+                acc[r][1] = __ffma2_rn(aa, make_float2(w0.z, w0.w), acc[r][1]);
+                aa = make_float2(a.y, a.y);
+                acc[r][0] = __ffma2_rn(aa, make_float2(w1.x, w1.y), acc[r][0]);
+                acc[r][1] = __ffma2_rn(aa, make_float2(w1.z, w1.w), acc[r][1]);
+                aa = make_float2(a.z, a.z);
+                acc[r][0] = __ffma2_rn(aa, make_float2(w2.x, w2.y), acc[r][0]);
+                acc[r][1] = __ffma2_rn(aa, make_float2(w2.z, w2.w), acc[r][1]);
+                aa = make_float2(a.w, a.w);
+                acc[r][0] = __ffma2_rn(aa, make_float2(w3.x, w3.y), acc[r][0]);
+                acc[r][1] = __ffma2_rn(aa, make_float2(w3.z, w3.w), acc[r][1]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            *reinterpret_cast<float4*>(Part + ((ks * RF_ROWS + rg * 8 + r) * Nc + c4 * 4)) =
+                make_float4(acc[r][0].x, acc[r][0].y, acc[r][1].x, acc[r][1].y);
+    }
+    RF_STAMP(rf_id, 0);
+    rf_bar_math();
+    RF_STAMP(rf_id + 1, 0);
+    for (int idx = tid; idx < RF_ROWS * nq; idx += 256) {
+        const int row = idx / nq, c4 = idx - row * nq;
+        const float* pp = Part + row * Nc + c4 * 4;
+        const float4 p0 = *reinterpret_cast<const float4*>(pp);
+        const float4 p1 = *reinterpret_cast<const float4*>(pp + RF_ROWS * Nc);
+        const float4 p2 = *reinterpret_cast<const float4*>(pp + 2 * RF_ROWS * Nc);
+        const float4 p3 = *reinterpret_cast<const float4*>(pp + 3 * RF_ROWS * Nc);
+        const float4 bv = *reinterpret_cast<const float4*>(bias_s + c4 * 4);
+        float4 o;
+        o.x = rf_act(((p0.x + p1.x) + (p2.x + p3.x)) + bv.x, act);
+        o.y = rf_act(((p0.y + p1.y) + (p2.y + p3.y)) + bv.y, act);
+        o.z = rf_act(((p0.z + p1.z) + (p2.z + p3.z)) + bv.z, act);
+        o.w = rf_act(((p0.w + p1.w) + (p2.w + p3.w)) + bv.w, act);
+        if (ALL_ROWS) {
+            float* qd = Hout + row * ldout + col0 + c4 * 4;
+            *reinterpret_cast<float4*>(qd) = o;
+            const unsigned off = rf_smem_u32(qd) - smem_base;
+#pragma unroll
+            for (int c = 1; c < RF_CS; ++c) rf_st_cluster_v4(rf_mapa(smem_base, (crank + (unsigned)c) % RF_CS) + off, o);
+        } else {
+            const unsigned owner = (unsigned)(row / RF_OWN);
+            float* qd = Hout + (row - (int)owner * RF_OWN) * ldout + col0 + c4 * 4;
+            if (owner == crank) *reinterpret_cast<float4*>(qd) = o;
+            else rf_st_cluster_v4(rf_mapa(smem_base, owner) + (rf_smem_u32(qd) - smem_base), o);
+        }
+    }
+}
+
+__global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
+    ppo_rollout2_kernel(const __grid_constant__ RfParams p) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned crank = cluster.block_rank();
+    extern __shared__ __align__(16) float smem[];
+    const unsigned smem_base = rf_smem_u32(smem);
+    unsigned peer_base[RF_CS - 1];
+#pragma unroll
+    for (int c = 1; c < RF_CS; ++c) peer_base[c - 1] = rf_mapa(smem_base, (crank + (unsigned)c) % RF_CS);
+    __shared__ int s_pos[RF_OWN], s_ep[RF_OWN], s_cnt[RF_OWN];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int D = p.D, H1 = p.H1, H2 = p.H2, A = p.A;
+    const int Nc1 = H1 / RF_CS, Nc2 = H2 / RF_CS;
+    const int ldwh = p.ldw[2];
+    float* W1s = smem + p.oW1;
+    float* W2s = smem + p.oW2;
+    float* Whs = smem + p.oWh;
+    float* B1s = smem + p.oB;
+    float* B2s = B1s + Nc1;
+    float* Bhs = B2s + Nc2;
+    float* X0 = smem + p.oX0;
+    float* Hb1 = smem + p.oH1;
+    float* Hb2 = smem + p.oH2;
+    float* Part = smem + p.oPart;
+    float* Zm = smem + p.oZf;
+    float* Zs = Zm + D;
+    float* EWs = smem + p.oEnv;
+    float* EWa = EWs + D * D;
+    float* S = smem + p.oS;
+    float* Nx = smem + p.oNext;
+    float* Ac = smem + p.oAct;
+    float* Sd = Ac + 2 * RF_OWN * A;     // (slot 1 = Mu of v1: unused here)
+    float* Zn = Sd + RF_OWN * A;
+    float* Hp = Zn + RF_OWN * A;         // [2][8][A] head partial sums of the two k halves
+    float* Eacc = smem + p.oPre;
+    float* Egx = Eacc + RF_OWN * D;
+    float* Erz = Egx + RF_OWN * D;
+    float* Eq = Erz + RF_OWN * D;
+    const long long row0 = (long long)(blockIdx.x / RF_CS) * RF_ROWS;
+
+    // ---- one-time loads (as v1)
+    for (int f = tid; f < D * (Nc1 >> 2); f += RF_THREADS) {
+        const int k = f / (Nc1 >> 2), q = f - k * (Nc1 >> 2);
+        cp_async16(W1s + k * Nc1 + q * 4, p.W[0] + (long long)k * p.ldw[0] + crank * Nc1 + q * 4, 16);
+    }
+    for (int f = tid; f < H1 * (Nc2 >> 2); f += RF_THREADS) {
+        const int k = f / (Nc2 >> 2), q = f - k * (Nc2 >> 2);
+        cp_async16(W2s + k * Nc2 + q * 4, p.W[1] + (long long)k * p.ldw[1] + crank * Nc2 + q * 4, 16);
+    }
+    for (int f = tid; f < (H2 * ldwh) >> 2; f += RF_THREADS) cp_async16(Whs + f * 4, p.W[2] + f * 4, 16);
+    for (int f = tid; f < (D * D) >> 2; f += RF_THREADS) cp_async16(EWs + f * 4, p.WsT + f * 4, 16);
+    for (int f = tid; f < (A * D) >> 2; f += RF_THREADS) cp_async16(EWa + f * 4, p.WaT + f * 4, 16);
+    cp_async_commit();
+    for (int n = tid; n < Nc1; n += RF_THREADS) B1s[n] = p.b[0][crank * Nc1 + n];
+    for (int n = tid; n < Nc2; n += RF_THREADS) B2s[n] = p.b[1][crank * Nc2 + n];
+    for (int n = tid; n < ldwh; n += RF_THREADS) Bhs[n] = (n < A) ? p.b[2][n] : 0.0f;
+    if (p.zf != nullptr) {
+        const float cnt = p.zf[2 * D];
+        for (int k = tid; k < D; k += RF_THREADS) {
+            const float mean = p.zf[k] / cnt;
+            const float var = p.zf[D + k] / cnt - mean * mean;
+            Zm[k] = mean;
+            Zs[k] = fmaxf(sqrtf(var), p.zf_eps);
+        }
+    }
+    if (tid < RF_OWN) {
+        const long long i = row0 + crank * RF_OWN + tid;
+        s_pos[tid] = (i < p.N) ? p.stage_pos[i] : 0;
+        s_ep[tid] = (i < p.N) ? p.ep_step[i] : 0;
+        s_cnt[tid] = 0;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < RF_ROWS * D; idx += RF_THREADS) {
+        const int m = idx / D, k = idx - m * D;
+        const long long i = row0 + m;
+        float v = (i < p.N) ? p.state[i * D + k] : 0.0f;
+        const int own = m - (int)crank * RF_OWN;
+        if (own >= 0 && own < RF_OWN) S[own * D + k] = v;
+        if (p.zf != nullptr) v = fminf(fmaxf((v - Zm[k]) / Zs[k], -5.0f), 5.0f);
+        X0[m * p.ldx0 + k] = (i < p.N) ? v : 0.0f;
+    }
+    const unsigned long long ctr0 = (p.step_ctr != nullptr) ? *p.step_ctr : 0ull;
+    cp_async_wait<0>();
+    cluster.sync();
+
+    const bool math = warp < RF_OWN;                  // warps 0..7: layers, then owner of actor `warp`
+    const int own = warp & (RF_OWN - 1);              // owned actor this warp works for (owner or env warp)
+    const bool owner = math;
+    const int m_own = (int)crank * RF_OWN + own;
+    const long long i_own = row0 + m_own;
+    const bool valid = owner && (i_own < p.N);
+    {
+        const float sc = (i_own < p.N && p.log_noise != nullptr) ? expf(p.log_noise[i_own]) : 1.0f;
+        if (owner && lane < A) Sd[own * A + lane] = __fmul_rn(expf(p.log_var[lane]), sc);
+    }
+    __syncthreads();
+
+    for (int t = 0; t < p.T; ++t) {
+        const unsigned long long ctr = ctr0 + (unsigned long long)t;
+        const bool final_step = (t == p.T - 1);
+        const int rf_t = t;
+        RF_STAMP(0, 0);
+        if (math) {
+            rf2_layer<true>(X0, p.ldx0, D, W1s, Nc1, B1s, p.act[0], Hb1, p.ldh1, (int)crank * Nc1, Part, smem_base, crank, rf_t, 1);
+            RF_STAMP(3, 0);
+            rf_cluster_arrive();
+            rf_cluster_wait();
+            RF_STAMP(4, 0);
+            rf2_layer<false>(Hb1, p.ldh1, H1, W2s, Nc2, B2s, p.act[1], Hb2, p.ldh2, (int)crank * Nc2, Part, smem_base, crank, rf_t, 5);
+            RF_STAMP(7, 0);
+            rf_cluster_arrive();
+            rf_cluster_wait();
+            RF_STAMP(8, 0);
+        } else {
+            // ---- env warp h: everything of this step that does not depend on the action (arithmetic and Philox keys of
+            // sample_one() / synth_env_block() in rollout.cu), concurrently with the layers
+            rf_cluster_arrive();                              // barrier 1: nothing to publish
+            RF_STAMP(16, 256);
+            const int h = own;
+            const long long ih = row0 + (int)crank * RF_OWN + h;
+            const float* sh = S + h * D;
+            float q = 0.0f;
+            for (int d = lane; d < D; d += 32) q += sh[d] * sh[d];
+            q = warp_sum(q);
+            const bool h_done = (p.max_steps > 0) && (s_ep[h] + 1 >= p.max_steps);
+            for (int d = lane; d < D; d += 32) {
+                float acc = 0.0f;
+#pragma unroll 8
+                for (int k = 0; k < D; ++k) acc = fmaf(EWs[k * D + d], sh[k], acc);
+                const Philox4 r = philox4x32_10(p.env_seed ^ 0x5851F42D4C957F2Dull, ctr,
+                                                ((unsigned long long)ih << 20) | (unsigned long long)d);
+                const float2 gz = box_muller(r.x, r.y);
+                Eacc[h * D + d] = acc;
+                Egx[h * D + d] = gz.x;
+                Erz[h * D + d] = h_done ? box_muller(r.z, r.w).x : 0.0f;
+                if (d == 0) {
+                    Eq[2 * h] = q;
+                    Eq[2 * h + 1] = gz.y;
+                }
+            }
+            if (!p.deterministic && lane < A) {
+                const int j = lane;
+                const Philox4 r = philox4x32_10(p.agent_seed, ctr, ((unsigned long long)ih << 16) | (unsigned long long)(j >> 2));
+                const float2 z01 = box_muller(r.x, r.y), z23 = box_muller(r.z, r.w);
+                const int c = j & 3;
+                Zn[h * A + j] = (c == 0) ? z01.x : (c == 1) ? z01.y : (c == 2) ? z23.x : z23.y;
+            }
+            RF_STAMP(17, 256);
+            rf_cluster_wait();
+            rf_cluster_arrive();
+            rf_cluster_wait();
+        }
+        // ---- head: warps w and w + 8 take the two k halves of owned actor w & 7
+        {
+            const int half = warp >> 3;
+            const float* hrow = Hb2 + own * p.ldh2;
+            const int kh = H2 >> 1;
+            for (int n8 = 0; n8 < A; n8 += 8) {
+                float s8[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) s8[jj] = 0.0f;
+                const bool second = (n8 + 4 < ldwh);
+                for (int k = half * kh + lane; k < (half + 1) * kh; k += 32) {
+                    const float hv = hrow[k];
+                    const float* wr = Whs + k * ldwh + n8;
+                    const float4 w0 = *reinterpret_cast<const float4*>(wr);
+                    s8[0] = fmaf(hv, w0.x, s8[0]); s8[1] = fmaf(hv, w0.y, s8[1]);
+                    s8[2] = fmaf(hv, w0.z, s8[2]); s8[3] = fmaf(hv, w0.w, s8[3]);
+                    if (second) {
+                        const float4 w1 = *reinterpret_cast<const float4*>(wr + 4);
+                        s8[4] = fmaf(hv, w1.x, s8[4]); s8[5] = fmaf(hv, w1.y, s8[5]);
+                        s8[6] = fmaf(hv, w1.z, s8[6]); s8[7] = fmaf(hv, w1.w, s8[7]);
+                    }
+                }
+                const float v = rf_reduce8(s8, lane);
+                const int j = n8 + (((lane >> 4) & 1) << 2) + (((lane >> 3) & 1) << 1) + ((lane >> 2) & 1);
+                if ((lane & 3) == 0 && j < A) Hp[(half * RF_OWN + own) * A + j] = v;
+            }
+        }
+        RF_STAMP(9, 0);
+        __syncthreads();
+        RF_STAMP(10, 0);
+        float rew = 0.0f, dn = 0.0f;
+        int slot = SLOT_NONE;
+        if (owner) {
+            const int pos = s_pos[own];
+            if (lane < A) {
+                const int j = lane;
+                const float mu = rf_act((Hp[own * A + j] + Hp[(RF_OWN + own) * A + j]) + Bhs[j], p.act[2]);
+                const float sd = Sd[own * A + j];
+                float a = mu;
+                if (!p.deterministic) a = __fadd_rn(__fmul_rn(Zn[own * A + j], sd), mu);
+                a = fminf(fmaxf(a, -1.0f), 1.0f);
+                Ac[own * A + j] = a;
+                if (valid) {
+                    p.stage_act[((long long)i_own * p.n_step + pos) * A + j] = a;
+                    p.stage_pd[((long long)i_own * p.n_step + pos) * 2 * A + j] = mu;
+                    p.stage_pd[((long long)i_own * p.n_step + pos) * 2 * A + A + j] = sd;
+                    if (final_step) {
+                        p.action[i_own * A + j] = a;
+                        p.pd[i_own * 2 * A + j] = mu;
+                        p.pd[i_own * 2 * A + A + j] = sd;
+                    }
+                }
+            }
+            __syncwarp();
+            float* sown = S + own * D;
+            const int ep = s_ep[own] + 1;
+            const bool is_done = (p.max_steps > 0) && (ep >= p.max_steps);
+            dn = is_done ? 1.0f : 0.0f;
+            rew = -Eq[2 * own] / (float)D + 0.1f * Eq[2 * own + 1];
+            for (int d = lane; d < D; d += 32) {
+                float acc = Eacc[own * D + d];
+#pragma unroll 4
+                for (int k = 0; k < A; ++k) acc = fmaf(EWa[k * D + d], Ac[own * A + k], acc);
+                const float nxt = tanhf(acc) + 0.01f * Egx[own * D + d];
+                Nx[own * D + d] = nxt;
+                sown[d] = is_done ? Erz[own * D + d] : nxt;
+                if (valid && final_step) p.obs_next[i_own * D + d] = nxt;
+            }
+            if (lane == 0) {
+                s_ep[own] = is_done ? 0 : ep;
+                if (valid && final_step) {
+                    p.reward[i_own] = rew;
+                    p.done[i_own] = dn;
+                }
+                if (valid && pos + 1 == p.n_step) {
+                    const int w = s_cnt[own];
+                    if (w < p.Wout) {
+                        slot = (int)(i_own * p.Wout + w);
+                        p.ev_step[slot] = t;
+                        s_cnt[own] = w + 1;
+                    } else {
+                        slot = SLOT_DROPPED;
+                    }
+                }
+            }
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            __syncwarp();
+        }
+        RF_STAMP(11, 0);
+        commit_actor(valid, (int)i_own, lane, 32, Nx + own * D, S + own * D, rew, dn, p.n_step, p.stride, D, A, s_pos + own,
+                     slot, p.stage_obs, p.stage_act, p.stage_pd, p.stage_rew, p.stage_done, p.o_obs, p.o_act, p.o_pd, p.o_rew,
+                     p.o_done);
+        RF_STAMP(12, 0);
+        if (owner) {
+            const int q4 = lane;
+            if (q4 < (D >> 2)) {
+                float4 v = *reinterpret_cast<const float4*>(S + own * D + q4 * 4);
+                if (i_own >= p.N) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.zf != nullptr) {
+                    const float4 zm = *reinterpret_cast<const float4*>(Zm + q4 * 4);
+                    const float4 zs = *reinterpret_cast<const float4*>(Zs + q4 * 4);
+                    v.x = fminf(fmaxf((v.x - zm.x) / zs.x, -5.0f), 5.0f);
+                    v.y = fminf(fmaxf((v.y - zm.y) / zs.y, -5.0f), 5.0f);
+                    v.z = fminf(fmaxf((v.z - zm.z) / zs.z, -5.0f), 5.0f);
+                    v.w = fminf(fmaxf((v.w - zm.w) / zs.w, -5.0f), 5.0f);
+                    if (i_own >= p.N) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                float* qx = X0 + m_own * p.ldx0 + q4 * 4;
+                *reinterpret_cast<float4*>(qx) = v;
+                const unsigned off = rf_smem_u32(qx) - smem_base;
+#pragma unroll
+                for (int c = 0; c < RF_CS - 1; ++c) rf_st_cluster_v4(peer_base[c] + off, v);
+            }
+        }
+        RF_STAMP(13, 0);
+        cluster.sync();
+        RF_STAMP(14, 0);
+    }
+
+    if (valid) {
+        for (int d = lane; d < D; d += 32) p.state[i_own * D + d] = S[own * D + d];
+        if (lane == 0) {
+            p.stage_pos[i_own] = s_pos[own];
+            p.ep_step[i_own] = s_ep[own];
+            p.ev_count[i_own] = s_cnt[own];
+        }
+    }
+}
+
 // ---- post-pass 1 (one block): rank the chunk's window completions in (step, actor) order, give them FIFO slots
 // with drop-oldest at capacity (fifo_replay.py:27), advance the queue and the shared step counter.
 __global__ void __launch_bounds__(1024) ppo_rollout_rank_kernel(const int* __restrict__ ev_step,
@@ -604,7 +1000,7 @@ bool rf_plan(const sb200_mlp* net, int D, int A, RfParams* p, size_t* smem_bytes
     const int oX0 = take(RF_ROWS * ldx0), oH1 = take(RF_ROWS * ldh1), oH2 = take(RF_OWN * ldh2);
     const int oPart = take(4LL * RF_ROWS * (Nc1 > Nc2 ? Nc1 : Nc2));
     const int oZf = take(2 * D), oEnv = take((long long)D * D + A * D);
-    const int oS = take(RF_OWN * D), oNext = take(RF_OWN * D), oAct = take(4 * RF_OWN * A);
+    const int oS = take(RF_OWN * D), oNext = take(RF_OWN * D), oAct = take(6 * RF_OWN * A);
     const int oPre = take(3 * RF_OWN * D + 2 * RF_OWN);
     if ((size_t)off * sizeof(float) > 224 * 1024) return false;
     if (p != nullptr) {
@@ -622,6 +1018,7 @@ bool rf_plan(const sb200_mlp* net, int D, int A, RfParams* p, size_t* smem_bytes
 int sb200_rollout_fused_init() {
     SB200_CUDA(cudaFuncSetAttribute(ppo_rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     SB200_CUDA(cudaFuncSetAttribute(ppo_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    SB200_CUDA(cudaFuncSetAttribute(ppo_rollout2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     return SB200_OK;
 }
 
@@ -699,7 +1096,10 @@ extern "C" int sb200_ppo_rollout_f32(const sb200_ppo_rollout* a, void* stream) {
     // packed fma.rn.f32x2 in the hidden layers (default; bit-identical results, fewer issue slots: 1.764 -> 1.696 ms per
     // 128-step chunk of 1024 actors).  SB200_RF_FFMA2=0 selects the scalar-FFMA instantiation.
     static const int f2 = [] { const char* e = getenv("SB200_RF_FFMA2"); return e ? atoi(e) : 1; }();
-    if (f2) ppo_rollout_kernel<true><<<(unsigned)(clusters * RF_CS), RF_THREADS, smem, (cudaStream_t)stream>>>(p);
+    // v2 (warp-specialised env warps, 8x4 register tiles) is the default; SB200_RF_V2=0 selects the v1 kernel
+    static const int v2 = [] { const char* e = getenv("SB200_RF_V2"); return e ? atoi(e) : 1; }();
+    if (v2) ppo_rollout2_kernel<<<(unsigned)(clusters * RF_CS), RF_THREADS, smem, (cudaStream_t)stream>>>(p);
+    else if (f2) ppo_rollout_kernel<true><<<(unsigned)(clusters * RF_CS), RF_THREADS, smem, (cudaStream_t)stream>>>(p);
     else ppo_rollout_kernel<false><<<(unsigned)(clusters * RF_CS), RF_THREADS, smem, (cudaStream_t)stream>>>(p);
     return sb200_launch_status();
 }
