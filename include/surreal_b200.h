@@ -227,6 +227,20 @@ int sb200_ppo_epochs_supported(const sb200_mlp* net);
 size_t sb200_ppo_epochs_workspace_bytes(void);
 int sb200_ppo_epochs_f32(const sb200_epochs* args, void* stream);
 
+/* Second generation (csrc/epoch2.cu): BOTH optimisers of PPOLearner._optimize -- `policy` (mode 0 / 1) and `value` (mode 2,
+ * may be NULL) -- in ONE launch of one CTA per SM: row blocks of 16 run forward -> loss -> input gradients without grid
+ * barriers, weight gradients are a second wave, an epoch costs 4 grid barriers (5 in adapt mode).  Same buffers, statistics
+ * and early-stop semantics as sb200_ppo_epochs_f32 called once per optimiser; `grid` / `cta_shift` / `workspace` of the
+ * argument blocks are ignored (grid = SM count, or policy->grid when smaller); `workspace` here must hold
+ * sb200_ppo_epochs2_workspace_bytes() bytes, 256-byte aligned.  Data-parallel: the two blocks must use DIFFERENT sb200_par
+ * channels (both exchange in the same phase). */
+int sb200_ppo_epochs2_supported(const sb200_epochs* policy, const sb200_epochs* value);
+size_t sb200_ppo_epochs2_workspace_bytes(const sb200_epochs* policy, const sb200_epochs* value);
+int sb200_ppo_epochs2_f32(const sb200_epochs* policy, const sb200_epochs* value, void* workspace, void* stream);
+/* accumulated clock64 cycles per phase of the launches on `workspace` (2 x 16: CTA 0, last CTA; see epoch2.cu) */
+int sb200_ppo_epochs2_profile(void* workspace, uint64_t* out32, int reset, void* stream);
+int sb200_ppo_epochs2_cta_profile(void* workspace, uint64_t* out_192x8, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * LSTM stem of RNN-mode PPO (csrc/lstm.cu; nn.LSTM(batch_first=True) of ppo_net.py:143-152,277-279,342-351; BPTT over
  * eff_len = n_step - horizon + 1 steps, ppo.py:389-406,507-525).  Gate order i, f, g, o; WhhT = [H][4H].

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libsurreal_b200.so')
+LIB_PATH = os.environ.get('SB200_LIB') or os.path.join(HERE, 'libsurreal_b200.so')     # SB200_LIB: a development build (tools/)
 MAX_LAYERS = 4
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
 
@@ -103,6 +103,11 @@ def _declare(lib):
         'sb200_ppo_epochs_supported': (I, [C.POINTER(Mlp)]),
         'sb200_ppo_epochs_workspace_bytes': (S, []),
         'sb200_ppo_epochs_f32': (I, [C.POINTER(Epochs), P]),
+        'sb200_ppo_epochs2_supported': (I, [C.POINTER(Epochs), C.POINTER(Epochs)]),
+        'sb200_ppo_epochs2_workspace_bytes': (S, [C.POINTER(Epochs), C.POINTER(Epochs)]),
+        'sb200_ppo_epochs2_f32': (I, [C.POINTER(Epochs), C.POINTER(Epochs), P, P]),
+        'sb200_ppo_epochs2_profile': (I, [P, C.POINTER(C.c_uint64), I, P]),
+        'sb200_ppo_epochs2_cta_profile': (I, [P, C.POINTER(C.c_uint64), P]),
         'sb200_rows_zfilter_f32': (I, [P, L, L, I, I, I, P, D, P, L, P]),
         'sb200_lstm_forward_f32': (I, [P, P, P, P, P, L, I, I, I, I, P, P, P, P, P, P, P]),
         'sb200_lstm_backward_f32': (I, [P, L, P, P, P, L, P, I, I, I, P, P]),

@@ -26,6 +26,7 @@ int sb200_gae_init();
 int sb200_rollout_fused_init();
 int sb200_mlp_tc5_init();
 int sb200_stem_init();
+int sb200_epochs2_init();
 
 extern "C" void sb200_launch_counter_add(uint64_t kernels) { g_sb200_launches += kernels; }
 
@@ -45,6 +46,8 @@ extern "C" int sb200_init(void) {
     rc = sb200_mlp_tc5_init();
     if (rc != SB200_OK) return rc;
     rc = sb200_stem_init();
+    if (rc != SB200_OK) return rc;
+    rc = sb200_epochs2_init();
     if (rc != SB200_OK) return rc;
     return sb200_rollout_fused_init();
 }

@@ -45,7 +45,53 @@ __device__ void normalize_all(float* adv, long long total, double* sh) {
     for (long long i = threadIdx.x; i < total; i += blockDim.x) adv[i] = (adv[i] - mean_f) / denom;
 }
 
-// MLP branch: horizon == n, one (adv, ret) per window.
+// One window with n == 32 * ITER, everything in registers: ALL loads of the window are issued before the first use (the
+// generic loop below exposes one DRAM round trip per 32 steps: 1.76 TB/s at 2^18 windows), and the shifted operands
+// V[k+1] / done[k-1] come from the neighbouring lane by shuffle instead of a second load.  Same operations on the same
+// operands in the same order as the generic loop -> bit-identical results.
+template <int ITER>
+__device__ __forceinline__ void gae_window_regs(const float* __restrict__ r, const float* __restrict__ v,
+                                                const float* __restrict__ d, const float* __restrict__ tab, int lane,
+                                                float gamma_f, float rscale, double& a_sum, double& r_sum, float& vn) {
+    constexpr int n = 32 * ITER;
+    float rr[ITER], vv[ITER], dd[ITER];
+#pragma unroll
+    for (int i = 0; i < ITER; ++i) {
+        rr[i] = __ldg(r + lane + 32 * i);
+        dd[i] = __ldg(d + lane + 32 * i);
+        vv[i] = __ldg(v + lane + 32 * i);
+    }
+    const float v_last = (lane == 31) ? __ldg(v + n) : 0.0f;
+    float vm[ITER + 1];                               // masked values V[k] (1 - done[k-1]) of this lane's steps
+#pragma unroll
+    for (int i = 0; i < ITER; ++i) {
+        float dprev = __shfl_up_sync(0xffffffffu, dd[i], 1);
+        if (i > 0) {
+            const float wrap = __shfl_sync(0xffffffffu, dd[i - 1], 31);
+            if (lane == 0) dprev = wrap;
+        }
+        vm[i] = (i == 0 && lane == 0) ? vv[0] : __fmul_rn(vv[i], __fsub_rn(1.0f, dprev));
+    }
+    vm[ITER] = __fmul_rn(v_last, __fsub_rn(1.0f, dd[ITER - 1]));     // lane 31: V[n] (1 - done[n-1])
+    a_sum = 0.0;
+    r_sum = 0.0;
+#pragma unroll
+    for (int i = 0; i < ITER; ++i) {
+        const int k = lane + 32 * i;
+        float v1 = __shfl_down_sync(0xffffffffu, vm[i], 1);
+        const float wrap = __shfl_sync(0xffffffffu, vm[i + 1], 0);
+        if (lane == 31) v1 = (i + 1 < ITER) ? wrap : vm[ITER];
+        const float g = tab[k], l = tab[n + k];
+        const float rk = __fmul_rn(rr[i], rscale);
+        const float td = __fsub_rn(__fadd_rn(rk, __fmul_rn(gamma_f, v1)), vm[i]);
+        a_sum += (double)__fmul_rn(__fmul_rn(td, g), l);
+        r_sum += (double)__fmul_rn(g, rk);
+    }
+    vn = __shfl_sync(0xffffffffu, vm[ITER], 31);
+}
+
+// MLP branch: horizon == n, one (adv, ret) per window.  ITER > 0: n == 32 * ITER, register-resident windows.
+template <int ITER>
 __global__ void __launch_bounds__(GAE_WARPS * 32) gae_full_kernel(const float* __restrict__ rewards,
                                                                    const float* __restrict__ values,
                                                                    const float* __restrict__ dones, int B, int n,
@@ -66,20 +112,25 @@ __global__ void __launch_bounds__(GAE_WARPS * 32) gae_full_kernel(const float* _
         const float* v = values + (long long)b * (n + 1);
         const float* d = dones + (long long)b * n;
         double a_sum = 0.0, r_sum = 0.0;
-        for (int k = lane; k < n; k += 32) {
-            const float g = tab[k], l = tab[n + k];
-            const float rk = __fmul_rn(r[k], rscale);   // ppo.py:452 (x reward_scale, rounded to fp32)
-            const float v0 = (k > 0) ? __fmul_rn(v[k], __fsub_rn(1.0f, d[k - 1])) : v[0];
-            const float v1 = __fmul_rn(v[k + 1], __fsub_rn(1.0f, d[k]));
-            // td = r + gamma*V[k+1] - V[k]; each op rounded separately like the eager reference
-            const float td = __fsub_rn(__fadd_rn(rk, __fmul_rn(gamma_f, v1)), v0);
-            a_sum += (double)__fmul_rn(__fmul_rn(td, g), l);
-            r_sum += (double)__fmul_rn(g, rk);
+        float vn = 0.0f;
+        if constexpr (ITER > 0) {
+            gae_window_regs<ITER>(r, v, d, tab, lane, gamma_f, rscale, a_sum, r_sum, vn);
+        } else {
+            for (int k = lane; k < n; k += 32) {
+                const float g = tab[k], l = tab[n + k];
+                const float rk = __fmul_rn(r[k], rscale);   // ppo.py:452 (x reward_scale, rounded to fp32)
+                const float v0 = (k > 0) ? __fmul_rn(v[k], __fsub_rn(1.0f, d[k - 1])) : v[0];
+                const float v1 = __fmul_rn(v[k + 1], __fsub_rn(1.0f, d[k]));
+                // td = r + gamma*V[k+1] - V[k]; each op rounded separately like the eager reference
+                const float td = __fsub_rn(__fadd_rn(rk, __fmul_rn(gamma_f, v1)), v0);
+                a_sum += (double)__fmul_rn(__fmul_rn(td, g), l);
+                r_sum += (double)__fmul_rn(g, rk);
+            }
+            if (lane == 0) vn = __fmul_rn(v[n], __fsub_rn(1.0f, d[n - 1]));
         }
         a_sum = warp_sum(a_sum);
         r_sum = warp_sum(r_sum);
         if (lane == 0) {
-            const float vn = __fmul_rn(v[n], __fsub_rn(1.0f, d[n - 1]));
             const float af = (float)a_sum;
             adv[b] = af;
             ret[b] = __fadd_rn((float)r_sum, __fmul_rn(vn, gamma_pow_n));
@@ -197,8 +248,16 @@ extern "C" int sb200_gae_window_f32(const float* rewards, const float* values, c
         // windows; windows are walked grid-stride
         const int pgrid = grid < GAE_MAX_GRID ? grid : GAE_MAX_GRID;
         const int mode = !norm_adv ? 0 : (B <= GAE_FUSED_NORM_MAX ? 1 : 2);
-        gae_full_kernel<<<pgrid, GAE_WARPS * 32, (size_t)2 * n * sizeof(float), st>>>(rewards, values, dones, B, n, gamma_f, lam_f, gpn, (float)reward_scale, mode,
-                                                         adv, ret, (GaeWs*)workspace);
+        const size_t tab_bytes = (size_t)2 * n * sizeof(float);
+#define SB200_GAE_LAUNCH(IT)                                                                                                      \
+    gae_full_kernel<IT><<<pgrid, GAE_WARPS * 32, tab_bytes, st>>>(rewards, values, dones, B, n, gamma_f, lam_f, gpn,             \
+                                                                  (float)reward_scale, mode, adv, ret, (GaeWs*)workspace)
+        if (n == 32) SB200_GAE_LAUNCH(1);
+        else if (n == 64) SB200_GAE_LAUNCH(2);
+        else if (n == 128) SB200_GAE_LAUNCH(4);
+        else if (n == 256) SB200_GAE_LAUNCH(8);
+        else SB200_GAE_LAUNCH(0);
+#undef SB200_GAE_LAUNCH
         if (mode == 2) {
             const long long nb = ((long long)B + 256 * 4 - 1) / (256 * 4);
             gae_normalize_kernel<<<(unsigned)(nb < 2048 ? nb : 2048), 256, 0, st>>>(adv, (long long)B, (const GaeWs*)workspace);

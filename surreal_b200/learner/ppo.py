@@ -203,6 +203,7 @@ class PPOLearner(Learner):
         self.use_epoch_kernel = os.environ.get('SB200_EPOCH_KERNEL', '1') != '0' and not self.pixel and not self.rnn and \
             ops.EpochKernel.supported(self.model.actor) and ops.EpochKernel.supported(self.model.critic)
         self._ek = None
+        self.epoch_kernel_gen = int(os.environ.get('SB200_EPOCH_KERNEL', '2'))     # 0: launch chain, 1: epoch.cu, 2: epoch2.cu
         self.epoch_history = []
         self._sync_hyper()
         self.last_n_policy_epochs = 0
@@ -619,8 +620,12 @@ class PPOLearner(Learner):
             if self.dp is not None:
                 pk.set_peer(self.dp.peer)
                 vk.set_peer(self.dp_v.peer)
-            self._ek = (key, pk, vk)
-        return self._ek[1], self._ek[2]
+            # second generation: both optimisers in ONE launch (csrc/epoch2.cu); data-parallel needs two distinct channels
+            pair = None
+            if self.epoch_kernel_gen >= 2 and (self.dp is None or self.dp_v is not self.dp) and ops.EpochPair.supported(pk, vk):
+                pair = ops.EpochPair(pk, vk)
+            self._ek = (key, pk, vk, pair)
+        return self._ek[1], self._ek[2], self._ek[3]
 
     def _optimize_device(self):
         """The whole of ppo.py:487-586 as one fixed launch sequence (CUDA-graph body).  The KL early stop
@@ -637,8 +642,10 @@ class PPOLearner(Learner):
         ek = self._epoch_kernels()
         if ek is not None:
             # one persistent kernel per optimiser (all epochs, early stop and -- data-parallel -- the exchanges inside)
-            pk, vk = ek
-            if fork:
+            pk, vk, pair = ek
+            if pair is not None:
+                self._cur_mean = pair.run()
+            elif fork:
                 if self._side_stream is None:
                     self._side_stream = torch.cuda.Stream(device=self.device)
                 main, side = torch.cuda.current_stream(), self._side_stream

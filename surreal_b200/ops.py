@@ -504,6 +504,43 @@ class EpochKernel:
         return self.trainer.out
 
 
+class EpochPair:
+    """Second-generation persistent learner kernel (csrc/epoch2.cu): the policy optimiser AND the value optimiser of one
+    ``learn()`` in ONE launch.  Built from two EpochKernel argument blocks (``value`` may be None)."""
+
+    def __init__(self, policy, value=None):
+        L = _lib.lib()
+        self.policy, self.value = policy, value
+        self._pa = C.byref(policy.args)
+        self._va = C.byref(value.args) if value is not None else None
+        nbytes = int(L.sb200_ppo_epochs2_workspace_bytes(self._pa, self._va))
+        assert nbytes > 0
+        self.ws = torch.zeros(nbytes + 256, dtype=torch.uint8, device=policy.trainer.net.device)
+        self._ws_ptr = (self.ws.data_ptr() + 255) // 256 * 256
+
+    @staticmethod
+    def supported(policy, value=None):
+        return bool(_lib.lib().sb200_ppo_epochs2_supported(C.byref(policy.args), C.byref(value.args) if value is not None else None))
+
+    def run(self):
+        check(_lib.lib().sb200_ppo_epochs2_f32(self._pa, self._va, C.c_void_p(self._ws_ptr), _stream()), 'sb200_ppo_epochs2_f32')
+        return self.policy.trainer.out
+
+    PHASES = ('setup', 'P1 rows', 'barrier', 'gate+stats', 'P2 dW', 'barrier', 'P3 reduce', 'barrier', 'P4 adam', 'barrier')
+
+    def profile(self, reset=True):
+        """Accumulated clock64 cycles per phase since the last reset: [(phase, CTA 0, last CTA)]."""
+        buf = (C.c_uint64 * 32)()
+        check(_lib.lib().sb200_ppo_epochs2_profile(C.c_void_p(self._ws_ptr), buf, int(reset), _stream()), 'sb200_ppo_epochs2_profile')
+        return [(name, int(buf[i]), int(buf[16 + i])) for i, name in enumerate(self.PHASES)]
+
+    def cta_profile(self):
+        """Per-CTA accumulated cycles [192][8] (0 P1, 1 P2, 2 forward, 3 forward GEMMs, 4 loss rows + d2, 5 d1 GEMM); cleared on read."""
+        buf = (C.c_uint64 * (192 * 8))()
+        check(_lib.lib().sb200_ppo_epochs2_cta_profile(C.c_void_p(self._ws_ptr), buf, _stream()), 'sb200_ppo_epochs2_cta_profile')
+        return [[int(buf[c * 8 + k]) for k in range(8)] for c in range(192)]
+
+
 class GraphRunner:
     """Capture a fixed launch sequence once into a CUDA graph and replay it (B200: a launch-bound inner loop of
     hundreds of small kernels becomes ONE submission).  Capture records without executing, so state is advanced

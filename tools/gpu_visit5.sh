@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout -k 10 300 python tools/prof_epoch2.py > gpurun_out/prof_epoch2.log 2>&1; echo "prof rc=$?"; tail -16 gpurun_out/prof_epoch2.log
+timeout -k 10 300 python tools/prof_epoch2.py adapt > gpurun_out/prof_epoch2_adapt.log 2>&1; echo "prof adapt rc=$?"; tail -16 gpurun_out/prof_epoch2_adapt.log

@@ -75,6 +75,9 @@ def traffic(pairs):
     bench.py's roofline objects report as `traffic`."""
     import json
     out = {}
+    path = os.path.join(PROF, 'traffic.json')
+    if os.path.exists(path):
+        out = json.load(open(path))            # keep the entries whose capture is not in gpurun_out/ this time
     for key, name in pairs:
         rep = os.path.join(OUT, name + '.ncu-rep')
         if not os.path.exists(rep):
@@ -124,9 +127,9 @@ if __name__ == '__main__':
     tag = sys.argv[1] if len(sys.argv) > 1 else 'r02'
     os.makedirs(PROF, exist_ok=True)
     launches(tag)
-    for n in ('prof_rollout', 'prof_tc5', 'prof_critic', 'prof_gae'):
+    for n in ('prof_rollout', 'prof_tc5', 'prof_critic', 'prof_gae', 'prof_epochs2', 'prof_gae_large'):
         report(n, tag)
-    traffic([('rollout', 'prof_rollout'), ('critic', 'prof_tc5')])
+    traffic([('rollout', 'prof_rollout'), ('critic', 'prof_tc5'), ('epochs2', 'prof_epochs2'), ('gae_large', 'prof_gae_large')])
     obj = os.path.join(ROOT, 'surreal_b200', 'build', 'mlp_fwd_tc5.o')
     if os.path.exists(obj):
         sass_excerpt(tag, obj, 'sass_tc5', ['UTC', 'LDTM', 'STTM', 'UBLKCP', 'UTMA', 'SYNCS', 'HMMA'])
