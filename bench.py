@@ -80,8 +80,18 @@ def load_profile_traffic(kernel):
         return None
 
 
+WORKLOAD = 'cfg2'          # --workload cfg5: BASELINE configs[4], 4096 actors x horizon 256 in TOTAL (strong scaling)
+
+
 def bench_config(world):
     """The `config` object of BOTH arms' JSON lines (identical: same workload, same keys, same values)."""
+    if WORKLOAD == 'cfg5':
+        return {'workload': 'PPO synthetic 64-dim obs, 4096 actors x horizon 256 in total, 2x256 MLP, data-parallel learner '
+                            '(BASELINE configs[4])',
+                'actors_per_gpu': N_ACTORS, 'horizon': HORIZON, 'obs_dim': OBS_DIM, 'action_dim': ACT_DIM, 'hidden': list(HIDDEN),
+                'ppo_mode': 'clip', 'epoch_policy': 10, 'epoch_baseline': 10, 'episode_length': EPISODE_LEN,
+                'global_windows_per_step': N_ACTORS * world, 'parallelism': 'dp%d' % world,
+                'l2': 'flushed between timed steps (192 MB fill)'}
     return {'workload': 'PPO synthetic 64-dim obs, 1024 actors x horizon 128, 2x256 MLP (BASELINE configs[1])',
             'actors_per_gpu': N_ACTORS, 'horizon': HORIZON, 'obs_dim': OBS_DIM, 'action_dim': ACT_DIM, 'hidden': list(HIDDEN),
             'ppo_mode': 'clip', 'epoch_policy': 10, 'epoch_baseline': 10, 'episode_length': EPISODE_LEN,
@@ -169,7 +179,7 @@ def run_ours(args):
     from surreal_b200.replay import FIFOReplay
     from surreal_b200.distributed import LocalHub
     _lib.lib()
-    lc, ec, sc = build_configs()
+    lc, ec, sc = build_configs(N_ACTORS, HORIZON)
     ec.seed = rank
     la = SurrealDefaultLauncher(PPOAgent, PPOLearner, FIFOReplay, sc, ec, lc)
     agent, replay, learner = la.setup_engine()
@@ -354,7 +364,7 @@ def run_ours(args):
         out = {
             'metric': 'env-steps/sec', 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'scaling': 'strong' if WORKLOAD == 'cfg5' else 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': bench_config(world),
             'engine': 'sequential' if eng is None else 'pipelined: actors (stream A) overlap the learner (stream L), '
                       'one-iteration policy lag',
@@ -852,7 +862,14 @@ if __name__ == '__main__':
     ap.add_argument('--impl', type=str, default='ours', choices=['ours', 'reference'])
     ap.add_argument('--sequential', action='store_true', help='rollout then learn on one stream (no actor/learner overlap)')
     ap.add_argument('--lite', action='store_true', help='skip the e2e and CPU-baseline legs (profiling runs under ncu)')
+    ap.add_argument('--workload', type=str, default='cfg2', choices=['cfg2', 'cfg5'],
+                    help='cfg2: BASELINE configs[1] (the metric; weak scaling).  cfg5: configs[4], 4096 actors x horizon 256 in total, '
+                         'sharded over the ranks (strong scaling; use with --lite)')
     a = ap.parse_args()
+    if a.workload == 'cfg5':
+        WORKLOAD = 'cfg5'
+        N_ACTORS, HORIZON = 4096 // int(os.environ.get('WORLD_SIZE', 1)), 256
+        EPISODE_LEN = 512
     if a.impl == 'reference':
         run_reference(a)
     else:

@@ -75,6 +75,11 @@ __device__ __forceinline__ float ld_sys1(const float* p) {
     asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");
     return r;
 }
+__device__ __forceinline__ float4 ld_sys4(const float* p) {
+    float4 r;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+    return r;
+}
 __device__ __forceinline__ double ld_sys_f64(const double* p) {
     double r;
     asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(r) : "l"(p) : "memory");
@@ -156,7 +161,8 @@ __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.
 // padding columns zero).  thread = (column octet co = tid & 31, row half rg = bit 5, k quarter kh = tid >> 6): an 8 x 8
 // register tile, so that a (warp-broadcast) LDS.128 of A feeds 32 FMAs per lane and the kernel is bound by the FMA pipe,
 // not by shared memory (the first version, 16 x 4 tiles, spent as long on its 16 LDS per k quad as on the 128 FFMA2).
-// W streams L2 -> registers (ld.global.cg.v4, coalesced: a warp reads 1 KB of a W row), two k quads ahead.  The partial
+// W streams L2 -> registers (ld.global.cg.v4, coalesced: a warp reads 1 KB of a W row), two k quads ahead; the k loop is
+// unrolled by 3 so that the rotation of the three register sets is renaming, not copies (0.84 -> 0.34 MOV per FFMA2).  The partial
 // tiles of the four k quarters go to Part [4][RB + 1][ldp] (row RB: column sums); the caller sums them after a barrier.
 // One call covers 32 column octets (pass c80 = first column quad); wider layers take several passes.
 template <bool COLSUM>
@@ -178,24 +184,29 @@ __device__ __forceinline__ void rb_gemm(const float* __restrict__ As, int lda, i
         for (int q = 0; q < 4; ++q) acc[r][q] = make_float2(0.0f, 0.0f);
     float4 cs0 = zero4(), cs1 = zero4();
     float4 w[4][2], w1[4][2], w2[4][2];
+    // No range predicates on the loads: a row index past K is clamped to K - 1 (A is zero there, so the product vanishes),
+    // a column quad past the layer reads quad 0 (its results are never stored); the two quads fetched past k_hi are unused.
+    const float* Wc1 = on1 ? Wc + 4 : Wc;
     auto loadq = [&](int k, float4 (&d)[4][2]) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const bool ok = k < k_hi && k + i < K;
-            d[i][0] = (ok && on0) ? gt::ldcg4(Wc + (long long)(k + i) * ldw) : zero4();
-            d[i][1] = (ok && on1) ? gt::ldcg4(Wc + (long long)(k + i) * ldw + 4) : zero4();
+            const long long row = (long long)max(min(k + i, K - 1), 0) * ldw;
+            d[i][0] = gt::ldcg4(Wc + row);
+            d[i][1] = gt::ldcg4(Wc1 + row);
         }
     };
     loadq(k_lo, w);
     loadq(k_lo + 4, w1);
+#pragma unroll 3
     for (int k = k_lo; k < k_hi; k += 4) {
         loadq(k + 8, w2);
         if (COLSUM) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                cs0.x += w[i][0].x; cs0.y += w[i][0].y; cs0.z += w[i][0].z; cs0.w += w[i][0].w;
-                cs1.x += w[i][1].x; cs1.y += w[i][1].y; cs1.z += w[i][1].z; cs1.w += w[i][1].w;
-            }
+            for (int i = 0; i < 4; ++i)
+                if (k + i < K) {
+                    cs0.x += w[i][0].x; cs0.y += w[i][0].y; cs0.z += w[i][0].z; cs0.w += w[i][0].w;
+                    cs1.x += w[i][1].x; cs1.y += w[i][1].y; cs1.z += w[i][1].z; cs1.w += w[i][1].w;
+                }
         }
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
@@ -272,6 +283,83 @@ __device__ __forceinline__ void hidden_layer(const Sm& sm, const float* As, int 
         }
         __syncthreads();
     }
+}
+
+// ---- one batch row of the policy loss on a whole warp: lane j holds action dimension j (NO <= 32).  The arithmetic is that
+// of ppo_dev::policy_row / policy_dlogvar / row_kl -- the per-dimension terms are formed in parallel and summed in index
+// order through shuffles (the serial version is a chain of ~1.5 K dependent instructions per row on one lane).
+__device__ __forceinline__ float seq_sum(float term, int n) {
+    float s = 0.0f;
+    for (int j = 0; j < n; ++j) s += __shfl_sync(0xffffffffu, term, j);
+    return s;
+}
+__device__ __forceinline__ float seq_sum_sq(float z, int n) {
+    float s = 0.0f;
+    for (int j = 0; j < n; ++j) {
+        const float zj = __shfl_sync(0xffffffffu, z, j);
+        s = fmaf(zj, zj, s);
+    }
+    return s;
+}
+// KL(ref || current) of one row (ppo_net.py:61-62)
+__device__ __forceinline__ float row_kl_warp(const float* rp, const float* mu, const float* s_sig, int A, int lane) {
+    const bool on = lane < A;
+    const float m0 = on ? rp[lane] : 0.0f, s0 = on ? rp[A + lane] : 1.0f, m1 = on ? mu[lane] : 0.0f, s1 = on ? s_sig[lane] : 1.0f;
+    const float d = m0 - m1;
+    const float t1 = seq_sum(logf(s1 / s0), A);
+    const float t2 = seq_sum((s0 * s0 + d * d) / (2.0f * s1 * s1), A);
+    return t1 + t2 - 0.5f * (float)A;
+}
+struct RowOut {
+    float surr, rowloss, klrow, dlogvar;      // dlogvar: this lane's dimension
+};
+__device__ __forceinline__ RowOut policy_row_warp(int mode, const float* mu_, const float* act_, const float* s_sig, const float* bp,
+                                                  const float* rp, float ad, int A, float c0, double invB, const double* hyper, double eta,
+                                                  double kl_target, double kl_mean, float* dpre_row, int ldd, int lane) {
+    const bool on = lane < A;
+    const float a = on ? act_[lane] : 0.0f, mu = on ? mu_[lane] : 0.0f, sg = on ? s_sig[lane] : 1.0f;
+    const float bm = on ? bp[lane] : 0.0f, bs = on ? bp[A + lane] : 1.0f, rm = on ? rp[lane] : 0.0f, rs = on ? rp[A + lane] : 1.0f;
+    RowOut o = {0.0f, 0.0f, 0.0f, 0.0f};
+    const float z = (a - mu) / sg;
+    const float ll = -0.5f * seq_sum_sq(z, A) - c0 - seq_sum(logf(sg), A);
+    const float Pl = expf(ll);
+    const float Ll = fmaxf(Pl, 1e-5f);
+    const bool live = Pl >= 1e-5f;                                    // clamp(min) passes grad where x >= min
+    const float zb = (a - bm) / bs;
+    const float llb = -0.5f * seq_sum_sq(zb, A) - c0 - seq_sum(logf(bs), A);
+    const float Lb = fmaxf(expf(llb), 1e-5f);
+    float g_ll = 0.0f, c_kl = 0.0f;
+    if (mode == 0) {
+        const float lo = (float)(1.0 - hyper[0]), hi = (float)(1.0 + hyper[0]);
+        const float ratio = Ll / Lb;
+        const float cr = fminf(fmaxf(ratio, lo), hi);
+        o.surr = -ratio * ad;
+        const float cs = -cr * ad;
+        o.rowloss = fmaxf(o.surr, cs);
+        const float g_ratio = (o.surr >= cs) ? -ad : 0.0f;            // max(1) routes grad to the first max
+        g_ll = live ? (float)((double)g_ratio * invB) * (Pl / Lb) : 0.0f;
+    } else {
+        const float d = rm - mu;
+        o.klrow = seq_sum(logf(sg / rs), A) + seq_sum((rs * rs + d * d) / (2.0f * sg * sg), A) - 0.5f * (float)A;
+        const float den = fmaxf(Lb, 1e-2f);
+        o.surr = -ad * (Ll / den);
+        o.rowloss = o.surr;
+        g_ll = live ? (float)((double)(-ad / den) * invB) * Pl : 0.0f;
+        double ck = hyper[1];
+        if (kl_mean - 2.0 * kl_target > 0.0) ck += 2.0 * eta * (kl_mean - 2.0 * kl_target);
+        c_kl = (float)(ck * invB);
+    }
+    // gradient w.r.t. the pre-tanh output (mean = tanh(pre)) and this dimension's share of d loss / d log_var
+    float dmu = g_ll * z / sg;
+    float dl = g_ll * (z * z - 1.0f);
+    if (mode == 1) {
+        const float d = rm - mu;
+        dmu += c_kl * (-(rm - mu) / (sg * sg));
+        dl += c_kl * (1.0f - (rs * rs + d * d) / (sg * sg));
+    }
+    if (lane < ldd) dpre_row[lane] = on ? dmu * (1.0f - mu * mu) : 0.0f;
+    o.dlogvar = on ? dl : 0.0f;
+    return o;
 }
 
 // ---- P1a: forward of one row block; leaves xs / h1s / h2s / outs in shared memory and the KL partial in kl_part[rb]
@@ -354,13 +442,12 @@ __device__ void fwd_item(const Job& p, const Sm& sm, int rb, bool first_epoch, c
     }
     __syncwarp();
     double klacc = 0.0;
-    if (p.mode != 2 && lane < 2) {
-        const int r = warp + E2W * lane;
-        if (r < RB && m0 + r < M) {
-            const float* rp = sm.refs + r * 2 * E2_MAX_OUT;
-            klacc = (double)ppo_dev::row_kl(rp, rp + NO, sm.outs + r * E2_MAX_OUT, s_sig, NO);
+    if (p.mode != 2)
+        for (int r = warp; r < RB; r += E2W) {
+            if (m0 + r >= M) continue;                       // warp-uniform
+            const float kl = row_kl_warp(sm.refs + r * 2 * E2_MAX_OUT, sm.outs + r * E2_MAX_OUT, s_sig, NO, lane);
+            if (lane == 0) klacc += (double)kl;
         }
-    }
     if (p.mode != 2) {
         const double t = block_sum(klacc, s_red);
         if (tid == 0) p.kl_part[rb] = t;
@@ -415,34 +502,44 @@ __device__ void bwd_item(const Job& p, const Sm& sm, int rb, bool resident, doub
     __syncthreads();
     const double invM = 1.0 / (double)M;
     const float c0 = (float)(0.5 * 1.8378770664093453 * (double)NO);
-    // loss rows: lanes 0 / 1 of every warp take rows warp / warp + 8 TOGETHER (the scalar chain of a row -- log-likelihoods,
-    // ratio, clip or KL penalty, gradient w.r.t. the pre-tanh mean -- is ~1.5 K dependent instructions; one lane doing its
-    // warp's two rows in turn cost 20 us per policy epoch).  Operands and results live in shared memory: no local arrays.
+    // loss rows.  Policy: a warp per row, lane j = action dimension j (policy_row_warp).  Value: lanes 0 / 1 of every warp take
+    // rows warp / warp + 8 together.  Operands and results live in shared memory: no local arrays.
     double acc_slot[4] = {0.0, 0.0, 0.0, 0.0};
-    const int my_r = warp + E2W * lane;
-    const bool row_on = lane < 2 && my_r < RB && m0 + my_r < M;
-    ppo_dev::PolicyRow pr = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-    if (lane < 2 && my_r < RB && !row_on)
-        for (int j = 0; j < p.ld_out; ++j) sm.dps[my_r * E2_MAX_OUT + j] = 0.0f;      // rows past the batch: no gradient
-    if (row_on) {
-        const int r = my_r, m = m0 + r;
-        const float* mu = sm.outs + r * E2_MAX_OUT;
-        float* dp = sm.dps + r * E2_MAX_OUT;
-        if (policy) {
-            pr = ppo_dev::policy_row(p.mode, mu, sm.acts + r * E2_MAX_OUT, s_sig, sm.behs + r * 2 * E2_MAX_OUT, sm.refs + r * 2 * E2_MAX_OUT,
-                                     sm.advs[r], NO, c0, invM, p.hyper, p.eta, p.kl_target, kl_mean_now, dp, NO);
-            acc_slot[0] = (double)pr.surr;
-            acc_slot[1] = (double)pr.rowloss;
-            acc_slot[2] = (double)pr.klrow;
-        } else {                                             // value_loss_kernel's arithmetic (ppo.py:311-332)
-            const float vv = mu[0], rr = sm.advs[r];
-            const float df = vv - rr;
-            const double d = (double)(rr - vv), rd = (double)rr;
-            dp[0] = (float)(2.0 * (double)df / (double)M);
-            acc_slot[0] = d; acc_slot[1] = d * d; acc_slot[2] = rd; acc_slot[3] = rd * rd;
+    double dl_acc = 0.0;                                     // policy: this lane's dimension of d loss / d log_var, both rows
+    if (policy) {
+        for (int r = warp; r < RB; r += E2W) {
+            const int m = m0 + r;
+            float* dp = sm.dps + r * E2_MAX_OUT;
+            if (m >= M) {                                    // rows past the batch: no gradient (warp-uniform)
+                if (lane < p.ld_out) dp[lane] = 0.0f;
+                continue;
+            }
+            const RowOut o = policy_row_warp(p.mode, sm.outs + r * E2_MAX_OUT, sm.acts + r * E2_MAX_OUT, s_sig, sm.behs + r * 2 * E2_MAX_OUT,
+                                             sm.refs + r * 2 * E2_MAX_OUT, sm.advs[r], NO, c0, invM, p.hyper, p.eta, p.kl_target,
+                                             kl_mean_now, dp, p.ld_out, lane);
+            if (lane == 0) {
+                acc_slot[0] += (double)o.surr;
+                acc_slot[1] += (double)o.rowloss;
+                acc_slot[2] += (double)o.klrow;
+            }
+            dl_acc += (double)o.dlogvar;
+            __syncwarp();
+            if (lane < p.ld_out) p.dpre[(long long)m * p.ld_out + lane] = dp[lane];
         }
-        for (int j = NO; j < p.ld_out; ++j) dp[j] = 0.0f;
-        for (int j = 0; j < p.ld_out; ++j) p.dpre[(long long)m * p.ld_out + j] = dp[j];
+    } else {
+        const int my_r = warp + E2W * lane;
+        if (lane < 2 && my_r < RB) {
+            float* dp = sm.dps + my_r * E2_MAX_OUT;
+            for (int j = 0; j < p.ld_out; ++j) dp[j] = 0.0f;
+            if (m0 + my_r < M) {                             // value_loss_kernel's arithmetic (ppo.py:311-332)
+                const float vv = sm.outs[my_r * E2_MAX_OUT], rr = sm.advs[my_r];
+                const float df = vv - rr;
+                const double d = (double)(rr - vv), rd = (double)rr;
+                dp[0] = (float)(2.0 * (double)df / (double)M);
+                acc_slot[0] = d; acc_slot[1] = d * d; acc_slot[2] = rd; acc_slot[3] = rd * rd;
+                for (int j = 0; j < p.ld_out; ++j) p.dpre[(long long)(m0 + my_r) * p.ld_out + j] = dp[j];
+            }
+        }
     }
     __syncwarp();
     // d2 = (dpre W3^T) * relu'(h2), a warp per row
@@ -473,15 +570,17 @@ __device__ void bwd_item(const Job& p, const Sm& sm, int rb, bool resident, doub
             const double t = block_sum(acc_slot[s], s_red);
             if (tid == 0) part[s] = t;
         }
-        if (policy)
-            for (int j = 0; j < NO; ++j) {
-                double dl = 0.0;
-                if (row_on)
-                    dl = (double)ppo_dev::policy_dlogvar(p.mode, j, sm.outs + my_r * E2_MAX_OUT, sm.acts + my_r * E2_MAX_OUT, s_sig,
-                                                         sm.refs + my_r * 2 * E2_MAX_OUT, pr, NO);
-                const double t = block_sum(dl, s_red);
-                if (tid == 0) part[4 + j] = t;
+        if (policy) {                                        // d loss / d log_var: sum over the warps, dimension by dimension
+            double* red = reinterpret_cast<double*>(sm.part);
+            __syncthreads();
+            red[warp * 32 + lane] = dl_acc;
+            __syncthreads();
+            if (tid < NO) {
+                double t = 0.0;
+                for (int w = 0; w < E2W; ++w) t += red[w * 32 + tid];
+                part[4 + tid] = t;
             }
+        }
     }
     __syncthreads();
     // this block's share of dW3 = h2^T dpre and db3 (16 rows, operands in shared memory): summed over the blocks in P2
@@ -832,7 +931,10 @@ __global__ void __launch_bounds__(E2T, 1) ppo_epochs2_kernel(const __grid_consta
                 w0[j] = n_w;
                 if (train[j]) n_w += (((p.H1 + RB - 1) / RB) + ((p.D + RB - 1) / RB) + 1) * p.s;
             }
-            for (int it = c; it < n_w; it += G) {
+            // CTA 0 spends this phase on the loss statistics (below, ~8 us of serial work): when the items fit on the other
+            // CTAs it takes none, so that nobody waits for it at the barrier
+            const int skip0 = (n_w <= G - 1) ? 1 : 0;
+            for (int it = c - skip0; it >= 0 && it < n_w; it += G) {
                 const int j = (NJ == 2 && train[1] && it >= w0[1]) ? 1 : 0;
                 const Job& p = P.job[j];
                 int q = it - w0[j];
@@ -889,7 +991,8 @@ __global__ void __launch_bounds__(E2T, 1) ppo_epochs2_kernel(const __grid_consta
                     const long long lo = (long long)cl * per;
                     const long long hi = (lo + per < p.n_params) ? lo + per : p.n_params;
                     float* mine = slot_of(p.par.peers[p.par.rank], p.par.max_floats, k & 1u);
-                    for (long long i = lo + tid; i < hi; i += E2T) mine[i] = __ldcg(p.grad + i);
+                    for (long long i = lo + (long long)tid * 4; i < hi; i += (long long)E2T * 4)
+                        *reinterpret_cast<float4*>(mine + i) = gt::ldcg4(p.grad + i);
                     __threadfence_system();
                     __syncthreads();
                     if (tid < p.par.world && tid != p.par.rank) {
@@ -899,12 +1002,48 @@ __global__ void __launch_bounds__(E2T, 1) ppo_epochs2_kernel(const __grid_consta
                     }
                     __syncthreads();
                     const float scale = 1.0f / (float)p.par.world;
-                    for (long long i = lo + tid; i < hi; i += E2T) {
-                        float a = 0.f;
-                        for (int q = 0; q < p.par.world; ++q) a += ld_sys1(slot_of(p.par.peers[q], p.par.max_floats, k & 1u) + i);
-                        a = __fmul_rn(a, scale);
-                        p.grad[i] = a;
-                        sq += (double)a * (double)a;
+                    if ((p.par.max_floats & 3) == 0) {
+                        // Peer loads are NVLink round trips (~3 us): a thread issues the loads of TWO quads from EVERY rank
+                        // before it touches the first result, then sums in rank order (bit-identical on all ranks).  The
+                        // scalar loop this replaces paid one round trip per element: +0.9 ms per learn() at N = 2.
+                        constexpr int CH = 2;
+                        for (long long base = lo + (long long)tid * 4; base < hi; base += (long long)E2T * 4 * CH) {
+                            float4 v[CH][PAR_MAX_WORLD];
+#pragma unroll
+                            for (int u = 0; u < CH; ++u) {
+                                const long long i = base + (long long)u * E2T * 4;
+#pragma unroll
+                                for (int q = 0; q < PAR_MAX_WORLD; ++q)      // slots past the world re-read the last rank (never summed)
+                                    v[u][q] = ld_sys4(slot_of(p.par.peers[min(q, p.par.world - 1)], p.par.max_floats, k & 1u) + min(i, hi - 4));
+                            }
+#pragma unroll
+                            for (int u = 0; u < CH; ++u) {
+                                const long long i = base + (long long)u * E2T * 4;
+                                if (i < hi) {
+                                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                                    for (int q = 0; q < PAR_MAX_WORLD; ++q)
+                                        if (q < p.par.world) {
+                                            a.x += v[u][q].x; a.y += v[u][q].y; a.z += v[u][q].z; a.w += v[u][q].w;
+                                        }
+                                    a.x = __fmul_rn(a.x, scale); a.y = __fmul_rn(a.y, scale);
+                                    a.z = __fmul_rn(a.z, scale); a.w = __fmul_rn(a.w, scale);
+                                    *reinterpret_cast<float4*>(p.grad + i) = a;
+                                    sq += (double)a.x * (double)a.x;
+                                    sq += (double)a.y * (double)a.y;
+                                    sq += (double)a.z * (double)a.z;
+                                    sq += (double)a.w * (double)a.w;
+                                }
+                            }
+                        }
+                    } else {
+                        for (long long i = lo + tid; i < hi; i += E2T) {
+                            float a = 0.f;
+                            for (int q = 0; q < p.par.world; ++q) a += ld_sys1(slot_of(p.par.peers[q], p.par.max_floats, k & 1u) + i);
+                            a = __fmul_rn(a, scale);
+                            p.grad[i] = a;
+                            sq += (double)a * (double)a;
+                        }
                     }
                     const double t = block_sum(sq, s_red);
                     if (tid == 0) p.sq_part[c] = t;
