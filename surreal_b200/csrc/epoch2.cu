@@ -36,7 +36,7 @@ namespace {
 
 using optim_dev::OptWs;
 
-constexpr int E2T = 256;              // threads per CTA
+constexpr int E2T = 512;              // threads per CTA (16 warps: the phases are latency-bound, 8 warps hid too little)
 constexpr int E2W = E2T / 32;
 constexpr int RB = 16;                // rows per block
 constexpr int E2_MAX_OUT = 32;
@@ -158,42 +158,40 @@ __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.
 
 // ---- the micro-kernel: C[16][N] (+ optional column sums of W) = A[16][K] . W[K][N]
 // A in shared memory ([RB][lda], zero padded to a multiple of 4 columns), W in global memory ([K][ldw], ldw % 4 == 0,
-// padding columns zero).  thread = (column octet co = tid & 31, row half rg = bit 5, k quarter kh = tid >> 6): an 8 x 8
-// register tile, so that a (warp-broadcast) LDS.128 of A feeds 32 FMAs per lane and the kernel is bound by the FMA pipe,
-// not by shared memory (the first version, 16 x 4 tiles, spent as long on its 16 LDS per k quad as on the 128 FFMA2).
-// W streams L2 -> registers (ld.global.cg.v4, coalesced: a warp reads 1 KB of a W row), two k quads ahead; the k loop is
-// unrolled by 3 so that the rotation of the three register sets is renaming, not copies (0.84 -> 0.34 MOV per FFMA2).  The partial
-// tiles of the four k quarters go to Part [4][RB + 1][ldp] (row RB: column sums); the caller sums them after a barrier.
-// One call covers 32 column octets (pass c80 = first column quad); wider layers take several passes.
+// padding columns zero).  512 threads = (column quad cq = tid & 63, row half rg = bit 6, k quarter kh = tid >> 7): an 8 x 4
+// register tile per thread (32 accumulators, so that 16 warps fit the register file -- the 8-warp version with 8 x 8 tiles
+// issued 17 % of the time: every phase here is bound by L2 / shared-memory latency, not by the FMA pipe).  W streams
+// L2 -> L1 -> registers two k quads ahead (the two row halves of a column quad are different warps and share the line
+// through L1, which the grid barrier's fence invalidates, so cached loads are coherent here); the k loop is unrolled by 3
+// so that the rotation of the three operand sets is renaming, not copies.  The partial tiles of the four k quarters go to
+// Part [4][RB + 1][ldp] (row RB: column sums); the caller sums them after a barrier.  One call covers 64 column quads
+// (pass c40); wider layers take several passes.
+__device__ __forceinline__ float4 ldw4(const float* p) {                 // L1-allocating load (see above)
+    float4 r;
+    asm volatile("ld.global.ca.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
 template <bool COLSUM>
 __device__ __forceinline__ void rb_gemm(const float* __restrict__ As, int lda, int K, const float* __restrict__ W, int ldw,
                                         float* __restrict__ Part, int ldp, int c40) {
-    const int tid = threadIdx.x, co = tid & 31, rg = (tid >> 5) & 1, kh = tid >> 6;
+    const int tid = threadIdx.x, cq = tid & 63, rg = (tid >> 6) & 1, kh = tid >> 7;
     const int Kp = (K + 3) & ~3;
     const int kq = (((Kp >> 2) + 3) >> 2) << 2;
     const int k_lo = kh * kq, k_hi = min(Kp, k_lo + kq);
     const int nq = ldw >> 2;
-    const int c4 = c40 + 2 * co;                               // this thread's two column quads: c4, c4 + 1
-    const bool on0 = c4 < nq, on1 = c4 + 1 < nq;
-    const float* Wc = W + (on0 ? c4 : 0) * 4;
+    const int c4 = c40 + cq;
+    const bool on = c4 < nq;
+    const float* Wc = W + (on ? c4 : 0) * 4;                   // a column quad past the layer reads quad 0 (never stored)
     const float* Ar = As + rg * 8 * lda;
-    float2 acc[8][4];
+    float2 acc[8][2];
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
+    for (int r = 0; r < 8; ++r) acc[r][0] = acc[r][1] = make_float2(0.0f, 0.0f);
+    float4 cs = zero4();
+    float4 w[4], w1[4], w2[4];
+    // no range predicates on the loads: a row index past K is clamped to K - 1 (A is zero there, so the product vanishes)
+    auto loadq = [&](int k, float4 (&d)[4]) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[r][q] = make_float2(0.0f, 0.0f);
-    float4 cs0 = zero4(), cs1 = zero4();
-    float4 w[4][2], w1[4][2], w2[4][2];
-    // No range predicates on the loads: a row index past K is clamped to K - 1 (A is zero there, so the product vanishes),
-    // a column quad past the layer reads quad 0 (its results are never stored); the two quads fetched past k_hi are unused.
-    const float* Wc1 = on1 ? Wc + 4 : Wc;
-    auto loadq = [&](int k, float4 (&d)[4][2]) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const long long row = (long long)max(min(k + i, K - 1), 0) * ldw;
-            d[i][0] = gt::ldcg4(Wc + row);
-            d[i][1] = gt::ldcg4(Wc1 + row);
-        }
+        for (int i = 0; i < 4; ++i) d[i] = ldw4(Wc + (long long)max(min(k + i, K - 1), 0) * ldw);
     };
     loadq(k_lo, w);
     loadq(k_lo + 4, w1);
@@ -204,8 +202,7 @@ __device__ __forceinline__ void rb_gemm(const float* __restrict__ As, int lda, i
 #pragma unroll
             for (int i = 0; i < 4; ++i)
                 if (k + i < K) {
-                    cs0.x += w[i][0].x; cs0.y += w[i][0].y; cs0.z += w[i][0].z; cs0.w += w[i][0].w;
-                    cs1.x += w[i][1].x; cs1.y += w[i][1].y; cs1.z += w[i][1].z; cs1.w += w[i][1].w;
+                    cs.x += w[i].x; cs.y += w[i].y; cs.z += w[i].z; cs.w += w[i].w;
                 }
         }
 #pragma unroll
@@ -214,35 +211,23 @@ __device__ __forceinline__ void rb_gemm(const float* __restrict__ As, int lda, i
             const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-#ifdef E2_SCALAR_FMA
-                acc[r][0].x = fmaf(av[i], w[i][0].x, acc[r][0].x); acc[r][0].y = fmaf(av[i], w[i][0].y, acc[r][0].y);
-                acc[r][1].x = fmaf(av[i], w[i][0].z, acc[r][1].x); acc[r][1].y = fmaf(av[i], w[i][0].w, acc[r][1].y);
-                acc[r][2].x = fmaf(av[i], w[i][1].x, acc[r][2].x); acc[r][2].y = fmaf(av[i], w[i][1].y, acc[r][2].y);
-                acc[r][3].x = fmaf(av[i], w[i][1].z, acc[r][3].x); acc[r][3].y = fmaf(av[i], w[i][1].w, acc[r][3].y);
-#else
                 const float2 aa = make_float2(av[i], av[i]);
-                acc[r][0] = __ffma2_rn(aa, make_float2(w[i][0].x, w[i][0].y), acc[r][0]);
-                acc[r][1] = __ffma2_rn(aa, make_float2(w[i][0].z, w[i][0].w), acc[r][1]);
-                acc[r][2] = __ffma2_rn(aa, make_float2(w[i][1].x, w[i][1].y), acc[r][2]);
-                acc[r][3] = __ffma2_rn(aa, make_float2(w[i][1].z, w[i][1].w), acc[r][3]);
-#endif
+                acc[r][0] = __ffma2_rn(aa, make_float2(w[i].x, w[i].y), acc[r][0]);
+                acc[r][1] = __ffma2_rn(aa, make_float2(w[i].z, w[i].w), acc[r][1]);
             }
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            w[i][0] = w1[i][0]; w[i][1] = w1[i][1];
-            w1[i][0] = w2[i][0]; w1[i][1] = w2[i][1];
+            w[i] = w1[i];
+            w1[i] = w2[i];
         }
     }
-    float* pp = Part + (size_t)kh * (RB + 1) * ldp + c4 * 4;
+    if (on) {
+        float* pp = Part + (size_t)kh * (RB + 1) * ldp + c4 * 4;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        if (on0) *reinterpret_cast<float4*>(pp + (rg * 8 + r) * ldp) = make_float4(acc[r][0].x, acc[r][0].y, acc[r][1].x, acc[r][1].y);
-        if (on1) *reinterpret_cast<float4*>(pp + (rg * 8 + r) * ldp + 4) = make_float4(acc[r][2].x, acc[r][2].y, acc[r][3].x, acc[r][3].y);
-    }
-    if (COLSUM && rg == 0) {
-        if (on0) *reinterpret_cast<float4*>(pp + RB * ldp) = cs0;
-        if (on1) *reinterpret_cast<float4*>(pp + RB * ldp + 4) = cs1;
+        for (int r = 0; r < 8; ++r)
+            *reinterpret_cast<float4*>(pp + (rg * 8 + r) * ldp) = make_float4(acc[r][0].x, acc[r][0].y, acc[r][1].x, acc[r][1].y);
+        if (COLSUM && rg == 0) *reinterpret_cast<float4*>(pp + RB * ldp) = cs;
     }
 }
 
