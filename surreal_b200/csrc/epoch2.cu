@@ -138,6 +138,47 @@ struct E2Params {
     int ld_xs, ld_h1s, ld_h2s, ldp;
 };
 
+// Mean over the ranks of grad[lo, hi) (quads), read from every rank's slot in rank order (bit-identical on all ranks);
+// returns this thread's share of the squared norm.  Peer loads are NVLink round trips (~3 us): a thread issues the loads of
+// CH quads from EVERY rank before it touches the first result (the scalar loop this replaces paid one round trip per
+// element: +0.9 ms per learn() at N = 2).  W = compile-time bound on the world size (slots past it re-read the last rank).
+template <int W, int CH>
+__device__ __forceinline__ double peer_sum_slice(const Job& p, long long lo, long long hi, unsigned int parity, float scale) {
+    double sq = 0.0;
+    const float* slot[W];
+#pragma unroll
+    for (int q = 0; q < W; ++q) slot[q] = slot_of(p.par.peers[min(q, p.par.world - 1)], p.par.max_floats, parity);
+    for (long long base = lo + (long long)threadIdx.x * 4; base < hi; base += (long long)E2T * 4 * CH) {
+        float4 v[CH][W];
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            const long long i = min(base + (long long)u * E2T * 4, hi - 4);
+#pragma unroll
+            for (int q = 0; q < W; ++q) v[u][q] = ld_sys4(slot[q] + i);
+        }
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            const long long i = base + (long long)u * E2T * 4;
+            if (i < hi) {
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < W; ++q)
+                    if (q < p.par.world) {
+                        a.x += v[u][q].x; a.y += v[u][q].y; a.z += v[u][q].z; a.w += v[u][q].w;
+                    }
+                a.x = __fmul_rn(a.x, scale); a.y = __fmul_rn(a.y, scale);
+                a.z = __fmul_rn(a.z, scale); a.w = __fmul_rn(a.w, scale);
+                *reinterpret_cast<float4*>(p.grad + i) = a;
+                sq += (double)a.x * (double)a.x;
+                sq += (double)a.y * (double)a.y;
+                sq += (double)a.z * (double)a.z;
+                sq += (double)a.w * (double)a.w;
+            }
+        }
+    }
+    return sq;
+}
+
 __device__ __forceinline__ void grid_bar(unsigned int* ctr, unsigned int& target) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -988,39 +1029,9 @@ __global__ void __launch_bounds__(E2T, 1) ppo_epochs2_kernel(const __grid_consta
                     __syncthreads();
                     const float scale = 1.0f / (float)p.par.world;
                     if ((p.par.max_floats & 3) == 0) {
-                        // Peer loads are NVLink round trips (~3 us): a thread issues the loads of TWO quads from EVERY rank
-                        // before it touches the first result, then sums in rank order (bit-identical on all ranks).  The
-                        // scalar loop this replaces paid one round trip per element: +0.9 ms per learn() at N = 2.
-                        constexpr int CH = 2;
-                        for (long long base = lo + (long long)tid * 4; base < hi; base += (long long)E2T * 4 * CH) {
-                            float4 v[CH][PAR_MAX_WORLD];
-#pragma unroll
-                            for (int u = 0; u < CH; ++u) {
-                                const long long i = base + (long long)u * E2T * 4;
-#pragma unroll
-                                for (int q = 0; q < PAR_MAX_WORLD; ++q)      // slots past the world re-read the last rank (never summed)
-                                    v[u][q] = ld_sys4(slot_of(p.par.peers[min(q, p.par.world - 1)], p.par.max_floats, k & 1u) + min(i, hi - 4));
-                            }
-#pragma unroll
-                            for (int u = 0; u < CH; ++u) {
-                                const long long i = base + (long long)u * E2T * 4;
-                                if (i < hi) {
-                                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                                    for (int q = 0; q < PAR_MAX_WORLD; ++q)
-                                        if (q < p.par.world) {
-                                            a.x += v[u][q].x; a.y += v[u][q].y; a.z += v[u][q].z; a.w += v[u][q].w;
-                                        }
-                                    a.x = __fmul_rn(a.x, scale); a.y = __fmul_rn(a.y, scale);
-                                    a.z = __fmul_rn(a.z, scale); a.w = __fmul_rn(a.w, scale);
-                                    *reinterpret_cast<float4*>(p.grad + i) = a;
-                                    sq += (double)a.x * (double)a.x;
-                                    sq += (double)a.y * (double)a.y;
-                                    sq += (double)a.z * (double)a.z;
-                                    sq += (double)a.w * (double)a.w;
-                                }
-                            }
-                        }
+                        if (p.par.world == 2) sq = peer_sum_slice<2, 3>(p, lo, hi, k & 1u, scale);
+                        else if (p.par.world <= 4) sq = peer_sum_slice<4, 3>(p, lo, hi, k & 1u, scale);
+                        else sq = peer_sum_slice<8, 1>(p, lo, hi, k & 1u, scale);
                     } else {
                         for (long long i = lo + tid; i < hi; i += E2T) {
                             float a = 0.f;

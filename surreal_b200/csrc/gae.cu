@@ -46,33 +46,41 @@ __device__ void normalize_all(float* adv, long long total, double* sh) {
 }
 
 // One window with n == 32 * ITER, everything in registers: ALL loads of the window are issued before the first use (the
-// generic loop below exposes one DRAM round trip per 32 steps: 1.76 TB/s at 2^18 windows), and the shifted operands
+// generic loop below exposes one DRAM round trip per 32 steps: 1.76 TB/s at 2^18 windows), the NEXT window of the warp is
+// loaded while the current one is reduced (two windows in flight per warp), and the shifted operands
 // V[k+1] / done[k-1] come from the neighbouring lane by shuffle instead of a second load.  Same operations on the same
 // operands in the same order as the generic loop -> bit-identical results.
 template <int ITER>
-__device__ __forceinline__ void gae_window_regs(const float* __restrict__ r, const float* __restrict__ v,
-                                                const float* __restrict__ d, const float* __restrict__ tab, int lane,
-                                                float gamma_f, float rscale, double& a_sum, double& r_sum, float& vn) {
+struct GaeRegs {
+    float rr[ITER], vv[ITER], dd[ITER], v_last;
+};
+template <int ITER>
+__device__ __forceinline__ void gae_window_load(const float* __restrict__ r, const float* __restrict__ v, const float* __restrict__ d,
+                                                int lane, GaeRegs<ITER>& g) {
     constexpr int n = 32 * ITER;
-    float rr[ITER], vv[ITER], dd[ITER];
 #pragma unroll
     for (int i = 0; i < ITER; ++i) {
-        rr[i] = __ldg(r + lane + 32 * i);
-        dd[i] = __ldg(d + lane + 32 * i);
-        vv[i] = __ldg(v + lane + 32 * i);
+        g.rr[i] = __ldg(r + lane + 32 * i);
+        g.dd[i] = __ldg(d + lane + 32 * i);
+        g.vv[i] = __ldg(v + lane + 32 * i);
     }
-    const float v_last = (lane == 31) ? __ldg(v + n) : 0.0f;
+    g.v_last = (lane == 31) ? __ldg(v + n) : 0.0f;
+}
+template <int ITER>
+__device__ __forceinline__ void gae_window_regs(const GaeRegs<ITER>& g, const float* __restrict__ tab, int lane, float gamma_f,
+                                                float rscale, double& a_sum, double& r_sum, float& vn) {
+    constexpr int n = 32 * ITER;
     float vm[ITER + 1];                               // masked values V[k] (1 - done[k-1]) of this lane's steps
 #pragma unroll
     for (int i = 0; i < ITER; ++i) {
-        float dprev = __shfl_up_sync(0xffffffffu, dd[i], 1);
+        float dprev = __shfl_up_sync(0xffffffffu, g.dd[i], 1);
         if (i > 0) {
-            const float wrap = __shfl_sync(0xffffffffu, dd[i - 1], 31);
+            const float wrap = __shfl_sync(0xffffffffu, g.dd[i - 1], 31);
             if (lane == 0) dprev = wrap;
         }
-        vm[i] = (i == 0 && lane == 0) ? vv[0] : __fmul_rn(vv[i], __fsub_rn(1.0f, dprev));
+        vm[i] = (i == 0 && lane == 0) ? g.vv[0] : __fmul_rn(g.vv[i], __fsub_rn(1.0f, dprev));
     }
-    vm[ITER] = __fmul_rn(v_last, __fsub_rn(1.0f, dd[ITER - 1]));     // lane 31: V[n] (1 - done[n-1])
+    vm[ITER] = __fmul_rn(g.v_last, __fsub_rn(1.0f, g.dd[ITER - 1]));     // lane 31: V[n] (1 - done[n-1])
     a_sum = 0.0;
     r_sum = 0.0;
 #pragma unroll
@@ -81,11 +89,11 @@ __device__ __forceinline__ void gae_window_regs(const float* __restrict__ r, con
         float v1 = __shfl_down_sync(0xffffffffu, vm[i], 1);
         const float wrap = __shfl_sync(0xffffffffu, vm[i + 1], 0);
         if (lane == 31) v1 = (i + 1 < ITER) ? wrap : vm[ITER];
-        const float g = tab[k], l = tab[n + k];
-        const float rk = __fmul_rn(rr[i], rscale);
+        const float gk = tab[k], l = tab[n + k];
+        const float rk = __fmul_rn(g.rr[i], rscale);
         const float td = __fsub_rn(__fadd_rn(rk, __fmul_rn(gamma_f, v1)), vm[i]);
-        a_sum += (double)__fmul_rn(__fmul_rn(td, g), l);
-        r_sum += (double)__fmul_rn(g, rk);
+        a_sum += (double)__fmul_rn(__fmul_rn(td, gk), l);
+        r_sum += (double)__fmul_rn(gk, rk);
     }
     vn = __shfl_sync(0xffffffffu, vm[ITER], 31);
 }
@@ -107,14 +115,24 @@ __global__ void __launch_bounds__(GAE_WARPS * 32) gae_full_kernel(const float* _
     }
     __syncthreads();
     double blk_s = 0.0, blk_q = 0.0;               // this warp's share of sum(adv), sum(adv^2) (large-batch path)
-    for (int b = blockIdx.x * GAE_WARPS + warp; b < B; b += gridDim.x * GAE_WARPS) {
+    const int b_first = blockIdx.x * GAE_WARPS + warp, b_step = gridDim.x * GAE_WARPS;
+    GaeRegs<(ITER > 0 ? ITER : 1)> cur, nxt;
+    if constexpr (ITER > 0) {
+        if (b_first < B)
+            gae_window_load<ITER>(rewards + (long long)b_first * n, values + (long long)b_first * (n + 1), dones + (long long)b_first * n, lane, cur);
+    }
+    for (int b = b_first; b < B; b += b_step) {
         const float* r = rewards + (long long)b * n;
         const float* v = values + (long long)b * (n + 1);
         const float* d = dones + (long long)b * n;
         double a_sum = 0.0, r_sum = 0.0;
         float vn = 0.0f;
         if constexpr (ITER > 0) {
-            gae_window_regs<ITER>(r, v, d, tab, lane, gamma_f, rscale, a_sum, r_sum, vn);
+            const int bn = b + b_step;
+            if (bn < B)
+                gae_window_load<ITER>(rewards + (long long)bn * n, values + (long long)bn * (n + 1), dones + (long long)bn * n, lane, nxt);
+            gae_window_regs<ITER>(cur, tab, lane, gamma_f, rscale, a_sum, r_sum, vn);
+            cur = nxt;
         } else {
             for (int k = lane; k < n; k += 32) {
                 const float g = tab[k], l = tab[n + k];

@@ -524,6 +524,36 @@ __device__ __forceinline__ void rf_bar_math() { asm volatile("bar.sync 1, 256;" 
 __device__ __forceinline__ void rf_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void rf_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
+// ---- mbarrier-signalled DSMEM hand-off (the ASYNC variant of the v2 kernel).  barrier.cluster.arrive.release compiles to
+// MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of the barrier (the kernel's global stores of the step must drain to L2
+// first) and the wait to a CCTL.IVALL: three times per env step.  st.async carries the data AND the completion count to
+// the consumer's mbarrier, so the producer needs no fence and the consumer polls its own shared memory.
+__device__ __forceinline__ void rf_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rf_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void rf_mbar_arm(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rf_smem_u32(bar)), "r"(bytes) : "memory");
+}
+// spin until the phase with this parity has completed; a transaction count that can never be met would hang the GPU, so
+// the spin is bounded (~1 s) and traps instead
+__device__ __forceinline__ void rf_mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned a = rf_smem_u32(bar);
+    for (unsigned spin = 0;; ++spin) {
+        unsigned ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return;
+        if (spin > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void rf_st_async_v4(unsigned dst_cluster_addr, const float4& v, unsigned mbar_cluster_addr) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(dst_cluster_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(mbar_cluster_addr) : "memory");
+}
+
 // sum over the 32 lanes of s[j], returned in the lanes with j == 4*bit4 + 2*bit3 + bit2 of the lane index (9 shuffles)
 __device__ __forceinline__ float rf_reduce8(const float (&s)[8], int lane) {
     const bool u4 = (lane & 16) != 0, u3 = (lane & 8) != 0, u2 = (lane & 4) != 0;
@@ -546,11 +576,11 @@ __device__ __forceinline__ float rf_reduce8(const float (&s)[8], int lane) {
 
 // One hidden layer on the 8 math warps (tid 0..255): warp = (row group rg = warp & 3: rows 8rg..8rg+7, k quarter pair),
 // lane = (column quad, k half) -> 4-way k split, partial tiles summed in a fixed order through Part [4][32][Nc].
-template <bool ALL_ROWS>
+template <bool ALL_ROWS, bool ASYNC>
 __device__ __forceinline__ void rf2_layer(const float* __restrict__ Xin, int ldin, int K, const float* __restrict__ Ws,
                                           int Nc, const float* __restrict__ bias_s, int act, float* __restrict__ Hout,
                                           int ldout, int col0, float* __restrict__ Part, unsigned smem_base,
-                                          unsigned crank, int rf_t, int rf_id) {
+                                          unsigned crank, int rf_t, int rf_id, unsigned bar_off) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rg = warp & 3, ks = ((warp >> 2) << 1) | (lane >> 4), cg0 = lane & 15;
     const int kq = (((K >> 2) + 3) >> 2) << 2;               // k span of one split (multiple of 4)
@@ -611,16 +641,26 @@ __device__ __forceinline__ void rf2_layer(const float* __restrict__ Xin, int ldi
             *reinterpret_cast<float4*>(qd) = o;
             const unsigned off = rf_smem_u32(qd) - smem_base;
 #pragma unroll
-            for (int c = 1; c < RF_CS; ++c) rf_st_cluster_v4(rf_mapa(smem_base, (crank + (unsigned)c) % RF_CS) + off, o);
+            for (int c = 1; c < RF_CS; ++c) {
+                const unsigned pb = rf_mapa(smem_base, (crank + (unsigned)c) % RF_CS);
+                if (ASYNC) rf_st_async_v4(pb + off, o, pb + bar_off);
+                else rf_st_cluster_v4(pb + off, o);
+            }
         } else {
             const unsigned owner = (unsigned)(row / RF_OWN);
             float* qd = Hout + (row - (int)owner * RF_OWN) * ldout + col0 + c4 * 4;
-            if (owner == crank) *reinterpret_cast<float4*>(qd) = o;
-            else rf_st_cluster_v4(rf_mapa(smem_base, owner) + (rf_smem_u32(qd) - smem_base), o);
+            if (owner == crank) {
+                *reinterpret_cast<float4*>(qd) = o;
+            } else {
+                const unsigned pb = rf_mapa(smem_base, owner);
+                if (ASYNC) rf_st_async_v4(pb + (rf_smem_u32(qd) - smem_base), o, pb + bar_off);
+                else rf_st_cluster_v4(pb + (rf_smem_u32(qd) - smem_base), o);
+            }
         }
     }
 }
 
+template <bool ASYNC>
 __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
     ppo_rollout2_kernel(const __grid_constant__ RfParams p) {
     cg::cluster_group cluster = cg::this_cluster();
@@ -631,6 +671,7 @@ __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
 #pragma unroll
     for (int c = 1; c < RF_CS; ++c) peer_base[c - 1] = rf_mapa(smem_base, (crank + (unsigned)c) % RF_CS);
     __shared__ int s_pos[RF_OWN], s_ep[RF_OWN], s_cnt[RF_OWN];
+    __shared__ __align__(8) unsigned long long s_bar[3];      // ASYNC: hidden layer 1 | last hidden layer rows | next input tile
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int D = p.D, H1 = p.H1, H2 = p.H2, A = p.A;
@@ -704,6 +745,15 @@ __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
         X0[m * p.ldx0 + k] = (i < p.N) ? v : 0.0f;
     }
     const unsigned long long ctr0 = (p.step_ctr != nullptr) ? *p.step_ctr : 0ull;
+    if (ASYNC && tid == 0) {
+        for (int i = 0; i < 3; ++i) rf_mbar_init(&s_bar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const unsigned bar_off_h1 = rf_smem_u32(&s_bar[0]) - smem_base, bar_off_h2 = rf_smem_u32(&s_bar[1]) - smem_base;
+    const unsigned bar_off_x0 = rf_smem_u32(&s_bar[2]) - smem_base;
+    // bytes a CTA receives from its three peers per step: their column quarters of hidden layer 1 for all 32 rows, their
+    // column quarters of the last hidden layer for the 8 owned rows, their 8 rows of the next input tile
+    const unsigned tx_h1 = 3u * RF_ROWS * Nc1 * 4u, tx_h2 = 3u * RF_OWN * Nc2 * 4u, tx_x0 = 3u * RF_OWN * D * 4u;
     cp_async_wait<0>();
     cluster.sync();
 
@@ -724,21 +774,39 @@ __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
         const bool final_step = (t == p.T - 1);
         const int rf_t = t;
         RF_STAMP(0, 0);
+        if (ASYNC && tid == 0) {                              // arm this step's phases (the previous ones were consumed)
+            rf_mbar_arm(&s_bar[0], tx_h1);
+            rf_mbar_arm(&s_bar[1], tx_h2);
+        }
         if (math) {
-            rf2_layer<true>(X0, p.ldx0, D, W1s, Nc1, B1s, p.act[0], Hb1, p.ldh1, (int)crank * Nc1, Part, smem_base, crank, rf_t, 1);
+            if (ASYNC && t > 0) {                             // the input tile: own rows (math warps wrote them) + the peers' rows
+                rf_bar_math();
+                rf_mbar_wait(&s_bar[2], (unsigned)(t - 1) & 1u);
+            }
+            if (ASYNC && tid == 0 && !final_step) rf_mbar_arm(&s_bar[2], tx_x0);     // next tile's phase: only now is the previous one complete
+            rf2_layer<true, ASYNC>(X0, p.ldx0, D, W1s, Nc1, B1s, p.act[0], Hb1, p.ldh1, (int)crank * Nc1, Part, smem_base, crank, rf_t, 1,
+                                   bar_off_h1);
             RF_STAMP(3, 0);
-            rf_cluster_arrive();
-            rf_cluster_wait();
+            if (ASYNC) {
+                rf_bar_math();
+                rf_mbar_wait(&s_bar[0], (unsigned)t & 1u);
+            } else {
+                rf_cluster_arrive();
+                rf_cluster_wait();
+            }
             RF_STAMP(4, 0);
-            rf2_layer<false>(Hb1, p.ldh1, H1, W2s, Nc2, B2s, p.act[1], Hb2, p.ldh2, (int)crank * Nc2, Part, smem_base, crank, rf_t, 5);
+            rf2_layer<false, ASYNC>(Hb1, p.ldh1, H1, W2s, Nc2, B2s, p.act[1], Hb2, p.ldh2, (int)crank * Nc2, Part, smem_base, crank, rf_t, 5,
+                                    bar_off_h2);
             RF_STAMP(7, 0);
-            rf_cluster_arrive();
-            rf_cluster_wait();
+            if (!ASYNC) {
+                rf_cluster_arrive();
+                rf_cluster_wait();
+            }
             RF_STAMP(8, 0);
         } else {
             // ---- env warp h: everything of this step that does not depend on the action (arithmetic and Philox keys of
             // sample_one() / synth_env_block() in rollout.cu), concurrently with the layers
-            rf_cluster_arrive();                              // barrier 1: nothing to publish
+            if (!ASYNC) rf_cluster_arrive();                  // barrier 1: nothing to publish
             RF_STAMP(16, 256);
             const int h = own;
             const long long ih = row0 + (int)crank * RF_OWN + h;
@@ -770,9 +838,15 @@ __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
                 Zn[h * A + j] = (c == 0) ? z01.x : (c == 1) ? z01.y : (c == 2) ? z23.x : z23.y;
             }
             RF_STAMP(17, 256);
-            rf_cluster_wait();
-            rf_cluster_arrive();
-            rf_cluster_wait();
+            if (!ASYNC) {
+                rf_cluster_wait();
+                rf_cluster_arrive();
+                rf_cluster_wait();
+            }
+        }
+        if (ASYNC) {                                          // last hidden layer: own columns (block barrier) + the peers' columns
+            __syncthreads();
+            rf_mbar_wait(&s_bar[1], (unsigned)t & 1u);
         }
         // ---- head: warps w and w + 8 take the two k halves of owned actor w & 7
         {
@@ -884,14 +958,22 @@ __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
                 float* qx = X0 + m_own * p.ldx0 + q4 * 4;
                 *reinterpret_cast<float4*>(qx) = v;
                 const unsigned off = rf_smem_u32(qx) - smem_base;
+                if (ASYNC) {
+                    if (!final_step) {
 #pragma unroll
-                for (int c = 0; c < RF_CS - 1; ++c) rf_st_cluster_v4(peer_base[c] + off, v);
+                        for (int c = 0; c < RF_CS - 1; ++c) rf_st_async_v4(peer_base[c] + off, v, peer_base[c] + bar_off_x0);
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < RF_CS - 1; ++c) rf_st_cluster_v4(peer_base[c] + off, v);
+                }
             }
         }
         RF_STAMP(13, 0);
-        cluster.sync();
+        if (!ASYNC) cluster.sync();
         RF_STAMP(14, 0);
     }
+    if (ASYNC) cluster.sync();                                // nobody leaves while a peer may still address its shared memory
 
     if (valid) {
         for (int d = lane; d < D; d += 32) p.state[i_own * D + d] = S[own * D + d];
@@ -1018,7 +1100,8 @@ bool rf_plan(const sb200_mlp* net, int D, int A, RfParams* p, size_t* smem_bytes
 int sb200_rollout_fused_init() {
     SB200_CUDA(cudaFuncSetAttribute(ppo_rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     SB200_CUDA(cudaFuncSetAttribute(ppo_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-    SB200_CUDA(cudaFuncSetAttribute(ppo_rollout2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    SB200_CUDA(cudaFuncSetAttribute(ppo_rollout2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    SB200_CUDA(cudaFuncSetAttribute(ppo_rollout2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     return SB200_OK;
 }
 
@@ -1098,7 +1181,11 @@ extern "C" int sb200_ppo_rollout_f32(const sb200_ppo_rollout* a, void* stream) {
     static const int f2 = [] { const char* e = getenv("SB200_RF_FFMA2"); return e ? atoi(e) : 1; }();
     // v2 (warp-specialised env warps, 8x4 register tiles) is the default; SB200_RF_V2=0 selects the v1 kernel
     static const int v2 = [] { const char* e = getenv("SB200_RF_V2"); return e ? atoi(e) : 1; }();
-    if (v2) ppo_rollout2_kernel<<<(unsigned)(clusters * RF_CS), RF_THREADS, smem, (cudaStream_t)stream>>>(p);
+    // SB200_RF_ASYNC=1: the same kernel with mbarrier-signalled st.async hand-offs instead of the three cluster barriers per step
+    static const int rf_async = [] { const char* e = getenv("SB200_RF_ASYNC"); return e ? atoi(e) : 0; }();
+    if (v2 && rf_async && a->D % 4 == 0 && (3u * RF_ROWS * (unsigned)(a->net->dims[1] / RF_CS) * 4u) < (1u << 20))
+        ppo_rollout2_kernel<true><<<(unsigned)(clusters * RF_CS), RF_THREADS, smem, (cudaStream_t)stream>>>(p);
+    else if (v2) ppo_rollout2_kernel<false><<<(unsigned)(clusters * RF_CS), RF_THREADS, smem, (cudaStream_t)stream>>>(p);
     else if (f2) ppo_rollout_kernel<true><<<(unsigned)(clusters * RF_CS), RF_THREADS, smem, (cudaStream_t)stream>>>(p);
     else ppo_rollout_kernel<false><<<(unsigned)(clusters * RF_CS), RF_THREADS, smem, (cudaStream_t)stream>>>(p);
     return sb200_launch_status();

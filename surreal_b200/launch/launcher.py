@@ -57,6 +57,9 @@ class PipelinedEngine:
         self.sA, self.sL = torch.cuda.Stream(), torch.cuda.Stream()
         self.ev_roll = self.ev_pop = self.ev_pub = self.ev_fetch = None
         self.iterations = 0
+        if hasattr(learner, 'before_epochs_hook'):
+            # learners whose epochs are ONE all-SM persistent kernel take the GPU after the rollout, not beside it
+            learner.before_epochs_hook = self._wait_rollout
         cur = torch.cuda.current_stream()
         self.sA.wait_stream(cur)
         self.sL.wait_stream(cur)
@@ -73,6 +76,12 @@ class PipelinedEngine:
             self.ev_fetch.record(self.sA)
             self.ev_roll = torch.cuda.Event()
             self.ev_roll.record(self.sA)
+
+    def _wait_rollout(self):
+        """Called by the learner between its head graph and its epochs graph (learner stream current): the rollout that
+        was enqueued before this learn() must have finished."""
+        if self.ev_roll is not None:
+            self.torch.cuda.current_stream().wait_event(self.ev_roll)
 
     def prime(self):
         """First rollout (nothing to overlap with yet)."""

@@ -195,6 +195,8 @@ class PPOLearner(Learner):
         # (631 us) -- both kernels are issue-bound, they do not add up -- so it stays an experiment
         self.dual_critic = os.environ.get("SB200_DUAL_CRITIC", "0") == "1"
         self._graph = ops.GraphRunner()
+        self._graph_head = ops.GraphRunner()
+        self.before_epochs_hook = None                    # see _optimize
         self._tc5 = ops.Tc5Forward(self.model.critic)     # critic pass on tcgen05 / TMEM when the shape qualifies
         self.tc5_min_rows = int(os.environ.get('SB200_TC5_MIN_ROWS', '4096'))
         self.dp = None
@@ -511,6 +513,7 @@ class PPOLearner(Learner):
         self._moments = torch.zeros(3, dtype=torch.float64, device=self.device)
         self._z_delta = torch.zeros_like(self.model.z_stats) if self.model.z_stats is not None else None
         self._graph = ops.GraphRunner()
+        self._graph_head = ops.GraphRunner()
         # One CUDA graph for the whole data-parallel learn(), NCCL collectives included (SB200_DP_GRAPH=0: the same
         # launches eagerly).  Capture stays on ONE stream (no dW side stream) and every collective shape is issued
         # once eagerly first: NCCL sets up its channels lazily, which must not happen under capture.
@@ -633,6 +636,11 @@ class PPOLearner(Learner):
         kernels of the remaining policy epochs turn into no-ops -- same parameters and statistics as breaking
         out of the loop, without a host round trip per epoch."""
         self._optimize_head()
+        self._optimize_epochs()
+
+    def _optimize_epochs(self):
+        """Everything of _optimize_device behind the head (critic pass, GAE, reference-policy forward): the epochs and
+        the closing statistics.  A separate graph when `before_epochs_hook` is set (see _optimize)."""
         # The value epochs (critic, returns) and the policy epochs (actor, advantages) share nothing but read-only
         # inputs: they run as two concurrent branches (a fork / join inside the captured graph), so the step costs
         # max(policy chain, value chain) instead of their sum.  With a data-parallel learner both branches would
@@ -678,7 +686,18 @@ class PPOLearner(Learner):
         B, n, A, D = self.batch_size, self.n_step, self.action_dim, self.low_dim
         m = self.model
         if self.use_cuda_graph and not self.profile_events and (self.dp is None or self.dp_graph):
-            self._graph.run(self._optimize_device)
+            ek = self._epoch_kernels()
+            if self.before_epochs_hook is not None and ek is not None and ek[2] is not None:
+                # The one-launch learner kernel wants every SM (a grid barrier needs all its CTAs resident), and so does the
+                # actors' persistent rollout kernel: launched side by side each holds SMs the other one waits for
+                # (measured: the rollout stretched from 1.5 to 2.5 ms).  A caller that runs actors concurrently
+                # (PipelinedEngine) therefore gets two graphs with a hook in between: the head overlaps the rollout on the
+                # SMs it leaves free, the hook waits for the rollout, then the epochs have the GPU to themselves.
+                self._graph_head.run(self._optimize_head)
+                self.before_epochs_hook()
+                self._graph.run(self._optimize_epochs)
+            else:
+                self._graph.run(self._optimize_device)
         elif self.use_cuda_graph:
             self._optimize_device()                               # same sequence, eager (per-kernel event timing)
         else:

@@ -553,12 +553,23 @@ class GraphRunner:
     def run(self, fn):
         L = _lib.lib()
         if self.graph is None:
+            import gc
             _lib.ensure_device()
+            # Objects of earlier learners (captured graphs with private memory pools) may be waiting for the garbage
+            # collector; if it ran DURING the capture their cudaFree would invalidate it (cudaErrorStreamCaptureInvalidated:
+            # seen in the full test suite, never in a fresh process).  Collect now, keep the collector off while capturing.
+            gc.collect()
             torch.cuda.synchronize()
             before = int(L.sb200_launch_counter(0))
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                fn()
+            gc_was_on = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(g):
+                    fn()
+            finally:
+                if gc_was_on:
+                    gc.enable()
             self.kernels = int(L.sb200_launch_counter(0)) - before    # recorded, not yet executed
             L.sb200_launch_counter_add(C.c_uint64(-self.kernels & 0xFFFFFFFFFFFFFFFF))
             self.graph = g
