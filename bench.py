@@ -312,8 +312,8 @@ def run_ours(args):
         byts = N * T * (D + 3 * A + 2) * 4 + 2 * N * ((T + 1) * D + 3 * T * A + 2 * T) * 4   # staging writes + window copy
         ach = flop / (avg_ms / 1e3) / 1e12
         ffma_peak = 148 * 128 * 2 * 1.9e9 / 1e12
-        roof_roll = {'kernel': 'ppo_rollout_kernel (persistent: %d env steps of %d actors per launch; 4-CTA clusters, '
-                               'resident weights, DSMEM exchange)' % (T, N),
+        roof_roll = {'kernel': 'ppo_rollout2_kernel (persistent: %d env steps of %d actors per launch; 4-CTA clusters, '
+                               'resident weights, warp-specialised env warps, st.async / mbarrier DSMEM hand-offs)' % (T, N),
                      'bound': 'tensor', 'achieved': ach, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
                      'frac': ach / peaks['bf16_tflops'], 'traffic': None, 'avg_ms': avg_ms,
                      'launches_per_step': per_step[rk][0], 'share_of_step_kernel_time': per_step[rk][1] / total_kernel_ms,
@@ -322,8 +322,9 @@ def run_ours(args):
                      'peak_source': peaks['source'],
                      'note': 'fp32 FFMA by necessity (1e-5 parity with the fp32 reference); the dense-bf16 tensor peak is '
                              'the mandated denominator, the fp32 FFMA ceiling (148 SMs x 128 lanes x 2 x 1.9 GHz) the '
-                             'meaningful one.  Per step the kernel is a dependent chain: layer -> cluster barrier -> '
-                             'layer -> cluster barrier -> head/sample/env -> cluster barrier'}
+                             'meaningful one (tools/fma_bench.cu measures 127 FMA/clk/SM for FFMA and FFMA2 alike).  Per '
+                             'step the kernel is a dependent chain: layer -> hand-off -> layer -> hand-off -> '
+                             'head / sample / env -> hand-off (profiles/r02b_rollout_trace_*.txt)'}
     # dram__bytes_read.sum + dram__bytes_write.sum per launch, from one `ncu --set full` capture each (profiles/)
     if roof_roll is not None:
         roof_roll['traffic'] = load_profile_traffic('rollout')

@@ -240,6 +240,33 @@ __global__ void __launch_bounds__(GAE_WARPS * 32) gae_horizon_kernel(const float
 
 }  // namespace
 
+static size_t tab_bytes_of(int n) { return (size_t)2 * n * sizeof(float); }
+
+template <int IT>
+static int gae_occ(size_t smem) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gae_full_kernel<IT>, GAE_WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 4;
+    return per_sm;
+}
+
+// CTAs of the MLP-branch kernel that are resident at once on this device (cached per window length class)
+static int gae_resident_ctas(int n, size_t smem) {
+    static int n_sm = 0;
+    static int cache[5] = {0, 0, 0, 0, 0};
+    if (n_sm == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n_sm = 148;
+    }
+    const int cls = (n == 32) ? 1 : (n == 64) ? 2 : (n == 128) ? 3 : (n == 256) ? 4 : 0;
+    if (cache[cls] == 0) {
+        const int per_sm = (cls == 1) ? gae_occ<1>(smem) : (cls == 2) ? gae_occ<2>(smem) : (cls == 3) ? gae_occ<4>(smem)
+                         : (cls == 4) ? gae_occ<8>(smem) : gae_occ<0>(smem);
+        cache[cls] = per_sm;
+    }
+    const int cap = n_sm * cache[cls];
+    return cap < GAE_MAX_GRID ? cap : GAE_MAX_GRID;
+}
+
 int sb200_gae_init() {
     SB200_CUDA(cudaFuncSetAttribute(gae_horizon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     return SB200_OK;
@@ -264,7 +291,10 @@ extern "C" int sb200_gae_window_f32(const float* rewards, const float* values, c
         SB200_REQUIRE((size_t)2 * n * sizeof(float) <= 48 * 1024);
         // persistent grid: the gamma^k / lam^k tables (2n double-precision pow) are built once per CTA, not once per 8
         // windows; windows are walked grid-stride
-        const int pgrid = grid < GAE_MAX_GRID ? grid : GAE_MAX_GRID;
+        // one resident wave: SM count x the occupancy the runtime reports for this instantiation (48 registers -> 5 CTAs per
+        // SM, not the 8 the first version assumed: 1184 CTAs ran as 1.6 waves, 0.41 of HBM peak at 2^18 windows)
+        const int cap = gae_resident_ctas(n, tab_bytes_of(n));
+        const int pgrid = grid < cap ? grid : cap;
         const int mode = !norm_adv ? 0 : (B <= GAE_FUSED_NORM_MAX ? 1 : 2);
         const size_t tab_bytes = (size_t)2 * n * sizeof(float);
 #define SB200_GAE_LAUNCH(IT)                                                                                                      \

@@ -17,6 +17,8 @@
 // same noise; the policy forward is fp32 FFMA (the per-step path uses 3xTF32 tensor-core products; both are
 // fp32-accurate, they differ by rounding order only).
 #include <cooperative_groups.h>
+
+#include <algorithm>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -33,12 +35,14 @@ constexpr int RF_THREADS = 512;     // 16 warps: thread (ty = row 0..31, tx = co
 
 // -DRF_TRACE (tools/rollout_trace.py builds that variant; never the shipped library): clock64 stamps of cluster 0's
 // first steps, one row per (CTA, step), read back through sb200_debug_rf_trace().
+// RF_TID: the thread index the stamps and the layer functions go by
+#define RF_TID threadIdx.x
 #ifdef RF_TRACE
 constexpr int RF_TR_STEPS = 8, RF_TR_IDS = 32;
 __device__ long long g_rf_trace[RF_CS][RF_TR_STEPS][RF_TR_IDS];
 #define RF_STAMP(id, who)                                                                           \
     do {                                                                                            \
-        if (blockIdx.x < RF_CS && threadIdx.x == (who) && rf_t >= 2 && rf_t < 2 + RF_TR_STEPS)      \
+        if (blockIdx.x < RF_CS && RF_TID == (who) && rf_t >= 2 && rf_t < 2 + RF_TR_STEPS)           \
             g_rf_trace[blockIdx.x][rf_t - 2][id] = clock64();                                       \
     } while (0)
 #else
@@ -87,6 +91,8 @@ struct RfParams {
     // shared-memory plan (float offsets)
     int oW1, oW2, oWh, oB, oX0, oH1, oH2, oPart, oZf, oEnv, oS, oNext, oAct, oPre;
     int ldx0, ldh1, ldh2;
+    int l1_direct;                  // v2: reduction-free first layer (rf2_layer1)
+    int head_mode;                  // v2: 1 = k-sliced head over all owned actors, 0 = two warps per actor
 };
 
 __device__ __forceinline__ float rf_act(float v, int act) {
@@ -581,7 +587,7 @@ __device__ __forceinline__ void rf2_layer(const float* __restrict__ Xin, int ldi
                                           int Nc, const float* __restrict__ bias_s, int act, float* __restrict__ Hout,
                                           int ldout, int col0, float* __restrict__ Part, unsigned smem_base,
                                           unsigned crank, int rf_t, int rf_id, unsigned bar_off) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = (int)RF_TID, warp = tid >> 5, lane = tid & 31;
     const int rg = warp & 3, ks = ((warp >> 2) << 1) | (lane >> 4), cg0 = lane & 15;
     const int kq = (((K >> 2) + 3) >> 2) << 2;               // k span of one split (multiple of 4)
     const int k_lo = ks * kq, k_hi = min(K, k_lo + kq);
@@ -660,6 +666,80 @@ __device__ __forceinline__ void rf2_layer(const float* __restrict__ Xin, int ldi
     }
 }
 
+// First hidden layer on the 8 math warps WITHOUT a shared-memory reduction: K = D is short (64), so the 4-way k split of
+// rf2_layer spent more on partial tiles, the barrier and the second pass (1.5 K cycles) than on its 4 k quads of FMAs.
+// Here warp w owns rows 4w..4w+3, lane = (column quad, k half); the two k halves of a lane pair are summed by shuffle
+// (each lane keeps two of the four rows) and the epilogue stores / pushes straight from registers.
+template <bool ASYNC>
+__device__ __forceinline__ void rf2_layer1(const float* __restrict__ Xin, int ldin, int K, const float* __restrict__ Ws, int Nc,
+                                           const float* __restrict__ bias_s, int act, float* __restrict__ Hout, int ldout,
+                                           int col0, unsigned smem_base, unsigned crank, unsigned bar_off, int rf_t) {
+    const int tid = (int)RF_TID, warp = tid >> 5, lane = tid & 31;
+    const int cg0 = lane & 15, kh = lane >> 4;
+    const bool up = kh != 0;
+    const int kq = (((K >> 2) + 1) >> 1) << 2;               // k span of one half (multiple of 4)
+    const int k_lo = kh * kq, k_hi = min(K, k_lo + kq);
+    const int nq = Nc >> 2;
+    const float* xr = Xin + (warp * 4) * ldin;
+    unsigned pb[RF_CS - 1];
+#pragma unroll
+    for (int c = 1; c < RF_CS; ++c) pb[c - 1] = rf_mapa(smem_base, (crank + (unsigned)c) % RF_CS);
+    for (int c4 = cg0; c4 < ((nq + 15) & ~15); c4 += 16) {    // uniform trip count: the shuffles need the whole warp
+        const bool on = c4 < nq;
+        const float* wp = Ws + (on ? c4 : 0) * 4;
+        float2 acc[4][2];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r][0] = acc[r][1] = make_float2(0.0f, 0.0f);
+#pragma unroll 2
+        for (int k = k_lo; k < k_hi; k += 4) {
+            const float4 w0 = *reinterpret_cast<const float4*>(wp + (k + 0) * Nc);
+            const float4 w1 = *reinterpret_cast<const float4*>(wp + (k + 1) * Nc);
+            const float4 w2 = *reinterpret_cast<const float4*>(wp + (k + 2) * Nc);
+            const float4 w3 = *reinterpret_cast<const float4*>(wp + (k + 3) * Nc);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float4 a = *reinterpret_cast<const float4*>(xr + r * ldin + k);
+                float2 aa = make_float2(a.x, a.x);
+                acc[r][0] = __ffma2_rn(aa, make_float2(w0.x, w0.y), acc[r][0]);
+                acc[r][1] = __ffma2_rn(aa, make_float2(w0.z, w0.w), acc[r][1]);
+                aa = make_float2(a.y, a.y);
+                acc[r][0] = __ffma2_rn(aa, make_float2(w1.x, w1.y), acc[r][0]);
+                acc[r][1] = __ffma2_rn(aa, make_float2(w1.z, w1.w), acc[r][1]);
+                aa = make_float2(a.z, a.z);
+                acc[r][0] = __ffma2_rn(aa, make_float2(w2.x, w2.y), acc[r][0]);
+                acc[r][1] = __ffma2_rn(aa, make_float2(w2.z, w2.w), acc[r][1]);
+                aa = make_float2(a.w, a.w);
+                acc[r][0] = __ffma2_rn(aa, make_float2(w3.x, w3.y), acc[r][0]);
+                acc[r][1] = __ffma2_rn(aa, make_float2(w3.z, w3.w), acc[r][1]);
+            }
+        }
+        const float4 bv = *reinterpret_cast<const float4*>(bias_s + (on ? c4 : 0) * 4);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const float2 s0 = up ? acc[r][0] : acc[r + 2][0], s1 = up ? acc[r][1] : acc[r + 2][1];
+            const float2 m0 = up ? acc[r + 2][0] : acc[r][0], m1 = up ? acc[r + 2][1] : acc[r][1];
+            float4 o;
+            o.x = rf_act((m0.x + __shfl_xor_sync(0xffffffffu, s0.x, 16)) + bv.x, act);
+            o.y = rf_act((m0.y + __shfl_xor_sync(0xffffffffu, s0.y, 16)) + bv.y, act);
+            o.z = rf_act((m1.x + __shfl_xor_sync(0xffffffffu, s1.x, 16)) + bv.z, act);
+            o.w = rf_act((m1.y + __shfl_xor_sync(0xffffffffu, s1.y, 16)) + bv.w, act);
+            if (on) {
+                const int row = warp * 4 + (up ? 2 : 0) + r;
+                float* qd = Hout + row * ldout + col0 + c4 * 4;
+                *reinterpret_cast<float4*>(qd) = o;
+                const unsigned off = rf_smem_u32(qd) - smem_base;
+#pragma unroll
+                for (int c = 0; c < RF_CS - 1; ++c) {
+                    if (ASYNC) rf_st_async_v4(pb[c] + off, o, pb[c] + bar_off);
+                    else rf_st_cluster_v4(pb[c] + off, o);
+                }
+            }
+        }
+    }
+    RF_STAMP(1, 0);
+    RF_STAMP(2, 0);
+}
+
 template <bool ASYNC>
 __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
     ppo_rollout2_kernel(const __grid_constant__ RfParams p) {
@@ -673,7 +753,9 @@ __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
     __shared__ int s_pos[RF_OWN], s_ep[RF_OWN], s_cnt[RF_OWN];
     __shared__ __align__(8) unsigned long long s_bar[3];      // ASYNC: hidden layer 1 | last hidden layer rows | next input tile
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // (tried: the two roles on swapped warp halves, in case the scheduler's preference for one end of the warp index range
+    // starved the layers -- no difference, profiles/r02b_rollout_trace_*)
+    const int tid = (int)RF_TID, lane = tid & 31, warp = tid >> 5;
     const int D = p.D, H1 = p.H1, H2 = p.H2, A = p.A;
     const int Nc1 = H1 / RF_CS, Nc2 = H2 / RF_CS;
     const int ldwh = p.ldw[2];
@@ -784,8 +866,11 @@ __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
                 rf_mbar_wait(&s_bar[2], (unsigned)(t - 1) & 1u);
             }
             if (ASYNC && tid == 0 && !final_step) rf_mbar_arm(&s_bar[2], tx_x0);     // next tile's phase: only now is the previous one complete
-            rf2_layer<true, ASYNC>(X0, p.ldx0, D, W1s, Nc1, B1s, p.act[0], Hb1, p.ldh1, (int)crank * Nc1, Part, smem_base, crank, rf_t, 1,
-                                   bar_off_h1);
+            if (p.l1_direct)                                   // 8 math warps x 4 rows: the reduction-free form
+                rf2_layer1<ASYNC>(X0, p.ldx0, D, W1s, Nc1, B1s, p.act[0], Hb1, p.ldh1, (int)crank * Nc1, smem_base, crank, bar_off_h1, rf_t);
+            else
+                rf2_layer<true, ASYNC>(X0, p.ldx0, D, W1s, Nc1, B1s, p.act[0], Hb1, p.ldh1, (int)crank * Nc1, Part, smem_base, crank, rf_t, 1,
+                                       bar_off_h1);
             RF_STAMP(3, 0);
             if (ASYNC) {
                 rf_bar_math();
@@ -848,8 +933,51 @@ __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
             __syncthreads();
             rf_mbar_wait(&s_bar[1], (unsigned)t & 1u);
         }
-        // ---- head: warps w and w + 8 take the two k halves of owned actor w & 7
-        {
+        // ---- head.  p.head_mode 1: warp w takes the k slice [w H2/16, (w+1) H2/16) for ALL 8 owned actors (lane = actor x 4 k
+        // sub-lanes), so the head weights are read from shared memory once per step instead of once per actor (the 2 x 8 KB
+        // per actor were 1 K cycles of the shared-memory pipe); the 16 slice sums meet in the (idle) Part buffer.
+        // head_mode 0: warps w and w + 8 take the two k halves of owned actor w & 7.
+        if (p.head_mode == 1) {
+            const int ks = H2 >> 4;                           // H2 % 16 == 0 (rf_plan)
+            const int a8 = lane >> 2, ksub = lane & 3;
+            const float* hrow = Hb2 + a8 * p.ldh2 + warp * ks;
+            const float* wbase = Whs + (warp * ks) * ldwh;
+            for (int n8 = 0; n8 < A; n8 += 8) {
+                float s8[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) s8[jj] = 0.0f;
+                const bool second = (n8 + 4 < ldwh);
+                for (int k = ksub; k < ks; k += 4) {
+                    const float hv = hrow[k];
+                    const float* wr = wbase + k * ldwh + n8;
+                    const float4 w0 = *reinterpret_cast<const float4*>(wr);
+                    s8[0] = fmaf(hv, w0.x, s8[0]); s8[1] = fmaf(hv, w0.y, s8[1]);
+                    s8[2] = fmaf(hv, w0.z, s8[2]); s8[3] = fmaf(hv, w0.w, s8[3]);
+                    if (second) {
+                        const float4 w1 = *reinterpret_cast<const float4*>(wr + 4);
+                        s8[4] = fmaf(hv, w1.x, s8[4]); s8[5] = fmaf(hv, w1.y, s8[5]);
+                        s8[6] = fmaf(hv, w1.z, s8[6]); s8[7] = fmaf(hv, w1.w, s8[7]);
+                    }
+                }
+                // sum over the 4 k sub-lanes: after two exchange rounds lane ksub holds outputs 2 ksub', 2 ksub' + 1
+                const bool u1 = (lane & 2) != 0, u0 = (lane & 1) != 0;
+                float t4[4], t2[2];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float recv = __shfl_xor_sync(0xffffffffu, u1 ? s8[i] : s8[i + 4], 2);
+                    t4[i] = (u1 ? s8[i + 4] : s8[i]) + recv;
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const float recv = __shfl_xor_sync(0xffffffffu, u0 ? t4[i] : t4[i + 2], 1);
+                    t2[i] = (u0 ? t4[i + 2] : t4[i]) + recv;
+                }
+                const int j0 = n8 + (u1 ? 4 : 0) + (u0 ? 2 : 0);
+                float* dst = Part + ((warp * RF_OWN + a8) * ldwh);
+                if (j0 < A) dst[j0] = t2[0];
+                if (j0 + 1 < A) dst[j0 + 1] = t2[1];
+            }
+        } else {
             const int half = warp >> 3;
             const float* hrow = Hb2 + own * p.ldh2;
             const int kh = H2 >> 1;
@@ -884,7 +1012,15 @@ __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
             const int pos = s_pos[own];
             if (lane < A) {
                 const int j = lane;
-                const float mu = rf_act((Hp[own * A + j] + Hp[(RF_OWN + own) * A + j]) + Bhs[j], p.act[2]);
+                float pre;
+                if (p.head_mode == 1) {
+                    pre = 0.0f;
+#pragma unroll 4
+                    for (int w = 0; w < RF_THREADS / 32; ++w) pre += Part[(w * RF_OWN + own) * ldwh + j];    // fixed order
+                } else {
+                    pre = Hp[own * A + j] + Hp[(RF_OWN + own) * A + j];
+                }
+                const float mu = rf_act(pre + Bhs[j], p.act[2]);
                 const float sd = Sd[own * A + j];
                 float a = mu;
                 if (!p.deterministic) a = __fadd_rn(__fmul_rn(Zn[own * A + j], sd), mu);
@@ -1181,8 +1317,14 @@ extern "C" int sb200_ppo_rollout_f32(const sb200_ppo_rollout* a, void* stream) {
     static const int f2 = [] { const char* e = getenv("SB200_RF_FFMA2"); return e ? atoi(e) : 1; }();
     // v2 (warp-specialised env warps, 8x4 register tiles) is the default; SB200_RF_V2=0 selects the v1 kernel
     static const int v2 = [] { const char* e = getenv("SB200_RF_V2"); return e ? atoi(e) : 1; }();
-    // SB200_RF_ASYNC=1: the same kernel with mbarrier-signalled st.async hand-offs instead of the three cluster barriers per step
-    static const int rf_async = [] { const char* e = getenv("SB200_RF_ASYNC"); return e ? atoi(e) : 0; }();
+    static const int l1_direct = [] { const char* e = getenv("SB200_RF_L1DIRECT"); return e ? atoi(e) : 1; }();
+    p.l1_direct = (l1_direct && RF_ROWS == 4 * RF_OWN) ? 1 : 0;
+    static const int head_mode = [] { const char* e = getenv("SB200_RF_HEAD"); return e ? atoi(e) : 1; }();
+    // the slice sums need 16 warps x 8 actors x ldw[2] floats of the Part buffer (4 x 32 x max(Nc1, Nc2))
+    p.head_mode = (head_mode == 1 && 16 * RF_OWN * a->net->ldw[2] <= 4 * RF_ROWS * std::max(a->net->dims[1], a->net->dims[2]) / RF_CS) ? 1 : 0;
+    // default: mbarrier-signalled st.async hand-offs instead of the three cluster barriers per step (1.47 -> 1.38 ms per
+    // 128-step chunk of 1024 actors, same results bit for bit); SB200_RF_ASYNC=0 selects the barrier.cluster variant
+    static const int rf_async = [] { const char* e = getenv("SB200_RF_ASYNC"); return e ? atoi(e) : 1; }();
     if (v2 && rf_async && a->D % 4 == 0 && (3u * RF_ROWS * (unsigned)(a->net->dims[1] / RF_CS) * 4u) < (1u << 20))
         ppo_rollout2_kernel<true><<<(unsigned)(clusters * RF_CS), RF_THREADS, smem, (cudaStream_t)stream>>>(p);
     else if (v2) ppo_rollout2_kernel<false><<<(unsigned)(clusters * RF_CS), RF_THREADS, smem, (cudaStream_t)stream>>>(p);

@@ -698,8 +698,8 @@ class PPOLearner(Learner):
                 self._graph.run(self._optimize_epochs)
             else:
                 self._graph.run(self._optimize_device)
-        elif self.use_cuda_graph:
-            self._optimize_device()                               # same sequence, eager (per-kernel event timing)
+        elif self.use_cuda_graph or (self._epoch_kernels() or (None, None, None))[2] is not None:
+            self._optimize_device()                               # same sequence, eager (per-kernel event timing, ncu launch lists)
         else:
             self._optimize_head()                                 # reference-style host loop: one sync per epoch
             for e in range(self.epoch_policy):
