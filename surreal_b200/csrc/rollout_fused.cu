@@ -865,6 +865,7 @@ __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
                 rf_bar_math();
                 rf_mbar_wait(&s_bar[2], (unsigned)(t - 1) & 1u);
             }
+            RF_STAMP(18, 0);
             if (ASYNC && tid == 0 && !final_step) rf_mbar_arm(&s_bar[2], tx_x0);     // next tile's phase: only now is the previous one complete
             if (p.l1_direct)                                   // 8 math warps x 4 rows: the reduction-free form
                 rf2_layer1<ASYNC>(X0, p.ldx0, D, W1s, Nc1, B1s, p.act[0], Hb1, p.ldh1, (int)crank * Nc1, smem_base, crank, bar_off_h1, rf_t);
@@ -1020,6 +1021,7 @@ __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
                 } else {
                     pre = Hp[own * A + j] + Hp[(RF_OWN + own) * A + j];
                 }
+                RF_STAMP(19, 0);
                 const float mu = rf_act(pre + Bhs[j], p.act[2]);
                 const float sd = Sd[own * A + j];
                 float a = mu;
@@ -1038,6 +1040,7 @@ __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
                 }
             }
             __syncwarp();
+            RF_STAMP(20, 0);
             float* sown = S + own * D;
             const int ep = s_ep[own] + 1;
             const bool is_done = (p.max_steps > 0) && (ep >= p.max_steps);
@@ -1052,6 +1055,7 @@ __global__ void __cluster_dims__(RF_CS, 1, 1) __launch_bounds__(RF_THREADS, 1)
                 sown[d] = is_done ? Erz[own * D + d] : nxt;
                 if (valid && final_step) p.obs_next[i_own * D + d] = nxt;
             }
+            RF_STAMP(21, 0);
             if (lane == 0) {
                 s_ep[own] = is_done ? 0 : ep;
                 if (valid && final_step) {

@@ -75,6 +75,9 @@ def main():
             print('   %-24s %7.0f' % (NAMES[i], per[i]))
         print('   %-24s %7.0f   (step period %0.f)' % ('sum', per.sum(), step))
         print('   helper warp: start +%0.f after cluster.sync 2, busy %0.f' % (np.median(d[:, 16] - d[:, 8]), np.median(d[:, 17] - d[:, 16])))
+        if d[:, 18].any():
+            print('   v2 detail: input-tile wait ends +%0.f after step top; phase 2: slice sums %0.f | mean/sample/stores %0.f | env finalize %0.f | bookkeeping %0.f'
+                  % (np.median(d[1:, 18] - d[1:, 0]), np.median(d[:, 19] - d[:, 10]), np.median(d[:, 20] - d[:, 19]), np.median(d[:, 21] - d[:, 20]), np.median(d[:, 11] - d[:, 21])))
 
 
 if __name__ == '__main__':
