@@ -1029,9 +1029,7 @@ __global__ void __launch_bounds__(E2T, 1) ppo_epochs2_kernel(const __grid_consta
                     __syncthreads();
                     const float scale = 1.0f / (float)p.par.world;
                     if ((p.par.max_floats & 3) == 0) {
-                        if (p.par.world == 2) sq = peer_sum_slice<2, 3>(p, lo, hi, k & 1u, scale);
-                        else if (p.par.world <= 4) sq = peer_sum_slice<4, 3>(p, lo, hi, k & 1u, scale);
-                        else sq = peer_sum_slice<8, 1>(p, lo, hi, k & 1u, scale);
+                        sq = peer_sum_slice<PAR_MAX_WORLD, 1>(p, lo, hi, k & 1u, scale);      // one path for every world size
                     } else {
                         for (long long i = lo + tid; i < hi; i += E2T) {
                             float a = 0.f;
