@@ -173,18 +173,19 @@ int sb200_par_allreduce_f32(const sb200_par* ctx, const float* x, float* out, in
 int sb200_par_allreduce_f64(const sb200_par* ctx, const double* x, double* out, int n, double scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Persistent learner kernel (csrc/epoch.cu): ALL minibatch epochs of one optimiser of PPOLearner._optimize
- * (surreal/learner/ppo.py:194-353 losses + updates, 541-557 epoch loops + KL early stop) in ONE launch -- forward, loss,
- * backward, slab reduction, gradient clip, Adam, post-step forward and KL of every epoch, phases separated by grid
- * barriers instead of launches.  It writes the same buffers and statistics as the launch chain it replaces
+ * Persistent learner kernel (csrc/epoch2.cu): ALL minibatch epochs of BOTH optimisers of PPOLearner._optimize
+ * (surreal/learner/ppo.py:194-353 losses + updates, 541-557 epoch loops + KL early stop) in ONE launch of one CTA per SM --
+ * forward, loss, backward, slab reduction, gradient clip, Adam, post-step forward and KL of every epoch; row blocks of 16 run
+ * forward -> loss -> input gradients without grid barriers, weight gradients are a second wave, an epoch costs 4 grid
+ * barriers (5 in adapt mode).  It writes the same buffers and statistics as the launch chain it replaces
  * (sb200_mlp_forward_f32 + sb200_ppo_policy_loss_f32 / sb200_value_loss_f32 + sb200_linear_bwd_* +
  * sb200_grad_reduce_norm_f32 + sb200_clip_adam_f32 + sb200_ppo_kl_f32).
- *   supported: 3 layers ReLU-ReLU-any, no aux input, head <= 32 wide.
+ *   sb200_epochs = the argument block of ONE optimiser: 3 layers ReLU-ReLU-any, no aux input, head <= 32 wide, widths <= 512.
  *   net->W / net->b must point INTO `params` (the flat buffer Adam updates); x_in/h1/h2/out/d1/d2/dpre are [M][ru4(width)]
  *   with zero padding columns (x_in receives the z-filtered input rows).
  *   mode 0 clip / 1 adapt (policy: out = tanh mean, log_var at params[extra_off..+A), early stop above stop_threshold),
- *   mode 2 value (MSE on `returns`).  grid: CTAs to launch (all must be able to be co-resident: <= 2 per SM);
- *   cta_shift rotates the tile -> CTA map so that two concurrent launches (policy || value) use different SMs.
+ *   mode 2 value (MSE on `returns`).  grid: upper bound on the CTAs to launch (0: one per SM); cta_shift and workspace of the
+ *   block are unused (the call takes the workspace).
  *   par != NULL with world > 1: data-parallel -- the KL scalar and the flat gradient are averaged over the ranks inside
  *   the kernel through the symmetric buffers of `par` (every rank must launch the same sequence). */
 typedef struct {
@@ -218,22 +219,14 @@ typedef struct {
     float* stats;
     int* stop_flag;
     int epochs;
-    void* workspace;                    /* sb200_ppo_epochs_workspace_bytes() */
+    void* workspace;                    /* unused (kept for layout) */
     int grid;
     int cta_shift;
     const sb200_par* par;
 } sb200_epochs;
-int sb200_ppo_epochs_supported(const sb200_mlp* net);
-size_t sb200_ppo_epochs_workspace_bytes(void);
-int sb200_ppo_epochs_f32(const sb200_epochs* args, void* stream);
-
-/* Second generation (csrc/epoch2.cu): BOTH optimisers of PPOLearner._optimize -- `policy` (mode 0 / 1) and `value` (mode 2,
- * may be NULL) -- in ONE launch of one CTA per SM: row blocks of 16 run forward -> loss -> input gradients without grid
- * barriers, weight gradients are a second wave, an epoch costs 4 grid barriers (5 in adapt mode).  Same buffers, statistics
- * and early-stop semantics as sb200_ppo_epochs_f32 called once per optimiser; `grid` / `cta_shift` / `workspace` of the
- * argument blocks are ignored (grid = SM count, or policy->grid when smaller); `workspace` here must hold
- * sb200_ppo_epochs2_workspace_bytes() bytes, 256-byte aligned.  Data-parallel: the two blocks must use DIFFERENT sb200_par
- * channels (both exchange in the same phase). */
+/* `policy` (mode 0 / 1) and `value` (mode 2, may be NULL) in one launch; `workspace` must hold
+ * sb200_ppo_epochs2_workspace_bytes() bytes, 256-byte aligned, zero-initialised once.  Data-parallel: the two blocks must use
+ * DIFFERENT sb200_par channels (both exchange in the same phase). */
 int sb200_ppo_epochs2_supported(const sb200_epochs* policy, const sb200_epochs* value);
 size_t sb200_ppo_epochs2_workspace_bytes(const sb200_epochs* policy, const sb200_epochs* value);
 int sb200_ppo_epochs2_f32(const sb200_epochs* policy, const sb200_epochs* value, void* workspace, void* stream);

@@ -100,9 +100,6 @@ def _declare(lib):
         'sb200_par_close': (I, [P, I]),
         'sb200_par_allreduce_f32': (I, [C.POINTER(Par), P, P, L, D, I, P, P, P]),
         'sb200_par_allreduce_f64': (I, [C.POINTER(Par), P, P, I, D, P]),
-        'sb200_ppo_epochs_supported': (I, [C.POINTER(Mlp)]),
-        'sb200_ppo_epochs_workspace_bytes': (S, []),
-        'sb200_ppo_epochs_f32': (I, [C.POINTER(Epochs), P]),
         'sb200_ppo_epochs2_supported': (I, [C.POINTER(Epochs), C.POINTER(Epochs)]),
         'sb200_ppo_epochs2_workspace_bytes': (S, [C.POINTER(Epochs), C.POINTER(Epochs)]),
         'sb200_ppo_epochs2_f32': (I, [C.POINTER(Epochs), C.POINTER(Epochs), P, P]),

@@ -2,7 +2,7 @@
 // value epochs on the critic; surreal/learner/ppo.py:194-353 losses and updates, 541-557 epoch loops and KL early stop)
 // in ONE launch of one CTA per SM.
 //
-// What the first generation (epoch.cu: one launch per optimiser, 64x64 tiles, a grid barrier after every layer) taught:
+// What the first generation (one launch per optimiser, 64x64 tiles, a grid barrier after every layer; removed) taught:
 // at 1024-row minibatches a layer is 64 tiles for 148 SMs and an epoch is 8-9 grid barriers, so the kernel spent its time
 // waiting (114 us per epoch for 0.5 GFLOP).  Two observations restructure it:
 //   * rows are independent through forward AND input-gradient: a CTA that owns a block of 16 rows runs
@@ -21,7 +21,7 @@
 //   P4  clip by global norm + Adam (torch's arithmetic, optim_dev.cuh), W2^T refresh    -> barrier
 // Everything is deterministic (static work assignment, fixed-order sums).  Buffers rewritten by other CTAs between
 // barriers are read with ld.global.cg only.  Data-parallel exchanges (KL scalar, flat gradients) happen inside the
-// kernel over NVLink peer memory with the protocol of peer_allreduce.cu, as in epoch.cu.
+// kernel over NVLink peer memory with the protocol of peer_allreduce.cu.
 #include <math.h>
 #include <stddef.h>
 
@@ -43,7 +43,7 @@ constexpr int E2_MAX_OUT = 32;
 constexpr int E2_SLOTS = 4 + E2_MAX_OUT;
 constexpr int E2_MAX_G = 192;
 
-// ---- peer exchange (same layout as peer_allreduce.cu / epoch.cu)
+// ---- peer exchange (same layout as peer_allreduce.cu)
 constexpr int PAR_MAX_WORLD = 8;
 constexpr int PAR_MAX_CTAS = 16;
 struct ParHeader {

@@ -1,6 +1,6 @@
 // 64x64 fp32 SIMT GEMM tiles as DEVICE functions (256 threads, 4x4 per thread, reduction chunk 16, register prefetch of
 // the next chunk) -- the bodies of mlp_bwd.cu's kernels plus a forward tile, callable with an explicit tile index so
-// that the persistent learner kernel (epoch.cu) can schedule them itself.
+// that a persistent kernel can schedule them itself (the first-generation learner kernel did; epoch2.cu borrows the helpers).
 //
 //   gt_tile_nn : C[m][n]  = act(zf(X)[m][:] . W[:][n] + b[n])                  forward          (reduce over K)
 //   gt_tile_nt : dX[m][k] = (dY[m][:] . W[k][:]) * relu'(Xact[m][k])           input gradient   (reduce over N)

@@ -14,7 +14,7 @@ namespace {
 using gt::TB;
 using gt::RK;
 
-// The tile bodies live in gemm_tiles.cuh (shared with the persistent learner kernel, epoch.cu).
+// The tile bodies live in gemm_tiles.cuh.
 __global__ void __launch_bounds__(SB200_THREADS) bwd_dx_kernel(const float* dY, long long ldy, const float* W, int ldw,
                                                                 const float* Xact, long long ldxa, float* dX,
                                                                 long long lddx, int M, int N, int K) {

@@ -1,5 +1,5 @@
 // Optimiser pieces shared by the stand-alone kernels (optim.cu, peer_allreduce.cu) and the persistent learner kernel
-// (epoch.cu): the device-resident workspace and torch's single-tensor Adam, operation by operation.
+// (epoch2.cu): the device-resident workspace and torch's single-tensor Adam, operation by operation.
 #pragma once
 #include "common.cuh"
 

@@ -1,5 +1,5 @@
 // Per-row pieces of the PPO losses (ppo.py:194-225 clip, 250-285 adapt; DiagGauss of ppo_net.py:29-72), shared by the
-// stand-alone loss kernels (ppo_loss.cu) and the persistent learner kernel (epoch.cu) so that both evaluate the same
+// stand-alone loss kernels (ppo_loss.cu) and the persistent learner kernel (epoch2.cu) so that both evaluate the same
 // arithmetic in the same order.
 #pragma once
 #include "common.cuh"

@@ -201,11 +201,11 @@ class PPOLearner(Learner):
         self.tc5_min_rows = int(os.environ.get('SB200_TC5_MIN_ROWS', '4096'))
         self.dp = None
         self.dp_v = None
-        # all epochs of one optimiser as ONE persistent kernel (csrc/epoch.cu) instead of ~13 launches per epoch
-        self.use_epoch_kernel = os.environ.get('SB200_EPOCH_KERNEL', '1') != '0' and not self.pixel and not self.rnn and \
-            ops.EpochKernel.supported(self.model.actor) and ops.EpochKernel.supported(self.model.critic)
+        # all epochs of BOTH optimisers as ONE persistent kernel (csrc/epoch2.cu) instead of ~10 launches per epoch;
+        # SB200_EPOCH_KERNEL=0 selects the launch chain (always the path of the pixel / RNN stems)
+        self.use_epoch_kernel = os.environ.get('SB200_EPOCH_KERNEL', '2') != '0' and not self.pixel and not self.rnn
         self._ek = None
-        self.epoch_kernel_gen = int(os.environ.get('SB200_EPOCH_KERNEL', '2'))     # 0: launch chain, 1: epoch.cu, 2: epoch2.cu
+        self.epoch_kernel_gen = 2 if self.use_epoch_kernel else 0
         self.epoch_history = []
         self._sync_hyper()
         self.last_n_policy_epochs = 0
@@ -607,6 +607,8 @@ class PPOLearner(Learner):
             return None
         if self.dp is not None and (self.dp.peer is None or self.dp_v.peer is None):
             return None
+        if self.model.actor.n_layers != 3 or self.model.critic.n_layers != 3:
+            return None                                           # the kernel is written for input -> 2 hidden -> head
         B, n, A, D = self.batch_size, self.n_step, self.action_dim, self.low_dim
         key = (self._obs_full.data_ptr(), self._actions.data_ptr(), self._pds.data_ptr(), id(self.dp))
         if self._ek is None or self._ek[0] != key:
@@ -623,11 +625,13 @@ class PPOLearner(Learner):
             if self.dp is not None:
                 pk.set_peer(self.dp.peer)
                 vk.set_peer(self.dp_v.peer)
-            # second generation: both optimisers in ONE launch (csrc/epoch2.cu); data-parallel needs two distinct channels
+            # both optimisers in ONE launch; data-parallel needs two distinct channels (both exchange in the same phase)
             pair = None
-            if self.epoch_kernel_gen >= 2 and (self.dp is None or self.dp_v is not self.dp) and ops.EpochPair.supported(pk, vk):
+            if (self.dp is None or self.dp_v is not self.dp) and ops.EpochPair.supported(pk, vk):
                 pair = ops.EpochPair(pk, vk)
             self._ek = (key, pk, vk, pair)
+        if self._ek[3] is None:
+            return None                                           # shape the kernel rejects: launch chain
         return self._ek[1], self._ek[2], self._ek[3]
 
     def _optimize_device(self):
@@ -649,22 +653,8 @@ class PPOLearner(Learner):
             (self.dp is None or (self.dp_graph and self.dp_v is not self.dp))
         ek = self._epoch_kernels()
         if ek is not None:
-            # one persistent kernel per optimiser (all epochs, early stop and -- data-parallel -- the exchanges inside)
-            pk, vk, pair = ek
-            if pair is not None:
-                self._cur_mean = pair.run()
-            elif fork:
-                if self._side_stream is None:
-                    self._side_stream = torch.cuda.Stream(device=self.device)
-                main, side = torch.cuda.current_stream(), self._side_stream
-                side.wait_stream(main)
-                with torch.cuda.stream(side):
-                    vk.run()
-                self._cur_mean = pk.run()
-                main.wait_stream(side)
-            else:
-                self._cur_mean = pk.run()
-                vk.run()
+            # one persistent kernel (all epochs of both optimisers, early stop and -- data-parallel -- the exchanges inside)
+            self._cur_mean = ek[2].run()
             self._optimize_tail(value_done=True)
             return
         if fork:

@@ -445,8 +445,9 @@ class MlpTrainer:
 
 
 class EpochKernel:
-    """The persistent learner kernel (csrc/epoch.cu) bound to one MlpTrainer: all epochs of one optimiser in ONE launch.
-    ``mode`` 0 clip / 1 adapt (policy) or 2 (value).  The argument block is built once (fixed buffers: graph-safe)."""
+    """Argument block (`sb200_epochs`) of the persistent learner kernel for ONE optimiser, bound to one MlpTrainer:
+    ``mode`` 0 clip / 1 adapt (policy) or 2 (value).  Built once (fixed buffers: graph-safe); two of them make an
+    EpochPair, which is what launches (csrc/epoch2.cu)."""
 
     def __init__(self, trainer, mode, x, ldx, M, zf_stats, zf_eps, stats, epochs, norm_out=None, stop_flag=None,
                  actions=None, lda=0, adv=None, behave_pd=None, ldb=0, ref_pd=None, ldr=0, returns=None, hyper=None,
@@ -454,10 +455,9 @@ class EpochKernel:
         from ._lib import Epochs
         L = _lib.lib()
         net = trainer.net
-        assert EpochKernel.supported(net) and M == trainer.M
+        assert M == trainer.M
         self.trainer = trainer
         self._desc = net.desc()
-        self.ws = torch.zeros(L.sb200_ppo_epochs_workspace_bytes(), dtype=torch.uint8, device=net.device)
         sm = C.c_int(0)
         check(L.sb200_device_info(C.byref(sm), None, None), 'sb200_device_info')
         self._keep = (x, zf_stats, stats, norm_out, stop_flag, actions, adv, behave_pd, ref_pd, returns, hyper)
@@ -484,24 +484,17 @@ class EpochKernel:
         a.returns, a.hyper = g(returns), g(hyper)
         a.eta, a.kl_target, a.stop_threshold = float(eta), float(kl_target), float(stop_threshold)
         a.stats, a.stop_flag, a.epochs = stats.data_ptr(), g(stop_flag), int(epochs)
-        a.workspace = self.ws.data_ptr()
+        a.workspace = None                                  # the pair owns the workspace
         a.grid = int(grid) if grid is not None else int(sm.value)
         a.cta_shift = int(cta_shift)
         a.par = None
         self.args = a
-
-    @staticmethod
-    def supported(net):
-        return bool(_lib.lib().sb200_ppo_epochs_supported(C.byref(net.desc())))
 
     def set_peer(self, peer):
         """Data-parallel: average the KL scalar and the flat gradient over the ranks of ``peer`` (a PeerChannel) in-kernel."""
         self._peer = peer
         self.args.par = C.addressof(peer.ctx) if peer is not None else None
 
-    def run(self):
-        check(_lib.lib().sb200_ppo_epochs_f32(C.byref(self.args), _stream()), 'sb200_ppo_epochs_f32')
-        return self.trainer.out
 
 
 class EpochPair:
