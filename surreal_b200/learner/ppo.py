@@ -621,7 +621,7 @@ class PPOLearner(Learner):
                                  stop_threshold=4.0 * self.kl_target, cta_shift=0)
             vk = ops.EpochKernel(self.critic_optim, 2, self._obs_full, (n + 1) * D, B, m.z_stats, m.z_eps, self._stats,
                                  self.epoch_baseline, norm_out=self._stats[S['GN_CRITIC']:S['GN_CRITIC'] + 1],
-                                 returns=self._ret, cta_shift=pk.args.grid // 2)
+                                 returns=self._ret)
             if self.dp is not None:
                 pk.set_peer(self.dp.peer)
                 vk.set_peer(self.dp_v.peer)

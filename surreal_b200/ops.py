@@ -458,8 +458,6 @@ class EpochKernel:
         assert M == trainer.M
         self.trainer = trainer
         self._desc = net.desc()
-        sm = C.c_int(0)
-        check(L.sb200_device_info(C.byref(sm), None, None), 'sb200_device_info')
         self._keep = (x, zf_stats, stats, norm_out, stop_flag, actions, adv, behave_pd, ref_pd, returns, hyper)
         a = Epochs()
         a.net = C.addressof(self._desc)
@@ -485,7 +483,7 @@ class EpochKernel:
         a.eta, a.kl_target, a.stop_threshold = float(eta), float(kl_target), float(stop_threshold)
         a.stats, a.stop_flag, a.epochs = stats.data_ptr(), g(stop_flag), int(epochs)
         a.workspace = None                                  # the pair owns the workspace
-        a.grid = int(grid) if grid is not None else int(sm.value)
+        a.grid = int(grid) if grid is not None else 0            # 0: one CTA per SM (the library asks the device)
         a.cta_shift = int(cta_shift)
         a.par = None
         self.args = a
